@@ -1,0 +1,146 @@
+/* polystokes_b200.h -- C ABI of the B200-native PolyStokes per-step Stokes solve.
+ *
+ * This library replaces everything below the DOP node of the reference, i.e. class
+ * HDK_PolyStokes::Solver (exec/HDK_PolyStokesSolver.h:27-887) and the lib/ linear algebra it calls,
+ * behind plain-C entry points (no C++ / torch / HDK types in any signature).  The Houdini node
+ * HDK_PolyStokes::solveGasSubclass (exec/HDK_PolyStokes.C:222-609) keeps its role as a thin
+ * marshaller: it copies the SIM_RawField voxels into dense x-fastest arrays, fills ps_params from the
+ * node's PRM accessors (exec/HDK_PolyStokes.h:23-43) and calls ps_step once per substep.
+ * INTEGRATION.md shows that binding.
+ *
+ * Layout of every field: dense, x fastest, then y, then z, sized by sample type for an nx*ny*nz grid:
+ *   centre (nx,ny,nz); face X (nx+1,ny,nz); face Y (nx,ny+1,nz); face Z (nx,ny,nz+1)
+ *   (exec/HDK_PolyStokesSolver.h:193-222, 294-314).
+ * Ownership of every pointer stays with the caller.  A handle is not thread safe.
+ */
+#ifndef POLYSTOKES_B200_H
+#define POLYSTOKES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* HDK_PolyStokes::Solver::SolverResult, exec/HDK_PolyStokesSolver.h:61-70 (same numeric values) */
+enum {
+    PS_UNSUPPORTED_SOLVER = -4, PS_INCOMPLETE = -3, PS_INVALID = -2, PS_FAILED = -1,
+    PS_NOCONVERGE = 0, PS_SUCCESS = 1, PS_NOCHANGE = 2
+};
+
+enum { PS_MEM_HOST = 0, PS_MEM_DEVICE = 1 };
+
+/* Node parameters: one field per PRM of the reference (exec/HDK_PolyStokes.h:23-43; defaults
+ * exec/HDK_PolyStokes.C:123-206; README.md:33-45) plus the grid description the Solver
+ * constructor receives (exec/HDK_PolyStokesSolver.cpp:18-68). */
+typedef struct ps_params {
+    int32_t nx, ny, nz;               /* velocityField->getTotalVoxelRes() */
+    double dx, dt;                    /* PS.C:319-320 */
+    double origin[3];                 /* field origin (enters no result, kept for the adaptor) */
+    double constantDensity;           /* densityField constant value, PS.C:298-304 */
+    double tolerance;                 /* SIM_NAME_TOLERANCE */
+    int32_t maxSolverIterations;
+    int32_t activeLiquidBoundaryLayerSize;
+    int32_t activeSolidBoundaryLayerSize;
+    int32_t doReducedRegions;
+    int32_t doTile;
+    int32_t tileSize;
+    int32_t tilePadding;
+    int32_t exportMatrices;
+    int32_t exportComponentMatrices;
+    int32_t exportStats;
+    char exportDataPrefix[256];
+    int32_t doSolve;
+    int32_t keepNonConvergedResults;
+    int32_t useWarmStart;             /* accepted; the live reference solver discards the guess (S.cpp:768) */
+    int32_t matrixSetup;              /* 0 = pressurestress (units.h:76-83); others -> PS_UNSUPPORTED_SOLVER */
+    int32_t solverType;               /* 0 = pcg_matrix_vector_products (units.h:85-94) */
+    int32_t useInputSurfaceWeights;   /* validated, ignored by the live weights builder (PS.C:351-352) */
+    int32_t useInputCollisionWeights;
+    double minDensity, maxDensity;    /* stored, never used by the reference (S.cpp:55-56) */
+    /* extensions (not in the reference) */
+    int32_t device;                   /* CUDA device ordinal */
+    int32_t checkEvery;               /* host polls the device-side convergence flag every N iterations (0 = default 25) */
+    int (*cancel_cb)(void*);          /* UT_Interrupt::opInterrupt() stand-in, polled with the flag */
+    void* cancel_ctx;
+} ps_params;
+
+/* Inputs of one step = the fields solveGasSubclass fetches (exec/HDK_PolyStokes.C:235-246). */
+typedef struct ps_fields_in {
+    int32_t memory;                   /* PS_MEM_HOST or PS_MEM_DEVICE */
+    const float* surface;             /* liquid SDF, centre sampled, < 0 inside liquid */
+    const float* collision;           /* solid SDF, centre sampled, < 0 inside solid */
+    const float* viscosity;           /* centre sampled */
+    const float* velocity[3];         /* face sampled */
+    const float* collisionvel[3];     /* face sampled */
+} ps_fields_in;
+
+/* Outputs: velocity overwritten on valid faces + the `valid` vector field (PS.C:562-584). */
+typedef struct ps_fields_out {
+    int32_t memory;
+    float* velocity[3];               /* must hold the input velocity on entry semantics: invalid faces are left untouched */
+    float* valid[3];
+} ps_fields_out;
+
+enum {
+    PS_STAGE_UPLOAD = 0, PS_STAGE_WEIGHTS, PS_STAGE_CLASSIFY, PS_STAGE_REDUCED, PS_STAGE_INDICES, PS_STAGE_REGION_MATRICES,
+    PS_STAGE_MATRIX_BLOCKS, PS_STAGE_ASSEMBLE, PS_STAGE_SOLVE, PS_STAGE_WRITEBACK, PS_STAGE_DOWNLOAD, PS_NUM_STAGES
+};
+
+/* Mirrors exportStats' dimData / solveData vectors (exec/HDK_PolyStokesSolver.cpp:574-606). */
+typedef struct ps_stats {
+    double dimData[27];
+    double solveData[6];              /* error, iterations, solve CPU ms, solve wall ms, setup CPU ms, setup wall ms */
+    int32_t result;                   /* SolverResult */
+    int32_t usedBiCGStab;             /* CG -> BiCGSTAB fallback taken (S.cpp:784-799) */
+    double stage_ms[PS_NUM_STAGES];   /* CUDA-event time per stage (same stage split as PS.C:350-568) */
+    int64_t gpu_launches;             /* kernels launched by this step */
+} ps_stats;
+
+typedef struct ps_solver* ps_handle;
+
+/* Solver constructor (S.cpp:18-155).  Returns PS_SUCCESS or PS_FAILED/PS_INVALID. */
+int ps_create(const ps_params* params, ps_handle* out);
+void ps_destroy(ps_handle h);
+/* One solveGasSubclass body (PS.C:344-608): weights, classify, assemble, PCG, write-back.
+ * Returns the SolverResult; `out` may be NULL (no write-back), `stats` may be NULL. */
+int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* stats);
+/* The two halves of ps_step, separately callable (setup = PS.C:344-476, solve = PS.C:508-584). */
+int ps_setup(ps_handle h, const ps_fields_in* in);
+int ps_solve(ps_handle h, ps_fields_out* out, ps_stats* stats);
+/* exportMatrices / exportComponentMatrices / exportStats (S.cpp:533-606): MatrixMarket files written with
+ * Eigen's saveMarket format.  `what` is a bit mask: 1 = b + solution, 2 = component matrices, 4 = stats. */
+int ps_export(ps_handle h, const char* prefix, int what);
+/* thread-local description of the last PS_FAILED / PS_INVALID */
+const char* ps_last_error(void);
+
+/* ---- introspection for parity tests (read-only views of the solver state, copied to HOST memory) ---- */
+/* counters by name: nCenter nFaceX nFaceY nFaceZ nEdgeYZ nEdgeXZ nEdgeXY nActiveVs nReducedVs nPressures
+ * nStresses nTotalDOFs nSystemSize regionCount iterations result usedBiCGStab nRowsExt */
+int64_t ps_get_count(ps_handle h, const char* name);
+double ps_get_real(ps_handle h, const char* name);     /* solveError */
+/* kind: 0 labels (int8 widened), 1 active indices, 2 reduced indices; slot: 0 centre, 1-3 face x/y/z,
+ * 4-6 edge YZ/XZ/XY.  `out` receives int32 values; returns the element count. */
+int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out);
+/* liquid != 0: liquid weights, else fluid weights; values k/8 as float */
+int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out);
+/* CSR export of a block by name (G Dt JG JDt Mc McInv uInv u Mr B BInv): call once with NULL arrays for
+ * the sizes, then with arrays.  Column indices sorted per row, explicit zeros kept (Eigen semantics). */
+int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz, int64_t* rowptr, int32_t* colidx, double* vals);
+/* dense vectors by name (activeRHS reducedRHS pressureRHS stressRHS b solution velSolution com bestFit
+ * MrDense ViscDense BinvDense); returns the length */
+int64_t ps_get_vector(ps_handle h, const char* name, double* out);
+/* y = A x with host vectors of length nSystemSize (ApplyPressureStressMatrix::apply, Apply.h:182-184) */
+int ps_apply(ps_handle h, const double* x, double* y);
+/* times `reps` back-to-back operator applies / CG iterations on the current system (CUDA events on the
+ * solver stream); used by bench.py for the roofline.  Returns average milliseconds per repetition. */
+double ps_time_apply(ps_handle h, int reps, int flushL2);
+double ps_time_cg_iteration(ps_handle h, int reps);
+/* algorithmic bytes of one operator apply / one CG iteration on the current system */
+double ps_apply_bytes(ps_handle h);
+double ps_cg_iteration_bytes(ps_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,356 @@
+// ps_api.cu -- the C ABI (include/polystokes_b200.h).  No exception crosses the boundary: every entry
+// point catches, stores the message for ps_last_error() and returns PS_FAILED / PS_INVALID, mirroring the
+// reference's "return false + addError" convention (exec/HDK_PolyStokes.C:251-314, 597-608).
+#include "ps_solver.hpp"
+#include <map>
+#include <array>
+#include <fstream>
+#include <limits>
+
+using namespace ps;
+
+struct ps_solver { Solver* S; };
+
+namespace {
+
+template <class Fn>
+int guarded(Fn&& fn) {
+    try { return fn(); }
+    catch (const std::exception& e) { g_lastError = e.what(); return PS_FAILED; }
+    catch (...) { g_lastError = "unknown error"; return PS_FAILED; }
+}
+
+// host CSR (export / parity only -- never on the solve path)
+struct HostCsr { int64_t rows = 0, cols = 0; std::vector<int64_t> ptr; std::vector<int32_t> idx; std::vector<double> val; };
+
+HostCsr diag_csr(const std::vector<double>& d) {
+    HostCsr m; m.rows = m.cols = (int64_t)d.size(); m.ptr.resize(d.size() + 1); m.idx.resize(d.size()); m.val = d;
+    for (size_t i = 0; i < d.size(); ++i) { m.ptr[i] = (int64_t)i; m.idx[i] = (int32_t)i; }
+    m.ptr[d.size()] = (int64_t)d.size();
+    return m;
+}
+HostCsr blockdiag_csr(const std::vector<double>& blocks, int R) {
+    HostCsr m; m.rows = m.cols = (int64_t)R * RDOF;
+    m.ptr.resize(m.rows + 1); m.idx.resize((size_t)R * RDOF * RDOF); m.val = blocks;
+    for (int64_t r = 0; r <= m.rows; ++r) m.ptr[r] = r * RDOF;
+    for (int b = 0; b < R; ++b) for (int i = 0; i < RDOF; ++i) for (int j = 0; j < RDOF; ++j) m.idx[((size_t)b * RDOF + i) * RDOF + j] = b * RDOF + j;
+    return m;
+}
+
+// G / D^T (active rows) and JG / JD^T (26 rows per region) rebuilt from the device ELL of K_ext
+// with the reference's CSR conventions (sorted columns, duplicates summed in traversal order,
+// explicit zeros kept: S_CMB:454-455, 524-525, 612-613)
+HostCsr k_block(Solver& S, const std::string& name) {
+    const Counts& C = S.C;
+    const int64_t nRows = C.nRowsExt, nP = C.nPressures, nT = C.nStresses;
+    std::vector<double> kv = S.K.val.to_host(S.st, (size_t)8 * nRows);
+    std::vector<int32_t> kc = S.K.col.to_host(S.st, (size_t)8 * nRows);
+    const bool pressure = (name == "G" || name == "JG");
+    const int64_t colLo = pressure ? 0 : nP, colHi = pressure ? nP : nP + nT;
+    HostCsr m; m.cols = colHi - colLo;
+    if (name == "G" || name == "Dt") {
+        m.rows = C.nActiveVs; m.ptr.assign(m.rows + 1, 0);
+        for (int64_t r = 0; r < m.rows; ++r) {
+            std::vector<std::pair<int32_t, double>> e;
+            for (int k = 0; k < 8; ++k) { const double v = kv[(size_t)k * nRows + r]; const int32_t c = kc[(size_t)k * nRows + r]; if (v != 0. && c >= colLo && c < colHi) e.push_back({(int32_t)(c - colLo), v}); }
+            std::sort(e.begin(), e.end(), [](auto& a, auto& b) { return a.first < b.first; });
+            for (auto& x : e) { m.idx.push_back(x.first); m.val.push_back(x.second); }
+            m.ptr[r + 1] = (int64_t)m.idx.size();
+        }
+        return m;
+    }
+    const int R = S.RG.count;
+    m.rows = (int64_t)R * RDOF; m.ptr.assign(m.rows + 1, 0);
+    if (R == 0) return m;
+    std::vector<int32_t> rowFace = S.RG.rowFace.to_host(S.st, (size_t)S.RG.nRows);
+    std::vector<int32_t> rowStart = S.RG.rowStart.to_host(S.st, (size_t)R + 1);
+    std::vector<double> com = S.RG.com.to_host(S.st, (size_t)3 * R);
+    for (int r = 0; r < R; ++r) {
+        std::map<int32_t, std::array<double, RDOF>> cols;
+        for (int32_t row = rowStart[r]; row < rowStart[r + 1]; ++row) {
+            const int32_t packed = rowFace[row];
+            const int axis = (packed >> 29) & 3;
+            const I3 f = delin(S.g, SL_FACE + axis, (int64_t)(packed & 0x1fffffff));
+            double p[3] = {(double)f.x, (double)f.y, (double)f.z};
+            p[axis] -= 0.5;
+            double c[RDOF];
+            conversion_coefficients(p[0] * S.g.dx - com[3 * r], p[1] * S.g.dx - com[3 * r + 1], p[2] * S.g.dx - com[3 * r + 2], axis, c);
+            const int64_t kr = C.nActiveVs + row;
+            for (int k = 0; k < 8; ++k) {
+                const double v = kv[(size_t)k * nRows + kr]; const int32_t cc = kc[(size_t)k * nRows + kr];
+                if (v == 0. || cc < colLo || cc >= colHi) continue;
+                auto it = cols.find((int32_t)(cc - colLo));
+                if (it == cols.end()) { std::array<double, RDOF> a; for (int n = 0; n < RDOF; ++n) a[n] = v * c[n]; cols.emplace((int32_t)(cc - colLo), a); }
+                else for (int n = 0; n < RDOF; ++n) it->second[n] += v * c[n];
+            }
+        }
+        for (int n = 0; n < RDOF; ++n) {
+            for (auto& kvp : cols) { m.idx.push_back(kvp.first); m.val.push_back(kvp.second[n]); }
+            m.ptr[(int64_t)r * RDOF + n + 1] = (int64_t)m.idx.size();
+        }
+    }
+    return m;
+}
+
+bool get_matrix(Solver& S, const std::string& name, HostCsr& out) {
+    const Counts& C = S.C;
+    const int R = S.RG.count;
+    if (name == "G" || name == "Dt" || name == "JG" || name == "JDt") { out = k_block(S, name); return true; }
+    if (name == "Mc") { out = diag_csr(S.mc.to_host(S.st, (size_t)C.nActiveVs)); return true; }
+    if (name == "McInv") { out = diag_csr(S.mcInv.to_host(S.st, (size_t)C.nActiveVs)); return true; }
+    if (name == "uInv") { out = diag_csr(S.uInv.to_host(S.st, (size_t)C.nStresses)); return true; }
+    if (name == "u") { out = diag_csr(S.uDiag.to_host(S.st, (size_t)C.nStresses)); return true; }
+    const size_t NN = (size_t)RDOF * RDOF;
+    if (name == "Mr") { out = blockdiag_csr(R ? S.RG.Mr.to_host(S.st, R * NN) : std::vector<double>(), R); return true; }
+    if (name == "BInv") { out = blockdiag_csr(R ? S.RG.Binv.to_host(S.st, R * NN) : std::vector<double>(), R); return true; }
+    if (name == "B") {
+        std::vector<double> b(R * NN);
+        if (R) { auto m = S.RG.Mr.to_host(S.st, R * NN); auto v = S.RG.Visc.to_host(S.st, R * NN); for (size_t i = 0; i < b.size(); ++i) b[i] = S.g.invDt * m[i] + 2. * v[i]; }
+        out = blockdiag_csr(b, R); return true;
+    }
+    return false;
+}
+
+bool get_vector(Solver& S, const std::string& n, std::vector<double>& out) {
+    const Counts& C = S.C; const int R = S.RG.count; const size_t NN = (size_t)RDOF * RDOF;
+    if (n == "activeRHS") out = S.rhsU.to_host(S.st, (size_t)C.nActiveVs);
+    else if (n == "oldActiveVs") out = S.oldVs.to_host(S.st, (size_t)C.nActiveVs);
+    else if (n == "reducedRHS") out = R ? S.RG.rhsR.to_host(S.st, (size_t)R * RDOF) : std::vector<double>();
+    else if (n == "pressureRHS") out = S.rhsPT.to_host(S.st, (size_t)C.nPressures);
+    else if (n == "stressRHS") { auto v = S.rhsPT.to_host(S.st, (size_t)C.nSystemSize); out.assign(v.begin() + C.nPressures, v.end()); }
+    else if (n == "b") out = S.b.to_host(S.st, (size_t)C.nSystemSize);
+    else if (n == "solution") out = S.x.to_host(S.st, (size_t)C.nSystemSize);
+    else if (n == "velSolution") out = S.velSol.to_host(S.st, (size_t)(C.nActiveVs + C.nReducedVs));
+    else if (n == "com") out = R ? S.RG.com.to_host(S.st, (size_t)3 * R) : std::vector<double>();
+    else if (n == "bestFit") out = R ? S.RG.bestFit.to_host(S.st, (size_t)R * RDOF) : std::vector<double>();
+    else if (n == "MrDense") out = R ? S.RG.Mr.to_host(S.st, R * NN) : std::vector<double>();
+    else if (n == "ViscDense") out = R ? S.RG.Visc.to_host(S.st, R * NN) : std::vector<double>();
+    else if (n == "BinvDense") out = R ? S.RG.Binv.to_host(S.st, R * NN) : std::vector<double>();
+    else return false;
+    return true;
+}
+
+// Eigen::saveMarket / saveMarketVector format (extern/eigen/unsupported/Eigen/src/SparseExtra/MarketIO.h:311-372)
+bool save_market(const HostCsr& m, const std::string& path) {
+    std::ofstream out(path.c_str(), std::ios::out);
+    if (!out) return false;
+    out.flags(std::ios_base::scientific); out.precision(std::numeric_limits<double>::digits10 + 2);
+    out << "%%MatrixMarket matrix coordinate  real general" << std::endl;
+    out << m.rows << " " << m.cols << " " << m.idx.size() << "\n";
+    for (int64_t r = 0; r < m.rows; ++r) for (int64_t p = m.ptr[r]; p < m.ptr[r + 1]; ++p) out << (r + 1) << " " << (m.idx[p] + 1) << " " << m.val[p] << "\n";
+    return true;
+}
+bool save_market_vector(const std::vector<double>& v, const std::string& path) {
+    std::ofstream out(path.c_str(), std::ios::out);
+    if (!out) return false;
+    out.flags(std::ios_base::scientific); out.precision(std::numeric_limits<double>::digits10 + 2);
+    out << "%%MatrixMarket matrix array real general\n" << v.size() << " " << 1 << "\n";
+    for (double x : v) out << x << "\n";
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ps_last_error(void) { return g_lastError.c_str(); }
+
+int ps_create(const ps_params* params, ps_handle* out) {
+    if (!params || !out) { g_lastError = "ps_create: null argument"; return PS_INVALID; }
+    *out = nullptr;
+    return guarded([&] { ps_solver* h = new ps_solver; h->S = new Solver(*params); *out = h; return (int)PS_SUCCESS; });
+}
+void ps_destroy(ps_handle h) { if (h) { delete h->S; delete h; } }
+
+int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* stats) {
+    if (!h || !in) { g_lastError = "ps_step: null argument"; return PS_INVALID; }
+    return guarded([&] {
+        Solver& S = *h->S;
+        const int res = S.step(*in, out, stats);
+        if (S.P.exportMatrices || S.P.exportComponentMatrices || S.P.exportStats)
+            ps_export(h, S.P.exportDataPrefix, (S.P.exportMatrices ? 1 : 0) | (S.P.exportComponentMatrices ? 2 : 0) | (S.P.exportStats ? 4 : 0));
+        return res;
+    });
+}
+int ps_setup(ps_handle h, const ps_fields_in* in) {
+    if (!h || !in) { g_lastError = "ps_setup: null argument"; return PS_INVALID; }
+    return guarded([&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; S.setInputs(*in); S.setup(); return (int)PS_SUCCESS; });
+}
+int ps_solve(ps_handle h, ps_fields_out* out, ps_stats* stats) {
+    if (!h) { g_lastError = "ps_solve: null handle"; return PS_INVALID; }
+    return guarded([&] {
+        Solver& S = *h->S;
+        if (!S.haveSetup) throw Error("ps_solve: call ps_setup first");
+        S.stageMs[PS_STAGE_SOLVE] = 0; S.stageMs[PS_STAGE_WRITEBACK] = 0;
+        const int res = S.solve();
+        if (out && res != PS_UNSUPPORTED_SOLVER) {
+            if (res == PS_SUCCESS || S.P.keepNonConvergedResults) S.recoverVelocityFromPressureStress();
+            S.applySolutionToVelocity(*out);
+        }
+        if (stats) S.fillStats(stats);
+        return res;
+    });
+}
+
+int64_t ps_get_count(ps_handle h, const char* name) {
+    if (!h || !name) return INT64_MIN;
+    const Solver& S = *h->S; const Counts& C = S.C; const std::string n(name);
+    if (n == "nCenter") return C.nCenter;
+    if (n == "nFaceX") return C.nFace[0]; if (n == "nFaceY") return C.nFace[1]; if (n == "nFaceZ") return C.nFace[2];
+    if (n == "nEdgeYZ") return C.nEdge[0]; if (n == "nEdgeXZ") return C.nEdge[1]; if (n == "nEdgeXY") return C.nEdge[2];
+    if (n == "nActiveVs") return C.nActiveVs; if (n == "nReducedVs") return C.nReducedVs;
+    if (n == "nPressures") return C.nPressures; if (n == "nStresses") return C.nStresses;
+    if (n == "nTotalDOFs") return C.nTotalDOFs; if (n == "nSystemSize") return C.nSystemSize;
+    if (n == "regionCount") return S.RG.count; if (n == "iterations") return S.solveIterations;
+    if (n == "result") return S.result; if (n == "usedBiCGStab") return S.usedBiCGStab;
+    if (n == "nRowsExt") return C.nRowsExt; if (n == "fixLoops") return S.fixLoops;
+    return INT64_MIN;
+}
+double ps_get_real(ps_handle h, const char* name) {
+    if (!h || !name) return NAN;
+    const std::string n(name);
+    if (n == "solveError") return h->S->solveError;
+    return NAN;
+}
+
+int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out) {
+    if (!h || slot < 0 || slot >= N_SLOTS || kind < 0 || kind > 2) return -1;
+    Solver& S = *h->S;
+    const size_t n = (size_t)S.g.n[slot];
+    if (!out) return (int64_t)n;
+    int rc = guarded([&] {
+        if (kind == 0) { std::vector<int8_t> v = S.dLabel[slot].to_host(S.st, n); for (size_t i = 0; i < n; ++i) out[i] = v[i]; }
+        else { std::vector<int32_t> v = (kind == 1 ? S.dAidx[slot] : S.dRidx[slot]).to_host(S.st, n); std::copy(v.begin(), v.end(), out); }
+        return 0;
+    });
+    return rc == 0 ? (int64_t)n : -1;
+}
+int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out) {
+    if (!h || slot < 0 || slot >= N_SLOTS) return -1;
+    Solver& S = *h->S;
+    const size_t n = (size_t)S.g.n[slot];
+    if (!out) return (int64_t)n;
+    int rc = guarded([&] { std::vector<uint8_t> v = (liquid ? S.dLiqW[slot] : S.dFluW[slot]).to_host(S.st, n); for (size_t i = 0; i < n; ++i) out[i] = (float)v[i] * 0.125f; return 0; });
+    return rc == 0 ? (int64_t)n : -1;
+}
+
+int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz, int64_t* rowptr, int32_t* colidx, double* vals) {
+    if (!h || !name) return PS_INVALID;
+    return guarded([&] {
+        HostCsr m;
+        if (!get_matrix(*h->S, name, m)) { g_lastError = std::string("ps_get_csr: unknown matrix ") + name; return (int)PS_INVALID; }
+        if (rows) *rows = m.rows; if (cols) *cols = m.cols; if (nnz) *nnz = (int64_t)m.idx.size();
+        if (rowptr) std::copy(m.ptr.begin(), m.ptr.end(), rowptr);
+        if (colidx) std::copy(m.idx.begin(), m.idx.end(), colidx);
+        if (vals) std::copy(m.val.begin(), m.val.end(), vals);
+        return (int)PS_SUCCESS;
+    });
+}
+int64_t ps_get_vector(ps_handle h, const char* name, double* out) {
+    if (!h || !name) return -1;
+    int64_t n = -1;
+    guarded([&] { std::vector<double> v; if (get_vector(*h->S, name, v)) { n = (int64_t)v.size(); if (out) std::copy(v.begin(), v.end(), out); } return 0; });
+    return n;
+}
+
+int ps_apply(ps_handle h, const double* x, double* y) {
+    if (!h || !x || !y) return PS_INVALID;
+    return guarded([&] {
+        Solver& S = *h->S;
+        if (!S.haveSetup) throw Error("ps_apply: call ps_setup first");
+        const size_t n = (size_t)S.C.nSystemSize;
+        static thread_local DBuf<double> dx, dy;
+        dx.alloc(n); dy.alloc(n);
+        copy_h2d(dx.p, x, n * sizeof(double), S.st);
+        S.applyOperator(dx.p, dy.p, nullptr);
+        copy_d2h(y, dy.p, n * sizeof(double), S.st);
+        return (int)PS_SUCCESS;
+    });
+}
+
+double ps_apply_bytes(ps_handle h) {
+    if (!h) return 0;
+    const Solver& S = *h->S; const Counts& C = S.C;
+    // ELL streams (12 B per stored slot), vectors read/written once
+    const double nE = (double)(C.nEdge[0] + C.nEdge[1] + C.nEdge[2]);
+    const double kSlots = 8.0 * C.nRowsExt, ktSlots = 6.0 * C.nPressures + 2.0 * 3 * C.nCenter + 4.0 * nE;
+    const double n = (double)C.nSystemSize;
+    double bytes = 12.0 * kSlots + 8.0 * n /*x*/ + 8.0 * C.nActiveVs /*Mc^-1*/ + 8.0 * C.nRowsExt /*w write*/;
+    bytes += 12.0 * ktSlots + 8.0 * C.nRowsExt /*w read*/ + 8.0 * C.nStresses /*mu^-1*/ + 8.0 * C.nStresses /*x_tau*/ + 8.0 * n /*y*/;
+    bytes += (double)S.RG.nRows * (4.0 + 8.0) * 2 /*row list + w, moments and expand*/ + (double)S.RG.count * (RDOF * RDOF + 3 * RDOF) * 8.0;
+    return bytes;
+}
+double ps_cg_iteration_bytes(ps_handle h) {
+    if (!h) return 0;
+    const double n = (double)h->S->C.nSystemSize;
+    return ps_apply_bytes(h) + 8.0 * n /*p for the dot*/ + 48.0 * n + 24.0 * n;
+}
+
+double ps_time_apply(ps_handle h, int reps, int) {
+    if (!h || reps <= 0) return -1;
+    double ms = -1;
+    guarded([&] {
+        Solver& S = *h->S;
+        if (!S.haveSetup) throw Error("ps_time_apply: call ps_setup first");
+#ifndef PS_EMULATE
+        cudaEvent_t a, b; PS_CUDA(cudaEventCreate(&a)); PS_CUDA(cudaEventCreate(&b));
+        S.applyOperator(S.b.p, S.Ap.p, nullptr);
+        PS_CUDA(cudaEventRecord(a, S.st));
+        for (int i = 0; i < reps; ++i) S.applyOperator(S.b.p, S.Ap.p, nullptr);
+        PS_CUDA(cudaEventRecord(b, S.st)); PS_CUDA(cudaEventSynchronize(b));
+        float t = 0; PS_CUDA(cudaEventElapsedTime(&t, a, b)); ms = t / reps;
+        cudaEventDestroy(a); cudaEventDestroy(b);
+#else
+        S.applyOperator(S.b.p, S.Ap.p, nullptr); ms = 0;
+#endif
+        return 0;
+    });
+    return ms;
+}
+double ps_time_cg_iteration(ps_handle h, int reps) {
+    if (!h || reps <= 0) return -1;
+    double ms = -1;
+    guarded([&] {
+        Solver& S = *h->S;
+        if (!S.haveSetup) throw Error("ps_time_cg_iteration: call ps_setup first");
+        const int savedMax = S.P.maxSolverIterations, savedEvery = S.P.checkEvery; const double savedTol = S.P.tolerance;
+        S.P.maxSolverIterations = reps; S.P.checkEvery = reps; S.P.tolerance = 0.0;   // never converges: exactly `reps` iterations
+        S.stageMs[PS_STAGE_SOLVE] = 0;
+        S.solve();
+        ms = S.stageMs[PS_STAGE_SOLVE] / reps;
+        S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
+        return 0;
+    });
+    return ms;
+}
+
+int ps_export(ps_handle h, const char* prefix, int what) {
+    if (!h || !prefix) return PS_INVALID;
+    return guarded([&] {
+        Solver& S = *h->S; const std::string pre(prefix);
+        bool ok = true;
+        std::vector<double> v;
+        if (what & 1) {   // exportMatrices / exportMatricesPostSolve (S.cpp:533-541, 568-572); A is implicit on this path
+            if (get_vector(S, "b", v)) ok &= save_market_vector(v, pre + "Vec_b.mtx");
+            if (get_vector(S, "solution", v)) ok &= save_market_vector(v, pre + "solutionVector.mtx");
+        }
+        if (what & 2) {   // exportComponentMatrices (S.cpp:543-566)
+            const char* mats[] = {"Mc", "McInv", "Mr", "B", "BInv", "u", "uInv", "G", "Dt", "JG", "JDt"};
+            const char* files[] = {"Mat_Mc.mtx", "Mat_McInv.mtx", "Mat_Mr.mtx", "Mat_Mr_plus_2JDtuDJ.mtx", "Mat_Inv_Mr_plus_2JDtuDJ.mtx", "Mat_u.mtx", "Mat_uInv.mtx",
+                                   "Mat_G.mtx", "Mat_Dt.mtx", "Mat_JG.mtx", "Mat_JDt.mtx"};
+            for (int i = 0; i < 11; ++i) { HostCsr m; if (get_matrix(S, mats[i], m)) ok &= save_market(m, pre + files[i]); }
+            const char* vecs[] = {"activeRHS", "reducedRHS", "pressureRHS", "stressRHS"};
+            const char* vfiles[] = {"Vec_activeRHS.mtx", "Vec_reducedRHS.mtx", "Vec_pressureRHS.mtx", "Vec_stressRHS.mtx"};
+            for (int i = 0; i < 4; ++i) if (get_vector(S, vecs[i], v)) ok &= save_market_vector(v, pre + vfiles[i]);
+        }
+        if (what & 4) {   // exportStats (S.cpp:574-606)
+            ps_stats st; S.fillStats(&st);
+            ok &= save_market_vector(std::vector<double>(st.dimData, st.dimData + 27), pre + "dimData.mtx");
+            ok &= save_market_vector(std::vector<double>(st.solveData, st.solveData + 6), pre + "solveData.mtx");
+        }
+        if (!ok) { g_lastError = "ps_export: could not write under prefix " + pre; return (int)PS_FAILED; }
+        return (int)PS_SUCCESS;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// ps_scan.cu -- DOF numbering primitives.
+//
+// tile_order_scan reproduces serialAssignFieldIndices (exec/HDK_PolyStokesSolver_Classifier.cpp:1738-1770):
+// a running counter over the voxels for which a predicate holds, visited in UT_VoxelArray order
+// (16^3 tiles, x->y->z, x fastest inside).  The reference does this serially; here one CTA owns one
+// 16^3 tile: (1) per-tile counts, (2) one-CTA exclusive scan of the tile counts, (3) per-tile local
+// scan + write.  A thread owns one 16-voxel x-row of its tile, so its reads are 16 contiguous bytes.
+#include "ps_solver.hpp"
+#ifndef PS_EMULATE
+#include <cub/device/device_radix_sort.cuh>
+#endif
+
+namespace ps {
+
+#ifndef PS_EMULATE
+
+struct TileGeom { int rx, ry, rz, tx, ty, tz; };
+
+__device__ __forceinline__ int row_count(const uint8_t* flag, const TileGeom& t, int tile, int tid, int64_t& rowBase, int& tw) {
+    const int ti = tile % t.tx, tj = (tile / t.tx) % t.ty, tk = tile / (t.tx * t.ty);
+    const int lj = tid & 15, lk = tid >> 4;
+    const int y = (tj << 4) + lj, z = (tk << 4) + lk, x0 = ti << 4;
+    tw = min(16, t.rx - x0);
+    if (y >= t.ry || z >= t.rz) { tw = 0; rowBase = 0; return 0; }
+    rowBase = (int64_t)x0 + (int64_t)t.rx * ((int64_t)y + (int64_t)t.ry * z);
+    int c = 0;
+    for (int i = 0; i < tw; ++i) c += flag[rowBase + i] ? 1 : 0;
+    return c;
+}
+
+// block-wide exclusive scan of one int per thread (256 threads), returns total in `total`
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int& total) {
+    __shared__ int warpSums[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) warpSums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < 8 ? warpSums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += n; }
+        if (lane < 8) warpSums[lane] = s;
+    }
+    __syncthreads();
+    total = warpSums[7];
+    const int warpBase = wid == 0 ? 0 : warpSums[wid - 1];
+    __syncthreads();
+    return warpBase + inc - v;
+}
+
+__global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* flag, TileGeom t, int32_t* tileCounts) {
+    int64_t rowBase; int tw;
+    const int c = row_count(flag, t, blockIdx.x, threadIdx.x, rowBase, tw);
+    int total;
+    block_exclusive_scan_256(c, total);
+    if (threadIdx.x == 0) tileCounts[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of nTiles counts in place; tileCounts[nTiles] = grand total
+__global__ void __launch_bounds__(256) tile_offsets_kernel(int32_t* tileCounts, int nTiles) {
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nTiles; base += 256) {
+        const int i = base + threadIdx.x;
+        const int v = i < nTiles ? tileCounts[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan_256(v, total);
+        const int c = carry;
+        if (i < nTiles) tileCounts[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tileCounts[nTiles] = carry;
+}
+
+__global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* flag, TileGeom t, const int32_t* tileOffsets, int32_t* out) {
+    int64_t rowBase; int tw;
+    const int c = row_count(flag, t, blockIdx.x, threadIdx.x, rowBase, tw);
+    int total;
+    int rank = tileOffsets[blockIdx.x] + block_exclusive_scan_256(c, total);
+    for (int i = 0; i < tw; ++i) {
+        const bool f = flag[rowBase + i] != 0;
+        out[rowBase + i] = f ? rank : -1;
+        rank += f ? 1 : 0;
+    }
+}
+
+int64_t tile_order_scan(cudaStream_t st, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts) {
+    TileGeom t;
+    t.rx = g.r[slot][0]; t.ry = g.r[slot][1]; t.rz = g.r[slot][2];
+    t.tx = (t.rx + 15) >> 4; t.ty = (t.ry + 15) >> 4; t.tz = (t.rz + 15) >> 4;
+    const int nTiles = t.tx * t.ty * t.tz;
+    tileCounts.alloc((size_t)nTiles + 1);
+    tile_count_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p);
+    PS_COUNT_LAUNCH(1);
+    tile_offsets_kernel<<<1, 256, 0, st>>>(tileCounts.p, nTiles);
+    PS_COUNT_LAUNCH(1);
+    tile_write_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p, out);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+    int32_t total = 0;
+    copy_d2h(&total, tileCounts.p + nTiles, sizeof(int32_t), st);
+    return total;
+}
+
+void sort_pairs_by_key(cudaStream_t st, int64_t n, int keyBits, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>& keysTmp, DBuf<int32_t>& valsTmp) {
+    if (n <= 0) return;
+    keysTmp.alloc((size_t)n); valsTmp.alloc((size_t)n);
+    size_t tmpBytes = 0;
+    PS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysTmp.p, vals.p, valsTmp.p, (int)n, 0, keyBits, st));
+    static thread_local DBuf<uint8_t> tmp;
+    tmp.alloc(tmpBytes);
+    PS_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysTmp.p, vals.p, valsTmp.p, (int)n, 0, keyBits, st));
+    copy_d2d(keys.p, keysTmp.p, (size_t)n * sizeof(int32_t), st);
+    copy_d2d(vals.p, valsTmp.p, (size_t)n * sizeof(int32_t), st);
+}
+
+#else  // ---- PS_EMULATE: serial twins (test-only build) ----
+
+int64_t tile_order_scan(cudaStream_t, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>&) {
+    const int rx = g.r[slot][0], ry = g.r[slot][1], rz = g.r[slot][2];
+    int32_t n = 0;
+    for (int tk = 0; tk < rz; tk += 16) for (int tj = 0; tj < ry; tj += 16) for (int ti = 0; ti < rx; ti += 16)
+        for (int k = tk; k < std::min(tk + 16, rz); ++k) for (int j = tj; j < std::min(tj + 16, ry); ++j) for (int i = ti; i < std::min(ti + 16, rx); ++i) {
+            const int64_t q = (int64_t)i + (int64_t)rx * ((int64_t)j + (int64_t)ry * k);
+            out[q] = flag[q] ? n++ : -1;
+        }
+    return n;
+}
+
+void sort_pairs_by_key(cudaStream_t, int64_t n, int, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>&, DBuf<int32_t>&) {
+    std::vector<int64_t> ord((size_t)n);
+    for (int64_t i = 0; i < n; ++i) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return keys.p[a] < keys.p[b]; });
+    std::vector<int32_t> k2((size_t)n), v2((size_t)n);
+    for (int64_t i = 0; i < n; ++i) { k2[i] = keys.p[ord[i]]; v2[i] = vals.p[ord[i]]; }
+    std::copy(k2.begin(), k2.end(), keys.p); std::copy(v2.begin(), v2.end(), vals.p);
+}
+
+#endif
+
+}  // namespace ps

@@ -1,0 +1,500 @@
+// ps_solver.cu -- host orchestration of one Stokes step: the same stage sequence as
+// HDK_PolyStokes::solveGasSubclass (exec/HDK_PolyStokes.C:344-584), every stage a few kernels on one stream.
+#include "ps_solver.hpp"
+#include <climits>
+#include <chrono>
+
+namespace ps {
+
+thread_local std::string g_lastError;
+thread_local int64_t g_launches = 0;
+
+// ---- small helper kernels (free functions: extended lambdas may not live in private members) ----
+static void k_flag_label(cudaStream_t st, int64_t n, const int8_t* L, int value, uint8_t* flag) {
+    ps_for(st, n, PS_LAMBDA(int64_t q) { flag[q] = (L[q] == value) ? 1 : 0; });
+}
+static void k_krow_active(cudaStream_t st, int64_t n, const int32_t* aidx, int32_t offset, int32_t* krow) {
+    ps_for(st, n, PS_LAMBDA(int64_t q) { const int a = aidx[q]; krow[q] = a >= 0 ? a + offset : -1; });
+}
+static void k_krow_reduced(cudaStream_t st, int64_t nRows, const int32_t* rowFace, int32_t base, int32_t* kr0, int32_t* kr1, int32_t* kr2) {
+    ps_for(st, nRows, PS_LAMBDA(int64_t i) {
+        const int32_t packed = rowFace[i];
+        const int axis = (packed >> 29) & 3;
+        int32_t* kr = axis == 0 ? kr0 : axis == 1 ? kr1 : kr2;
+        kr[packed & 0x1fffffff] = base + (int32_t)i;
+    });
+}
+static void k_count_by_region(cudaStream_t st, int64_t n, const int32_t* region, int* counts) {
+    ps_for(st, n, PS_LAMBDA(int64_t i) { atomic_add(&counts[region[i]], 1); });
+}
+static void k_scale_rows(cudaStream_t st, int64_t n, const double* a, const double* b, double* out) {
+    ps_for(st, n, PS_LAMBDA(int64_t i) { out[i] = a[i] * b[i]; });
+}
+static void k_copy_reduced_solution(cudaStream_t st, int64_t n, const double* s, double* velSolReduced) {
+    ps_for(st, n, PS_LAMBDA(int64_t i) { velSolReduced[i] = s[i]; });
+}
+
+// ---- stage timers ----
+struct StageTimer {
+#ifndef PS_EMULATE
+    cudaEvent_t a, b; cudaStream_t st; double* acc;
+    StageTimer(cudaStream_t s, double* dst) : st(s), acc(dst) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    ~StageTimer() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); *acc += ms; cudaEventDestroy(a); cudaEventDestroy(b); }
+#else
+    std::chrono::steady_clock::time_point t0; double* acc;
+    StageTimer(cudaStream_t, double* dst) : t0(std::chrono::steady_clock::now()), acc(dst) {}
+    ~StageTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+#endif
+};
+
+Solver::Solver(const ps_params& p) : P(p) {
+    if (p.nx <= 0 || p.ny <= 0 || p.nz <= 0 || !(p.dx > 0) || !(p.dt > 0)) throw Error("ps_create: invalid grid / dx / dt");
+    if ((int64_t)(p.nx + 1) * (p.ny + 1) * (p.nz + 1) >= (1ll << 29)) throw Error("ps_create: grid too large for 29-bit packed face indices");
+    g = make_geom(p.nx, p.ny, p.nz, p.dx, p.dt, p.constantDensity);
+#ifndef PS_EMULATE
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error("ps_create: no CUDA device (this library has no CPU path)");
+    PS_CUDA(cudaSetDevice(p.device));
+    PS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+#endif
+    flags.alloc(64);
+    scal.alloc(1);
+    scal.zero(st, 1);
+    memset(&F, 0, sizeof F);
+}
+
+Solver::~Solver() {
+#ifndef PS_EMULATE
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+#endif
+}
+
+void Solver::setInputs(const ps_fields_in& in) {
+    StageTimer T(st, &stageMs[PS_STAGE_UPLOAD]);
+    if (!in.surface || !in.collision || !in.viscosity) throw Error("ps_step: surface / collision / viscosity field missing");
+    for (int a = 0; a < 3; ++a) if (!in.velocity[a] || !in.collisionvel[a]) throw Error("ps_step: velocity / collisionvel field missing");
+    const bool dev = in.memory == PS_MEM_DEVICE;
+    const size_t nc = (size_t)g.n[SL_CENTER];
+    dSurface.alloc(nc); dCollision.alloc(nc); dViscosity.alloc(nc);
+    copy_any2d(dSurface.p, in.surface, nc * sizeof(float), dev, st);
+    copy_any2d(dCollision.p, in.collision, nc * sizeof(float), dev, st);
+    copy_any2d(dViscosity.p, in.viscosity, nc * sizeof(float), dev, st);
+    for (int a = 0; a < 3; ++a) {
+        const size_t nf = (size_t)g.n[SL_FACE + a];
+        dVel[a].alloc(nf); dColVel[a].alloc(nf);
+        copy_any2d(dVel[a].p, in.velocity[a], nf * sizeof(float), dev, st);
+        copy_any2d(dColVel[a].p, in.collisionvel[a], nf * sizeof(float), dev, st);
+        F.vel[a] = dVel[a].p; F.colvel[a] = dColVel[a].p;
+    }
+    F.surface = dSurface.p; F.collision = dCollision.p; F.viscosity = dViscosity.p;
+    // labels / indices start UNASSIGNED (S.cpp:94-152); byte 0xFF = -1 for int8 and int32 alike
+    for (int s = 0; s < N_SLOTS; ++s) {
+        const size_t n = (size_t)g.n[s];
+        dLiqW[s].alloc(n); dFluW[s].alloc(n); dLabel[s].alloc(n); dAidx[s].alloc(n); dRidx[s].alloc(n);
+        dLabel[s].fill_byte(st, 0xFF, n); dAidx[s].fill_byte(st, 0xFF, n); dRidx[s].fill_byte(st, 0xFF, n);
+        F.liqW[s] = dLiqW[s].p; F.fluW[s] = dFluW[s].p; F.label[s] = dLabel[s].p; F.aidx[s] = dAidx[s].p; F.ridx[s] = dRidx[s].p;
+    }
+    for (int a = 0; a < 3; ++a) { dKrow[a].alloc((size_t)g.n[SL_FACE + a]); F.krow[a] = dKrow[a].p; }
+    size_t nmax = 0;
+    for (int s = 0; s < N_SLOTS; ++s) nmax = std::max(nmax, (size_t)g.n[s]);
+    for (auto& b : scratch8) b.alloc(nmax);
+    for (auto& b : scratch32) b.alloc(nmax);
+    haveSetup = false;
+}
+
+void Solver::buildIntegrationWeightsAlt() {
+    StageTimer T(st, &stageMs[PS_STAGE_WEIGHTS]);
+    k_build_weights(st, g, F);
+}
+
+void Solver::classifyCells() {
+    k_classify_cells(st, g, F, /*genericToActive=*/!P.doReducedRegions);
+}
+
+// constructReducedRegions (S_Cls:179-190)
+void Solver::constructReducedRegions() {
+    uint8_t* stamp = scratch8[0].p;
+    const int L = P.activeLiquidBoundaryLayerSize, S = P.activeSolidBoundaryLayerSize;
+    if (L > 255 || S > 255) throw Error("boundary layer size > 255 not supported");
+    if (L - 1 >= 1) {   // for (layer = 0; layer < L-1; ++layer) { commit; if (layer < L-2) grow; }
+        k_air_layer_seed(st, g, F, stamp);
+        k_layer_commit(st, g, F, stamp, 1);
+        for (int layer = 1; layer <= L - 2; ++layer) { k_air_layer_grow(st, g, F, stamp, layer); k_layer_commit(st, g, F, stamp, layer + 1); }
+    }
+    if (S >= 1) {
+        k_solid_layer_seed(st, g, F, stamp);
+        k_layer_commit(st, g, F, stamp, 1);
+        for (int layer = 1; layer <= S - 1; ++layer) { k_solid_layer_grow(st, g, F, stamp, layer); k_layer_commit(st, g, F, stamp, layer + 1); }
+    }
+    k_tiles_and_reduce(st, g, F, P.doTile != 0, P.tileSize, P.tilePadding);
+}
+
+void Solver::classifyFaces() { k_classify_faces(st, g, F); }
+void Solver::classifyEdges() { k_classify_edges(st, g, F); }
+
+static int read_flag(cudaStream_t st, const int* dflag) { int v = 0; copy_d2h(&v, dflag, sizeof(int), st); return v; }
+
+// constructCenterReducedIndices (S_Cls:217-239): connected components, stencil-overlap fix, small regions
+void Solver::constructCenterReducedIndices() {
+    const int64_t nc = g.n[SL_CENTER];
+    int32_t* parent = scratch32[0].p; int32_t* minKey = scratch32[1].p; int32_t* firstRank = scratch32[2].p; int32_t* rootId = scratch32[3].p;
+    int* dflag = flags.p;
+    k_cc_init(st, g, F, parent);
+    for (int sweep = 0; sweep < 100000; ++sweep) {
+        dev_memset(dflag, 0, sizeof(int), st);
+        k_cc_sweep(st, g, F, parent, dflag);
+        if (!read_flag(st, dflag)) break;
+    }
+    dev_memset(minKey, 0x7f, (size_t)nc * sizeof(int32_t), st);
+    k_cc_minkey(st, g, parent, minKey);
+    uint8_t* first = scratch8[0].p;
+    k_cc_first_flags(st, g, parent, minKey, first);
+    int64_t R = tile_order_scan(st, g, SL_CENTER, first, firstRank, tileCounts);
+    k_cc_publish(st, g, parent, first, firstRank, rootId);
+    k_cc_assign(st, g, F, parent, rootId);
+
+    // fixReducedRegionBoundaries (S_Cls:1073-1172), see ps_classify.cu for the recurrence
+    fixLoops = 0;
+    if (R > 0) {
+        uint8_t* cand = scratch8[0].p; uint8_t* fa = scratch8[1].p; uint8_t* fb = scratch8[2].p;
+        for (;;) {
+            fixLoops++;
+            dev_memset(dflag, 0, 2 * sizeof(int), st);
+            k_fix_candidates(st, g, F, cand, fa, fb, dflag);
+            if (!read_flag(st, dflag)) break;            // sweep finds nothing to fix -> done
+            uint8_t* in = fa; uint8_t* out = fb;
+            for (int it = 0; it < 1000000; ++it) {
+                dev_memset(dflag, 0, sizeof(int), st);
+                k_fix_iterate(st, g, F, cand, in, out, dflag);
+                std::swap(in, out);
+                if (!read_flag(st, dflag)) break;
+            }
+            dev_memset(dflag + 1, 0, sizeof(int), st);
+            k_fix_apply(st, g, F, in, dflag + 1);
+            if (!read_flag(st, dflag + 1)) break;
+        }
+    }
+
+    // fixSmallReducedRegions (S_Cls:1174-1262)
+    if (R > 0) {
+        static thread_local DBuf<int> bb;
+        bb.alloc((size_t)6 * R);
+        dev_memset(bb.p, 0x7f, (size_t)3 * R * sizeof(int), st);
+        dev_memset(bb.p + 3 * R, 0x80, (size_t)3 * R * sizeof(int), st);
+        k_region_bbox(st, g, F, bb.p, bb.p + 3 * R);
+        std::vector<int> h = bb.to_host(st, (size_t)6 * R);
+        std::vector<int32_t> remap((size_t)R, -1);
+        int32_t next = 0;
+        for (int64_t r = 0; r < R; ++r) {
+            bool remove = false;
+            for (int a = 0; a < 3; ++a) {
+                const int mn = h[3 * r + a], mx = h[3 * R + 3 * r + a];
+                if (mx < 0) { remove = true; continue; }          // region emptied by the boundary fix
+                if (mx == mn) remove = true;
+                if (mn > mx - 3) remove = true;
+            }
+            if (!remove) remap[r] = next++;
+        }
+        if (next < R) {
+            static thread_local DBuf<int32_t> dremap;
+            dremap.from_host(st, remap.data(), (size_t)R);
+            k_region_remap(st, g, F, dremap.p);
+            R = next;
+        }
+    }
+    RG.count = (int32_t)R;
+}
+
+void Solver::constructFacesReducedIndices() { k_faces_reduced(st, g, F); }
+void Solver::constructEdgesReducedIndices() { k_edges_reduced(st, g, F); }
+
+// construct{Center,Faces,Edges}ActiveIndices (S_Cls:257-284)
+void Solver::constructActiveIndices() {
+    uint8_t* flag = scratch8[0].p;
+    int64_t cnt[N_SLOTS];
+    for (int s = 0; s < N_SLOTS; ++s) {
+        k_generic_to_active_flags(st, g, s, F.label[s], flag);
+        cnt[s] = tile_order_scan(st, g, s, flag, F.aidx[s], tileCounts);
+    }
+    C = Counts();
+    C.nCenter = cnt[SL_CENTER];
+    for (int a = 0; a < 3; ++a) { C.nFace[a] = cnt[SL_FACE + a]; C.nEdge[a] = cnt[SL_EDGE + a]; }
+    // constructMatrixBlocks dimension block (S_CMB:12-21)
+    C.nActiveVs = C.nFace[0] + C.nFace[1] + C.nFace[2];
+    C.nReducedVs = (int64_t)RG.count * RDOF;
+    C.nPressures = C.nCenter;
+    C.nStresses = 3 * C.nCenter + C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
+    C.nTotalDOFs = C.nActiveVs + C.nReducedVs + C.nPressures + C.nStresses;
+    C.nSystemSize = C.nPressures + C.nStresses;
+    C.faceOff[0] = 0; C.faceOff[1] = C.nFace[0]; C.faceOff[2] = C.nFace[0] + C.nFace[1];
+    C.stressOff[0] = 0; C.stressOff[1] = C.nCenter; C.stressOff[2] = 2 * C.nCenter;
+    C.stressOff[3] = 3 * C.nCenter; C.stressOff[4] = 3 * C.nCenter + C.nEdge[0]; C.stressOff[5] = 3 * C.nCenter + C.nEdge[0] + C.nEdge[1];
+    if (C.nSystemSize >= INT32_MAX || C.nActiveVs + 26 >= INT32_MAX) throw Error("system too large for int32 column indices");
+}
+
+static int key_bits(int64_t n) { int b = 1; while ((1ll << b) < n + 1 && b < 31) ++b; return b; }
+
+// builds (region, begin, end) chunk tables of at most `chunk` items for lists sorted by region
+static void build_chunks(const std::vector<int>& perRegion, int chunk, std::vector<int32_t>& start, std::vector<int32_t>& table, std::vector<int32_t>& chunkStart) {
+    const size_t R = perRegion.size();
+    start.assign(R + 1, 0); chunkStart.assign(R + 1, 0); table.clear();
+    for (size_t r = 0; r < R; ++r) start[r + 1] = start[r] + perRegion[r];
+    for (size_t r = 0; r < R; ++r) {
+        chunkStart[r] = (int32_t)(table.size() / 3);
+        for (int32_t b = start[r]; b < start[r + 1]; b += chunk) { table.push_back((int32_t)r); table.push_back(b); table.push_back(std::min(b + chunk, start[r + 1])); }
+    }
+    chunkStart[R] = (int32_t)(table.size() / 3);
+}
+
+// computeCenterOfMasses + computeLeastSquaresFits + computeReducedMassMatrices +
+// computeReducedViscosityMatricesInteriorOnly (S.cpp:328-490) + the AssembleBlocks dense part (S_AB)
+void Solver::computeReducedRegionMatrices() {
+    const int R = RG.count;
+    if (R <= 0) return;
+    const int64_t nc = g.n[SL_CENTER];
+    static thread_local DBuf<unsigned long long> sums;
+    sums.alloc((size_t)4 * R);
+    RG.com.alloc((size_t)3 * R);
+    k_region_com(st, g, F, R, sums.p, RG.com.p);
+    // REDUCED cells sorted by (region, voxel order)
+    uint8_t* flag = scratch8[0].p; int32_t* rank = scratch32[0].p;
+    k_flag_label(st, nc, F.label[SL_CENTER], L_REDUCED, flag);
+    const int64_t nRed = tile_order_scan(st, g, SL_CENTER, flag, rank, tileCounts);
+    static thread_local DBuf<int32_t> keys, kt, vt;
+    keys.alloc((size_t)nRed); RG.cellList.alloc((size_t)nRed);
+    k_collect_region_keys(st, g, rank, flag, F.ridx[SL_CENTER], nc, 0, 0, keys.p, RG.cellList.p);
+    sort_pairs_by_key(st, nRed, key_bits(R), keys, RG.cellList, kt, vt);
+    std::vector<unsigned long long> hs = sums.to_host(st, (size_t)4 * R);
+    std::vector<int> perRegion((size_t)R);
+    for (int r = 0; r < R; ++r) perRegion[r] = (int)hs[4 * r + 3];
+    std::vector<int32_t> start, table, chunkStart;
+    build_chunks(perRegion, 256, start, table, chunkStart);
+    RG.nCellChunks = (int32_t)(table.size() / 3);
+    RG.cellStart.from_host(st, start.data(), start.size());
+    RG.cellChunk.from_host(st, table.data(), table.size());
+    RG.cellChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
+    const size_t NN = (size_t)RDOF * RDOF;
+    RG.partial.alloc((size_t)RG.nCellChunks * (3 * NN + RDOF));
+    RG.Mr.alloc(R * NN); RG.Visc.alloc(R * NN); RG.N.alloc(R * NN); RG.Binv.alloc(R * NN);
+    RG.lsqRhs.alloc((size_t)R * RDOF); RG.bestFit.alloc((size_t)R * RDOF); RG.rhsR.alloc((size_t)R * RDOF);
+    RG.t.alloc((size_t)R * RDOF); RG.s.alloc((size_t)R * RDOF);
+    region_gram_partials(st, g, F, RG, RG.partial.p);
+    region_gram_finish(st, g, RG, RG.nCellChunks);
+}
+
+// constructMatrixBlocks (S_CMB:9-868): row numbering of K_ext, then the ELL fills
+void Solver::constructMatrixBlocks() {
+    const int R = RG.count;
+    for (int a = 0; a < 3; ++a) k_krow_active(st, g.n[SL_FACE + a], F.aidx[SL_FACE + a], (int32_t)C.faceOff[a], F.krow[a]);
+    RG.nRows = 0; RG.nRowChunks = 0;
+    if (R > 0) {
+        int64_t cnt[3], off[3];
+        for (int a = 0; a < 3; ++a) {
+            k_flag_coupled_faces(st, g, F, a, scratch8[a].p);
+            cnt[a] = tile_order_scan(st, g, SL_FACE + a, scratch8[a].p, scratch32[a].p, tileCounts);
+        }
+        off[0] = 0; off[1] = cnt[0]; off[2] = cnt[0] + cnt[1];
+        const int64_t nRows = cnt[0] + cnt[1] + cnt[2];
+        RG.nRows = nRows;
+        RG.rowFace.alloc((size_t)nRows); RG.rowRegion.alloc((size_t)nRows);
+        for (int a = 0; a < 3; ++a)
+            k_collect_region_keys(st, g, scratch32[a].p, scratch8[a].p, F.ridx[SL_FACE + a], g.n[SL_FACE + a], (int32_t)(a << 29), (int32_t)off[a], RG.rowRegion.p, RG.rowFace.p);
+        static thread_local DBuf<int32_t> kt, vt;
+        sort_pairs_by_key(st, nRows, key_bits(R), RG.rowRegion, RG.rowFace, kt, vt);
+        if (C.nActiveVs + nRows >= INT32_MAX) throw Error("K_ext has too many rows for int32");
+        k_krow_reduced(st, nRows, RG.rowFace.p, (int32_t)C.nActiveVs, F.krow[0], F.krow[1], F.krow[2]);
+        static thread_local DBuf<int> rc;
+        rc.alloc((size_t)R); rc.zero(st, (size_t)R);
+        k_count_by_region(st, nRows, RG.rowRegion.p, rc.p);
+        std::vector<int> perRegion = rc.to_host(st, (size_t)R);
+        std::vector<int32_t> start, table, chunkStart;
+        build_chunks(perRegion, 1024, start, table, chunkStart);
+        RG.nRowChunks = (int32_t)(table.size() / 3);
+        RG.rowStart.from_host(st, start.data(), start.size());
+        RG.rowChunk.from_host(st, table.data(), table.size());
+        RG.rowChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
+        RG.partial.alloc(std::max((size_t)RG.nRowChunks * RDOF, RG.partial.n));
+    }
+    C.nRowsExt = C.nActiveVs + RG.nRows;
+    K.alloc(8, C.nRowsExt);
+    mcInv.alloc((size_t)C.nActiveVs); mc.alloc((size_t)C.nActiveVs); rhsU.alloc((size_t)C.nActiveVs); oldVs.alloc((size_t)C.nActiveVs);
+    k_assemble_K(st, g, F, C, K.val.p, K.col.p, mcInv.p, mc.p, rhsU.p, oldVs.p);
+    const int64_t nE = C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
+    KtP.alloc(6, C.nPressures); KtC.alloc(2, 3 * C.nCenter); KtE.alloc(4, nE);
+    uInv.alloc((size_t)C.nStresses); uDiag.alloc((size_t)C.nStresses); rhsPT.alloc((size_t)C.nSystemSize);
+    k_assemble_Kt(st, g, F, C, KtP, KtC, KtE, uInv.p, uDiag.p, rhsPT.p);
+    const size_t n = (size_t)C.nSystemSize;
+    b.alloc(n); x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); w.alloc((size_t)C.nRowsExt + 1);
+    velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
+    dotPartial.alloc(4096);
+}
+
+static OpArgs make_op(const Solver& S) {
+    OpArgs A;
+    A.nRowsExt = S.C.nRowsExt; A.nActiveVs = S.C.nActiveVs; A.nP = S.C.nPressures; A.nT = S.C.nStresses; A.nC = S.C.nCenter;
+    A.nE = S.C.nEdge[0] + S.C.nEdge[1] + S.C.nEdge[2];
+    A.kval = S.K.val.p; A.kcol = S.K.col.p;
+    A.ktpVal = S.KtP.val.p; A.ktpCol = S.KtP.col.p; A.ktcVal = S.KtC.val.p; A.ktcCol = S.KtC.col.p; A.kteVal = S.KtE.val.p; A.kteCol = S.KtE.col.p;
+    A.mcInv = S.mcInv.p; A.uInv = S.uInv.p;
+    return A;
+}
+
+// assembleSystemPressureStressFactored (S_AS:432-470):
+//   b = -[G^T; D] Mc^-1 rhs_u - (1/dt) [JG^T; DJ^T] B^-1 rhs_r + [rhs_p; rhs_tau]  =  -K_ext^T w + rhs_pt
+//   with  w_active = Mc^-1 rhs_u,  w_reduced(f) = (1/dt) c_f . (B^-1 rhs_r)
+void Solver::assemble() {
+    const OpArgs A = make_op(*this);
+    w.zero(st, (size_t)C.nRowsExt);
+    k_scale_rows(st, C.nActiveVs, mcInv.p, rhsU.p, w.p);
+    if (RG.count > 0) {
+        reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, RG.rhsR.p, 1.0, 0.0);
+        k_reduced_expand(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, g.invDt);
+    }
+    k_pass2(st, A, w.p, nullptr, b.p, 0.0, rhsPT.p, nullptr, 0, nullptr, 0);
+}
+
+// y = A x (ApplyPressureStressMatrix::applyMatrixVectorProducts, Apply.h:102-179)
+void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
+    const OpArgs A = make_op(*this);
+    k_pass1(st, A, xin, w.p, g.dt, nullptr);
+    if (RG.count > 0) {
+        reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, nullptr, 0.0, 1.0);
+        k_reduced_expand(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, 1.0);
+    }
+    k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, 0, nullptr, 0);
+}
+
+// solveSPDwithMatrixVectorPCG (S.cpp:734-812) -> pcg_external_matrix_A (pcg.h:268-340): identity
+// preconditioner (Preconditioner.cpp:271-274), zero start, stop test min(rr, rr/xx) < tol^2.
+int Solver::solve() {
+    StageTimer T(st, &stageMs[PS_STAGE_SOLVE]);
+    if (P.matrixSetup != 0 || P.solverType != 0) { result = R_UNSUPPORTED_SOLVER; return result; }
+    const OpArgs A = make_op(*this);
+    const int64_t n = C.nSystemSize;
+    const int maxIt = P.maxSolverIterations;
+    const int every = P.checkEvery > 0 ? P.checkEvery : 25;
+    usedBiCGStab = 0;
+    PcgScalars h; memset(&h, 0, sizeof h);
+    if (n == 0) { solveIterations = 0; solveError = 0; result = R_SUCCESS; return result; }
+    k_cg_init(st, n, b.p, x.p, r.p, p.p, dotPartial.p, 0, scal.p, P.tolerance, maxIt);
+    bool cancelled = false;
+    for (int it = 0; it < maxIt;) {
+        const int batch = std::min(every, maxIt - it);
+        for (int k = 0; k < batch; ++k) {
+            k_pass1(st, A, p.p, w.p, g.dt, scal.p);
+            if (RG.count > 0) {
+                reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, nullptr, 0.0, 1.0);
+                k_reduced_expand(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, 1.0);
+            }
+            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, 0, scal.p, 1);
+            k_cg_update_xr(st, n, x.p, r.p, p.p, Ap.p, dotPartial.p, 0, scal.p);
+            k_cg_update_p(st, n, p.p, r.p, scal.p);
+        }
+        it += batch;
+        copy_d2h(&h, scal.p, sizeof h, st);
+        if (h.done) break;
+        if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
+    }
+    copy_d2h(&h, scal.p, sizeof h, st);
+    if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
+    // b == 0: the reference would divide 0/0 (pcg.h:313); we return x = 0 after 0 iterations instead
+    solveIterations = (h.done == 1) ? h.iter : maxIt;
+    solveError = std::sqrt(h.rre);
+    result = (solveIterations == maxIt) ? R_NOCONVERGE : R_SUCCESS;
+    return result;
+}
+
+// recoverVelocityFromPressureStress (S.cpp:492-510)
+void Solver::recoverVelocityFromPressureStress() {
+    const OpArgs A = make_op(*this);
+    k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau); reduced rows: K_red x
+    k_recover_active(st, g, C.nActiveVs, w.p, mcInv.p, rhsU.p, velSol.p);
+    if (RG.count > 0) {
+        reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, RG.rhsR.p, g.invDt, -1.0);   // B^-1 (rhs_r/dt - J x)
+        k_copy_reduced_solution(st, (int64_t)RG.count * RDOF, RG.s.p, velSol.p + C.nActiveVs);
+    }
+}
+
+// buildValidFaces (S_Cls:4-54) + applySolutionToVelocity (S.cpp:937-1028)
+void Solver::applySolutionToVelocity(const ps_fields_out& out) {
+    const bool dev = out.memory == PS_MEM_DEVICE;
+    const bool writeVel = (result == R_SUCCESS || P.keepNonConvergedResults);
+    for (int a = 0; a < 3; ++a) {
+        const size_t nf = (size_t)g.n[SL_FACE + a];
+        float* velDev = nullptr; float* validDev = nullptr;
+        // velocity staging starts as the input velocity: invalid faces are left untouched (S.cpp:975-978)
+        if (out.velocity[a] && writeVel) {
+            if (dev) { velDev = out.velocity[a]; if (velDev != dVel[a].p) copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
+            else { velDev = (float*)scratch32[0].p; copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
+        }
+        if (out.valid[a]) validDev = dev ? out.valid[a] : (float*)scratch32[1].p;
+        k_writeback_velocity(st, g, F, C, RG, velSol.p, a, velDev, validDev != nullptr, validDev);
+        if (!dev) {
+            if (velDev) copy_d2any(out.velocity[a], velDev, nf * sizeof(float), false, st);
+            if (validDev) copy_d2any(out.valid[a], validDev, nf * sizeof(float), false, st);
+            stream_sync(st);
+        }
+    }
+    stream_sync(st);
+}
+
+void Solver::setup() {
+    buildIntegrationWeightsAlt();
+    {
+        StageTimer T(st, &stageMs[PS_STAGE_CLASSIFY]);
+        classifyCells();
+        if (P.doReducedRegions) constructReducedRegions();
+        classifyFaces();
+        classifyEdges();
+    }
+    RG.count = 0;
+    {
+        StageTimer T(st, &stageMs[PS_STAGE_REDUCED]);
+        if (P.doReducedRegions) { constructCenterReducedIndices(); constructFacesReducedIndices(); constructEdgesReducedIndices(); }
+    }
+    { StageTimer T(st, &stageMs[PS_STAGE_INDICES]); constructActiveIndices(); }
+    { StageTimer T(st, &stageMs[PS_STAGE_REGION_MATRICES]); if (P.doReducedRegions) computeReducedRegionMatrices(); }
+    { StageTimer T(st, &stageMs[PS_STAGE_MATRIX_BLOCKS]); constructMatrixBlocks(); }
+    { StageTimer T(st, &stageMs[PS_STAGE_ASSEMBLE]); assemble(); }
+    haveSetup = true;
+    result = R_INCOMPLETE;
+}
+
+int Solver::step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* stats) {
+    for (double& m : stageMs) m = 0;
+    g_launches = 0;
+    setInputs(in);
+    setup();
+    int res = R_INCOMPLETE;
+    if (P.doSolve) res = solve();
+    if (res == R_UNSUPPORTED_SOLVER) { if (stats) fillStats(stats); return res; }
+    if (out) {
+        StageTimer T(st, &stageMs[PS_STAGE_WRITEBACK]);
+        if (P.doSolve && (res == R_SUCCESS || P.keepNonConvergedResults)) recoverVelocityFromPressureStress();
+        applySolutionToVelocity(*out);
+    }
+    if (stats) fillStats(stats);
+    return res;
+}
+
+// exportStats (S.cpp:574-606)
+void Solver::fillStats(ps_stats* s) const {
+    memset(s, 0, sizeof *s);
+    const double d[27] = {(double)C.nCenter, (double)C.nFace[0], (double)C.nFace[1], (double)C.nFace[2],
+                          (double)C.nEdge[0], (double)C.nEdge[1], (double)C.nEdge[2], (double)C.nActiveVs,
+                          (double)C.nFace[0], (double)C.nFace[1], (double)C.nFace[2], (double)C.nReducedVs,
+                          (double)C.nPressures, (double)C.nStresses, (double)C.nCenter, (double)C.nCenter, (double)C.nCenter,
+                          (double)C.nEdge[0], (double)C.nEdge[1], (double)C.nEdge[2], (double)C.nTotalDOFs, (double)C.nSystemSize,
+                          148.0 /* "thread count": SMs */, 0.0, (double)RG.count, g.dx, g.dt};
+    for (int i = 0; i < 27; ++i) s->dimData[i] = d[i];
+    double setupMs = 0;
+    for (int i = PS_STAGE_WEIGHTS; i <= PS_STAGE_ASSEMBLE; ++i) setupMs += stageMs[i];
+    s->solveData[0] = solveError; s->solveData[1] = solveIterations;
+    s->solveData[2] = stageMs[PS_STAGE_SOLVE]; s->solveData[3] = stageMs[PS_STAGE_SOLVE];
+    s->solveData[4] = setupMs; s->solveData[5] = setupMs;
+    s->result = result; s->usedBiCGStab = usedBiCGStab;
+    for (int i = 0; i < PS_NUM_STAGES; ++i) s->stage_ms[i] = stageMs[i];
+    s->gpu_launches = g_launches;
+}
+
+}  // namespace ps

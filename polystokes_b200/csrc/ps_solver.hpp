@@ -1,0 +1,181 @@
+// ps_solver.hpp -- host-side Solver mirroring HDK_PolyStokes::Solver (exec/HDK_PolyStokesSolver.h:27-887):
+// same stage names, same call order (exec/HDK_PolyStokes.C:344-584); every stage is one or a few CUDA
+// kernels on the solver's stream, all state is device resident.
+#pragma once
+#include "ps_grid.hpp"
+#include "../../include/polystokes_b200.h"
+
+namespace ps {
+
+// blocked-ELL storage of K_ext = [G D^T] (face rows) and of its transpose (DOF rows), slot-major so
+// that a warp reads 32 consecutive rows of one slot (coalesced 8 B values / 4 B columns).
+struct Ell {
+    int width = 0;
+    int64_t rows = 0;
+    DBuf<double> val;   // [width][rows]
+    DBuf<int32_t> col;  // [width][rows]
+    void alloc(int w, int64_t r) { width = w; rows = r; val.alloc((size_t)w * r); col.alloc((size_t)w * r); }
+};
+
+struct RegionData {
+    int32_t count = 0;
+    DBuf<double> com;        // [R][3]
+    DBuf<double> Mr, Visc, N, Binv;   // [R][26*26]
+    DBuf<double> lsqRhs, bestFit, rhsR;  // [R][26]
+    DBuf<int32_t> cellList;  // REDUCED cells sorted by (region, tile order)
+    DBuf<int32_t> cellStart; // [R+1]
+    // coupled reduced face rows of K_ext, sorted by (region, axis, tile order)
+    int64_t nRows = 0;
+    DBuf<int32_t> rowFace;   // packed dense face index | axis << 29
+    DBuf<int32_t> rowRegion; // region of each row
+    DBuf<int32_t> rowStart;  // [R+1] row range of each region (relative to nActiveVs)
+    // chunk tables (fixed-size pieces of the sorted lists, each inside one region)
+    int32_t nCellChunks = 0, nRowChunks = 0;
+    DBuf<int32_t> cellChunk, rowChunk;   // [nChunks][3] = region, begin, end
+    DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
+    DBuf<double> partial;    // per-chunk partial sums
+    DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
+};
+
+struct Counts {
+    int64_t nCenter = 0, nFace[3] = {0, 0, 0}, nEdge[3] = {0, 0, 0};
+    int64_t nActiveVs = 0, nReducedVs = 0, nPressures = 0, nStresses = 0, nTotalDOFs = 0, nSystemSize = 0;
+    int64_t faceOff[3] = {0, 0, 0};     // faceVelocityDOF offsets (S.h:628-642)
+    int64_t stressOff[6] = {0, 0, 0, 0, 0, 0};   // XX,YY,ZZ,YZ,XZ,XY offsets inside the stress block (S.h:586-606)
+    int64_t nRowsExt = 0;               // nActiveVs + coupled reduced rows
+};
+
+struct PcgScalars {   // device-resident CG state: no host round trip inside an iteration
+    double rsold, pAp, alpha, beta, rsnew, xmag, rre;
+    int iter, done, maxIter, pad;
+    double tol2;
+    unsigned int ticket[4];   // last-CTA-done tickets of the fused dot products
+};
+
+class Solver {
+public:
+    explicit Solver(const ps_params& p);
+    ~Solver();
+    ps_params P;
+    Geom g;
+    cudaStream_t st = nullptr;
+    Counts C;
+    int result = R_INCOMPLETE;
+    int solveIterations = -1;
+    double solveError = -1;
+    int usedBiCGStab = 0;
+    int fixLoops = 0;
+    double stageMs[PS_NUM_STAGES] = {0};
+
+    // ---- the reference's per-step sequence (exec/HDK_PolyStokes.C:344-584) ----
+    void setInputs(const ps_fields_in& in);
+    void buildIntegrationWeightsAlt();
+    void classifyCells();
+    void constructReducedRegions();
+    void classifyFaces();
+    void classifyEdges();
+    void constructCenterReducedIndices();
+    void constructFacesReducedIndices();
+    void constructEdgesReducedIndices();
+    void constructActiveIndices();      // constructCenter/Faces/EdgesActiveIndices
+    void computeReducedRegionMatrices();// computeCenterOfMasses, LeastSquaresFits, ReducedMassMatrices, ViscosityMatricesInteriorOnly
+    void constructMatrixBlocks();
+    void assemble();                    // assembleSystemPressureStressFactored
+    int solve();                        // solveSPDwithMatrixVectorPCG
+    void buildValidFaces(const ps_fields_out& out);
+    void recoverVelocityFromPressureStress();
+    void applySolutionToVelocity(const ps_fields_out& out);
+
+    void setup();                       // weights .. assemble
+    int step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* stats);
+    void fillStats(ps_stats* s) const;
+
+    // operator y = A x on device vectors (Apply.h:102-179)
+    void applyOperator(const double* x, double* y, double* pApPartial);
+
+    // ---- device state ----
+    Fields F;
+    DBuf<float> dSurface, dCollision, dViscosity, dVel[3], dColVel[3];
+    DBuf<uint8_t> dLiqW[N_SLOTS], dFluW[N_SLOTS];
+    DBuf<int8_t> dLabel[N_SLOTS];
+    DBuf<int32_t> dAidx[N_SLOTS], dRidx[N_SLOTS], dKrow[3];
+    DBuf<uint8_t> scratch8[3];
+    DBuf<int32_t> scratch32[4];
+    DBuf<int32_t> tileCounts;
+    DBuf<int> flags;             // small device flag / counter block
+    RegionData RG;
+    // matrices + vectors
+    Ell K;                        // rows = nRowsExt, width 8
+    Ell KtP, KtC, KtE;            // transpose blocks: pressure rows (6), centre-stress rows (2), edge-stress rows (4)
+    DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
+    DBuf<double> x, r, p, Ap, w, velSol;
+    DBuf<double> dotPartial;
+    DBuf<PcgScalars> scal;
+    bool inputsOnDevice = false;
+    bool haveSetup = false;
+};
+
+// ---- kernels (free functions; see the .cu files for the reference citations) ----
+void k_build_weights(cudaStream_t, const Geom&, const Fields&);
+void k_classify_cells(cudaStream_t, const Geom&, const Fields&, bool genericToActive);
+void k_air_layer_seed(cudaStream_t, const Geom&, const Fields&, uint8_t* stamp);
+void k_layer_commit(cudaStream_t, const Geom&, const Fields&, const uint8_t* stamp, int layerStamp);
+void k_air_layer_grow(cudaStream_t, const Geom&, const Fields&, uint8_t* stamp, int prevStamp);
+void k_solid_layer_seed(cudaStream_t, const Geom&, const Fields&, uint8_t* stamp);
+void k_solid_layer_grow(cudaStream_t, const Geom&, const Fields&, uint8_t* stamp, int prevStamp);
+void k_tiles_and_reduce(cudaStream_t, const Geom&, const Fields&, bool doTile, int tileSize, int tilePadding);
+void k_classify_faces(cudaStream_t, const Geom&, const Fields&);
+void k_classify_edges(cudaStream_t, const Geom&, const Fields&);
+void k_cc_init(cudaStream_t, const Geom&, const Fields&, int32_t* parent);
+void k_cc_sweep(cudaStream_t, const Geom&, const Fields&, int32_t* parent, int* changed);
+void k_cc_minkey(cudaStream_t, const Geom&, const int32_t* parent, int32_t* minKey);
+void k_cc_first_flags(cudaStream_t, const Geom&, const int32_t* parent, const int32_t* minKey, uint8_t* flag);
+void k_cc_publish(cudaStream_t, const Geom&, const int32_t* parent, const uint8_t* flag, const int32_t* firstRank, int32_t* rootId);
+void k_cc_assign(cudaStream_t, const Geom&, const Fields&, const int32_t* parent, const int32_t* rootId);
+void k_fix_candidates(cudaStream_t, const Geom&, const Fields&, uint8_t* cand, uint8_t* firedA, uint8_t* firedB, int* anyCand);
+void k_fix_iterate(cudaStream_t, const Geom&, const Fields&, const uint8_t* cand, const uint8_t* firedIn, uint8_t* firedOut, int* changed);
+void k_fix_apply(cudaStream_t, const Geom&, const Fields&, const uint8_t* fired, int* anyFired);
+void k_region_bbox(cudaStream_t, const Geom&, const Fields&, int* bbMin, int* bbMax);
+void k_region_remap(cudaStream_t, const Geom&, const Fields&, const int32_t* remap);
+void k_faces_reduced(cudaStream_t, const Geom&, const Fields&);
+void k_edges_reduced(cudaStream_t, const Geom&, const Fields&);
+void k_generic_to_active_flags(cudaStream_t, const Geom&, int slot, int8_t* L, uint8_t* flag);
+void k_valid_faces(cudaStream_t, const Geom&, const Fields&, float* const valid[3]);
+
+// tile-order exclusive scan of a dense 0/1 flag field: out[q] = rank among flagged voxels in the
+// reference's voxel iteration order, -1 where the flag is 0.  Returns the total (host sync).
+int64_t tile_order_scan(cudaStream_t, const Geom&, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts);
+// stable sort of (key, value) pairs by key (keys < 2^keyBits)
+void sort_pairs_by_key(cudaStream_t, int64_t n, int keyBits, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>& keysTmp, DBuf<int32_t>& valsTmp);
+
+// ps_reduced.cu
+void k_region_com(cudaStream_t, const Geom&, const Fields&, int32_t R, unsigned long long* sums, double* com);
+void k_collect_region_keys(cudaStream_t, const Geom&, const int32_t* rank, const uint8_t* flag, const int32_t* region, int64_t n, int32_t tag, int32_t rankOffset, int32_t* keys, int32_t* vals);
+void region_gram_partials(cudaStream_t, const Geom&, const Fields&, const RegionData&, double* partial);
+void region_gram_finish(cudaStream_t, const Geom&, RegionData&, int nChunks);
+void k_flag_coupled_faces(cudaStream_t, const Geom&, const Fields&, int axis, uint8_t* flag);
+
+// ps_assemble.cu
+void k_assemble_K(cudaStream_t, const Geom&, const Fields&, const Counts&, double* kval, int32_t* kcol, double* mcInv, double* mc, double* rhsU, double* oldVs);
+void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, Ell& KtP, Ell& KtC, Ell& KtE, double* uInv, double* uDiag, double* rhsPT);
+
+// ps_pcg.cu
+struct OpArgs {   // everything one operator apply touches
+    int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
+    const double* kval; const int32_t* kcol;
+    const double* ktpVal; const int32_t* ktpCol; const double* ktcVal; const int32_t* ktcCol; const double* kteVal; const int32_t* kteCol;
+    const double* mcInv; const double* uInv;
+};
+void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal);
+void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, int nPartials, PcgScalars* scal, int mode);
+void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, int64_t nActiveVs, const double* extraRhs, double extraScale, double resultScale);
+void k_reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, int64_t nActiveVs, double scale);
+void k_cg_update_xr(cudaStream_t, int64_t n, double* x, double* r, const double* p, const double* Ap, double* dotPartial, int nPartials, PcgScalars* scal);
+void k_cg_update_p(cudaStream_t, int64_t n, double* p, const double* r, const PcgScalars* scal);
+void k_cg_init(cudaStream_t, int64_t n, const double* b, double* x, double* r, double* p, double* dotPartial, int nPartials, PcgScalars* scal, double tol, int maxIter);
+void k_recover_active(cudaStream_t, const Geom&, int64_t nActiveVs, const double* wAct, const double* mcInv, const double* rhsU, double* velSol);
+void k_writeback_velocity(cudaStream_t, const Geom&, const Fields&, const Counts&, const RegionData&, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut);
+
+extern thread_local std::string g_lastError;
+
+}  // namespace ps
