@@ -132,13 +132,16 @@ int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int6
 int64_t ps_get_vector(ps_handle h, const char* name, double* out);
 /* y = A x with host vectors of length nSystemSize (ApplyPressureStressMatrix::apply, Apply.h:182-184) */
 int ps_apply(ps_handle h, const double* x, double* y);
-/* times `reps` back-to-back operator applies / CG iterations on the current system (CUDA events on the
- * solver stream); used by bench.py for the roofline.  Returns average milliseconds per repetition. */
-double ps_time_apply(ps_handle h, int reps, int flushL2);
-double ps_time_cg_iteration(ps_handle h, int reps);
-/* algorithmic bytes of one operator apply / one CG iteration on the current system */
-double ps_apply_bytes(ps_handle h);
-double ps_cg_iteration_bytes(ps_handle h);
+/* Roofline support for bench.py.  `name` is one of
+ *   "pass1"  w = dt Mc^-1 K_ext x            (SpMV over the 8-wide face-row ELL)
+ *   "pass2"  y = -K_ext^T w - 1/2 mu^-1 x    (SpMV over the 6/2/4-wide DOF-row ELL)
+ *   "apply"  the whole operator (pass1 + reduced-region moments/expand + pass2)
+ *   "cg_iteration"  one full CG iteration (apply + the two fused vector kernels)
+ * ps_time_kernel runs it `reps` times back to back on the solver stream between CUDA events (after one
+ * warm-up run) and returns the average milliseconds; ps_kernel_bytes returns the ALGORITHMIC bytes of one
+ * run on the current system.  Both need a prior ps_setup / ps_step. */
+double ps_time_kernel(ps_handle h, const char* name, int reps);
+double ps_kernel_bytes(ps_handle h, const char* name);
 
 #ifdef __cplusplus
 }

@@ -55,8 +55,7 @@ class ps_stats(C.Structure):
 
 # every symbol include/polystokes_b200.h declares
 SYMBOLS = ["ps_create", "ps_destroy", "ps_step", "ps_setup", "ps_solve", "ps_export", "ps_last_error", "ps_get_count", "ps_get_real",
-           "ps_get_index_field", "ps_get_weight_field", "ps_get_csr", "ps_get_vector", "ps_apply", "ps_time_apply",
-           "ps_time_cg_iteration", "ps_apply_bytes", "ps_cg_iteration_bytes"]
+           "ps_get_index_field", "ps_get_weight_field", "ps_get_csr", "ps_get_vector", "ps_apply", "ps_time_kernel", "ps_kernel_bytes"]
 
 _cache = {}
 
@@ -85,9 +84,7 @@ def load(path=None):
     L.ps_get_csr.argtypes = [H, C.c_char_p] + [C.POINTER(C.c_int64)] * 3 + [C.c_void_p] * 3; L.ps_get_csr.restype = C.c_int
     L.ps_get_vector.argtypes = [H, C.c_char_p, C.c_void_p]; L.ps_get_vector.restype = C.c_int64
     L.ps_apply.argtypes = [H, C.c_void_p, C.c_void_p]; L.ps_apply.restype = C.c_int
-    L.ps_time_apply.argtypes = [H, C.c_int, C.c_int]; L.ps_time_apply.restype = C.c_double
-    L.ps_time_cg_iteration.argtypes = [H, C.c_int]; L.ps_time_cg_iteration.restype = C.c_double
-    L.ps_apply_bytes.argtypes = [H]; L.ps_apply_bytes.restype = C.c_double
-    L.ps_cg_iteration_bytes.argtypes = [H]; L.ps_cg_iteration_bytes.restype = C.c_double
+    L.ps_time_kernel.argtypes = [H, C.c_char_p, C.c_int]; L.ps_time_kernel.restype = C.c_double
+    L.ps_kernel_bytes.argtypes = [H, C.c_char_p]; L.ps_kernel_bytes.restype = C.c_double
     _cache[path] = L
     return L

@@ -268,57 +268,51 @@ int ps_apply(ps_handle h, const double* x, double* y) {
     });
 }
 
-double ps_apply_bytes(ps_handle h) {
-    if (!h) return 0;
-    const Solver& S = *h->S; const Counts& C = S.C;
-    // ELL streams (12 B per stored slot), vectors read/written once
+double ps_kernel_bytes(ps_handle h, const char* name) {
+    if (!h || !name) return 0;
+    const Solver& S = *h->S; const Counts& C = S.C; const std::string nm(name);
+    // ELL streams cost 12 B per stored slot, every vector is read / written once
     const double nE = (double)(C.nEdge[0] + C.nEdge[1] + C.nEdge[2]);
     const double kSlots = 8.0 * C.nRowsExt, ktSlots = 6.0 * C.nPressures + 2.0 * 3 * C.nCenter + 4.0 * nE;
     const double n = (double)C.nSystemSize;
-    double bytes = 12.0 * kSlots + 8.0 * n /*x*/ + 8.0 * C.nActiveVs /*Mc^-1*/ + 8.0 * C.nRowsExt /*w write*/;
-    bytes += 12.0 * ktSlots + 8.0 * C.nRowsExt /*w read*/ + 8.0 * C.nStresses /*mu^-1*/ + 8.0 * C.nStresses /*x_tau*/ + 8.0 * n /*y*/;
-    bytes += (double)S.RG.nRows * (4.0 + 8.0) * 2 /*row list + w, moments and expand*/ + (double)S.RG.count * (RDOF * RDOF + 3 * RDOF) * 8.0;
-    return bytes;
-}
-double ps_cg_iteration_bytes(ps_handle h) {
-    if (!h) return 0;
-    const double n = (double)h->S->C.nSystemSize;
-    return ps_apply_bytes(h) + 8.0 * n /*p for the dot*/ + 48.0 * n + 24.0 * n;
+    const double pass1 = 12.0 * kSlots + 8.0 * n /*x*/ + 8.0 * C.nActiveVs /*Mc^-1*/ + 8.0 * C.nRowsExt /*w write*/;
+    const double pass2 = 12.0 * ktSlots + 8.0 * C.nRowsExt /*w read*/ + 8.0 * C.nStresses /*mu^-1*/ + 8.0 * C.nStresses /*x_tau*/ + 8.0 * n /*y*/;
+    const double reduced = (double)S.RG.nRows * (4.0 + 8.0) * 2 /*row list + w: moments, expand*/ + (double)S.RG.count * (RDOF * RDOF + 3 * RDOF) * 8.0;
+    if (nm == "pass1") return pass1;
+    if (nm == "pass2") return pass2;
+    if (nm == "apply") return pass1 + pass2 + reduced;
+    if (nm == "cg_iteration") return pass1 + pass2 + reduced + 8.0 * n /*p for p.Ap*/ + 48.0 * n /*x,r update*/ + 24.0 * n /*p update*/;
+    return 0;
 }
 
-double ps_time_apply(ps_handle h, int reps, int) {
-    if (!h || reps <= 0) return -1;
+double ps_time_kernel(ps_handle h, const char* name, int reps) {
+    if (!h || !name || reps <= 0) return -1;
     double ms = -1;
     guarded([&] {
-        Solver& S = *h->S;
-        if (!S.haveSetup) throw Error("ps_time_apply: call ps_setup first");
+        Solver& S = *h->S; const std::string nm(name);
+        if (!S.haveSetup) throw Error("ps_time_kernel: call ps_setup first");
+        if (nm == "cg_iteration") {
+            const int savedMax = S.P.maxSolverIterations, savedEvery = S.P.checkEvery; const double savedTol = S.P.tolerance;
+            S.P.maxSolverIterations = reps; S.P.checkEvery = reps; S.P.tolerance = 0.0;   // never converges: exactly `reps` iterations
+            S.stageMs[PS_STAGE_SOLVE] = 0;
+            S.solve();
+            ms = S.stageMs[PS_STAGE_SOLVE] / reps;
+            S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
+            return 0;
+        }
+        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : -1;
+        if (which < 0) throw Error("ps_time_kernel: unknown kernel name");
 #ifndef PS_EMULATE
         cudaEvent_t a, b; PS_CUDA(cudaEventCreate(&a)); PS_CUDA(cudaEventCreate(&b));
-        S.applyOperator(S.b.p, S.Ap.p, nullptr);
+        S.timedOperator(which);
         PS_CUDA(cudaEventRecord(a, S.st));
-        for (int i = 0; i < reps; ++i) S.applyOperator(S.b.p, S.Ap.p, nullptr);
+        for (int i = 0; i < reps; ++i) S.timedOperator(which);
         PS_CUDA(cudaEventRecord(b, S.st)); PS_CUDA(cudaEventSynchronize(b));
         float t = 0; PS_CUDA(cudaEventElapsedTime(&t, a, b)); ms = t / reps;
         cudaEventDestroy(a); cudaEventDestroy(b);
 #else
-        S.applyOperator(S.b.p, S.Ap.p, nullptr); ms = 0;
+        S.timedOperator(which); ms = 0;
 #endif
-        return 0;
-    });
-    return ms;
-}
-double ps_time_cg_iteration(ps_handle h, int reps) {
-    if (!h || reps <= 0) return -1;
-    double ms = -1;
-    guarded([&] {
-        Solver& S = *h->S;
-        if (!S.haveSetup) throw Error("ps_time_cg_iteration: call ps_setup first");
-        const int savedMax = S.P.maxSolverIterations, savedEvery = S.P.checkEvery; const double savedTol = S.P.tolerance;
-        S.P.maxSolverIterations = reps; S.P.checkEvery = reps; S.P.tolerance = 0.0;   // never converges: exactly `reps` iterations
-        S.stageMs[PS_STAGE_SOLVE] = 0;
-        S.solve();
-        ms = S.stageMs[PS_STAGE_SOLVE] / reps;
-        S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
         return 0;
     });
     return ms;

@@ -364,6 +364,13 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, 0, nullptr, 0);
 }
 
+void Solver::timedOperator(int which) {
+    const OpArgs A = make_op(*this);
+    if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
+    if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
+    else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, 0, nullptr, 0);
+}
+
 // solveSPDwithMatrixVectorPCG (S.cpp:734-812) -> pcg_external_matrix_A (pcg.h:268-340): identity
 // preconditioner (Preconditioner.cpp:271-274), zero start, stop test min(rr, rr/xx) < tol^2.
 int Solver::solve() {

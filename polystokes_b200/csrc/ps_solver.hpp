@@ -92,6 +92,7 @@ public:
 
     // operator y = A x on device vectors (Apply.h:102-179)
     void applyOperator(const double* x, double* y, double* pApPartial);
+    void timedOperator(int which);     // 0 = whole apply, 1 = pass 1 only, 2 = pass 2 only (on b -> Ap)
 
     // ---- device state ----
     Fields F;

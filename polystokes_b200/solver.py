@@ -225,17 +225,15 @@ class PolyStokesSolver:
             raise PolyStokesError(f"ps_apply failed: {self.last_error()}")
         return y
 
-    def time_apply(self, reps=20):
-        return float(self.lib.ps_time_apply(self.h, int(reps), 0))
+    def time_kernel(self, name, reps=20):
+        """Average ms of `name` in ("pass1", "pass2", "apply", "cg_iteration") over `reps` runs (CUDA events)."""
+        t = float(self.lib.ps_time_kernel(self.h, name.encode(), int(reps)))
+        if t < 0:
+            raise PolyStokesError(f"ps_time_kernel({name}) failed: {self.last_error()}")
+        return t
 
-    def time_cg_iteration(self, reps=20):
-        return float(self.lib.ps_time_cg_iteration(self.h, int(reps)))
-
-    def apply_bytes(self):
-        return float(self.lib.ps_apply_bytes(self.h))
-
-    def cg_iteration_bytes(self):
-        return float(self.lib.ps_cg_iteration_bytes(self.h))
+    def kernel_bytes(self, name):
+        return float(self.lib.ps_kernel_bytes(self.h, name.encode()))
 
     def stage_ms(self):
         return {n: self.stats.stage_ms[i] for i, n in enumerate(STAGE_NAMES)} if self.stats is not None else {}

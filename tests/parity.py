@@ -1,0 +1,110 @@
+"""Shared parity checks: the C-ABI library (CUDA product, or its host-emulation twin) vs the CPU oracle.
+
+Gates: labels / DOF indices / counts / CSR patterns bit-exact; matrix values
+<= 1e-8 relative (the K factors and diagonals are in fact bit-equal); b <= 1e-10; solved velocity within
+10*tol (inf-norm, relative); CG iterations within max(2, 1%).
+"""
+import os
+
+import numpy as np
+
+from polystokes_b200 import PolyStokesSolver, scenes
+from oracle.oracle import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_LIB = os.path.join(ROOT, "polystokes_b200", "libpolystokes_emul.so")
+
+COUNTS = ["nCenter", "nFaceX", "nFaceY", "nFaceZ", "nEdgeYZ", "nEdgeXZ", "nEdgeXY", "regionCount", "nSystemSize",
+          "nActiveVs", "nReducedVs", "nPressures", "nStresses", "nTotalDOFs"]
+BITEXACT_MATS = ["G", "Dt", "Mc", "McInv", "uInv", "u"]
+TOL_MATS = ["JG", "JDt", "Mr", "B", "BInv"]
+
+# the scene matrix used by both the emulation tests (CPU) and the GPU tests
+SCENE_CASES = {
+    "uniform_box24": lambda: (scenes.box_scene(24, doReduced=0, tolerance=1e-6), {}),
+    "tiles8pad1_box40": lambda: (scenes.box_scene(40, tileSize=8, tilePadding=1), {}),
+    "blob40": lambda: (scenes.blob_scene(40), {}),
+    "blob40_layers31": lambda: (scenes.blob_scene(40, seed=11, tile=8, pad=2, liquidLayers=3, solidLayers=1), {}),
+    "blob_ragged_36x44x52": lambda: (scenes.blob_scene((36, 44, 52), seed=5, tile=16, pad=1), {}),
+    "blob40_notile": lambda: (scenes.blob_scene(40, seed=3, doTile=0), {}),
+    "blob33_uniform": lambda: (scenes.blob_scene(33, seed=9, doReduced=0), {}),
+    "empty_air": lambda: (empty_scene(), {}),
+}
+
+
+def empty_scene():
+    """No liquid at all: every count is 0, the solve is trivially successful."""
+    sc = scenes.box_scene(16, doReduced=1)
+    sc.surface[...] = 1.0
+    return sc
+
+
+def rel(a, b):
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(float(np.abs(a).max()), 1e-300))
+
+
+def check_classification(o, s):
+    for k in COUNTS:
+        assert o.count(k) == s.count(k), f"count {k}: oracle {o.count(k)} vs {s.count(k)}"
+    for slot in range(7):
+        for liquid in (1, 0):
+            assert np.array_equal(o.weight_field(liquid, slot), s.weight_field(liquid, slot)), f"weights slot {slot} liquid {liquid}"
+        for kind, name in ((0, "labels"), (1, "active"), (2, "reduced")):
+            a, b = o.index_field(kind, slot), s.index_field(kind, slot)
+            assert np.array_equal(a, b.astype(np.int64)), f"{name} field of slot {slot}: {(a != b).sum()} of {a.size} differ"
+
+
+def check_matrices(o, s):
+    for m in BITEXACT_MATS + TOL_MATS:
+        so, po, io, vo = o.csr(m)
+        ss, ps_, is_, vs = s.csr(m)
+        assert tuple(so) == tuple(ss), f"{m} shape"
+        assert np.array_equal(po, ps_) and np.array_equal(io, is_), f"{m} sparsity pattern differs"
+        if m in BITEXACT_MATS:
+            assert np.array_equal(vo, vs), f"{m} values not bit-equal (rel {rel(vo, vs):.2e})"
+        else:
+            assert rel(vo, vs) <= 1e-8, f"{m} values rel {rel(vo, vs):.2e}"
+    for v in ["activeRHS", "pressureRHS", "stressRHS", "com"]:
+        assert np.array_equal(o.vector(v), s.vector(v)), f"{v} not bit-equal"
+    for v, tol in (("reducedRHS", 1e-8), ("bestFit", 1e-6), ("MrDense", 1e-8), ("ViscDense", 1e-8), ("BinvDense", 1e-8), ("b", 1e-10)):
+        assert rel(o.vector(v), s.vector(v)) <= tol, f"{v} rel {rel(o.vector(v), s.vector(v)):.2e}"
+
+
+def check_operator(o, s, seed=0):
+    n = o.count("nSystemSize")
+    if n == 0:
+        return
+    x = np.random.default_rng(seed).standard_normal(n)
+    ya, yb = o.apply(x), s.apply(x)
+    assert rel(ya, yb) <= 1e-12, f"operator apply rel {rel(ya, yb):.2e}"
+
+
+def check_solve(sc, o, s, ov):
+    ro = o.solve()
+    ovel, ovalid = o.writeback()
+    rs, vel, valid = s.step_scene(sc)
+    assert ro == rs, f"solver result oracle {ro} vs {rs}"
+    io, is_ = o.count("iterations"), s.count("iterations")
+    assert abs(io - is_) <= max(2, int(0.01 * io)), f"iterations oracle {io} vs {is_}"
+    tol = 10 * dict(sc.params, **ov)["tolerance"]
+    for a in range(3):
+        assert np.array_equal(ovalid[a], valid[a]), f"valid field axis {a}"
+        scale = max(float(np.abs(ovel[a]).max()), 1e-30)
+        assert float(np.abs(ovel[a] - vel[a]).max()) <= tol * scale, f"velocity axis {a}"
+    return io, is_
+
+
+def run_case(name, lib_path=None, solve=True):
+    sc, ov = SCENE_CASES[name]()
+    o = Oracle(sc, **ov).setup()
+    s = PolyStokesSolver.from_scene(sc, lib_path=lib_path, **ov)
+    s.setup_scene(sc)
+    check_classification(o, s)
+    check_matrices(o, s)
+    check_operator(o, s)
+    if solve:
+        check_solve(sc, o, s, ov)
+    s.close()
+    return o

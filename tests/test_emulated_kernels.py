@@ -1,0 +1,11 @@
+"""CPU-only check of the kernel logic: the product sources compiled with -DPS_EMULATE (every per-thread
+kernel body executed serially by g++) against the oracle.  This is NOT a product path -- the python package
+never loads libpolystokes_emul.so; it exists so index/stencil bugs are caught on machines without a GPU."""
+import pytest
+
+import parity
+
+
+@pytest.mark.parametrize("case", list(parity.SCENE_CASES))
+def test_emulated_step_matches_oracle(built, case):
+    parity.run_case(case, lib_path=parity.EMUL_LIB)
