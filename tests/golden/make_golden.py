@@ -1,0 +1,52 @@
+"""Regenerates tests/golden/*.npz from the oracle (run from the repo root: python tests/golden/make_golden.py).
+
+The reference has no fixtures of its own and cannot be run here, so these vectors pin the *oracle's* behaviour at the
+time they were generated; the KATs in tests/test_oracle_kat.py pin it analytically.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from polystokes_b200 import scenes  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+
+CASES = {
+    "blob20_tile8_pad1": lambda: scenes.blob_scene(20, seed=21, tile=8, pad=1),
+    "box16_uniform": lambda: scenes.box_scene(16, doReduced=0, tolerance=1e-6),
+}
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def collect(sc):
+    o = Oracle(sc).setup()
+    out = {}
+    for slot in range(7):
+        out[f"labels{slot}"] = o.index_field(0, slot).astype(np.int8)
+        out[f"active{slot}"] = o.index_field(1, slot).astype(np.int32)
+        out[f"reduced{slot}"] = o.index_field(2, slot).astype(np.int32)
+    for m in ("G", "Dt", "JG", "JDt"):
+        shape, ptr, idx, val = o.csr(m)
+        out[f"{m}_shape"] = np.array(shape)
+        out[f"{m}_pattern_sha256"] = np.frombuffer(bytes.fromhex(digest(ptr) + digest(idx)), dtype=np.uint8)
+        out[f"{m}_values"] = val
+    out["b"] = o.vector("b")
+    o.solve()
+    vel, valid = o.writeback()
+    out["iterations"] = np.array([o.count("iterations")])
+    for a in range(3):
+        out[f"vel{a}"] = vel[a]
+        out[f"valid{a}"] = valid[a].astype(np.uint8)
+    return out
+
+
+if __name__ == "__main__":
+    for name, mk in CASES.items():
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **collect(mk()))
+        print("wrote", name)
