@@ -133,7 +133,8 @@ int64_t ps_get_vector(ps_handle h, const char* name, double* out);
 /* y = A x with host vectors of length nSystemSize (ApplyPressureStressMatrix::apply, Apply.h:182-184) */
 int ps_apply(ps_handle h, const double* x, double* y);
 /* Roofline support for bench.py.  `name` is one of
- *   "pass1"  w = dt Mc^-1 K_ext x            (SpMV over the 8-wide face-row ELL)
+ *   "pass1"  w = dt Mc^-1 K x on the active face rows   (SpMV over the 8-wide face-row ELL)
+ *   "reduced" the coupled reduced rows: K_red x -> moments -> B^-1 -> w_f  (3 small kernels)
  *   "pass2"  y = -K_ext^T w - 1/2 mu^-1 x    (SpMV over the 6/2/4-wide DOF-row ELL)
  *   "apply"  the whole operator (pass1 + reduced-region moments/expand + pass2)
  *   "cg_iteration"  one full CG iteration (apply + the two fused vector kernels)

@@ -275,11 +275,14 @@ double ps_kernel_bytes(ps_handle h, const char* name) {
     const double nE = (double)(C.nEdge[0] + C.nEdge[1] + C.nEdge[2]);
     const double kSlots = 8.0 * C.nRowsExt, ktSlots = 6.0 * C.nPressures + 2.0 * 3 * C.nCenter + 4.0 * nE;
     const double n = (double)C.nSystemSize;
-    const double pass1 = 12.0 * kSlots + 8.0 * n /*x*/ + 8.0 * C.nActiveVs /*Mc^-1*/ + 8.0 * C.nRowsExt /*w write*/;
+    const double nRed = (double)S.RG.nRows;
+    const double pass1 = 12.0 * kSlots /*ELL slots*/ + 8.0 * n /*x*/ + 8.0 * C.nActiveVs /*Mc^-1*/ + 8.0 * C.nRowsExt /*w write*/;
     const double pass2 = 12.0 * ktSlots + 8.0 * C.nRowsExt /*w read*/ + 8.0 * C.nStresses /*mu^-1*/ + 8.0 * C.nStresses /*x_tau*/ + 8.0 * n /*y*/;
-    const double reduced = (double)S.RG.nRows * (4.0 + 8.0) * 2 /*row list + w: moments, expand*/ + (double)S.RG.count * (RDOF * RDOF + 3 * RDOF) * 8.0;
+    // reduced rows: w read + packed coordinates (moments), packed coordinates + w write (expand), B^-1 + t,s,sigma per region
+    const double reduced = nRed * (8.0 + 4.0) + nRed * (4.0 + 8.0) + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
     if (nm == "pass1") return pass1;
     if (nm == "pass2") return pass2;
+    if (nm == "reduced") return reduced;
     if (nm == "apply") return pass1 + pass2 + reduced;
     if (nm == "cg_iteration") return pass1 + pass2 + reduced + 8.0 * n /*p for p.Ap*/ + 48.0 * n /*x,r update*/ + 24.0 * n /*p update*/;
     return 0;
@@ -300,7 +303,7 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
             S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
             return 0;
         }
-        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : -1;
+        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : nm == "reduced" ? 3 : -1;
         if (which < 0) throw Error("ps_time_kernel: unknown kernel name");
 #ifndef PS_EMULATE
         cudaEvent_t a, b; PS_CUDA(cudaEventCreate(&a)); PS_CUDA(cudaEventCreate(&b));

@@ -4,10 +4,11 @@
 // Reference: y = A x as a product of stored factors (lib/include/ApplyPressureStressMatrix.h:102-179)
 //     y = -dt K^T Mc^-1 K x  -  J^T B^-1 J x  -  1/2 [0; mu^-1 x_tau],   K = [G D^T], J = [JG JD^T]
 // and the CG loop lib/include/pcg.h:268-340.  Here J is never stored: J = C K_red (see ps_assemble.cu), so
-//   pass 1 : w = K_ext x             (one thread per face row, 8-wide slot-major ELL, coalesced 8B/4B
-//                                     streams, x gathered through L1/L2); active rows scaled by dt Mc^-1
-//   moments: t_r = sum_f c_f w_f,  s_r = B_r^-1 t_r   (one CTA per chunk of a region's rows, then per region)
-//   expand : w_f = c_f . s_r          on the reduced rows
+//   pass 1 : w = K_ext x, one thread per face row (8-wide slot-major ELL, coalesced 8B/4B streams, x gathered
+//            through L1/L2); active rows are scaled by dt Mc^-1, coupled reduced rows keep the raw product
+//   reduced: one CTA per (region, axis) chunk of coupled reduced rows accumulates the 10 monomial moments of w_f;
+//            one warp per region sums the chunk partials in order, t_r -> s_r = B_r^-1 t_r -> sigma_r;
+//            expand overwrites w_f = sigma . monomials(f)
 //   pass 2 : y = -K_ext^T w - 1/2 mu^-1 x_tau         (one thread per DOF row, ELL widths 6/2/4), fused with
 //            the p.Ap dot product (warp shuffle -> CTA partial -> last CTA finishes in fixed order)
 // All CG scalars live in device memory; the host only polls a convergence flag every few iterations.
@@ -96,28 +97,59 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
     return last;
 }
 
+// One ELL row (face row of K_ext or DOF row of K_ext^T) with a compile-time width: W coalesced value/column streams, W gathers of w.
+template <int W>
+__device__ __forceinline__ double kt_block_row(const double* __restrict__ val, const int32_t* __restrict__ col, int64_t rows, int64_t j, const double* __restrict__ w) {
+    double v[W]; int32_t c[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) { v[k] = __ldcs(val + (int64_t)k * rows + j); c[k] = __ldcs(col + (int64_t)k * rows + j); }
+    double s = 0.;
+#pragma unroll
+    for (int k = 0; k < W; ++k) s += v[k] * w[c[k]];
+    return s;
+}
 __global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
     if (S && S->done) return;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.nRowsExt; r += (int64_t)gridDim.x * blockDim.x) {
-        const double s = k_row(A, r, x);
-        w[r] = r < A.nActiveVs ? activeScale * A.mcInv[r] * s : s;
+        const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
+        w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
     }
 }
-// mode bit 0: accumulate dot(x, y) and finish p.Ap / alpha in the last CTA
-__global__ void __launch_bounds__(HOT_THREADS) pass2_kernel(OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
-                                                           double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode) {
+// y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) and finish p.Ap / alpha in the last CTA.
+// The three row blocks (pressure 6-wide, centre stress 2-wide, edge stress 4-wide) are swept by separate
+// grid-stride loops so each loop body is branch-free and fully unrolled.
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass2_kernel(OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
+                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode) {
     if (S && S->done) return;
-    const int64_t n = A.nP + A.nT;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const bool dot = mode & 1;
     double acc = 0.;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        double v = -kt_row(A, j, w);
-        const double xj = (mode & 1) || j >= A.nP ? (x ? x[j] : 0.) : 0.;
-        if (j >= A.nP && muScale != 0.) v -= muScale * A.uInv[j - A.nP] * xj;
+    for (int64_t j = tid; j < A.nP; j += stride) {
+        double v = -kt_block_row<6>(A.ktpVal, A.ktpCol, A.nP, j, w);
         if (add) v += add[j];
         y[j] = v;
+        if (dot) acc += x[j] * v;
+    }
+    const int64_t nCR = 3 * A.nC;
+    for (int64_t j = tid; j < nCR; j += stride) {
+        double v = -kt_block_row<2>(A.ktcVal, A.ktcCol, nCR, j, w);
+        const int64_t jj = A.nP + j;
+        const double xj = x ? x[jj] : 0.;
+        if (muScale != 0.) v -= muScale * A.uInv[j] * xj;
+        if (add) v += add[jj];
+        y[jj] = v;
         acc += xj * v;
     }
-    if (mode & 1) {
+    for (int64_t j = tid; j < A.nE; j += stride) {
+        double v = -kt_block_row<4>(A.kteVal, A.kteCol, A.nE, j, w);
+        const int64_t jt = nCR + j, jj = A.nP + jt;
+        const double xj = x ? x[jj] : 0.;
+        if (muScale != 0.) v -= muScale * A.uInv[jt] * xj;
+        if (add) v += add[jj];
+        y[jj] = v;
+        acc += xj * v;
+    }
+    if (dot) {
         const double bs = block_sum(acc);
         if (threadIdx.x == 0) dotPartial[blockIdx.x] = bs;
         if (last_block(&S->ticket[0])) { const double t = block_sum_partials(dotPartial, gridDim.x); if (threadIdx.x == 0) finish_pAp(S, t); }
@@ -161,31 +193,48 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(int64_t n, const d
         }
     }
 }
-static inline int hot_blocks(int64_t n) { int64_t b = (n + HOT_THREADS - 1) / HOT_THREADS; if (b > HOT_MAX_BLOCKS) b = HOT_MAX_BLOCKS; if (b < 1) b = 1; return (int)b; }
+// persistent grid-stride sizing: exactly one wave = SM count x resident CTAs of this kernel (no partial second wave)
+template <class K>
+static inline int hot_blocks(K kernel, int64_t n) {
+    static thread_local std::vector<std::pair<const void*, int>> cache;
+    int resident = 0;
+    for (auto& e : cache) if (e.first == (const void*)kernel) resident = e.second;
+    if (!resident) {
+        int dev = 0, sms = 148, per = 1;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, HOT_THREADS, 0);
+        resident = std::min(sms * std::max(per, 1), HOT_MAX_BLOCKS);
+        cache.push_back({(const void*)kernel, resident});
+    }
+    int64_t b = (n + HOT_THREADS - 1) / HOT_THREADS;
+    if (b > resident) b = resident;
+    if (b < 1) b = 1;
+    return (int)b;
+}
 
 void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
     if (A.nRowsExt <= 0) return;
-    pass1_kernel<<<hot_blocks(A.nRowsExt), HOT_THREADS, 0, st>>>(A, x, w, activeScale, S);
+    pass1_kernel<<<hot_blocks(pass1_kernel, A.nRowsExt), HOT_THREADS, 0, st>>>(A, x, w, activeScale, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, int, PcgScalars* scal, int mode) {
-    pass2_kernel<<<hot_blocks(A.nP + A.nT), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode);
+    pass2_kernel<<<hot_blocks(pass2_kernel, A.nP + A.nT), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_update_xr(cudaStream_t st, int64_t n, double* x, double* r, const double* p, const double* Ap, double* dotPartial, int, PcgScalars* scal) {
-    cg_update_xr_kernel<<<hot_blocks(n), HOT_THREADS, 0, st>>>(n, x, r, p, Ap, dotPartial, scal);
+    cg_update_xr_kernel<<<hot_blocks(cg_update_xr_kernel, n), HOT_THREADS, 0, st>>>(n, x, r, p, Ap, dotPartial, scal);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_update_p(cudaStream_t st, int64_t n, double* p, const double* r, const PcgScalars* scal) {
-    cg_update_p_kernel<<<hot_blocks(n), HOT_THREADS, 0, st>>>(n, p, r, scal);
+    cg_update_p_kernel<<<hot_blocks(cg_update_p_kernel, n), HOT_THREADS, 0, st>>>(n, p, r, scal);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_init(cudaStream_t st, int64_t n, const double* b, double* x, double* r, double* p, double* dotPartial, int, PcgScalars* scal, double tol, int maxIter) {
-    cg_init_kernel<<<hot_blocks(n), HOT_THREADS, 0, st>>>(n, b, x, r, p, dotPartial, scal, tol, maxIter);
+    cg_init_kernel<<<hot_blocks(cg_init_kernel, n), HOT_THREADS, 0, st>>>(n, b, x, r, p, dotPartial, scal, tol, maxIter);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -224,114 +273,181 @@ void k_cg_init(cudaStream_t, int64_t n, const double* b, double* x, double* r, d
 }
 #endif
 
-// ---- reduced regions: t_r = sum_f c_f w_f over the region's coupled rows; s_r = B_r^-1 (extraScale*extra_r + tScale*t_r) ----
-#ifdef PS_EMULATE
-PS_D void row_basis(const Geom& g, const RegionData& RG, const double* com, int64_t row, int region, double* c) {
-    const int32_t packed = RG.rowFace.p[row];
-    const int axis = (packed >> 29) & 3;
-    const I3 f = delin(g, SL_FACE + axis, (int64_t)(packed & 0x1fffffff));
-    double ox, oy, oz;
-    face_offset(g, f, axis, com + 3 * region, ox, oy, oz);
-    conversion_coefficients(ox, oy, oz, axis, c);
+// ---- reduced regions -------------------------------------------------------------------------------
+// t_r = J_r x = sum_f c_f (K_red x)_f ;  s_r = B_r^-1 (extraScale*extra_r + tScale*t_r) ;  w_f = scale * c_f . s_r
+// Every entry of c_f is +-{1, 1/2, 2} times one of the 10 monomials {1,x,y,z,xx,xy,xz,yy,yz,zz} of the face
+// offset (S.cpp:2107-2149), so a chunk of same-axis rows only accumulates 10 moments per row; the 26-vector
+// t_r is a fixed sparse image of the 3x10 moments, and w_f is a 10-term polynomial with coefficients
+// sigma[axis] = (that image)^T s_r.
+PS_D void row_monomials(double dx, uint32_t packed, const double* com, double* m) {
+    const int axis = (int)(packed >> 30);
+    double px = (double)(packed & 1023u), py = (double)((packed >> 10) & 1023u), pz = (double)((packed >> 20) & 1023u);
+    if (axis == 0) px -= 0.5; else if (axis == 1) py -= 0.5; else pz -= 0.5;
+    const double ox = sub_rn(mul_rn(px, dx), com[0]), oy = sub_rn(mul_rn(py, dx), com[1]), oz = sub_rn(mul_rn(pz, dx), com[2]);
+    m[0] = 1.; m[1] = ox; m[2] = oy; m[3] = oz; m[4] = ox * ox; m[5] = ox * oy; m[6] = ox * oz; m[7] = oy * oy; m[8] = oy * oz; m[9] = oz * oz;
 }
-#endif
+// t (26) from the per-axis moments M[3][10]
+PS_D void moments_to_t(const double* M, double* t) {
+    for (int n = 0; n < RDOF; ++n) t[n] = 0.;
+    const double* A = M; const double* B = M + 10; const double* Cz = M + 20;
+    t[0] = A[0]; t[3] = A[1]; t[4] = A[2]; t[5] = A[3]; for (int k = 0; k < 6; ++k) t[6 + k] = A[4 + k];
+    t[1] = B[0]; t[12] = B[1]; t[13] = B[2]; t[14] = B[3]; for (int k = 0; k < 6; ++k) t[15 + k] = B[4 + k];
+    t[2] += Cz[0]; t[3] += -Cz[3]; t[6] += -2. * Cz[6]; t[7] += -Cz[8]; t[8] += -0.5 * Cz[9];
+    t[13] += -Cz[3]; t[16] += -Cz[6]; t[18] += -2. * Cz[8]; t[19] += -0.5 * Cz[9];
+    t[21] += Cz[1]; t[22] += Cz[2]; t[23] += Cz[4]; t[24] += Cz[5]; t[25] += Cz[7];
+}
+// sigma[3][10] from s (26): w_f = sum_m sigma[axis][m] * mono_m
+PS_D void s_to_sigma(const double* s, double* sg) {
+    sg[0] = s[0]; sg[1] = s[3]; sg[2] = s[4]; sg[3] = s[5]; for (int k = 0; k < 6; ++k) sg[4 + k] = s[6 + k];
+    sg[10] = s[1]; sg[11] = s[12]; sg[12] = s[13]; sg[13] = s[14]; for (int k = 0; k < 6; ++k) sg[14 + k] = s[15 + k];
+    double* z = sg + 20;
+    z[0] = s[2]; z[1] = s[21]; z[2] = s[22]; z[3] = -s[3] - s[13]; z[4] = s[23]; z[5] = s[24];
+    z[6] = -2. * s[6] - s[16]; z[7] = s[25]; z[8] = -s[7] - 2. * s[18]; z[9] = -0.5 * s[8] - 0.5 * s[19];
+}
 
 #ifndef PS_EMULATE
-constexpr int MOM_THREADS = 128;
-__global__ void __launch_bounds__(MOM_THREADS) moments_partial_kernel(Geom g, const int32_t* __restrict__ rowFace, const int32_t* __restrict__ chunk, const double* __restrict__ com,
-                                                                     const double* __restrict__ wRows, double* __restrict__ partial) {
-    __shared__ double red[MOM_THREADS / 32][RDOF];
-    const int region = chunk[3 * blockIdx.x], begin = chunk[3 * blockIdx.x + 1], end = chunk[3 * blockIdx.x + 2];
-    double acc[RDOF];
+constexpr int RED_THREADS = 256;
+// one CTA per (region, axis) chunk of coupled reduced rows: 10 monomial moments of w_f = (K_red x)_f (written by pass 1)
+__global__ void __launch_bounds__(RED_THREADS) reduced_moments_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk,
+                                                                     const double* __restrict__ com, const double* __restrict__ wRows, double* __restrict__ partial, const PcgScalars* S) {
+    if (S && S->done) return;
+    __shared__ double red[RED_THREADS / 32][10];
+    const int region = chunk[4 * blockIdx.x], begin = chunk[4 * blockIdx.x + 1], end = chunk[4 * blockIdx.x + 2];
+    const double c0 = com[3 * region], c1 = com[3 * region + 1], c2 = com[3 * region + 2];
+    const double cm[3] = {c0, c1, c2};
+    double acc[10];
 #pragma unroll
-    for (int n = 0; n < RDOF; ++n) acc[n] = 0.;
-    for (int row = begin + threadIdx.x; row < end; row += MOM_THREADS) {
-        const int32_t packed = rowFace[row];
-        const int axis = (packed >> 29) & 3;
-        const I3 f = delin(g, SL_FACE + axis, (int64_t)(packed & 0x1fffffff));
-        double ox, oy, oz, c[RDOF];
-        face_offset(g, f, axis, com + 3 * region, ox, oy, oz);
-        conversion_coefficients(ox, oy, oz, axis, c);
-        const double wv = wRows[row];
+    for (int k = 0; k < 10; ++k) acc[k] = 0.;
+    for (int row = begin + threadIdx.x; row < end; row += RED_THREADS) {
+        const double gk = wRows[row];
+        double m[10];
+        row_monomials(dx, rowXYZ[row], cm, m);
 #pragma unroll
-        for (int n = 0; n < RDOF; ++n) acc[n] += c[n] * wv;
+        for (int k = 0; k < 10; ++k) acc[k] += m[k] * gk;
     }
 #pragma unroll
-    for (int n = 0; n < RDOF; ++n) {
-        double v = acc[n];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][n] = v;
+    for (int k = 0; k < 10; ++k) {
+        const double v = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
     }
     __syncthreads();
-    if (threadIdx.x < RDOF) {
+    if (threadIdx.x < 10) {
         double s = 0.;
-        for (int wI = 0; wI < MOM_THREADS / 32; ++wI) s += red[wI][threadIdx.x];
-        partial[(size_t)blockIdx.x * RDOF + threadIdx.x] = s;
+#pragma unroll
+        for (int wI = 0; wI < RED_THREADS / 32; ++wI) s += red[wI][threadIdx.x];
+        partial[(size_t)blockIdx.x * 10 + threadIdx.x] = s;
     }
 }
-// one warp per region: sum chunk partials in order, then the 26x26 B^-1 GEMV
-__global__ void __launch_bounds__(32) moments_finish_kernel(int R, const int32_t* __restrict__ chunkStart, const double* __restrict__ partial, const double* __restrict__ Binv,
-                                                           const double* __restrict__ extra, double extraScale, double tScale, double* __restrict__ tOut, double* __restrict__ sOut) {
-    __shared__ double t[RDOF];
-    const int r = blockIdx.x;
-    if (threadIdx.x < RDOF) {
+// one warp per region: ordered sum of the chunk partials -> t -> s = B^-1 t -> sigma
+__global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __restrict__ chunkStart, const int32_t* __restrict__ chunk, const double* __restrict__ partial,
+                                                           const double* __restrict__ Binv, const double* __restrict__ extra, double extraScale, double tScale,
+                                                           double* __restrict__ tOut, double* __restrict__ sOut, double* __restrict__ sigma, const PcgScalars* S) {
+    if (S && S->done) return;
+    __shared__ double M[30], t[RDOF], sv[RDOF];
+    const int r = blockIdx.x, lane = threadIdx.x;
+    if (lane < 30) {
+        const int axis = lane / 10, k = lane % 10;
         double s = 0.;
-        for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) s += partial[(size_t)ch * RDOF + threadIdx.x];
-        double v = tScale * s;
-        if (extra) v += extraScale * extra[(size_t)r * RDOF + threadIdx.x];
-        t[threadIdx.x] = v;
-        tOut[(size_t)r * RDOF + threadIdx.x] = v;
+        if (tScale != 0.)
+            for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) if (chunk[4 * ch + 3] == axis) s += partial[(size_t)ch * 10 + k];
+        M[lane] = s;
     }
     __syncwarp();
-    if (threadIdx.x < RDOF) {
-        const double* B = Binv + (size_t)r * RDOF * RDOF + threadIdx.x * RDOF;
+    if (lane == 0) moments_to_t(M, t);
+    __syncwarp();
+    if (lane < RDOF) {
+        double v = tScale * t[lane];
+        if (extra) v += extraScale * extra[(size_t)r * RDOF + lane];
+        t[lane] = v; tOut[(size_t)r * RDOF + lane] = v;
+    }
+    __syncwarp();
+    if (lane < RDOF) {
+        const double* B = Binv + (size_t)r * RDOF * RDOF + lane * RDOF;
         double s = 0.;
 #pragma unroll
         for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
-        sOut[(size_t)r * RDOF + threadIdx.x] = s;
+        sv[lane] = s; sOut[(size_t)r * RDOF + lane] = s;
+    }
+    __syncwarp();
+    if (lane == 0) { double sg[30]; s_to_sigma(sv, sg); for (int k = 0; k < 30; ++k) sigma[(size_t)r * 30 + k] = sg[k]; }
+}
+// one CTA per chunk: w_f = scale * sigma[region][axis] . monomials(f)
+__global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk, const double* __restrict__ com,
+                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S) {
+    if (S && S->done) return;
+    const int region = chunk[4 * blockIdx.x], begin = chunk[4 * blockIdx.x + 1], end = chunk[4 * blockIdx.x + 2], axis = chunk[4 * blockIdx.x + 3];
+    const double cm[3] = {com[3 * region], com[3 * region + 1], com[3 * region + 2]};
+    double sg[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sg[k] = sigma[(size_t)region * 30 + axis * 10 + k];
+    for (int row = begin + threadIdx.x; row < end; row += RED_THREADS) {
+        double m[10];
+        row_monomials(dx, rowXYZ[row], cm, m);
+        double v = 0.;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v += sg[k] * m[k];
+        wRows[row] = scale * v;
     }
 }
-void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, int64_t, const double* extraRhs, double extraScale, double tScale) {
-    if (RG.count <= 0) return;
-    if (RG.nRowChunks > 0) moments_partial_kernel<<<RG.nRowChunks, MOM_THREADS, 0, st>>>(g, RG.rowFace.p, RG.rowChunk.p, RG.com.p, wRows, RG.partial.p);
+void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S) {
+    if (RG.nRowChunks <= 0) return;
+    reduced_moments_kernel<<<RG.nRowChunks, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, wRows, RG.partial.p, S);
     PS_COUNT_LAUNCH(1);
-    moments_finish_kernel<<<RG.count, 32, 0, st>>>(RG.count, RG.rowChunkStart.p, RG.partial.p, RG.Binv.p, extraRhs, extraScale, tScale, RG.t.p, RG.s.p);
+    PS_CUDA(cudaGetLastError());
+}
+void reduced_finish(cudaStream_t st, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S) {
+    if (RG.count <= 0) return;
+    reduced_finish_kernel<<<RG.count, 32, 0, st>>>(RG.rowChunkStart.p, RG.rowChunk.p, RG.partial.p, RG.Binv.p, extra, extraScale, tScale, RG.t.p, RG.s.p, RG.sigma.p, S);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void reduced_expand(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    if (RG.nRowChunks <= 0) return;
+    reduced_expand_kernel<<<RG.nRowChunks, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, RG.sigma.p, wRows, scale, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 #else
-void reduced_moments(cudaStream_t, const Geom& g, const RegionData& RG, const double* wRows, int64_t, const double* extraRhs, double extraScale, double tScale) {
+void reduced_moments(cudaStream_t, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S) {
+    if (S && S->done) return;
+    for (int ch = 0; ch < RG.nRowChunks; ++ch) {
+        const int region = RG.rowChunk.p[4 * ch], begin = RG.rowChunk.p[4 * ch + 1], end = RG.rowChunk.p[4 * ch + 2];
+        double acc[10] = {0};
+        for (int row = begin; row < end; ++row) {
+            const double gk = wRows[row];
+            double m[10]; row_monomials(g.dx, RG.rowXYZ.p[row], RG.com.p + 3 * region, m);
+            for (int k = 0; k < 10; ++k) acc[k] += m[k] * gk;
+        }
+        for (int k = 0; k < 10; ++k) RG.partial.p[(size_t)ch * 10 + k] = acc[k];
+    }
+}
+void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S) {
+    if (S && S->done) return;
     for (int r = 0; r < RG.count; ++r) {
-        double t[RDOF];
-        for (int n = 0; n < RDOF; ++n) t[n] = 0.;
-        for (int ch = RG.rowChunkStart.p[r]; ch < RG.rowChunkStart.p[r + 1]; ++ch)
-            for (int row = RG.rowChunk.p[3 * ch + 1]; row < RG.rowChunk.p[3 * ch + 2]; ++row) {
-                double c[RDOF]; row_basis(g, RG, RG.com.p, row, r, c);
-                for (int n = 0; n < RDOF; ++n) t[n] += c[n] * wRows[row];
-            }
-        for (int n = 0; n < RDOF; ++n) { t[n] = tScale * t[n] + (extraRhs ? extraScale * extraRhs[r * RDOF + n] : 0.); RG.t.p[r * RDOF + n] = t[n]; }
-        for (int i = 0; i < RDOF; ++i) { double s = 0.; for (int j = 0; j < RDOF; ++j) s += RG.Binv.p[(size_t)r * RDOF * RDOF + i * RDOF + j] * t[j]; RG.s.p[r * RDOF + i] = s; }
+        double M[30] = {0}, t[RDOF], sv[RDOF], sg[30];
+        if (tScale != 0.)
+            for (int ch = RG.rowChunkStart.p[r]; ch < RG.rowChunkStart.p[r + 1]; ++ch)
+                for (int k = 0; k < 10; ++k) M[RG.rowChunk.p[4 * ch + 3] * 10 + k] += RG.partial.p[(size_t)ch * 10 + k];
+        moments_to_t(M, t);
+        for (int n = 0; n < RDOF; ++n) { t[n] = tScale * t[n] + (extra ? extraScale * extra[(size_t)r * RDOF + n] : 0.); RG.t.p[(size_t)r * RDOF + n] = t[n]; }
+        for (int i = 0; i < RDOF; ++i) { double s = 0.; for (int j = 0; j < RDOF; ++j) s += RG.Binv.p[(size_t)r * RDOF * RDOF + i * RDOF + j] * t[j]; sv[i] = s; RG.s.p[(size_t)r * RDOF + i] = s; }
+        s_to_sigma(sv, sg);
+        for (int k = 0; k < 30; ++k) RG.sigma.p[(size_t)r * 30 + k] = sg[k];
+    }
+}
+void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    if (S && S->done) return;
+    for (int ch = 0; ch < RG.nRowChunks; ++ch) {
+        const int region = RG.rowChunk.p[4 * ch], begin = RG.rowChunk.p[4 * ch + 1], end = RG.rowChunk.p[4 * ch + 2], axis = RG.rowChunk.p[4 * ch + 3];
+        for (int row = begin; row < end; ++row) {
+            double m[10]; row_monomials(g.dx, RG.rowXYZ.p[row], RG.com.p + 3 * region, m);
+            double v = 0.;
+            for (int k = 0; k < 10; ++k) v += RG.sigma.p[(size_t)region * 30 + axis * 10 + k] * m[k];
+            wRows[row] = scale * v;
+        }
     }
 }
 #endif
-
-// w_f = scale * c_f . s_r on the coupled reduced rows (wRows points at row nActiveVs of w)
-void k_reduced_expand(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, int64_t, double scale) {
-    if (RG.nRows <= 0) return;
-    const int32_t* rowFace = RG.rowFace.p; const int32_t* rowRegion = RG.rowRegion.p; const double* com = RG.com.p; const double* s = RG.s.p;
-    ps_for(st, RG.nRows, PS_LAMBDA(int64_t row) {
-        const int region = rowRegion[row];
-        const int32_t packed = rowFace[row];
-        const int axis = (packed >> 29) & 3;
-        const I3 f = delin(g, SL_FACE + axis, (int64_t)(packed & 0x1fffffff));
-        double ox, oy, oz, c[RDOF];
-        face_offset(g, f, axis, com + 3 * region, ox, oy, oz);
-        conversion_coefficients(ox, oy, oz, axis, c);
-        double v = 0.;
-        for (int n = 0; n < RDOF; ++n) v += c[n] * s[(int64_t)region * RDOF + n];
-        wRows[row] = scale * v;
-    });
-}
 
 // W1 recoverVelocityFromPressureStress, active part (S.cpp:507): u = dt Mc^-1 (rhs_u/dt - G p - D^T tau)
 // (wAct already holds dt Mc^-1 K x from pass 1)

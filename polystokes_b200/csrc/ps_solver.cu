@@ -24,8 +24,15 @@ static void k_krow_reduced(cudaStream_t st, int64_t nRows, const int32_t* rowFac
         kr[packed & 0x1fffffff] = base + (int32_t)i;
     });
 }
-static void k_count_by_region(cudaStream_t st, int64_t n, const int32_t* region, int* counts) {
-    ps_for(st, n, PS_LAMBDA(int64_t i) { atomic_add(&counts[region[i]], 1); });
+// per (region, face axis) row counts + the bit-field form of the row list used by the hot kernels
+static void k_rows_finalize(cudaStream_t st, const Geom& g, int64_t n, const int32_t* region, const int32_t* rowFace, int* counts, uint32_t* rowXYZ) {
+    ps_for(st, n, PS_LAMBDA(int64_t i) {
+        const int32_t packed = rowFace[i];
+        const int axis = (packed >> 29) & 3;
+        const I3 f = delin(g, SL_FACE + axis, (int64_t)(packed & 0x1fffffff));
+        rowXYZ[i] = (uint32_t)f.x | ((uint32_t)f.y << 10) | ((uint32_t)f.z << 20) | ((uint32_t)axis << 30);
+        atomic_add(&counts[3 * region[i] + axis], 1);
+    });
 }
 static void k_scale_rows(cudaStream_t st, int64_t n, const double* a, const double* b, double* out) {
     ps_for(st, n, PS_LAMBDA(int64_t i) { out[i] = a[i] * b[i]; });
@@ -50,6 +57,7 @@ struct StageTimer {
 Solver::Solver(const ps_params& p) : P(p) {
     if (p.nx <= 0 || p.ny <= 0 || p.nz <= 0 || !(p.dx > 0) || !(p.dt > 0)) throw Error("ps_create: invalid grid / dx / dt");
     if ((int64_t)(p.nx + 1) * (p.ny + 1) * (p.nz + 1) >= (1ll << 29)) throw Error("ps_create: grid too large for 29-bit packed face indices");
+    if (p.nx + 1 > 1023 || p.ny + 1 > 1023 || p.nz + 1 > 1023) throw Error("ps_create: grid axis longer than 1022 cells (10-bit packed row coordinates)");
     g = make_geom(p.nx, p.ny, p.nz, p.dx, p.dt, p.constantDensity);
 #ifndef PS_EMULATE
     int ndev = 0;
@@ -304,16 +312,28 @@ void Solver::constructMatrixBlocks() {
         if (C.nActiveVs + nRows >= INT32_MAX) throw Error("K_ext has too many rows for int32");
         k_krow_reduced(st, nRows, RG.rowFace.p, (int32_t)C.nActiveVs, F.krow[0], F.krow[1], F.krow[2]);
         static thread_local DBuf<int> rc;
-        rc.alloc((size_t)R); rc.zero(st, (size_t)R);
-        k_count_by_region(st, nRows, RG.rowRegion.p, rc.p);
-        std::vector<int> perRegion = rc.to_host(st, (size_t)R);
-        std::vector<int32_t> start, table, chunkStart;
-        build_chunks(perRegion, 1024, start, table, chunkStart);
-        RG.nRowChunks = (int32_t)(table.size() / 3);
+        rc.alloc((size_t)3 * R); rc.zero(st, (size_t)3 * R);
+        RG.rowXYZ.alloc((size_t)nRows);
+        k_rows_finalize(st, g, nRows, RG.rowRegion.p, RG.rowFace.p, rc.p, RG.rowXYZ.p);
+        std::vector<int> perRA = rc.to_host(st, (size_t)3 * R);
+        // chunk table: rows are sorted by (region, axis, voxel order); a chunk holds <= 2048 rows of one (region, axis)
+        std::vector<int32_t> start((size_t)R + 1, 0), chunkStart((size_t)R + 1, 0), table;
+        int32_t pos = 0;
+        for (int r = 0; r < R; ++r) {
+            start[r] = pos; chunkStart[r] = (int32_t)(table.size() / 4);
+            for (int a = 0; a < 3; ++a) {
+                const int32_t e = pos + perRA[3 * r + a];
+                for (int32_t b = pos; b < e; b += 2048) { table.push_back(r); table.push_back(b); table.push_back(std::min(b + 2048, e)); table.push_back(a); }
+                pos = e;
+            }
+        }
+        start[R] = pos; chunkStart[R] = (int32_t)(table.size() / 4);
+        RG.nRowChunks = (int32_t)(table.size() / 4);
         RG.rowStart.from_host(st, start.data(), start.size());
         RG.rowChunk.from_host(st, table.data(), table.size());
         RG.rowChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
-        RG.partial.alloc(std::max((size_t)RG.nRowChunks * RDOF, RG.partial.n));
+        RG.partial.alloc(std::max((size_t)RG.nRowChunks * 10, RG.partial.n));
+        RG.sigma.alloc((size_t)R * 30);
     }
     C.nRowsExt = C.nActiveVs + RG.nRows;
     K.alloc(8, C.nRowsExt);
@@ -347,8 +367,8 @@ void Solver::assemble() {
     w.zero(st, (size_t)C.nRowsExt);
     k_scale_rows(st, C.nActiveVs, mcInv.p, rhsU.p, w.p);
     if (RG.count > 0) {
-        reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, RG.rhsR.p, 1.0, 0.0);
-        k_reduced_expand(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, g.invDt);
+        reduced_finish(st, g, RG, RG.rhsR.p, 1.0, 0.0, nullptr);                     // s = B^-1 rhs_r
+        reduced_expand(st, g, RG, w.p + C.nActiveVs, g.invDt, nullptr);
     }
     k_pass2(st, A, w.p, nullptr, b.p, 0.0, rhsPT.p, nullptr, 0, nullptr, 0);
 }
@@ -358,8 +378,9 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
     const OpArgs A = make_op(*this);
     k_pass1(st, A, xin, w.p, g.dt, nullptr);
     if (RG.count > 0) {
-        reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, nullptr, 0.0, 1.0);
-        k_reduced_expand(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, 1.0);
+        reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr);
+        reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr);
+        reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     }
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, 0, nullptr, 0);
 }
@@ -368,6 +389,7 @@ void Solver::timedOperator(int which) {
     const OpArgs A = make_op(*this);
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
     if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
+    else if (which == 3) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
     else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, 0, nullptr, 0);
 }
 
@@ -390,8 +412,9 @@ int Solver::solve() {
         for (int k = 0; k < batch; ++k) {
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);
             if (RG.count > 0) {
-                reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, nullptr, 0.0, 1.0);
-                k_reduced_expand(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, 1.0);
+                reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p);
+                reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p);
+                reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
             }
             k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, 0, scal.p, 1);
             k_cg_update_xr(st, n, x.p, r.p, p.p, Ap.p, dotPartial.p, 0, scal.p);
@@ -414,10 +437,11 @@ int Solver::solve() {
 // recoverVelocityFromPressureStress (S.cpp:492-510)
 void Solver::recoverVelocityFromPressureStress() {
     const OpArgs A = make_op(*this);
-    k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau); reduced rows: K_red x
+    k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau)
     k_recover_active(st, g, C.nActiveVs, w.p, mcInv.p, rhsU.p, velSol.p);
     if (RG.count > 0) {
-        reduced_moments(st, g, RG, w.p + C.nActiveVs, C.nActiveVs, RG.rhsR.p, g.invDt, -1.0);   // B^-1 (rhs_r/dt - J x)
+        reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr);
+        reduced_finish(st, g, RG, RG.rhsR.p, g.invDt, -1.0, nullptr);                            // B^-1 (rhs_r/dt - J x)
         k_copy_reduced_solution(st, (int64_t)RG.count * RDOF, RG.s.p, velSol.p + C.nActiveVs);
     }
 }

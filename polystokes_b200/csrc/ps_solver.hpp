@@ -27,11 +27,14 @@ struct RegionData {
     // coupled reduced face rows of K_ext, sorted by (region, axis, tile order)
     int64_t nRows = 0;
     DBuf<int32_t> rowFace;   // packed dense face index | axis << 29
+    DBuf<uint32_t> rowXYZ;   // the same rows as x | y<<10 | z<<20 | axis<<30 (cheap decode in the hot kernels)
+    DBuf<double> sigma;      // [R][3][10] polynomial coefficients of w_f per face axis
     DBuf<int32_t> rowRegion; // region of each row
     DBuf<int32_t> rowStart;  // [R+1] row range of each region (relative to nActiveVs)
     // chunk tables (fixed-size pieces of the sorted lists, each inside one region)
     int32_t nCellChunks = 0, nRowChunks = 0;
-    DBuf<int32_t> cellChunk, rowChunk;   // [nChunks][3] = region, begin, end
+    DBuf<int32_t> cellChunk;   // [nChunks][3] = region, begin, end
+    DBuf<int32_t> rowChunk;    // [nChunks][4] = region, begin, end, face axis (a chunk never mixes axes)
     DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
@@ -169,8 +172,9 @@ struct OpArgs {   // everything one operator apply touches
 };
 void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal);
 void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, int nPartials, PcgScalars* scal, int mode);
-void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, int64_t nActiveVs, const double* extraRhs, double extraScale, double resultScale);
-void k_reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, int64_t nActiveVs, double scale);
+void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal);
+void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
+void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
 void k_cg_update_xr(cudaStream_t, int64_t n, double* x, double* r, const double* p, const double* Ap, double* dotPartial, int nPartials, PcgScalars* scal);
 void k_cg_update_p(cudaStream_t, int64_t n, double* p, const double* r, const PcgScalars* scal);
 void k_cg_init(cudaStream_t, int64_t n, const double* b, double* x, double* r, double* p, double* dotPartial, int nPartials, PcgScalars* scal, double tol, int maxIter);

@@ -36,7 +36,7 @@ print("counts:", {k: s.count(k) for k in ["nCenter","nActiveVs","nSystemSize","r
 peak = 6448.7
 try: peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception: pass
-for k in ["pass1", "pass2", "apply", "cg_iteration"]:
+for k in ["pass1", "reduced", "pass2", "apply", "cg_iteration"]:
     ms = s.time_kernel(k, a.reps); by = s.kernel_bytes(k)
     print(f"{k:13s} {ms:8.4f} ms  {by/1e9:7.3f} GB algorithmic  -> {by/ms/1e6:8.1f} GB/s  ({by/ms/1e6/peak*100:5.1f}% of {peak} GB/s measured peak)", flush=True)
 print("velocity out max:", [float(v.abs().max()) for v in vout], "valid:", [int(v.sum()) for v in valid])
