@@ -114,6 +114,22 @@ int ps_export(ps_handle h, const char* prefix, int what);
 /* thread-local description of the last PS_FAILED / PS_INVALID */
 const char* ps_last_error(void);
 
+/* ---- several GPUs: one process per GPU, the grid slab-decomposed along z ----
+ * The reference is single-node shared-memory (TBB / OpenMP inside one Solver); the slab decomposition replaces that
+ * intra-solver parallelism.  Call order: every rank creates its handle on its own device; rank 0 calls
+ * ps_comm_unique_id and ships the 128 bytes to the others with any host transport (torch.distributed, MPI, a file);
+ * every rank then calls ps_comm_init (collective).  Afterwards ps_step / ps_setup / ps_solve / ps_apply /
+ * ps_time_kernel("cg_iteration") are collective calls: every rank passes the SAME full-grid input fields (the
+ * classification is computed redundantly, in the reference's global numbering) and owns the z-slab reported by
+ * ps_get_partition.  Output contract: a rank's velocity is final on the closure of its slab (cells z in [zLo, zHi),
+ * z-faces zLo..zHi inclusive); elsewhere faces carrying a DOF of another rank keep their input value.  `valid` is
+ * complete on every rank.  Reduced regions need doTile with tilePadding >= 1 (untiled regions may span slabs).
+ * cancel_cb must answer identically on all ranks. */
+int ps_comm_unique_id(void* id128);
+int ps_comm_init(ps_handle h, int rank, int nranks, const void* id128);
+/* z cuts of all ranks: zCut[nranks+1] (may be NULL); returns nranks, this rank's slab in *zLo, *zHi */
+int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int32_t* zCut);
+
 /* ---- introspection for parity tests (read-only views of the solver state, copied to HOST memory) ---- */
 /* counters by name: nCenter nFaceX nFaceY nFaceZ nEdgeYZ nEdgeXZ nEdgeXY nActiveVs nReducedVs nPressures
  * nStresses nTotalDOFs nSystemSize regionCount iterations result usedBiCGStab nRowsExt */
@@ -128,7 +144,8 @@ int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out);
  * the sizes, then with arrays.  Column indices sorted per row, explicit zeros kept (Eigen semantics). */
 int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz, int64_t* rowptr, int32_t* colidx, double* vals);
 /* dense vectors by name (activeRHS reducedRHS pressureRHS stressRHS b solution velSolution com bestFit
- * MrDense ViscDense BinvDense); returns the length */
+ * MrDense ViscDense BinvDense); returns the length.  With several ranks b / solution / region data are zero
+ * outside the calling rank's share, so the sum over ranks is the global vector. */
 int64_t ps_get_vector(ps_handle h, const char* name, double* out);
 /* y = A x with host vectors of length nSystemSize (ApplyPressureStressMatrix::apply, Apply.h:182-184) */
 int ps_apply(ps_handle h, const double* x, double* y);

@@ -110,6 +110,12 @@ bool get_matrix(Solver& S, const std::string& name, HostCsr& out) {
     }
     return false;
 }
+// several ranks: region blocks exist only on their owner
+void mask_region_blocks(const Solver& S, const std::string& name, HostCsr& m) {
+    if (!S.part.multi() || !(name == "Mr" || name == "B" || name == "BInv")) return;
+    const size_t NN = (size_t)RDOF * RDOF;
+    for (size_t i = 0; i < m.val.size(); ++i) { const int r = (int)(i / NN); if (r < S.RG.regLo || r >= S.RG.regHi) m.val[i] = 0.; }
+}
 
 bool get_vector(Solver& S, const std::string& n, std::vector<double>& out) {
     const Counts& C = S.C; const int R = S.RG.count; const size_t NN = (size_t)RDOF * RDOF;
@@ -127,6 +133,19 @@ bool get_vector(Solver& S, const std::string& n, std::vector<double>& out) {
     else if (n == "ViscDense") out = R ? S.RG.Visc.to_host(S.st, R * NN) : std::vector<double>();
     else if (n == "BinvDense") out = R ? S.RG.Binv.to_host(S.st, R * NN) : std::vector<double>();
     else return false;
+    // several ranks: keep only this rank's share (the sum over ranks is the global vector)
+    if (S.part.multi()) {
+        if (n == "b" || n == "solution") { for (size_t i = 0; i < out.size(); ++i) if (!S.ownSys.has((int64_t)i)) out[i] = 0.; }
+        else if (n == "velSolution") {
+            for (size_t i = 0; i < out.size(); ++i) {
+                const bool mine = (int64_t)i < C.nActiveVs ? S.ownK.has((int64_t)i) : ((int64_t)(i - C.nActiveVs) / RDOF >= S.RG.regLo && (int64_t)(i - C.nActiveVs) / RDOF < S.RG.regHi);
+                if (!mine) out[i] = 0.;
+            }
+        } else if (n == "reducedRHS" || n == "bestFit" || n == "MrDense" || n == "ViscDense" || n == "BinvDense") {
+            const size_t per = (n == "reducedRHS" || n == "bestFit") ? (size_t)RDOF : NN;
+            for (size_t i = 0; i < out.size(); ++i) { const int r = (int)(i / per); if (r < S.RG.regLo || r >= S.RG.regHi) out[i] = 0.; }
+        }
+    }
     return true;
 }
 
@@ -161,6 +180,38 @@ int ps_create(const ps_params* params, ps_handle* out) {
     return guarded([&] { ps_solver* h = new ps_solver; h->S = new Solver(*params); *out = h; return (int)PS_SUCCESS; });
 }
 void ps_destroy(ps_handle h) { if (h) { delete h->S; delete h; } }
+
+#ifndef PS_EMULATE
+int ps_comm_unique_id(void* id128) {
+    if (!id128) { g_lastError = "ps_comm_unique_id: null argument"; return PS_INVALID; }
+    return guarded([&] { nccl_unique_id(id128); return (int)PS_SUCCESS; });
+}
+int ps_comm_init(ps_handle h, int rank, int nranks, const void* id128) {
+    if (!h || !id128) { g_lastError = "ps_comm_init: null argument"; return PS_INVALID; }
+    return guarded([&] {
+        PS_CUDA(cudaSetDevice(h->S->P.device));
+        h->S->initComm(make_nccl_comm(rank, nranks, id128));
+        return (int)PS_SUCCESS;
+    });
+}
+#else
+// the emulation twin has no NCCL: tests/ hand it host callbacks (torch.distributed / gloo) instead
+int ps_comm_unique_id(void* id128) { if (id128) memset(id128, 0, 128); return PS_SUCCESS; }
+int ps_comm_init(ps_handle, int, int, const void*) { g_lastError = "ps_comm_init: the emulation twin takes ps_comm_init_callbacks"; return PS_FAILED; }
+int ps_comm_init_callbacks(ps_handle h, int rank, int nranks, ps_allreduce_cb ar, ps_sendrecv_cb sr, void* ctx) {
+    if (!h || !ar || !sr) return PS_INVALID;
+    return guarded([&] { h->S->initComm(make_callback_comm(rank, nranks, ar, sr, ctx)); return (int)PS_SUCCESS; });
+}
+#endif
+int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int32_t* zCut) {
+    if (!h) return -1;
+    const Partition& p = h->S->part;
+    if (rank) *rank = p.rank;
+    if (zLo) *zLo = p.zCut[p.rank];
+    if (zHi) *zHi = p.zCut[p.rank + 1];
+    if (zCut) for (int k = 0; k <= p.nranks; ++k) zCut[k] = p.zCut[k];
+    return p.nranks;
+}
 
 int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* stats) {
     if (!h || !in) { g_lastError = "ps_step: null argument"; return PS_INVALID; }
@@ -239,6 +290,7 @@ int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int6
     return guarded([&] {
         HostCsr m;
         if (!get_matrix(*h->S, name, m)) { g_lastError = std::string("ps_get_csr: unknown matrix ") + name; return (int)PS_INVALID; }
+        mask_region_blocks(*h->S, name, m);
         if (rows) *rows = m.rows; if (cols) *cols = m.cols; if (nnz) *nnz = (int64_t)m.idx.size();
         if (rowptr) std::copy(m.ptr.begin(), m.ptr.end(), rowptr);
         if (colidx) std::copy(m.idx.begin(), m.idx.end(), colidx);
@@ -262,6 +314,7 @@ int ps_apply(ps_handle h, const double* x, double* y) {
         static thread_local DBuf<double> dx, dy;
         dx.alloc(n); dy.alloc(n);
         copy_h2d(dx.p, x, n * sizeof(double), S.st);
+        dy.zero(S.st, n);                       // several ranks: rows of other ranks stay 0 (sum over ranks = A x)
         S.applyOperator(dx.p, dy.p, nullptr);
         copy_d2h(y, dy.p, n * sizeof(double), S.st);
         return (int)PS_SUCCESS;

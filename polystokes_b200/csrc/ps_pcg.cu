@@ -43,14 +43,17 @@ PS_D double kt_row(const OpArgs& A, int64_t j, const double* __restrict__ w) {
 // fixed-order finish of a dot product: called by the last CTA (or the emulation) over the CTA partials
 PS_D double sum_partials(const double* p, int n) { double s = 0.; for (int i = 0; i < n; ++i) s += p[i]; return s; }
 
-// CG bookkeeping after p.Ap is known (pcg.h:313)
-PS_D void finish_pAp(PcgScalars* S, double pAp) { S->pAp = pAp; S->alpha = S->rsold / pAp; }
-// ... and after r.r, x.x are known (pcg.h:316-336): stop test min(rr, rr/xx) < tol^2, else beta / rsold / iter
-PS_D void finish_xr(PcgScalars* S, double rr, double xx) {
-    S->rsnew = rr; S->xmag = xx;
-    double rre = rr;
-    if (rr / xx < rre) rre = rr / xx;
-    S->rre = rre;
+// CG scalar bookkeeping.  Every dot product is first summed per rank (fixed order) into S->red[], then --
+// with more than one rank -- all-reduced in place by the host-enqueued collective; the consumers below read the
+// global value.  alpha = rsold / p.Ap (pcg.h:313).
+PS_D double cg_alpha(const PcgScalars* S) { return S->rsold / S->red[0]; }
+// stop test of pcg.h:316-325: min(rr, rr/xx) < tol^2
+PS_D double cg_rre(const PcgScalars* S) { const double rr = S->red[1], xx = S->red[2]; double rre = rr; if (rr / xx < rre) rre = rr / xx; return rre; }
+// once per iteration, after every reader of rsold is done (last CTA of the p update): pcg.h:326-336
+PS_D void cg_advance(PcgScalars* S) {
+    const double rr = S->red[1];
+    const double rre = cg_rre(S);
+    S->rsnew = rr; S->xmag = S->red[2]; S->rre = rre; S->pAp = S->red[0];
     if (rre < S->tol2) { S->done = 1; return; }
     S->beta = rr / S->rsold;
     S->rsold = rr;
@@ -110,57 +113,64 @@ __device__ __forceinline__ double kt_block_row(const double* __restrict__ val, c
 }
 __global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
     if (S && S->done) return;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.nRowsExt; r += (int64_t)gridDim.x * blockDim.x) {
-        const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
-        w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (int k = 0; k < A.rowsK.n; ++k) {       // owned row ranges: x, y, z faces + coupled reduced rows (one range per GPU when alone)
+        const int64_t end = A.rowsK.lo[k] + A.rowsK.count(k);
+        for (int64_t r = A.rowsK.lo[k] + tid; r < end; r += stride) {
+            const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
+            w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
+        }
     }
 }
 // y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) and finish p.Ap / alpha in the last CTA.
 // The three row blocks (pressure 6-wide, centre stress 2-wide, edge stress 4-wide) are swept by separate
 // grid-stride loops so each loop body is branch-free and fully unrolled.
-__global__ void __launch_bounds__(HOT_THREADS, 6) pass2_kernel(OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
+// one row block of K_ext^T (width W) over the owned row ranges; all pointers are pre-offset to the block so the
+// loop carries a single index.  Returns this thread's share of dot(x, y).
+template <int W, bool STRESS>
+__device__ __forceinline__ double kt_sweep(const double* __restrict__ val, const int32_t* __restrict__ col, int64_t ld, const RowSet& set, int64_t tid, int64_t stride,
+                                           const double* __restrict__ w, const double* __restrict__ xb, double* __restrict__ yb, const double* __restrict__ uInv,
+                                           double muScale, const double* __restrict__ addb, bool dot) {
+    double acc = 0.;
+#pragma unroll 1
+    for (int k = 0; k < set.n; ++k) {
+        const int64_t end = set.lo[k] + set.count(k);
+        for (int64_t j = set.lo[k] + tid; j < end; j += stride) {
+            double v = -kt_block_row<W>(val, col, ld, j, w);
+            const double xj = (xb && (STRESS || dot)) ? xb[j] : 0.;
+            if (STRESS && muScale != 0.) v -= muScale * uInv[j] * xj;
+            if (addb) v += addb[j];
+            yb[j] = v;
+            acc += xj * v;
+        }
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
                                                               double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode) {
     if (S && S->done) return;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const bool dot = mode & 1;
-    double acc = 0.;
-    for (int64_t j = tid; j < A.nP; j += stride) {
-        double v = -kt_block_row<6>(A.ktpVal, A.ktpCol, A.nP, j, w);
-        if (add) v += add[j];
-        y[j] = v;
-        if (dot) acc += x[j] * v;
-    }
-    const int64_t nCR = 3 * A.nC;
-    for (int64_t j = tid; j < nCR; j += stride) {
-        double v = -kt_block_row<2>(A.ktcVal, A.ktcCol, nCR, j, w);
-        const int64_t jj = A.nP + j;
-        const double xj = x ? x[jj] : 0.;
-        if (muScale != 0.) v -= muScale * A.uInv[j] * xj;
-        if (add) v += add[jj];
-        y[jj] = v;
-        acc += xj * v;
-    }
-    for (int64_t j = tid; j < A.nE; j += stride) {
-        double v = -kt_block_row<4>(A.kteVal, A.kteCol, A.nE, j, w);
-        const int64_t jt = nCR + j, jj = A.nP + jt;
-        const double xj = x ? x[jj] : 0.;
-        if (muScale != 0.) v -= muScale * A.uInv[jt] * xj;
-        if (add) v += add[jj];
-        y[jj] = v;
-        acc += xj * v;
-    }
+    const int64_t nCR = 3 * A.nC, oC = A.nP, oE = A.nP + nCR;
+    double acc = kt_sweep<6, false>(A.ktpVal, A.ktpCol, A.nP, A.rowsP, tid, stride, w, x, y, nullptr, 0., add, dot);
+    acc += kt_sweep<2, true>(A.ktcVal, A.ktcCol, nCR, A.rowsC, tid, stride, w, x ? x + oC : nullptr, y + oC, A.uInv, muScale, add ? add + oC : nullptr, dot);
+    acc += kt_sweep<4, true>(A.kteVal, A.kteCol, A.nE, A.rowsE, tid, stride, w, x ? x + oE : nullptr, y + oE, A.uInv + nCR, muScale, add ? add + oE : nullptr, dot);
     if (dot) {
         const double bs = block_sum(acc);
         if (threadIdx.x == 0) dotPartial[blockIdx.x] = bs;
-        if (last_block(&S->ticket[0])) { const double t = block_sum_partials(dotPartial, gridDim.x); if (threadIdx.x == 0) finish_pAp(S, t); }
+        if (last_block(&S->ticket[0])) { const double t = block_sum_partials(dotPartial, gridDim.x); if (threadIdx.x == 0) S->red[0] = t; }
     }
 }
-__global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap,
+__global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(RangeSet own, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap,
                                                                   double* dotPartial, PcgScalars* S) {
     if (S->done) return;
-    const double alpha = S->alpha;
+    const double alpha = cg_alpha(S);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     double rr = 0., xx = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll 1
+    for (int k = 0; k < own.n; ++k)
+    for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) {
         const double xi = x[i] + alpha * p[i], ri = r[i] - alpha * Ap[i];
         x[i] = xi; r[i] = ri;
         rr += ri * ri; xx += xi * xi;
@@ -169,17 +179,28 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(int64_t n, do
     if (threadIdx.x == 0) { dotPartial[blockIdx.x] = brr; dotPartial[gridDim.x + blockIdx.x] = bxx; }
     if (last_block(&S->ticket[1])) {
         const double trr = block_sum_partials(dotPartial, gridDim.x), txx = block_sum_partials(dotPartial + gridDim.x, gridDim.x);
-        if (threadIdx.x == 0) finish_xr(S, trr, txx);
+        if (threadIdx.x == 0) { S->red[1] = trr; S->red[2] = txx; S->alpha = alpha; }
     }
 }
-__global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(int64_t n, double* __restrict__ p, const double* __restrict__ r, const PcgScalars* S) {
+// p = r + beta p unless the stop test fired; the last CTA then advances the CG state (every CTA has read rsold by then)
+__global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, double* __restrict__ p, const double* __restrict__ r, PcgScalars* S) {
     if (S->done) return;
-    const double beta = S->beta;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = r[i] + beta * p[i];
+    const bool converged = cg_rre(S) < S->tol2;
+    const double beta = S->red[1] / S->rsold;
+    if (!converged) {
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    #pragma unroll 1
+    for (int k = 0; k < own.n; ++k)
+            for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) p[i] = r[i] + beta * p[i];
+    }
+    if (last_block(&S->ticket[3]) && threadIdx.x == 0) cg_advance(S);
 }
-__global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(int64_t n, const double* __restrict__ b, double* x, double* r, double* p, double* dotPartial, PcgScalars* S, double tol, int maxIter) {
+__global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, const double* __restrict__ b, double* x, double* r, double* p, double* dotPartial, PcgScalars* S, double tol, int maxIter) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     double rr = 0.;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll 1
+    for (int k = 0; k < own.n; ++k)
+    for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) {
         const double bi = b[i];
         x[i] = 0.; r[i] = bi; p[i] = bi; rr += bi * bi;
     }
@@ -188,10 +209,21 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(int64_t n, const d
     if (last_block(&S->ticket[2])) {
         const double rs = block_sum_partials(dotPartial, gridDim.x);
         if (threadIdx.x == 0) {
-            S->rsold = rs; S->pAp = 0.; S->alpha = 0.; S->beta = 0.; S->rsnew = 0.; S->xmag = 0.; S->rre = 0.;
-            S->iter = 0; S->done = (rs == 0.) ? 1 : 0; S->maxIter = maxIter; S->tol2 = tol * tol;
+            S->rsold = 0.; S->pAp = 0.; S->alpha = 0.; S->beta = 0.; S->rsnew = 0.; S->xmag = 0.; S->rre = 0.;
+            S->red[0] = 0.; S->red[1] = 0.; S->red[2] = 0.; S->red[3] = rs;
+            S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
         }
     }
+}
+// after the all-reduce of b.b: rsold, and the b == 0 early out
+__global__ void cg_begin_kernel(PcgScalars* S) { S->rsold = S->red[3]; S->done = (S->red[3] == 0.) ? 1 : 0; }
+__global__ void __launch_bounds__(256) halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf, const PcgScalars* S) {
+    if (S && S->done) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] = v[idx[i]];
+}
+__global__ void __launch_bounds__(256) halo_unpack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ v, const PcgScalars* S) {
+    if (S && S->done) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[idx[i]] = buf[i];
 }
 // persistent grid-stride sizing: exactly one wave = SM count x resident CTAs of this kernel (no partial second wave)
 template <class K>
@@ -213,65 +245,104 @@ static inline int hot_blocks(K kernel, int64_t n) {
 }
 
 void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
-    if (A.nRowsExt <= 0) return;
-    pass1_kernel<<<hot_blocks(pass1_kernel, A.nRowsExt), HOT_THREADS, 0, st>>>(A, x, w, activeScale, S);
+    if (A.rowsK.total() <= 0) return;
+    pass1_kernel<<<hot_blocks(pass1_kernel, A.rowsK.total()), HOT_THREADS, 0, st>>>(A, x, w, activeScale, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, int, PcgScalars* scal, int mode) {
-    pass2_kernel<<<hot_blocks(pass2_kernel, A.nP + A.nT), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode);
+    pass2_kernel<<<hot_blocks(pass2_kernel, A.rowsP.total() + A.rowsC.total() + A.rowsE.total()), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_update_xr(cudaStream_t st, int64_t n, double* x, double* r, const double* p, const double* Ap, double* dotPartial, int, PcgScalars* scal) {
-    cg_update_xr_kernel<<<hot_blocks(cg_update_xr_kernel, n), HOT_THREADS, 0, st>>>(n, x, r, p, Ap, dotPartial, scal);
+void k_cg_update_xr(cudaStream_t st, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal) {
+    cg_update_xr_kernel<<<hot_blocks(cg_update_xr_kernel, own.total()), HOT_THREADS, 0, st>>>(own, x, r, p, Ap, dotPartial, scal);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_update_p(cudaStream_t st, int64_t n, double* p, const double* r, const PcgScalars* scal) {
-    cg_update_p_kernel<<<hot_blocks(cg_update_p_kernel, n), HOT_THREADS, 0, st>>>(n, p, r, scal);
+void k_cg_update_p(cudaStream_t st, const RangeSet& own, double* p, const double* r, PcgScalars* scal) {
+    cg_update_p_kernel<<<hot_blocks(cg_update_p_kernel, own.total()), HOT_THREADS, 0, st>>>(own, p, r, scal);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_init(cudaStream_t st, int64_t n, const double* b, double* x, double* r, double* p, double* dotPartial, int, PcgScalars* scal, double tol, int maxIter) {
-    cg_init_kernel<<<hot_blocks(cg_init_kernel, n), HOT_THREADS, 0, st>>>(n, b, x, r, p, dotPartial, scal, tol, maxIter);
+void k_cg_init(cudaStream_t st, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter) {
+    cg_init_kernel<<<hot_blocks(cg_init_kernel, own.total()), HOT_THREADS, 0, st>>>(own, b, x, r, p, dotPartial, scal, tol, maxIter);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_cg_begin(cudaStream_t st, PcgScalars* scal) {
+    cg_begin_kernel<<<1, 1, 0, st>>>(scal);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_halo_pack(cudaStream_t st, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) {
+    if (n <= 0) return;
+    halo_pack_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, 0, st>>>(n, idx, v, buf, S);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) {
+    if (n <= 0) return;
+    halo_unpack_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, 0, st>>>(n, idx, buf, v, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 #else  // ---- serial twins ----
 void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
     if (S && S->done) return;
-    for (int64_t r = 0; r < A.nRowsExt; ++r) { const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInv[r] * s : s; }
+    for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInv[r] * s : s; }
 }
 void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, int, PcgScalars* S, int mode) {
     if (S && S->done) return;
-    const int64_t n = A.nP + A.nT;
     double acc = 0.;
-    for (int64_t j = 0; j < n; ++j) {
+    auto row = [&](int64_t j) {
         double v = -kt_row(A, j, w);
         const double xj = (mode & 1) || j >= A.nP ? (x ? x[j] : 0.) : 0.;
         if (j >= A.nP && muScale != 0.) v -= muScale * A.uInv[j - A.nP] * xj;
         if (add) v += add[j];
         y[j] = v; acc += xj * v;
-    }
-    if (mode & 1) finish_pAp(S, acc);
+    };
+    for (int64_t l = 0; l < A.rowsP.total(); ++l) row(A.rowsP.at(l));
+    for (int64_t l = 0; l < A.rowsC.total(); ++l) row(A.nP + A.rowsC.at(l));
+    for (int64_t l = 0; l < A.rowsE.total(); ++l) row(A.nP + 3 * A.nC + A.rowsE.at(l));
+    if (mode & 1) S->red[0] = acc;
 }
-void k_cg_update_xr(cudaStream_t, int64_t n, double* x, double* r, const double* p, const double* Ap, double*, int, PcgScalars* S) {
+void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double*, PcgScalars* S) {
     if (S->done) return;
+    const double alpha = cg_alpha(S);
     double rr = 0., xx = 0.;
-    for (int64_t i = 0; i < n; ++i) { x[i] += S->alpha * p[i]; r[i] -= S->alpha * Ap[i]; rr += r[i] * r[i]; xx += x[i] * x[i]; }
-    finish_xr(S, rr, xx);
+    for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rr += r[i] * r[i]; xx += x[i] * x[i]; }
+    S->red[1] = rr; S->red[2] = xx; S->alpha = alpha;
 }
-void k_cg_update_p(cudaStream_t, int64_t n, double* p, const double* r, const PcgScalars* S) {
+void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* S) {
     if (S->done) return;
-    for (int64_t i = 0; i < n; ++i) p[i] = r[i] + S->beta * p[i];
+    const bool converged = cg_rre(S) < S->tol2;
+    const double beta = S->red[1] / S->rsold;
+    if (!converged) for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); p[i] = r[i] + beta * p[i]; }
+    cg_advance(S);
 }
-void k_cg_init(cudaStream_t, int64_t n, const double* b, double* x, double* r, double* p, double*, int, PcgScalars* S, double tol, int maxIter) {
+void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double*, PcgScalars* S, double tol, int maxIter) {
     double rr = 0.;
-    for (int64_t i = 0; i < n; ++i) { x[i] = 0.; r[i] = b[i]; p[i] = b[i]; rr += b[i] * b[i]; }
-    S->rsold = rr; S->pAp = S->alpha = S->beta = S->rsnew = S->xmag = S->rre = 0.; S->iter = 0; S->done = rr == 0. ? 1 : 0; S->maxIter = maxIter; S->tol2 = tol * tol;
+    for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); x[i] = 0.; r[i] = b[i]; p[i] = b[i]; rr += b[i] * b[i]; }
+    S->rsold = S->pAp = S->alpha = S->beta = S->rsnew = S->xmag = S->rre = 0.; S->red[0] = S->red[1] = S->red[2] = 0.; S->red[3] = rr;
+    S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
 }
+void k_cg_begin(cudaStream_t, PcgScalars* S) { S->rsold = S->red[3]; S->done = (S->red[3] == 0.) ? 1 : 0; }
+void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) buf[i] = v[idx[i]]; }
+void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) v[idx[i]] = buf[i]; }
 #endif
+
+// halo discovery: flag[c] = 1 for every column c of the given ELL rows that `colsOwned` contains
+template <class Owned>
+void k_mark_columns(cudaStream_t st, const int32_t* col, int width, int64_t ldRows, const RowSet& rows, const Owned& colsOwned, uint8_t* flag) {
+    const RowSet R = rows; const Owned Cs = colsOwned;
+    ps_for(st, R.total(), PS_LAMBDA(int64_t l) {
+        const int64_t r = R.at(l);
+        for (int k = 0; k < width; ++k) { const int32_t c = col[(int64_t)k * ldRows + r]; if (Cs.has(c)) flag[c] = 1; }
+    });
+}
+template void k_mark_columns<RangeSet>(cudaStream_t, const int32_t*, int, int64_t, const RowSet&, const RangeSet&, uint8_t*);
+template void k_mark_columns<RowSet>(cudaStream_t, const int32_t*, int, int64_t, const RowSet&, const RowSet&, uint8_t*);
 
 // ---- reduced regions -------------------------------------------------------------------------------
 // t_r = J_r x = sum_f c_f (K_red x)_f ;  s_r = B_r^-1 (extraScale*extra_r + tScale*t_r) ;  w_f = scale * c_f . s_r
@@ -309,10 +380,11 @@ PS_D void s_to_sigma(const double* s, double* sg) {
 constexpr int RED_THREADS = 256;
 // one CTA per (region, axis) chunk of coupled reduced rows: 10 monomial moments of w_f = (K_red x)_f (written by pass 1)
 __global__ void __launch_bounds__(RED_THREADS) reduced_moments_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk,
-                                                                     const double* __restrict__ com, const double* __restrict__ wRows, double* __restrict__ partial, const PcgScalars* S) {
+                                                                     const double* __restrict__ com, const double* __restrict__ wRows, double* __restrict__ partial, const PcgScalars* S, int chunk0) {
     if (S && S->done) return;
     __shared__ double red[RED_THREADS / 32][10];
-    const int region = chunk[4 * blockIdx.x], begin = chunk[4 * blockIdx.x + 1], end = chunk[4 * blockIdx.x + 2];
+    const int ch = chunk0 + blockIdx.x;
+    const int region = chunk[4 * ch], begin = chunk[4 * ch + 1], end = chunk[4 * ch + 2];
     const double c0 = com[3 * region], c1 = com[3 * region + 1], c2 = com[3 * region + 2];
     const double cm[3] = {c0, c1, c2};
     double acc[10];
@@ -335,16 +407,16 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_moments_kernel(double dx,
         double s = 0.;
 #pragma unroll
         for (int wI = 0; wI < RED_THREADS / 32; ++wI) s += red[wI][threadIdx.x];
-        partial[(size_t)blockIdx.x * 10 + threadIdx.x] = s;
+        partial[(size_t)ch * 10 + threadIdx.x] = s;
     }
 }
 // one warp per region: ordered sum of the chunk partials -> t -> s = B^-1 t -> sigma
 __global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __restrict__ chunkStart, const int32_t* __restrict__ chunk, const double* __restrict__ partial,
                                                            const double* __restrict__ Binv, const double* __restrict__ extra, double extraScale, double tScale,
-                                                           double* __restrict__ tOut, double* __restrict__ sOut, double* __restrict__ sigma, const PcgScalars* S) {
+                                                           double* __restrict__ tOut, double* __restrict__ sOut, double* __restrict__ sigma, const PcgScalars* S, int region0) {
     if (S && S->done) return;
     __shared__ double M[30], t[RDOF], sv[RDOF];
-    const int r = blockIdx.x, lane = threadIdx.x;
+    const int r = region0 + blockIdx.x, lane = threadIdx.x;
     if (lane < 30) {
         const int axis = lane / 10, k = lane % 10;
         double s = 0.;
@@ -373,9 +445,10 @@ __global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __res
 }
 // one CTA per chunk: w_f = scale * sigma[region][axis] . monomials(f)
 __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk, const double* __restrict__ com,
-                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S) {
+                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S, int chunk0) {
     if (S && S->done) return;
-    const int region = chunk[4 * blockIdx.x], begin = chunk[4 * blockIdx.x + 1], end = chunk[4 * blockIdx.x + 2], axis = chunk[4 * blockIdx.x + 3];
+    const int ch = chunk0 + blockIdx.x;
+    const int region = chunk[4 * ch], begin = chunk[4 * ch + 1], end = chunk[4 * ch + 2], axis = chunk[4 * ch + 3];
     const double cm[3] = {com[3 * region], com[3 * region + 1], com[3 * region + 2]};
     double sg[10];
 #pragma unroll
@@ -390,27 +463,27 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, 
     }
 }
 void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S) {
-    if (RG.nRowChunks <= 0) return;
-    reduced_moments_kernel<<<RG.nRowChunks, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, wRows, RG.partial.p, S);
+    if (RG.rowChunkHi <= RG.rowChunkLo) return;
+    reduced_moments_kernel<<<RG.rowChunkHi - RG.rowChunkLo, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, wRows, RG.partial.p, S, RG.rowChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void reduced_finish(cudaStream_t st, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S) {
-    if (RG.count <= 0) return;
-    reduced_finish_kernel<<<RG.count, 32, 0, st>>>(RG.rowChunkStart.p, RG.rowChunk.p, RG.partial.p, RG.Binv.p, extra, extraScale, tScale, RG.t.p, RG.s.p, RG.sigma.p, S);
+    if (RG.regHi <= RG.regLo) return;
+    reduced_finish_kernel<<<RG.regHi - RG.regLo, 32, 0, st>>>(RG.rowChunkStart.p, RG.rowChunk.p, RG.partial.p, RG.Binv.p, extra, extraScale, tScale, RG.t.p, RG.s.p, RG.sigma.p, S, RG.regLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void reduced_expand(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
-    if (RG.nRowChunks <= 0) return;
-    reduced_expand_kernel<<<RG.nRowChunks, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, RG.sigma.p, wRows, scale, S);
+    if (RG.rowChunkHi <= RG.rowChunkLo) return;
+    reduced_expand_kernel<<<RG.rowChunkHi - RG.rowChunkLo, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.rowChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 #else
 void reduced_moments(cudaStream_t, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S) {
     if (S && S->done) return;
-    for (int ch = 0; ch < RG.nRowChunks; ++ch) {
+    for (int ch = RG.rowChunkLo; ch < RG.rowChunkHi; ++ch) {
         const int region = RG.rowChunk.p[4 * ch], begin = RG.rowChunk.p[4 * ch + 1], end = RG.rowChunk.p[4 * ch + 2];
         double acc[10] = {0};
         for (int row = begin; row < end; ++row) {
@@ -423,7 +496,7 @@ void reduced_moments(cudaStream_t, const Geom& g, const RegionData& RG, const do
 }
 void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S) {
     if (S && S->done) return;
-    for (int r = 0; r < RG.count; ++r) {
+    for (int r = RG.regLo; r < RG.regHi; ++r) {
         double M[30] = {0}, t[RDOF], sv[RDOF], sg[30];
         if (tScale != 0.)
             for (int ch = RG.rowChunkStart.p[r]; ch < RG.rowChunkStart.p[r + 1]; ++ch)
@@ -437,7 +510,7 @@ void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const doubl
 }
 void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
     if (S && S->done) return;
-    for (int ch = 0; ch < RG.nRowChunks; ++ch) {
+    for (int ch = RG.rowChunkLo; ch < RG.rowChunkHi; ++ch) {
         const int region = RG.rowChunk.p[4 * ch], begin = RG.rowChunk.p[4 * ch + 1], end = RG.rowChunk.p[4 * ch + 2], axis = RG.rowChunk.p[4 * ch + 3];
         for (int row = begin; row < end; ++row) {
             double m[10]; row_monomials(g.dx, RG.rowXYZ.p[row], RG.com.p + 3 * region, m);
@@ -451,13 +524,15 @@ void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* w
 
 // W1 recoverVelocityFromPressureStress, active part (S.cpp:507): u = dt Mc^-1 (rhs_u/dt - G p - D^T tau)
 // (wAct already holds dt Mc^-1 K x from pass 1)
-void k_recover_active(cudaStream_t st, const Geom& g, int64_t nActiveVs, const double* wAct, const double* mcInv, const double* rhsU, double* velSol) {
+void k_recover_active(cudaStream_t st, const Geom& g, const RowSet& rows, const double* wAct, const double* mcInv, const double* rhsU, double* velSol) {
     const double dt = g.dt, invDt = g.invDt;
-    ps_for(st, nActiveVs, PS_LAMBDA(int64_t i) { velSol[i] = dt * (mcInv[i] * (invDt * rhsU[i])) - wAct[i]; });
+    const RowSet R = rows;
+    ps_for(st, R.total(), PS_LAMBDA(int64_t l) { const int64_t i = R.at(l); velSol[i] = dt * (mcInv[i] * (invDt * rhsU[i])) - wAct[i]; });
 }
 
-// W2 applySolutionToVelocity (S.cpp:937-1028) fused with buildValidFaces (S_Cls:4-54)
-void k_writeback_velocity(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, const RegionData& RG, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut) {
+// W2 applySolutionToVelocity (S.cpp:937-1028) fused with buildValidFaces (S_Cls:4-54).  With several ranks a
+// face carrying a DOF is written by the rank that owns the DOF; faces without one are written by everybody.
+void k_writeback_velocity(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, const RegionData& RG, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut, FaceOwner own) {
     const int8_t* FL = F.label[SL_FACE + axis]; const int32_t* FA = F.aidx[SL_FACE + axis]; const int32_t* FR = F.ridx[SL_FACE + axis];
     const float* cvel = F.colvel[axis];
     const double* com = RG.com.p;
@@ -472,14 +547,32 @@ void k_writeback_velocity(cudaStream_t st, const Geom& g, const Fields& F, const
         const int ri = haveReduced ? FR[q] : -1;
         const int ai = FA[q];
         if (ri >= 0) {
+            if (ri < own.regLo || ri >= own.regHi) return;
             const I3 f = delin(g, SL_FACE + axis, q);
             double ox, oy, oz, c[RDOF];
             face_offset(g, f, axis, com + 3 * ri, ox, oy, oz);
             conversion_coefficients(ox, oy, oz, axis, c);
             for (int n = 0; n < RDOF; ++n) v += velSol[nAct + (int64_t)RDOF * ri + n] * c[n];
-        } else if (ai >= 0) v = velSol[faceOff + ai];
+        } else if (ai >= 0) {
+            if (ai < own.aLo || ai >= own.aHi) return;
+            v = velSol[faceOff + ai];
+        }
         else if (lab == L_SOLID) v = (double)cvel[q];
         velOut[q] = (float)v;
+    });
+}
+
+// the z-face plane shared by two slabs holds DOFs of both ranks: take the peer's value where the peer owns the DOF
+void k_merge_face_plane(cudaStream_t st, const Geom& g, const Fields& F, int axis, int k, const float* peerPlane, float* velOut, FaceOwner own) {
+    const int8_t* FL = F.label[SL_FACE + axis]; const int32_t* FA = F.aidx[SL_FACE + axis]; const int32_t* FR = F.ridx[SL_FACE + axis];
+    const int64_t plane = (int64_t)g.r[SL_FACE + axis][0] * g.r[SL_FACE + axis][1], base = plane * k;
+    ps_for(st, plane, PS_LAMBDA(int64_t i) {
+        const int64_t q = base + i;
+        const int lab = FL[q];
+        if (lab == L_UNSOLVED || lab == L_UNASSIGNED) return;
+        const int ri = FR[q], ai = FA[q];
+        const bool mine = ri >= 0 ? (ri >= own.regLo && ri < own.regHi) : (ai >= 0 ? (ai >= own.aLo && ai < own.aHi) : true);
+        if (!mine) velOut[q] = peerPlane[i];
     });
 }
 

@@ -141,12 +141,13 @@ constexpr int GRAM_THREADS = 256;
 constexpr int GRAM_BATCH = 128;   // faces staged per pass (128 * (26+26+3) doubles = 56 KB smem)
 
 __global__ void __launch_bounds__(GRAM_THREADS) gram_partial_kernel(Geom g, Fields F, const double* __restrict__ com, const int32_t* __restrict__ cellList,
-                                                                   const int32_t* __restrict__ chunk, double* __restrict__ partial) {
+                                                                   const int32_t* __restrict__ chunk, double* __restrict__ partial, int chunk0) {
     extern __shared__ double sm[];
     double* sc = sm;                              // [GRAM_BATCH][26]
     double* sd = sc + GRAM_BATCH * RDOF;          // [GRAM_BATCH][26]
     double* sw = sd + GRAM_BATCH * RDOF;          // [GRAM_BATCH][3]  wM, wN, u*wN
-    const int region = chunk[3 * blockIdx.x + 0], begin = chunk[3 * blockIdx.x + 1], end = chunk[3 * blockIdx.x + 2];
+    const int ch = chunk0 + blockIdx.x;
+    const int region = chunk[3 * ch + 0], begin = chunk[3 * ch + 1], end = chunk[3 * ch + 2];
     const int nFaces = (end - begin) * 6;
     // each thread owns up to 3 of the 676 (i,j) entries
     double accM[3] = {0, 0, 0}, accN[3] = {0, 0, 0}, accV[3] = {0, 0, 0};
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram_partial_kernel(Geom g, Fiel
             accR = rr;
         }
     }
-    double* out = partial + (size_t)blockIdx.x * GRAM_STRIDE;
+    double* out = partial + (size_t)ch * GRAM_STRIDE;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int e = threadIdx.x + k * GRAM_THREADS;
@@ -195,17 +196,17 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram_partial_kernel(Geom g, Fiel
 }
 
 void region_gram_partials(cudaStream_t st, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
-    if (RG.nCellChunks <= 0) return;
+    if (RG.cellChunkHi <= RG.cellChunkLo) return;
     const size_t smem = (size_t)GRAM_BATCH * (2 * RDOF + 3) * sizeof(double);
     static bool attr = false;
     if (!attr) { PS_CUDA(cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    gram_partial_kernel<<<RG.nCellChunks, GRAM_THREADS, smem, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial);
+    gram_partial_kernel<<<RG.cellChunkHi - RG.cellChunkLo, GRAM_THREADS, smem, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial, RG.cellChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 #else
 void region_gram_partials(cudaStream_t, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
-    for (int ch = 0; ch < RG.nCellChunks; ++ch) {
+    for (int ch = RG.cellChunkLo; ch < RG.cellChunkHi; ++ch) {
         const int region = RG.cellChunk.p[3 * ch], begin = RG.cellChunk.p[3 * ch + 1], end = RG.cellChunk.p[3 * ch + 2];
         double* out = partial + (size_t)ch * GRAM_STRIDE;
         for (int e = 0; e < GRAM_STRIDE; ++e) out[e] = 0.;
@@ -281,13 +282,15 @@ PS_D void solve_full_piv(double* lu, const double* rhs, double* x, int* rowT, in
 //   B  = M/dt + 2 V ; B^-1 = B.inverse()                (assembleReducedInvertedBlock, S_AB:195-244)
 //   rhs_r = M v*                                        (assembleReducedRHSVector, S_AB:356-367)
 void region_gram_finish(cudaStream_t st, const Geom& g, RegionData& RG, int nChunks) {
-    const int R = RG.count;
+    // only the regions this rank owns [regLo, regHi) (all of them on one GPU)
+    const int R0 = RG.regLo, R = RG.regHi - RG.regLo;
     if (R <= 0) return;
     const double* partial = RG.partial.p; const int32_t* chunkStart = RG.cellChunkStart.p;
     double* Mr = RG.Mr.p; double* Vi = RG.Visc.p; double* Nm = RG.N.p; double* Binv = RG.Binv.p;
     double* lsq = RG.lsqRhs.p; double* fit = RG.bestFit.p; double* rhsR = RG.rhsR.p;
     const int NN = RDOF * RDOF;
-    ps_for(st, (int64_t)R * NN, PS_LAMBDA(int64_t q) {
+    ps_for(st, (int64_t)R * NN, PS_LAMBDA(int64_t ql) {
+        const int64_t q = ql + (int64_t)R0 * NN;
         const int r = (int)(q / NN), e = (int)(q % NN);
         double m = 0., n = 0., v = 0.;
         for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) {
@@ -296,7 +299,8 @@ void region_gram_finish(cudaStream_t st, const Geom& g, RegionData& RG, int nChu
         }
         Mr[q] = m; Nm[q] = n; Vi[q] = v;
     });
-    ps_for(st, (int64_t)R * RDOF, PS_LAMBDA(int64_t q) {
+    ps_for(st, (int64_t)R * RDOF, PS_LAMBDA(int64_t ql) {
+        const int64_t q = ql + (int64_t)R0 * RDOF;
         const int r = (int)(q / RDOF), e = (int)(q % RDOF);
         double s = 0.;
         for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) s += partial[(size_t)ch * GRAM_STRIDE + 3 * NN + e];
@@ -308,8 +312,9 @@ void region_gram_finish(cudaStream_t st, const Geom& g, RegionData& RG, int nChu
     luA.alloc((size_t)R * NN); luB.alloc((size_t)R * NN); piv.alloc((size_t)R * 3 * RDOF);
     double* A = luA.p; double* B = luB.p; int* pv = piv.p;
     const double invDt = g.invDt;
-    ps_for(st, R, PS_LAMBDA(int64_t r) {
-        double* a = A + r * NN; double* b = B + r * NN; int* p3 = pv + r * 3 * RDOF;
+    ps_for(st, R, PS_LAMBDA(int64_t rl) {
+        const int64_t r = rl + R0;
+        double* a = A + rl * NN; double* b = B + rl * NN; int* p3 = pv + rl * 3 * RDOF;
         for (int e = 0; e < NN; ++e) { a[e] = Nm[r * NN + e]; b[e] = invDt * Mr[r * NN + e] + 2. * Vi[r * NN + e]; }
         solve_full_piv(a, lsq + r * RDOF, fit + r * RDOF, p3, p3 + RDOF);
         inverse_partial_piv(b, Binv + r * NN, p3 + 2 * RDOF);

@@ -8,6 +8,8 @@
 #include "ps_solver.hpp"
 #ifndef PS_EMULATE
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #endif
 
 namespace ps {
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* flag, Ti
     }
 }
 
-int64_t tile_order_scan(cudaStream_t st, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts) {
+int64_t tile_order_scan(cudaStream_t st, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts,
+                        const std::vector<int>* zCut, std::vector<int64_t>* cuts) {
     TileGeom t;
     t.rx = g.r[slot][0]; t.ry = g.r[slot][1]; t.rz = g.r[slot][2];
     t.tx = (t.rx + 15) >> 4; t.ty = (t.ry + 15) >> 4; t.tz = (t.rz + 15) >> 4;
@@ -102,9 +105,48 @@ int64_t tile_order_scan(cudaStream_t st, const Geom& g, int slot, const uint8_t*
     tile_write_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p, out);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
+    if (zCut && cuts) {
+        // tiles are visited z-slowest, so the rank of the first voxel of a z cut is the offset of the cut's first tile
+        std::vector<int32_t> off = tileCounts.to_host(st, (size_t)nTiles + 1);
+        const int nc = (int)zCut->size();
+        cuts->assign((size_t)nc, 0);
+        for (int k = 0; k < nc; ++k) {
+            const int z = (*zCut)[k];
+            const int64_t tile = (int64_t)(z >> 4) * t.tx * t.ty;
+            (*cuts)[k] = (k == nc - 1 || tile >= nTiles) ? off[nTiles] : off[tile];
+        }
+        (*cuts)[0] = 0;
+        return off[nTiles];
+    }
     int32_t total = 0;
     copy_d2h(&total, tileCounts.p + nTiles, sizeof(int32_t), st);
     return total;
+}
+
+// ascending list of the indices i < n with flag[i] != 0, written to out[outOffset...]; returns the count
+int64_t select_flagged(cudaStream_t st, int64_t n, const uint8_t* flag, DBuf<int32_t>& out, int64_t outOffset) {
+    if (n <= 0) return 0;
+    static thread_local DBuf<uint8_t> tmp;
+    static thread_local DBuf<int32_t> cnt, staging;
+    cnt.alloc(1); staging.alloc((size_t)n);
+    cub::CountingInputIterator<int32_t> idx(0);
+    size_t tmpBytes = 0;
+    PS_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, idx, flag, staging.p, cnt.p, (int)n, st));
+    tmp.alloc(tmpBytes);
+    PS_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmpBytes, idx, flag, staging.p, cnt.p, (int)n, st));
+    PS_COUNT_LAUNCH(1);
+    int32_t c = 0;
+    copy_d2h(&c, cnt.p, sizeof c, st);
+    if (c > 0) {
+        if (out.n < (size_t)(outOffset + c)) {      // grow, keeping what is already there
+            DBuf<int32_t> bigger; bigger.alloc((size_t)(outOffset + c));
+            if (outOffset > 0) copy_d2d(bigger.p, out.p, (size_t)outOffset * sizeof(int32_t), st);
+            stream_sync(st);
+            std::swap(out.p, bigger.p); std::swap(out.n, bigger.n);
+        }
+        copy_d2d(out.p + outOffset, staging.p, (size_t)c * sizeof(int32_t), st);
+    }
+    return c;
 }
 
 void sort_pairs_by_key(cudaStream_t st, int64_t n, int keyBits, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>& keysTmp, DBuf<int32_t>& valsTmp) {
@@ -121,15 +163,30 @@ void sort_pairs_by_key(cudaStream_t st, int64_t n, int keyBits, DBuf<int32_t>& k
 
 #else  // ---- PS_EMULATE: serial twins (test-only build) ----
 
-int64_t tile_order_scan(cudaStream_t, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>&) {
+int64_t tile_order_scan(cudaStream_t, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>&,
+                        const std::vector<int>* zCut, std::vector<int64_t>* cuts) {
     const int rx = g.r[slot][0], ry = g.r[slot][1], rz = g.r[slot][2];
     int32_t n = 0;
-    for (int tk = 0; tk < rz; tk += 16) for (int tj = 0; tj < ry; tj += 16) for (int ti = 0; ti < rx; ti += 16)
+    if (zCut && cuts) cuts->assign(zCut->size(), -1);
+    for (int tk = 0; tk < rz; tk += 16) for (int tj = 0; tj < ry; tj += 16) for (int ti = 0; ti < rx; ti += 16) {
+        if (zCut && cuts && tj == 0 && ti == 0) for (size_t k = 0; k < zCut->size(); ++k) if ((*zCut)[k] == tk) (*cuts)[k] = n;
         for (int k = tk; k < std::min(tk + 16, rz); ++k) for (int j = tj; j < std::min(tj + 16, ry); ++j) for (int i = ti; i < std::min(ti + 16, rx); ++i) {
             const int64_t q = (int64_t)i + (int64_t)rx * ((int64_t)j + (int64_t)ry * k);
             out[q] = flag[q] ? n++ : -1;
         }
+    }
+    if (zCut && cuts) { for (size_t k = 0; k < cuts->size(); ++k) if ((*cuts)[k] < 0 || k + 1 == cuts->size()) (*cuts)[k] = n; (*cuts)[0] = 0; }
     return n;
+}
+
+int64_t select_flagged(cudaStream_t, int64_t n, const uint8_t* flag, DBuf<int32_t>& out, int64_t outOffset) {
+    std::vector<int32_t> keep;
+    if (outOffset > 0) keep.assign(out.p, out.p + outOffset);
+    for (int64_t i = 0; i < n; ++i) if (flag[i]) keep.push_back((int32_t)i);
+    const int64_t c = (int64_t)keep.size() - outOffset;
+    if (out.n < keep.size()) { DBuf<int32_t> bigger; bigger.alloc(keep.size()); std::swap(out.p, bigger.p); std::swap(out.n, bigger.n); }
+    std::copy(keep.begin(), keep.end(), out.p);
+    return c;
 }
 
 void sort_pairs_by_key(cudaStream_t, int64_t n, int, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>&, DBuf<int32_t>&) {

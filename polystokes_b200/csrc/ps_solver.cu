@@ -3,6 +3,7 @@
 #include "ps_solver.hpp"
 #include <climits>
 #include <chrono>
+#include <memory>
 
 namespace ps {
 
@@ -69,9 +70,36 @@ Solver::Solver(const ps_params& p) : P(p) {
     scal.alloc(1);
     scal.zero(st, 1);
     memset(&F, 0, sizeof F);
+    part.zCut = {0, p.nz};
+}
+
+static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// z cuts at multiples of lcm(16, tileSize), as even as the unit allows (ps_part.hpp)
+void Solver::initComm(Comm* c) {
+    std::unique_ptr<Comm> guard(c);
+    if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks) throw Error("ps_comm_init: bad rank / nranks");
+    int unit = 16;
+    if (P.doReducedRegions) {
+        if (c->nranks > 1 && (!P.doTile || P.tilePadding < 1 || P.tileSize < 1))
+            throw Error("ps_comm_init: reduced regions need doTile with tilePadding >= 1 on more than one GPU (untiled regions may span slabs)");
+        if (P.doTile && P.tileSize >= 1) unit = 16 / gcd_i(16, P.tileSize) * P.tileSize;
+    }
+    const int nUnits = (g.nz + unit - 1) / unit;
+    if (c->nranks > nUnits) throw Error("ps_comm_init: more ranks than z-slabs of lcm(16, tileSize) cells");
+    part.rank = c->rank; part.nranks = c->nranks;
+    part.zCut.assign((size_t)c->nranks + 1, 0);
+    for (int k = 0; k <= c->nranks; ++k) part.zCut[k] = std::min(g.nz, (int)(((int64_t)k * nUnits + c->nranks / 2) / c->nranks) * unit);
+    part.zCut[0] = 0; part.zCut[c->nranks] = g.nz;
+    for (int k = 0; k < c->nranks; ++k) if (part.zCut[k + 1] <= part.zCut[k]) throw Error("ps_comm_init: empty z-slab");
+    g.zLo = part.zCut[c->rank]; g.zHi = part.zCut[c->rank + 1];
+    delete comm;
+    comm = guard.release();
+    haveSetup = false;
 }
 
 Solver::~Solver() {
+    delete comm;
 #ifndef PS_EMULATE
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
 #endif
@@ -222,7 +250,8 @@ void Solver::constructActiveIndices() {
     int64_t cnt[N_SLOTS];
     for (int s = 0; s < N_SLOTS; ++s) {
         k_generic_to_active_flags(st, g, s, F.label[s], flag);
-        cnt[s] = tile_order_scan(st, g, s, flag, F.aidx[s], tileCounts);
+        if (part.multi()) cnt[s] = tile_order_scan(st, g, s, flag, F.aidx[s], tileCounts, &part.zCut, &part.slotCut[s]);
+        else { cnt[s] = tile_order_scan(st, g, s, flag, F.aidx[s], tileCounts); part.slotCut[s] = {0, cnt[s]}; }
     }
     C = Counts();
     C.nCenter = cnt[SL_CENTER];
@@ -258,6 +287,8 @@ static void build_chunks(const std::vector<int>& perRegion, int chunk, std::vect
 // computeReducedViscosityMatricesInteriorOnly (S.cpp:328-490) + the AssembleBlocks dense part (S_AB)
 void Solver::computeReducedRegionMatrices() {
     const int R = RG.count;
+    part.regionCut.assign((size_t)part.nranks + 1, 0);
+    RG.regLo = RG.regHi = 0; RG.cellChunkLo = RG.cellChunkHi = 0;
     if (R <= 0) return;
     const int64_t nc = g.n[SL_CENTER];
     static thread_local DBuf<unsigned long long> sums;
@@ -275,9 +306,24 @@ void Solver::computeReducedRegionMatrices() {
     std::vector<unsigned long long> hs = sums.to_host(st, (size_t)4 * R);
     std::vector<int> perRegion((size_t)R);
     for (int r = 0; r < R; ++r) perRegion[r] = (int)hs[4 * r + 3];
+    // region -> rank: regions are numbered by their first cell in voxel order (z-slowest tiles) and never span a
+    // z cut, so every rank owns one contiguous id range
+    {
+        int owner = 0;
+        for (int r = 0; r < R; ++r) {
+            const int zmean = (int)(hs[4 * r + 2] / std::max<unsigned long long>(hs[4 * r + 3], 1ull));
+            int k = 0;
+            while (k + 1 < part.nranks && zmean >= part.zCut[k + 1]) ++k;
+            if (k < owner) throw Error("region numbering is not monotone in z: cannot slab-decompose these reduced regions");
+            while (owner < k) part.regionCut[++owner] = r;
+        }
+        while (owner < part.nranks) part.regionCut[++owner] = R;
+    }
+    RG.regLo = part.regionCut[part.rank]; RG.regHi = part.regionCut[part.rank + 1];
     std::vector<int32_t> start, table, chunkStart;
     build_chunks(perRegion, 256, start, table, chunkStart);
     RG.nCellChunks = (int32_t)(table.size() / 3);
+    RG.cellChunkLo = chunkStart[RG.regLo]; RG.cellChunkHi = chunkStart[RG.regHi];
     RG.cellStart.from_host(st, start.data(), start.size());
     RG.cellChunk.from_host(st, table.data(), table.size());
     RG.cellChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
@@ -294,7 +340,8 @@ void Solver::computeReducedRegionMatrices() {
 void Solver::constructMatrixBlocks() {
     const int R = RG.count;
     for (int a = 0; a < 3; ++a) k_krow_active(st, g.n[SL_FACE + a], F.aidx[SL_FACE + a], (int32_t)C.faceOff[a], F.krow[a]);
-    RG.nRows = 0; RG.nRowChunks = 0;
+    RG.nRows = 0; RG.nRowChunks = 0; RG.rowChunkLo = RG.rowChunkHi = 0;
+    part.redRowCut.assign((size_t)part.nranks + 1, 0);
     if (R > 0) {
         int64_t cnt[3], off[3];
         for (int a = 0; a < 3; ++a) {
@@ -329,6 +376,8 @@ void Solver::constructMatrixBlocks() {
         }
         start[R] = pos; chunkStart[R] = (int32_t)(table.size() / 4);
         RG.nRowChunks = (int32_t)(table.size() / 4);
+        RG.rowChunkLo = chunkStart[RG.regLo]; RG.rowChunkHi = chunkStart[RG.regHi];
+        for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
         RG.rowStart.from_host(st, start.data(), start.size());
         RG.rowChunk.from_host(st, table.data(), table.size());
         RG.rowChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
@@ -347,7 +396,89 @@ void Solver::constructMatrixBlocks() {
     b.alloc(n); x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); w.alloc((size_t)C.nRowsExt + 1);
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
     dotPartial.alloc(4096);
+    computeOwnership();
+    buildHalos();
 }
+
+// ---- ownership (ps_part.hpp): row / DOF ranges of rank k in the global numbering ----
+RowSet Solver::rowsK(int k) const {
+    RowSet r;
+    for (int a = 0; a < 3; ++a) r.add(C.faceOff[a] + part.slotCut[SL_FACE + a][k], C.faceOff[a] + part.slotCut[SL_FACE + a][k + 1]);
+    r.add(C.nActiveVs + part.redRowCut[k], C.nActiveVs + part.redRowCut[k + 1]);
+    return r;
+}
+RowSet Solver::rowsP(int k) const { return one_range(part.slotCut[SL_CENTER][k], part.slotCut[SL_CENTER][k + 1]); }
+RowSet Solver::rowsC(int k) const {   // numbering inside the centre-stress block [xx | yy | zz]
+    RowSet r;
+    for (int a = 0; a < 3; ++a) r.add(a * C.nCenter + part.slotCut[SL_CENTER][k], a * C.nCenter + part.slotCut[SL_CENTER][k + 1]);
+    return r;
+}
+RowSet Solver::rowsE(int k) const {   // numbering inside the edge-stress block [yz | xz | xy]
+    RowSet r;
+    for (int e = 0; e < 3; ++e) { const int64_t off = C.stressOff[3 + e] - 3 * C.nCenter; r.add(off + part.slotCut[SL_EDGE + e][k], off + part.slotCut[SL_EDGE + e][k + 1]); }
+    return r;
+}
+RangeSet Solver::rowsSys(int k) const {  // x = [p | xx | yy | zz | yz | xz | xy]
+    RangeSet r;
+    const RowSet p = rowsP(k), c = rowsC(k), e = rowsE(k);
+    r.add(p.lo[0], p.lo[0] + p.total());
+    for (int a = 0; a < 3; ++a) r.add(C.nPressures + c.lo[a], C.nPressures + c.lo[a] + (c.pre[a + 1] - c.pre[a]));
+    for (int a = 0; a < 3; ++a) r.add(C.nPressures + 3 * C.nCenter + e.lo[a], C.nPressures + 3 * C.nCenter + e.lo[a] + (e.pre[a + 1] - e.pre[a]));
+    return r;
+}
+void Solver::computeOwnership() {
+    if (part.regionCut.size() != (size_t)part.nranks + 1) part.regionCut.assign((size_t)part.nranks + 1, 0);   // no reduced regions
+    ownK = rowsK(part.rank); ownP = rowsP(part.rank); ownC = rowsC(part.rank); ownE = rowsE(part.rank); ownSys = rowsSys(part.rank);
+}
+
+// Halo lists.  Matrices are replicated, so a rank derives BOTH directions locally and the two sides of a pair
+// agree by construction: what I receive from h = columns of my rows that h owns; what I send to h = columns of
+// h's rows that I own.  Lists are ascending in the global index.
+void Solver::buildHalos() {
+    haloX.reset(); haloW.reset();
+    if (!part.multi()) return;
+    const int64_t n = C.nSystemSize, nRows = C.nRowsExt;
+    const int64_t nE = C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
+    static thread_local DBuf<uint8_t> flag;
+    flag.alloc((size_t)std::max(n, nRows) + 1);
+    const int me = part.rank;
+    const int peers[2] = {me > 0 ? me - 1 : -1, me + 1 < part.nranks ? me + 1 : -1};
+    auto listX = [&](int rowsOf, int colsOf, DBuf<int32_t>& out, int64_t off) {
+        flag.zero(st, (size_t)n);
+        k_mark_columns(st, K.col.p, 8, nRows, rowsK(rowsOf), rowsSys(colsOf), flag.p);
+        return select_flagged(st, n, flag.p, out, off);
+    };
+    auto listW = [&](int rowsOf, int colsOf, DBuf<int32_t>& out, int64_t off) {
+        flag.zero(st, (size_t)nRows);
+        const RowSet owned = rowsK(colsOf);
+        k_mark_columns(st, KtP.col.p, 6, C.nPressures, rowsP(rowsOf), owned, flag.p);
+        k_mark_columns(st, KtC.col.p, 2, 3 * C.nCenter, rowsC(rowsOf), owned, flag.p);
+        k_mark_columns(st, KtE.col.p, 4, nE, rowsE(rowsOf), owned, flag.p);
+        return select_flagged(st, nRows, flag.p, out, off);
+    };
+    for (int i = 0; i < 2; ++i) {
+        haloX.peers[i] = haloW.peers[i] = peers[i];
+        if (peers[i] < 0) continue;
+        haloX.nRecv[i] = listX(me, peers[i], haloX.recvIdx, i ? haloX.nRecv[0] : 0);
+        haloX.nSend[i] = listX(peers[i], me, haloX.sendIdx, i ? haloX.nSend[0] : 0);
+        haloW.nRecv[i] = listW(me, peers[i], haloW.recvIdx, i ? haloW.nRecv[0] : 0);
+        haloW.nSend[i] = listW(peers[i], me, haloW.sendIdx, i ? haloW.nSend[0] : 0);
+    }
+    for (Halo* H : {&haloX, &haloW}) { H->sendBuf.alloc((size_t)H->sendTotal() + 1); H->recvBuf.alloc((size_t)H->recvTotal() + 1); H->sendIdx.alloc(1); H->recvIdx.alloc(1); }
+}
+
+// pack -> grouped send/recv with the z-neighbours -> scatter into the global-length vector
+void Solver::exchange(Halo& H, double* v, const PcgScalars* S) {
+    if (!part.multi() || !comm) return;
+    k_halo_pack(st, H.sendTotal(), H.sendIdx.p, v, H.sendBuf.p, S);
+    const void* sb[2] = {H.sendBuf.p, H.sendBuf.p + H.nSend[0]};
+    void* rb[2] = {H.recvBuf.p, H.recvBuf.p + H.nRecv[0]};
+    const size_t sbytes[2] = {(size_t)H.nSend[0] * sizeof(double), (size_t)H.nSend[1] * sizeof(double)};
+    const size_t rbytes[2] = {(size_t)H.nRecv[0] * sizeof(double), (size_t)H.nRecv[1] * sizeof(double)};
+    comm->sendrecv(2, H.peers, sb, sbytes, rb, rbytes, st);
+    k_halo_unpack(st, H.recvTotal(), H.recvIdx.p, H.recvBuf.p, v, S);
+}
+void Solver::allreduce(double* devBuf, int n) { if (part.multi() && comm) comm->allreduce_sum(devBuf, n, st); }
 
 static OpArgs make_op(const Solver& S) {
     OpArgs A;
@@ -356,6 +487,7 @@ static OpArgs make_op(const Solver& S) {
     A.kval = S.K.val.p; A.kcol = S.K.col.p;
     A.ktpVal = S.KtP.val.p; A.ktpCol = S.KtP.col.p; A.ktcVal = S.KtC.val.p; A.ktcCol = S.KtC.col.p; A.kteVal = S.KtE.val.p; A.kteCol = S.KtE.col.p;
     A.mcInv = S.mcInv.p; A.uInv = S.uInv.p;
+    A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsC = S.ownC; A.rowsE = S.ownE;
     return A;
 }
 
@@ -370,6 +502,7 @@ void Solver::assemble() {
         reduced_finish(st, g, RG, RG.rhsR.p, 1.0, 0.0, nullptr);                     // s = B^-1 rhs_r
         reduced_expand(st, g, RG, w.p + C.nActiveVs, g.invDt, nullptr);
     }
+    exchange(haloW, w.p, nullptr);            // the neighbours' coupled reduced rows (active rows are replicated above)
     k_pass2(st, A, w.p, nullptr, b.p, 0.0, rhsPT.p, nullptr, 0, nullptr, 0);
 }
 
@@ -382,6 +515,7 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
         reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr);
         reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     }
+    exchange(haloW, w.p, nullptr);
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, 0, nullptr, 0);
 }
 
@@ -389,7 +523,7 @@ void Solver::timedOperator(int which) {
     const OpArgs A = make_op(*this);
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
     if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
-    else if (which == 3) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
+    else if (which == 3 && RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
     else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, 0, nullptr, 0);
 }
 
@@ -405,20 +539,26 @@ int Solver::solve() {
     usedBiCGStab = 0;
     PcgScalars h; memset(&h, 0, sizeof h);
     if (n == 0) { solveIterations = 0; solveError = 0; result = R_SUCCESS; return result; }
-    k_cg_init(st, n, b.p, x.p, r.p, p.p, dotPartial.p, 0, scal.p, P.tolerance, maxIt);
+    k_cg_init(st, ownSys, b.p, x.p, r.p, p.p, dotPartial.p, scal.p, P.tolerance, maxIt);
+    allreduce(scal.p->red + 3, 1);
+    k_cg_begin(st, scal.p);
     bool cancelled = false;
     for (int it = 0; it < maxIt;) {
         const int batch = std::min(every, maxIt - it);
         for (int k = 0; k < batch; ++k) {
+            exchange(haloX, p.p, scal.p);
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);
             if (RG.count > 0) {
                 reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p);
                 reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p);
                 reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
             }
+            exchange(haloW, w.p, scal.p);
             k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, 0, scal.p, 1);
-            k_cg_update_xr(st, n, x.p, r.p, p.p, Ap.p, dotPartial.p, 0, scal.p);
-            k_cg_update_p(st, n, p.p, r.p, scal.p);
+            allreduce(scal.p->red, 1);
+            k_cg_update_xr(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p);
+            allreduce(scal.p->red + 1, 2);
+            k_cg_update_p(st, ownSys, p.p, r.p, scal.p);
         }
         it += batch;
         copy_d2h(&h, scal.p, sizeof h, st);
@@ -437,12 +577,15 @@ int Solver::solve() {
 // recoverVelocityFromPressureStress (S.cpp:492-510)
 void Solver::recoverVelocityFromPressureStress() {
     const OpArgs A = make_op(*this);
+    exchange(haloX, x.p, nullptr);
     k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau)
-    k_recover_active(st, g, C.nActiveVs, w.p, mcInv.p, rhsU.p, velSol.p);
-    if (RG.count > 0) {
+    RowSet act;                                                      // the owned active face rows
+    for (int a = 0; a < 3; ++a) act.add(ownK.lo[a], ownK.lo[a] + (ownK.pre[a + 1] - ownK.pre[a]));
+    k_recover_active(st, g, act, w.p, mcInv.p, rhsU.p, velSol.p);
+    if (RG.regHi > RG.regLo) {
         reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr);
         reduced_finish(st, g, RG, RG.rhsR.p, g.invDt, -1.0, nullptr);                            // B^-1 (rhs_r/dt - J x)
-        k_copy_reduced_solution(st, (int64_t)RG.count * RDOF, RG.s.p, velSol.p + C.nActiveVs);
+        k_copy_reduced_solution(st, (int64_t)(RG.regHi - RG.regLo) * RDOF, RG.s.p + (size_t)RG.regLo * RDOF, velSol.p + C.nActiveVs + (size_t)RG.regLo * RDOF);
     }
 }
 
@@ -459,7 +602,21 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
             else { velDev = (float*)scratch32[0].p; copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
         }
         if (out.valid[a]) validDev = dev ? out.valid[a] : (float*)scratch32[1].p;
-        k_writeback_velocity(st, g, F, C, RG, velSol.p, a, velDev, validDev != nullptr, validDev);
+        const FaceOwner own = {(int32_t)part.slotCut[SL_FACE + a][part.rank], (int32_t)part.slotCut[SL_FACE + a][part.rank + 1], RG.regLo, RG.regHi};
+        k_writeback_velocity(st, g, F, C, RG, velSol.p, a, velDev, validDev != nullptr, validDev, own);
+        if (a == 2 && part.multi() && comm && velDev) {
+            // the z-face plane on a slab cut carries DOFs of both neighbours (active: upper rank, reduced: lower rank's regions)
+            const size_t plane = (size_t)g.nx * g.ny;
+            static thread_local DBuf<float> planes;
+            planes.alloc(2 * plane);
+            const int peers[2] = {part.rank > 0 ? part.rank - 1 : -1, part.rank + 1 < part.nranks ? part.rank + 1 : -1};
+            const int kz[2] = {g.zLo, g.zHi};
+            const void* sb[2] = {velDev + plane * kz[0], velDev + plane * kz[1]};
+            void* rb[2] = {planes.p, planes.p + plane};
+            const size_t bytes[2] = {peers[0] >= 0 ? plane * sizeof(float) : 0, peers[1] >= 0 ? plane * sizeof(float) : 0};
+            comm->sendrecv(2, peers, sb, bytes, rb, bytes, st);
+            for (int i = 0; i < 2; ++i) if (peers[i] >= 0) k_merge_face_plane(st, g, F, a, kz[i], planes.p + plane * i, velDev, own);
+        }
         if (!dev) {
             if (velDev) copy_d2any(out.velocity[a], velDev, nf * sizeof(float), false, st);
             if (validDev) copy_d2any(out.valid[a], validDev, nf * sizeof(float), false, st);
@@ -478,7 +635,8 @@ void Solver::setup() {
         classifyFaces();
         classifyEdges();
     }
-    RG.count = 0;
+    RG.count = 0; RG.regLo = RG.regHi = 0; RG.cellChunkLo = RG.cellChunkHi = 0; RG.rowChunkLo = RG.rowChunkHi = 0;
+    part.regionCut.assign((size_t)part.nranks + 1, 0);
     {
         StageTimer T(st, &stageMs[PS_STAGE_REDUCED]);
         if (P.doReducedRegions) { constructCenterReducedIndices(); constructFacesReducedIndices(); constructEdgesReducedIndices(); }

@@ -3,6 +3,8 @@
 // kernels on the solver's stream, all state is device resident.
 #pragma once
 #include "ps_grid.hpp"
+#include "ps_part.hpp"
+#include "ps_comm.hpp"
 #include "../../include/polystokes_b200.h"
 
 namespace ps {
@@ -38,6 +40,20 @@ struct RegionData {
     DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
+    // owned pieces of this rank (everything on one GPU): regions [regLo, regHi) and their chunk ranges
+    int32_t regLo = 0, regHi = 0, cellChunkLo = 0, cellChunkHi = 0, rowChunkLo = 0, rowChunkHi = 0;
+};
+
+// halo of one distributed vector: entries this rank must send to / receive from its z-neighbours
+// (global indices, ascending; the two peers' lists are concatenated [below | above])
+struct Halo {
+    int peers[2] = {-1, -1};
+    int64_t nSend[2] = {0, 0}, nRecv[2] = {0, 0};
+    DBuf<int32_t> sendIdx, recvIdx;
+    DBuf<double> sendBuf, recvBuf;
+    void reset() { for (int i = 0; i < 2; ++i) { peers[i] = -1; nSend[i] = nRecv[i] = 0; } }
+    int64_t sendTotal() const { return nSend[0] + nSend[1]; }
+    int64_t recvTotal() const { return nRecv[0] + nRecv[1]; }
 };
 
 struct Counts {
@@ -53,6 +69,7 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     int iter, done, maxIter, pad;
     double tol2;
     unsigned int ticket[4];   // last-CTA-done tickets of the fused dot products
+    double red[4];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.x, [3] b.b
 };
 
 class Solver {
@@ -92,6 +109,20 @@ public:
     void setup();                       // weights .. assemble
     int step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* stats);
     void fillStats(ps_stats* s) const;
+
+    // ---- multi-GPU (one process per GPU; ps_part.hpp) ----
+    Partition part;
+    Comm* comm = nullptr;
+    void initComm(Comm* c);             // takes ownership; computes the z cuts
+    void computeOwnership();            // owned row / DOF ranges of every rank from the replicated numbering
+    void buildHalos();                  // send / receive index lists of p (system vector) and w (K_ext rows)
+    void exchange(Halo& H, double* v, const PcgScalars* S);
+    void allreduce(double* devBuf, int n);
+    RowSet rowsK(int rank) const, rowsP(int rank) const, rowsC(int rank) const, rowsE(int rank) const;
+    RangeSet rowsSys(int rank) const;
+    RowSet ownK, ownP, ownC, ownE;
+    RangeSet ownSys;
+    Halo haloX, haloW;
 
     // operator y = A x on device vectors (Apply.h:102-179)
     void applyOperator(const double* x, double* y, double* pApPartial);
@@ -148,7 +179,9 @@ void k_valid_faces(cudaStream_t, const Geom&, const Fields&, float* const valid[
 
 // tile-order exclusive scan of a dense 0/1 flag field: out[q] = rank among flagged voxels in the
 // reference's voxel iteration order, -1 where the flag is 0.  Returns the total (host sync).
-int64_t tile_order_scan(cudaStream_t, const Geom&, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts);
+// If `zCut` is given, cuts[k] receives the rank of the first flagged voxel with z >= zCut[k] (cuts multiple of 16).
+int64_t tile_order_scan(cudaStream_t, const Geom&, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts,
+                        const std::vector<int>* zCut = nullptr, std::vector<int64_t>* cuts = nullptr);
 // stable sort of (key, value) pairs by key (keys < 2^keyBits)
 void sort_pairs_by_key(cudaStream_t, int64_t n, int keyBits, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>& keysTmp, DBuf<int32_t>& valsTmp);
 
@@ -166,6 +199,7 @@ void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, Ell&
 // ps_pcg.cu
 struct OpArgs {   // everything one operator apply touches
     int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
+    RowSet rowsK, rowsP, rowsC, rowsE;   // rows this rank computes (all rows on one GPU)
     const double* kval; const int32_t* kcol;
     const double* ktpVal; const int32_t* ktpCol; const double* ktcVal; const int32_t* ktcCol; const double* kteVal; const int32_t* kteCol;
     const double* mcInv; const double* uInv;
@@ -175,11 +209,20 @@ void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, doub
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-void k_cg_update_xr(cudaStream_t, int64_t n, double* x, double* r, const double* p, const double* Ap, double* dotPartial, int nPartials, PcgScalars* scal);
-void k_cg_update_p(cudaStream_t, int64_t n, double* p, const double* r, const PcgScalars* scal);
-void k_cg_init(cudaStream_t, int64_t n, const double* b, double* x, double* r, double* p, double* dotPartial, int nPartials, PcgScalars* scal, double tol, int maxIter);
-void k_recover_active(cudaStream_t, const Geom&, int64_t nActiveVs, const double* wAct, const double* mcInv, const double* rhsU, double* velSol);
-void k_writeback_velocity(cudaStream_t, const Geom&, const Fields&, const Counts&, const RegionData&, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut);
+void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal);
+void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* scal);
+void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter);
+void k_cg_begin(cudaStream_t, PcgScalars* scal);
+void k_recover_active(cudaStream_t, const Geom&, const RowSet& rows, const double* wAct, const double* mcInv, const double* rhsU, double* velSol);
+// faces this rank writes: active faces with index in [aLo, aHi), reduced faces of regions [regLo, regHi), every face without a DOF
+struct FaceOwner { int32_t aLo, aHi, regLo, regHi; };
+void k_writeback_velocity(cudaStream_t, const Geom&, const Fields&, const Counts&, const RegionData&, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut, FaceOwner own);
+void k_merge_face_plane(cudaStream_t, const Geom&, const Fields&, int axis, int k, const float* peerPlane, float* velOut, FaceOwner own);
+// halo plumbing
+void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* scal);
+void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* scal);
+template <class Owned> void k_mark_columns(cudaStream_t, const int32_t* col, int width, int64_t ldRows, const RowSet& rows, const Owned& colsOwned, uint8_t* flag);
+int64_t select_flagged(cudaStream_t, int64_t n, const uint8_t* flag, DBuf<int32_t>& out, int64_t outOffset);
 
 extern thread_local std::string g_lastError;
 

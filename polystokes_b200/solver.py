@@ -100,6 +100,37 @@ class PolyStokesSolver:
         except Exception:
             pass
 
+    # ---- several GPUs: one process per GPU (include/polystokes_b200.h, "several GPUs") ----
+    def init_distributed(self, group=None):
+        """Collective over a torch.distributed process group: rank 0 creates the NCCL unique id, torch.distributed
+        (any backend) carries its 128 bytes to the other ranks, then every rank joins the solver's own NCCL
+        communicator.  After this, step / setup / solve / apply are collective calls on the z-slab decomposition."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            rc = self.lib.ps_comm_unique_id(buf)
+            if rc != PS_SUCCESS:
+                raise PolyStokesError(f"ps_comm_unique_id failed ({rc}): {self.last_error()}")
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        rc = self.lib.ps_comm_init(self.h, rank, world, ident)
+        if rc != PS_SUCCESS:
+            raise PolyStokesError(f"ps_comm_init failed ({rc}): {self.last_error()}")
+        return self.partition()
+
+    def partition(self):
+        """(rank, nranks, zLo, zHi, zCut[nranks+1]) of the slab decomposition (single GPU: one slab)."""
+        r, lo, hi = C.c_int32(), C.c_int32(), C.c_int32()
+        n = self.lib.ps_get_partition(self.h, C.byref(r), C.byref(lo), C.byref(hi), None)
+        cuts = (C.c_int32 * (n + 1))()
+        self.lib.ps_get_partition(self.h, C.byref(r), C.byref(lo), C.byref(hi), cuts)
+        return r.value, n, lo.value, hi.value, list(cuts)
+
     def last_error(self):
         e = self.lib.ps_last_error()
         return e.decode() if e else ""

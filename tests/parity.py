@@ -32,6 +32,15 @@ SCENE_CASES = {
 }
 
 
+# scenes for the slab-decomposed runs (nz >= 16 * ranks; reduced regions tiled with padding >= 1)
+DIST_CASES = {
+    "blob48_tile8": lambda: (scenes.blob_scene(48, seed=21, tile=8, pad=1), {}),
+    "box48_uniform": lambda: (scenes.box_scene(48, doReduced=0, tolerance=1e-6), {}),
+    "blob_36x40x64_tile16": lambda: (scenes.blob_scene((36, 40, 64), seed=8, tile=16, pad=2), {}),
+    "blob64_tile16": lambda: (scenes.blob_scene(64, seed=13, tile=16, pad=2), {}),
+}
+
+
 def empty_scene():
     """No liquid at all: every count is 0, the solve is trivially successful."""
     sc = scenes.box_scene(16, doReduced=1)
@@ -108,3 +117,50 @@ def run_case(name, lib_path=None, solve=True):
         check_solve(sc, o, s, ov)
     s.close()
     return o
+
+
+def check_distributed(case, ranks):
+    """`ranks`: per-rank result dicts written by tests/dist_worker.py (or the GPU twin); merged and compared with the oracle."""
+    sc, ov = DIST_CASES[case]()
+    o = Oracle(sc, **ov).setup()
+    world = len(ranks)
+    cuts = list(ranks[0]["cuts"])
+    assert cuts[0] == 0 and cuts[-1] == sc.nz and all(b > a and a % 16 == 0 for a, b in zip(cuts[:-1], cuts[1:]))
+    for r in ranks:
+        assert int(r["nranks"]) == world and list(r["cuts"]) == cuts
+        # the classification is replicated and bit-exact on every rank
+        for k in COUNTS:
+            assert o.count(k) == int(r["count_" + k]), f"rank {int(r['rank'])} count {k}"
+        for slot in range(7):
+            for kind, name in ((0, "labels"), (1, "active"), (2, "reduced")):
+                assert np.array_equal(o.index_field(kind, slot), r[f"{name}{slot}"].astype(np.int64)), f"{name} slot {slot} on rank {int(r['rank'])}"
+    # every global vector is the sum of the ranks' shares
+    tot = lambda key: sum(r[key] for r in ranks)
+    assert rel(o.vector("b"), tot("vec_b")) <= 1e-10, f"b rel {rel(o.vector('b'), tot('vec_b')):.2e}"
+    for v in ("reducedRHS", "BinvDense", "MrDense"):
+        assert rel(o.vector(v), tot("vec_" + v)) <= 1e-8, f"{v} rel {rel(o.vector(v), tot('vec_' + v)):.2e}"
+    n = o.count("nSystemSize")
+    if n:
+        x = np.random.default_rng(0).standard_normal(n)
+        assert rel(o.apply(x), tot("apply")) <= 1e-12, f"apply rel {rel(o.apply(x), tot('apply')):.2e}"
+    ro = o.solve()
+    ovel, ovalid = o.writeback()
+    its = [int(r["iterations"]) for r in ranks]
+    assert all(int(r["rc"]) == ro for r in ranks) and len(set(its)) == 1, f"results {[int(r['rc']) for r in ranks]} iterations {its} (oracle {ro})"
+    io = o.count("iterations")
+    assert abs(io - its[0]) <= max(2, int(0.01 * io)), f"iterations oracle {io} vs {its[0]}"
+    tol = 10 * dict(sc.params, **ov)["tolerance"]
+    for a in range(3):
+        merged = np.empty_like(ovel[a])
+        for r in ranks:
+            lo, hi = int(r["zlo"]), int(r["zhi"])
+            assert np.array_equal(r[f"valid{a}"], ovalid[a]), f"valid axis {a} rank {int(r['rank'])}"
+            top = hi + 1 if (a == 2) else hi          # z-faces: the closure of the slab
+            merged[lo:top] = r[f"vel{a}"][lo:top]
+            if a == 2 and lo > 0:                     # the shared plane must agree with the lower rank's copy
+                below = [q for q in ranks if int(q["zhi"]) == lo][0]
+                assert np.array_equal(below["vel2"][lo], r["vel2"][lo]), f"shared z-face plane {lo} differs between ranks"
+        scale = max(float(np.abs(ovel[a]).max()), 1e-30)
+        assert float(np.abs(ovel[a] - merged).max()) <= tol * scale, f"velocity axis {a}: {float(np.abs(ovel[a] - merged).max()) / scale:.2e}"
+    assert all(bool(r["repeat_ok"]) for r in ranks), "second step on the same handle differs"
+    return io, its[0]
