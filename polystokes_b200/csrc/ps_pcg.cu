@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(OpArgs A, const doub
 #pragma unroll 1
     for (int k = 0; k < A.rowsK.n; ++k) {       // owned row ranges: x, y, z faces + coupled reduced rows (one range per GPU when alone)
         const int64_t end = A.rowsK.lo[k] + A.rowsK.count(k);
+#pragma unroll 2
         for (int64_t r = A.rowsK.lo[k] + tid; r < end; r += stride) {
             const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
             w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
@@ -136,6 +137,7 @@ __device__ __forceinline__ double kt_sweep(const double* __restrict__ val, const
 #pragma unroll 1
     for (int k = 0; k < set.n; ++k) {
         const int64_t end = set.lo[k] + set.count(k);
+#pragma unroll 2
         for (int64_t j = set.lo[k] + tid; j < end; j += stride) {
             double v = -kt_block_row<W>(val, col, ld, j, w);
             const double xj = (xb && (STRESS || dot)) ? xb[j] : 0.;
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(RangeSet own,
     double rr = 0., xx = 0.;
 #pragma unroll 1
     for (int k = 0; k < own.n; ++k)
+#pragma unroll 4
     for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) {
         const double xi = x[i] + alpha * p[i], ri = r[i] - alpha * Ap[i];
         x[i] = xi; r[i] = ri;
