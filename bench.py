@@ -282,8 +282,9 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": elapsed / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": dict(config, parallelism="single GPU" if world == 1 else
-                                                   f"z-slab decomposition over {world} GPUs, cuts {part[4]} (one process per GPU; NCCL halo exchange of p and w + "
-                                                   "2 scalar all-reduces per CG iteration; classification replicated)",
+                                                   f"z-slab decomposition over {world} GPUs, cuts {part[4]} (one process per GPU; per CG iteration: halo exchange of p and w + "
+                                                   "2 scalar all-reduces, " + ("fused into the kernels over NVLink peer memory" if solver.count("peerTransport") else "NCCL") +
+                                                   "; classification replicated)",
                                                    counts=counts, timing="wall clock between device synchronisations (the step has host-side control points); "
                                                    "device_ms_per_step = sum of per-stage CUDA-event times"),
                "device_ms_per_step": dev_ms / a.steps, "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},

@@ -191,6 +191,7 @@ int ps_comm_init(ps_handle h, int rank, int nranks, const void* id128) {
     return guarded([&] {
         PS_CUDA(cudaSetDevice(h->S->P.device));
         h->S->initComm(make_nccl_comm(rank, nranks, id128));
+        h->S->setupPeer();
         return (int)PS_SUCCESS;
     });
 }
@@ -253,6 +254,7 @@ int64_t ps_get_count(ps_handle h, const char* name) {
     if (n == "nPressures") return C.nPressures; if (n == "nStresses") return C.nStresses;
     if (n == "nTotalDOFs") return C.nTotalDOFs; if (n == "nSystemSize") return C.nSystemSize;
     if (n == "regionCount") return S.RG.count; if (n == "iterations") return S.solveIterations;
+    if (n == "peerTransport") return S.peer.on ? 1 : 0;
     if (n == "result") return S.result; if (n == "usedBiCGStab") return S.usedBiCGStab;
     if (n == "nRowsExt") return C.nRowsExt; if (n == "fixLoops") return S.fixLoops;
     return INT64_MIN;

@@ -18,6 +18,7 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -38,6 +39,7 @@ NcclApi& nccl() {
     PS_NCCL_SYM(CommDestroy, "ncclCommDestroy");
     PS_NCCL_SYM(GetErrorString, "ncclGetErrorString");
     PS_NCCL_SYM(AllReduce, "ncclAllReduce");
+    PS_NCCL_SYM(AllGather, "ncclAllGather");
     PS_NCCL_SYM(Send, "ncclSend");
     PS_NCCL_SYM(Recv, "ncclRecv");
     PS_NCCL_SYM(GroupStart, "ncclGroupStart");
@@ -57,6 +59,10 @@ struct NcclComm : Comm {
     ~NcclComm() override { if (comm) nccl().CommDestroy(comm); }
     void allreduce_sum(double* buf, int n, cudaStream_t st) override {
         PS_NCCL(nccl().AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, comm, st));
+        PS_COUNT_LAUNCH(1);
+    }
+    void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) override {
+        PS_NCCL(nccl().AllGather(send, recv, bytes, ncclChar, comm, st));
         PS_COUNT_LAUNCH(1);
     }
     void sendrecv(int npeers, const int* peers, const void* const* sendBuf, const size_t* sendBytes, void* const* recvBuf, const size_t* recvBytes, cudaStream_t st) override {
@@ -99,6 +105,7 @@ namespace {
 struct CallbackComm : Comm {
     ps_allreduce_cb ar; ps_sendrecv_cb sr; void* ctx;
     void allreduce_sum(double* buf, int n, cudaStream_t) override { ar(ctx, buf, n); }
+    void allgather(const void*, void*, size_t, cudaStream_t) override { throw Error("allgather: not available in the emulation twin"); }
     void sendrecv(int npeers, const int* peers, const void* const* sendBuf, const size_t* sendBytes, void* const* recvBuf, const size_t* recvBytes, cudaStream_t) override {
         sr(ctx, npeers, peers, sendBuf, sendBytes, recvBuf, recvBytes);
     }

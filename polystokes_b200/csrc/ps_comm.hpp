@@ -16,6 +16,8 @@ struct Comm {
     virtual ~Comm() {}
     // in-place sum of n doubles living in device memory
     virtual void allreduce_sum(double* buf, int n, cudaStream_t st) = 0;
+    // every rank contributes `bytes` from send; recv receives nranks * bytes in rank order (device buffers)
+    virtual void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
     // one grouped exchange: for every i send sendBytes[i] from sendBuf[i] to peers[i] and receive recvBytes[i] into recvBuf[i]
     virtual void sendrecv(int npeers, const int* peers, const void* const* sendBuf, const size_t* sendBytes,
                           void* const* recvBuf, const size_t* recvBytes, cudaStream_t st) = 0;

@@ -19,7 +19,11 @@ struct RangeSetN {
     int n = 0;
     int64_t lo[N] = {};
     int64_t pre[N + 1] = {};     // pre[k] = items before range k; pre[n] = total
-    void add(int64_t a, int64_t b) { if (b < a) b = a; lo[n] = a; pre[n + 1] = pre[n] + (b - a); ++n; }
+    void add(int64_t a, int64_t b) {             // adjacent ranges are merged, empty ones dropped: one GPU => one range
+        if (b <= a) return;
+        if (n > 0 && lo[n - 1] + count(n - 1) == a) { pre[n] += b - a; return; }
+        lo[n] = a; pre[n + 1] = pre[n] + (b - a); ++n;
+    }
     PS_HD int64_t total() const { return pre[n]; }
     PS_HD int64_t count(int k) const { return pre[k + 1] - pre[k]; }
     PS_HD int64_t at(int64_t l) const {
@@ -33,6 +37,26 @@ struct RangeSetN {
 #pragma unroll
         for (int i = 0; i < N; ++i) if (i < n && gidx >= lo[i] && gidx < lo[i] + (pre[i + 1] - pre[i])) in = true;
         return in;
+    }
+};
+// Grid-stride walk over the concatenation of the ranges: thread t visits local items t, t+stride, ... so the work
+// is balanced over the whole set (no per-range tail), and the common step is one add + one compare.
+template <int N>
+struct RangeWalk {
+    int k; int64_t j, end;
+    PS_HD RangeWalk(const RangeSetN<N>& s, int64_t l) {
+        k = 0;
+        while (k < s.n && l >= s.pre[k + 1]) ++k;
+        if (k < s.n) { j = s.lo[k] + (l - s.pre[k]); end = s.lo[k] + s.count(k); } else { j = 0; end = 0; }
+    }
+    PS_HD bool valid(const RangeSetN<N>& s) const { return k < s.n; }
+    PS_HD void step(const RangeSetN<N>& s, int64_t stride) {
+        j += stride;
+        while (j >= end) {
+            const int64_t over = j - end;
+            if (++k >= s.n) return;
+            j = s.lo[k] + over; end = s.lo[k] + s.count(k);
+        }
     }
 };
 typedef RangeSetN<7> RangeSet;    // the system vector: p | xx | yy | zz | yz | xz | xy

@@ -13,6 +13,7 @@
 //            the p.Ap dot product (warp shuffle -> CTA partial -> last CTA finishes in fixed order)
 // All CG scalars live in device memory; the host only polls a convergence flag every few iterations.
 #include "ps_solver.hpp"
+#include "ps_peer.hpp"
 
 namespace ps {
 
@@ -48,7 +49,8 @@ PS_D double sum_partials(const double* p, int n) { double s = 0.; for (int i = 0
 // global value.  alpha = rsold / p.Ap (pcg.h:313).
 PS_D double cg_alpha(const PcgScalars* S) { return S->rsold / S->red[0]; }
 // stop test of pcg.h:316-325: min(rr, rr/xx) < tol^2
-PS_D double cg_rre(const PcgScalars* S) { const double rr = S->red[1], xx = S->red[2]; double rre = rr; if (rr / xx < rre) rre = rr / xx; return rre; }
+PS_D double cg_rre2(double rr, double xx) { double rre = rr; if (rr / xx < rre) rre = rr / xx; return rre; }
+PS_D double cg_rre(const PcgScalars* S) { return cg_rre2(S->red[1], S->red[2]); }
 // once per iteration, after every reader of rsold is done (last CTA of the p update): pcg.h:326-336
 PS_D void cg_advance(PcgScalars* S) {
     const double rr = S->red[1];
@@ -114,19 +116,22 @@ __device__ __forceinline__ double kt_block_row(const double* __restrict__ val, c
 __global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
     if (S && S->done) return;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-#pragma unroll 1
-    for (int k = 0; k < A.rowsK.n; ++k) {       // owned row ranges: x, y, z faces + coupled reduced rows (one range per GPU when alone)
-        const int64_t end = A.rowsK.lo[k] + A.rowsK.count(k);
+    // owned rows: one range on a single GPU; x, y, z faces + coupled reduced rows of the slab otherwise
 #pragma unroll 2
-        for (int64_t r = A.rowsK.lo[k] + tid; r < end; r += stride) {
-            const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
-            w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
-        }
+    for (RangeWalk<4> it(A.rowsK, tid); it.valid(A.rowsK); it.step(A.rowsK, stride)) {
+        const int64_t r = it.j;
+        const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
+        w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
     }
 }
-// y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) and finish p.Ap / alpha in the last CTA.
-// The three row blocks (pressure 6-wide, centre stress 2-wide, edge stress 4-wide) are swept by separate
-// grid-stride loops so each loop body is branch-free and fully unrolled.
+// last CTA of a producer: a, b are valid in thread 0; every rank's block receives this rank's partial sums
+__device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, double a, double b, int nvals) {
+    __shared__ double pv[2];
+    if (threadIdx.x == 0) { pv[0] = a; pv[1] = b; }
+    __syncthreads();
+    const double vals[2] = {pv[0], pv[1]};
+    peer_reduce_push(P, slot, vals, nvals);
+}
 // one row block of K_ext^T (width W) over the owned row ranges; all pointers are pre-offset to the block so the
 // loop carries a single index.  Returns this thread's share of dot(x, y).
 template <int W, bool STRESS>
@@ -134,23 +139,20 @@ __device__ __forceinline__ double kt_sweep(const double* __restrict__ val, const
                                            const double* __restrict__ w, const double* __restrict__ xb, double* __restrict__ yb, const double* __restrict__ uInv,
                                            double muScale, const double* __restrict__ addb, bool dot) {
     double acc = 0.;
-#pragma unroll 1
-    for (int k = 0; k < set.n; ++k) {
-        const int64_t end = set.lo[k] + set.count(k);
 #pragma unroll 2
-        for (int64_t j = set.lo[k] + tid; j < end; j += stride) {
-            double v = -kt_block_row<W>(val, col, ld, j, w);
-            const double xj = (xb && (STRESS || dot)) ? xb[j] : 0.;
-            if (STRESS && muScale != 0.) v -= muScale * uInv[j] * xj;
-            if (addb) v += addb[j];
-            yb[j] = v;
-            acc += xj * v;
-        }
+    for (RangeWalk<4> it(set, tid); it.valid(set); it.step(set, stride)) {
+        const int64_t j = it.j;
+        double v = -kt_block_row<W>(val, col, ld, j, w);
+        const double xj = (xb && (STRESS || dot)) ? xb[j] : 0.;
+        if (STRESS && muScale != 0.) v -= muScale * uInv[j] * xj;
+        if (addb) v += addb[j];
+        yb[j] = v;
+        acc += xj * v;
     }
     return acc;
 }
 __global__ void __launch_bounds__(HOT_THREADS, 6) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
-                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode) {
+                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {
     if (S && S->done) return;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const bool dot = mode & 1;
@@ -161,19 +163,24 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) pass2_kernel(const __grid_cons
     if (dot) {
         const double bs = block_sum(acc);
         if (threadIdx.x == 0) dotPartial[blockIdx.x] = bs;
-        if (last_block(&S->ticket[0])) { const double t = block_sum_partials(dotPartial, gridDim.x); if (threadIdx.x == 0) S->red[0] = t; }
+        if (last_block(&S->ticket[0])) {
+            const double t = block_sum_partials(dotPartial, gridDim.x);
+            if (threadIdx.x == 0) S->red[0] = t;
+            if (P.nranks > 1) publish_partials(P, 0, t, 0., 1);     // fused all-reduce, producer side (ps_peer.hpp)
+        }
     }
 }
 __global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(RangeSet own, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap,
-                                                                  double* dotPartial, PcgScalars* S) {
+                                                                  double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P) {
     if (S->done) return;
-    const double alpha = cg_alpha(S);
+    double pAp = S->red[0];
+    if (P.nranks > 1 && !peer_reduce_wait(P, 0, &pAp, 1)) { if (threadIdx.x == 0) S->peerError = 1; return; }    // fused all-reduce, consumer side
+    const double alpha = S->rsold / pAp;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     double rr = 0., xx = 0.;
-#pragma unroll 1
-    for (int k = 0; k < own.n; ++k)
 #pragma unroll 4
-    for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) {
+    for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) {
+        const int64_t i = it.j;
         const double xi = x[i] + alpha * p[i], ri = r[i] - alpha * Ap[i];
         x[i] = xi; r[i] = ri;
         rr += ri * ri; xx += xi * xi;
@@ -182,28 +189,31 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(RangeSet own,
     if (threadIdx.x == 0) { dotPartial[blockIdx.x] = brr; dotPartial[gridDim.x + blockIdx.x] = bxx; }
     if (last_block(&S->ticket[1])) {
         const double trr = block_sum_partials(dotPartial, gridDim.x), txx = block_sum_partials(dotPartial + gridDim.x, gridDim.x);
-        if (threadIdx.x == 0) { S->red[1] = trr; S->red[2] = txx; S->alpha = alpha; }
+        if (threadIdx.x == 0) { S->red[1] = trr; S->red[2] = txx; S->alpha = alpha; if (P.nranks > 1) S->red[0] = pAp; }
+        if (P.nranks > 1) publish_partials(P, 1, trr, txx, 2);
     }
 }
 // p = r + beta p unless the stop test fired; the last CTA then advances the CG state (every CTA has read rsold by then)
-__global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, double* __restrict__ p, const double* __restrict__ r, PcgScalars* S) {
+__global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, double* __restrict__ p, const double* __restrict__ r, PcgScalars* S, const __grid_constant__ PeerCtx P) {
     if (S->done) return;
-    const bool converged = cg_rre(S) < S->tol2;
-    const double beta = S->red[1] / S->rsold;
+    double rx[2] = {S->red[1], S->red[2]};
+    if (P.nranks > 1 && !peer_reduce_wait(P, 1, rx, 2)) { if (threadIdx.x == 0) S->peerError = 1; return; }
+    const bool converged = cg_rre2(rx[0], rx[1]) < S->tol2;
+    const double beta = rx[0] / S->rsold;
     if (!converged) {
         const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     #pragma unroll 1
     for (int k = 0; k < own.n; ++k)
             for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) p[i] = r[i] + beta * p[i];
     }
-    if (last_block(&S->ticket[3]) && threadIdx.x == 0) cg_advance(S);
+    if (last_block(&S->ticket[3]) && threadIdx.x == 0) { S->red[1] = rx[0]; S->red[2] = rx[1]; cg_advance(S); }
 }
-__global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, const double* __restrict__ b, double* x, double* r, double* p, double* dotPartial, PcgScalars* S, double tol, int maxIter) {
+__global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, const double* __restrict__ b, double* x, double* r, double* p, double* dotPartial, PcgScalars* S, double tol, int maxIter,
+                                                             const __grid_constant__ PeerCtx P) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     double rr = 0.;
-#pragma unroll 1
-    for (int k = 0; k < own.n; ++k)
-    for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) {
+    for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) {
+        const int64_t i = it.j;
         const double bi = b[i];
         x[i] = 0.; r[i] = bi; p[i] = bi; rr += bi * bi;
     }
@@ -215,11 +225,60 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, cons
             S->rsold = 0.; S->pAp = 0.; S->alpha = 0.; S->beta = 0.; S->rsnew = 0.; S->xmag = 0.; S->rre = 0.;
             S->red[0] = 0.; S->red[1] = 0.; S->red[2] = 0.; S->red[3] = rs;
             S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
+            S->ticket[0] = 0; S->ticket[1] = 0; S->ticket[3] = 0;      // nothing else is in flight: heal tickets after an aborted solve
         }
+        if (P.nranks > 1) publish_partials(P, 2, rs, 0., 1);
     }
 }
 // after the all-reduce of b.b: rsold, and the b == 0 early out
-__global__ void cg_begin_kernel(PcgScalars* S) { S->rsold = S->red[3]; S->done = (S->red[3] == 0.) ? 1 : 0; }
+__global__ void cg_begin_kernel(PcgScalars* S, const __grid_constant__ PeerCtx P) {
+    double bb = S->red[3];
+    if (P.nranks > 1 && !peer_reduce_wait(P, 2, &bb, 1)) { if (threadIdx.x == 0) { S->peerError = 1; S->done = 1; } return; }
+    if (threadIdx.x == 0) { S->red[3] = bb; S->rsold = bb; S->done = (bb == 0.) ? 1 : 0; }
+}
+// halo exchange over peer memory, sender side: gather the boundary entries and store them straight into the
+// neighbours' receive buffers (NVLink), then raise their sequence flags once every CTA's stores are fenced
+__global__ void __launch_bounds__(256) halo_push_kernel(int64_t n0, int64_t n1, const int32_t* __restrict__ idx, const double* __restrict__ v,
+                                                       double* __restrict__ dst0, double* __restrict__ dst1, unsigned long long* flag0, unsigned long long* flag1,
+                                                       unsigned long long seq, PcgScalars* S, int respectDone, unsigned int* ticket) {
+    if (respectDone && S->done) return;
+    const int64_t n = n0 + n1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double val = v[idx[i]];
+        if (i < n0) dst0[i] = val; else dst1[i - n0] = val;
+    }
+    // One system fence per CTA, not per thread (membar.sys by every warp costs ~20 us here): the CTA barrier orders
+    // all threads' stores before thread 0's fence, the fence makes them visible system-wide before the ticket,
+    // and the last CTA's release store publishes the flag after every CTA's fence (cumulative).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            if (flag0) peer_st_flag(flag0, seq);
+            if (flag1) peer_st_flag(flag1, seq);
+        }
+    }
+}
+// receiver side: wait for the neighbours' flags, then scatter the received entries into the global-length vector
+__global__ void __launch_bounds__(256) halo_wait_unpack_kernel(int64_t n0, int64_t n1, const int32_t* __restrict__ idx, const double* src0, const double* src1,
+                                                              const unsigned long long* flag0, const unsigned long long* flag1, unsigned long long seq,
+                                                              double* __restrict__ v, PcgScalars* S, int respectDone) {
+    if (respectDone && S->done) return;
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        bool good = true;
+        if (flag0) good = peer_wait_flag(flag0, seq) && good;
+        if (flag1) good = peer_wait_flag(flag1, seq) && good;
+        ok = good ? 1 : 0;
+    }
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) S->peerError = 1; return; }
+    const int64_t n = n0 + n1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[idx[i]] = __ldcg(i < n0 ? src0 + i : src1 + (i - n0));
+}
 __global__ void __launch_bounds__(256) halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf, const PcgScalars* S) {
     if (S && S->done) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] = v[idx[i]];
@@ -253,34 +312,48 @@ void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, doubl
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, int, PcgScalars* scal, int mode) {
-    pass2_kernel<<<hot_blocks(pass2_kernel, A.rowsP.total() + A.rowsC.total() + A.rowsE.total()), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode);
+void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode) {
+    pass2_kernel<<<hot_blocks(pass2_kernel, A.rowsP.total() + A.rowsC.total() + A.rowsE.total()), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_update_xr(cudaStream_t st, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal) {
-    cg_update_xr_kernel<<<hot_blocks(cg_update_xr_kernel, own.total()), HOT_THREADS, 0, st>>>(own, x, r, p, Ap, dotPartial, scal);
+void k_cg_update_xr(cudaStream_t st, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P) {
+    cg_update_xr_kernel<<<hot_blocks(cg_update_xr_kernel, own.total()), HOT_THREADS, 0, st>>>(own, x, r, p, Ap, dotPartial, scal, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_update_p(cudaStream_t st, const RangeSet& own, double* p, const double* r, PcgScalars* scal) {
-    cg_update_p_kernel<<<hot_blocks(cg_update_p_kernel, own.total()), HOT_THREADS, 0, st>>>(own, p, r, scal);
+void k_cg_update_p(cudaStream_t st, const RangeSet& own, double* p, const double* r, PcgScalars* scal, const PeerCtx& P) {
+    cg_update_p_kernel<<<hot_blocks(cg_update_p_kernel, own.total()), HOT_THREADS, 0, st>>>(own, p, r, scal, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_init(cudaStream_t st, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter) {
-    cg_init_kernel<<<hot_blocks(cg_init_kernel, own.total()), HOT_THREADS, 0, st>>>(own, b, x, r, p, dotPartial, scal, tol, maxIter);
+void k_cg_init(cudaStream_t st, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P) {
+    cg_init_kernel<<<hot_blocks(cg_init_kernel, own.total()), HOT_THREADS, 0, st>>>(own, b, x, r, p, dotPartial, scal, tol, maxIter, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_begin(cudaStream_t st, PcgScalars* scal) {
-    cg_begin_kernel<<<1, 1, 0, st>>>(scal);
+void k_cg_begin(cudaStream_t st, PcgScalars* scal, const PeerCtx& P) {
+    cg_begin_kernel<<<1, 32, 0, st>>>(scal, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_pack(cudaStream_t st, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) {
     if (n <= 0) return;
     halo_pack_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, 0, st>>>(n, idx, v, buf, S);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_halo_push_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
+                      unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket) {
+    const int64_t n = n0 + n1;
+    halo_push_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, 0, st>>>(n0, n1, idx, v, dst0, dst1, flag0, flag1, seq, S, respectDone ? 1 : 0, ticket);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_halo_unpack_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* src0, const double* src1, const unsigned long long* flag0, const unsigned long long* flag1,
+                        unsigned long long seq, double* v, PcgScalars* S, bool respectDone) {
+    const int64_t n = n0 + n1;
+    halo_wait_unpack_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 2)), 256, 0, st>>>(n0, n1, idx, src0, src1, flag0, flag1, seq, v, S, respectDone ? 1 : 0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -295,7 +368,7 @@ void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double a
     if (S && S->done) return;
     for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInv[r] * s : s; }
 }
-void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, int, PcgScalars* S, int mode) {
+void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode) {
     if (S && S->done) return;
     double acc = 0.;
     auto row = [&](int64_t j) {
@@ -310,27 +383,27 @@ void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, do
     for (int64_t l = 0; l < A.rowsE.total(); ++l) row(A.nP + 3 * A.nC + A.rowsE.at(l));
     if (mode & 1) S->red[0] = acc;
 }
-void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double*, PcgScalars* S) {
+void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double*, PcgScalars* S, const PeerCtx&) {
     if (S->done) return;
     const double alpha = cg_alpha(S);
     double rr = 0., xx = 0.;
     for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rr += r[i] * r[i]; xx += x[i] * x[i]; }
     S->red[1] = rr; S->red[2] = xx; S->alpha = alpha;
 }
-void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* S) {
+void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* S, const PeerCtx&) {
     if (S->done) return;
     const bool converged = cg_rre(S) < S->tol2;
     const double beta = S->red[1] / S->rsold;
     if (!converged) for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); p[i] = r[i] + beta * p[i]; }
     cg_advance(S);
 }
-void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double*, PcgScalars* S, double tol, int maxIter) {
+void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double*, PcgScalars* S, double tol, int maxIter, const PeerCtx&) {
     double rr = 0.;
     for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); x[i] = 0.; r[i] = b[i]; p[i] = b[i]; rr += b[i] * b[i]; }
     S->rsold = S->pAp = S->alpha = S->beta = S->rsnew = S->xmag = S->rre = 0.; S->red[0] = S->red[1] = S->red[2] = 0.; S->red[3] = rr;
     S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
 }
-void k_cg_begin(cudaStream_t, PcgScalars* S) { S->rsold = S->red[3]; S->done = (S->red[3] == 0.) ? 1 : 0; }
+void k_cg_begin(cudaStream_t, PcgScalars* S, const PeerCtx&) { S->rsold = S->red[3]; S->done = (S->red[3] == 0.) ? 1 : 0; }
 void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) buf[i] = v[idx[i]]; }
 void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) v[idx[i]] = buf[i]; }
 #endif

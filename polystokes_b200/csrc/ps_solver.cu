@@ -98,7 +98,74 @@ void Solver::initComm(Comm* c) {
     haveSetup = false;
 }
 
+// ---- NVLink peer-memory transport (ps_peer.hpp) ----
+void Solver::closePeer() {
+#ifndef PS_EMULATE
+    if (st) cudaStreamSynchronize(st);
+    for (int r = 0; r < PEER_MAX_RANKS; ++r) {
+        if (!peer.block[r]) continue;
+        if (r == peer.rank) cudaFree(peer.block[r]); else cudaIpcCloseMemHandle(peer.block[r]);
+        peer.block[r] = nullptr;
+    }
+#endif
+    peer = PeerLink();
+}
+
+// Collective.  Every rank allocates its symmetric block (flags + reduction slots + 8 halo receive buffers), the IPC
+// handles travel by one NCCL all-gather, every rank maps every other block.  Any failure on any rank (no peer
+// access, IPC refused) switches ALL ranks back to the NCCL path -- agreed on with one all-reduce.
+void Solver::setupPeer() {
+#ifndef PS_EMULATE
+    closePeer();
+    if (!comm || !part.multi() || part.nranks > PEER_MAX_RANKS) return;
+    const char* env = getenv("PS_COMM");
+    if (env && std::string(env) == "nccl") return;
+    peer.rank = part.rank; peer.nranks = part.nranks;
+    peer.cap = (size_t)12 * (g.nx + 1) * (g.ny + 1);
+    double okLocal = 1.;
+    void* mine = nullptr;
+    if (cudaMalloc(&mine, peer.bytes()) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; mine = nullptr; }
+    cudaIpcMemHandle_t hMine; memset(&hMine, 0, sizeof hMine);
+    if (mine) {
+        PS_CUDA(cudaMemsetAsync(mine, 0, peer.bytes(), st));
+        if (cudaIpcGetMemHandle(&hMine, mine) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; }
+    }
+    DBuf<uint8_t> dSend, dAll;
+    DBuf<double> dOk;
+    dSend.alloc(sizeof hMine); dAll.alloc(sizeof hMine * (size_t)part.nranks); dOk.alloc(1);
+    copy_h2d(dSend.p, &hMine, sizeof hMine, st);
+    comm->allgather(dSend.p, dAll.p, sizeof hMine, st);
+    std::vector<uint8_t> all = dAll.to_host(st, sizeof hMine * (size_t)part.nranks);
+    peer.block[part.rank] = mine;
+    if (okLocal > 0.) {
+        for (int r = 0; r < part.nranks && okLocal > 0.; ++r) {
+            if (r == part.rank) continue;
+            cudaIpcMemHandle_t h; memcpy(&h, all.data() + sizeof h * (size_t)r, sizeof h);
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; break; }
+            peer.block[r] = ptr;
+        }
+    }
+    copy_h2d(dOk.p, &okLocal, sizeof(double), st);
+    comm->allreduce_sum(dOk.p, 1, st);            // also the barrier: every block is zeroed before anybody writes into it
+    double okAll = 0.;
+    copy_d2h(&okAll, dOk.p, sizeof(double), st);
+    if (okAll < part.nranks - 0.5) { const int rk = part.rank, n = part.nranks; closePeer(); peer.rank = rk; peer.nranks = n; return; }
+    peer.on = true;
+#endif
+}
+
+PeerCtx Solver::reduceCtx(int slotIn, int slotOut) {
+    PeerCtx c = peer.ctx();
+    if (peer.on) {
+        if (slotIn >= 0) c.seqIn = peer.seqRed[slotIn];           // produced by the previous kernel of the chain
+        if (slotOut >= 0) c.seqOut = ++peer.seqRed[slotOut];
+    }
+    return c;
+}
+
 Solver::~Solver() {
+    closePeer();
     delete comm;
 #ifndef PS_EMULATE
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -421,9 +488,9 @@ RowSet Solver::rowsE(int k) const {   // numbering inside the edge-stress block 
 RangeSet Solver::rowsSys(int k) const {  // x = [p | xx | yy | zz | yz | xz | xy]
     RangeSet r;
     const RowSet p = rowsP(k), c = rowsC(k), e = rowsE(k);
-    r.add(p.lo[0], p.lo[0] + p.total());
-    for (int a = 0; a < 3; ++a) r.add(C.nPressures + c.lo[a], C.nPressures + c.lo[a] + (c.pre[a + 1] - c.pre[a]));
-    for (int a = 0; a < 3; ++a) r.add(C.nPressures + 3 * C.nCenter + e.lo[a], C.nPressures + 3 * C.nCenter + e.lo[a] + (e.pre[a + 1] - e.pre[a]));
+    for (int i = 0; i < p.n; ++i) r.add(p.lo[i], p.lo[i] + p.count(i));
+    for (int i = 0; i < c.n; ++i) r.add(C.nPressures + c.lo[i], C.nPressures + c.lo[i] + c.count(i));
+    for (int i = 0; i < e.n; ++i) r.add(C.nPressures + 3 * C.nCenter + e.lo[i], C.nPressures + 3 * C.nCenter + e.lo[i] + e.count(i));
     return r;
 }
 void Solver::computeOwnership() {
@@ -470,6 +537,27 @@ void Solver::buildHalos() {
 // pack -> grouped send/recv with the z-neighbours -> scatter into the global-length vector
 void Solver::exchange(Halo& H, double* v, const PcgScalars* S) {
     if (!part.multi() || !comm) return;
+#ifndef PS_EMULATE
+    if (peer.on) {
+        // sender stores straight into the neighbour's receive buffer over NVLink and raises its flag; the receiver
+        // waits on its own flag and scatters.  My lower neighbour sees me as its "above" side (1), the upper one as "below" (0).
+        const int kind = (&H == &haloW) ? 1 : 0;
+        const unsigned long long seq = ++peer.seqHalo[kind];
+        const int par = (int)(seq & 1ull);
+        for (int i = 0; i < 2; ++i) if ((size_t)H.nSend[i] > peer.cap || (size_t)H.nRecv[i] > peer.cap) throw Error("halo larger than the peer receive buffer");
+        double* dst[2] = {nullptr, nullptr}; unsigned long long* dflag[2] = {nullptr, nullptr};
+        const double* src[2] = {nullptr, nullptr}; const unsigned long long* sflag[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; ++i) {
+            const int pr = H.peers[i];
+            if (pr < 0) continue;
+            dst[i] = peer.recv(pr, kind, par, 1 - i); dflag[i] = &peer.sync(pr)->haloFlag[kind][par][1 - i];
+            src[i] = peer.recv(part.rank, kind, par, i); sflag[i] = &peer.sync(part.rank)->haloFlag[kind][par][i];
+        }
+        k_halo_push_peer(st, H.nSend[0], H.nSend[1], H.sendIdx.p, v, dst[0], dst[1], dflag[0], dflag[1], seq, scal.p, S != nullptr, &scal.p->ticket[4 + kind]);
+        k_halo_unpack_peer(st, H.nRecv[0], H.nRecv[1], H.recvIdx.p, src[0], src[1], sflag[0], sflag[1], seq, v, scal.p, S != nullptr);
+        return;
+    }
+#endif
     k_halo_pack(st, H.sendTotal(), H.sendIdx.p, v, H.sendBuf.p, S);
     const void* sb[2] = {H.sendBuf.p, H.sendBuf.p + H.nSend[0]};
     void* rb[2] = {H.recvBuf.p, H.recvBuf.p + H.nRecv[0]};
@@ -478,7 +566,7 @@ void Solver::exchange(Halo& H, double* v, const PcgScalars* S) {
     comm->sendrecv(2, H.peers, sb, sbytes, rb, rbytes, st);
     k_halo_unpack(st, H.recvTotal(), H.recvIdx.p, H.recvBuf.p, v, S);
 }
-void Solver::allreduce(double* devBuf, int n) { if (part.multi() && comm) comm->allreduce_sum(devBuf, n, st); }
+void Solver::allreduce(double* devBuf, int n) { if (part.multi() && comm && !peer.on) comm->allreduce_sum(devBuf, n, st); }
 
 static OpArgs make_op(const Solver& S) {
     OpArgs A;
@@ -503,7 +591,7 @@ void Solver::assemble() {
         reduced_expand(st, g, RG, w.p + C.nActiveVs, g.invDt, nullptr);
     }
     exchange(haloW, w.p, nullptr);            // the neighbours' coupled reduced rows (active rows are replicated above)
-    k_pass2(st, A, w.p, nullptr, b.p, 0.0, rhsPT.p, nullptr, 0, nullptr, 0);
+    k_pass2(st, A, w.p, nullptr, b.p, 0.0, rhsPT.p, nullptr, PeerCtx(), nullptr, 0);
 }
 
 // y = A x (ApplyPressureStressMatrix::applyMatrixVectorProducts, Apply.h:102-179)
@@ -516,7 +604,7 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
         reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     }
     exchange(haloW, w.p, nullptr);
-    k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, 0, nullptr, 0);
+    k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, PeerCtx(), nullptr, 0);
 }
 
 void Solver::timedOperator(int which) {
@@ -524,7 +612,7 @@ void Solver::timedOperator(int which) {
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
     if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
     else if (which == 3 && RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
-    else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, 0, nullptr, 0);
+    else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, PeerCtx(), nullptr, 0);
 }
 
 // solveSPDwithMatrixVectorPCG (S.cpp:734-812) -> pcg_external_matrix_A (pcg.h:268-340): identity
@@ -539,33 +627,56 @@ int Solver::solve() {
     usedBiCGStab = 0;
     PcgScalars h; memset(&h, 0, sizeof h);
     if (n == 0) { solveIterations = 0; solveError = 0; result = R_SUCCESS; return result; }
-    k_cg_init(st, ownSys, b.p, x.p, r.p, p.p, dotPartial.p, scal.p, P.tolerance, maxIt);
+    k_cg_init(st, ownSys, b.p, x.p, r.p, p.p, dotPartial.p, scal.p, P.tolerance, maxIt, reduceCtx(-1, 2));
     allreduce(scal.p->red + 3, 1);
-    k_cg_begin(st, scal.p);
+    k_cg_begin(st, scal.p, reduceCtx(2, -1));
     bool cancelled = false;
+    // PS_TRACE=<iteration>: CUDA-event timeline of that CG iteration on stderr (diagnostic; events cost a few us each)
+    static const int traceIter = getenv("PS_TRACE") ? atoi(getenv("PS_TRACE")) : -1;
+    std::vector<std::pair<const char*, double>> trace;
+#ifndef PS_EMULATE
+    std::vector<cudaEvent_t> tev; std::vector<const char*> tname;
+    auto mark = [&](bool on, const char* what) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); tname.push_back(what); };
+#else
+    auto mark = [&](bool, const char*) {};
+#endif
     for (int it = 0; it < maxIt;) {
         const int batch = std::min(every, maxIt - it);
         for (int k = 0; k < batch; ++k) {
-            exchange(haloX, p.p, scal.p);
-            k_pass1(st, A, p.p, w.p, g.dt, scal.p);
+            const bool tr = (it + k == traceIter);
+            mark(tr, "start");
+            exchange(haloX, p.p, scal.p);                       mark(tr, "halo p");
+            k_pass1(st, A, p.p, w.p, g.dt, scal.p);             mark(tr, "pass1");
             if (RG.count > 0) {
                 reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p);
                 reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p);
                 reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
             }
-            exchange(haloW, w.p, scal.p);
-            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, 0, scal.p, 1);
-            allreduce(scal.p->red, 1);
-            k_cg_update_xr(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p);
-            allreduce(scal.p->red + 1, 2);
-            k_cg_update_p(st, ownSys, p.p, r.p, scal.p);
+            mark(tr, "reduced x3");
+            exchange(haloW, w.p, scal.p);                       mark(tr, "halo w");
+            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, reduceCtx(-1, 0), scal.p, 1);   // + this rank's p.Ap to every rank
+            allreduce(scal.p->red, 1);                          mark(tr, "pass2 (+allreduce)");
+            k_cg_update_xr(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, reduceCtx(0, 1));    // global p.Ap in, r.r / x.x out
+            allreduce(scal.p->red + 1, 2);                      mark(tr, "update x,r (+allreduce)");
+            k_cg_update_p(st, ownSys, p.p, r.p, scal.p, reduceCtx(1, -1));
+            mark(tr, "update p");
         }
         it += batch;
         copy_d2h(&h, scal.p, sizeof h, st);
+#ifndef PS_EMULATE
+        if (!tev.empty()) {
+            fprintf(stderr, "[ps trace rank %d] CG iteration %d:", part.rank, traceIter);
+            for (size_t i = 1; i < tev.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, tev[i - 1], tev[i]); fprintf(stderr, "  %s %.1f us", tname[i], ms * 1e3); }
+            float tot = 0; cudaEventElapsedTime(&tot, tev.front(), tev.back()); fprintf(stderr, "  | total %.1f us\n", tot * 1e3);
+            for (auto e : tev) cudaEventDestroy(e);
+            tev.clear(); tname.clear();
+        }
+#endif
         if (h.done) break;
         if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
     }
     copy_d2h(&h, scal.p, sizeof h, st);
+    if (h.peerError) { result = R_FAILED; throw Error("a peer-memory wait timed out (another rank died or fell out of step)"); }
     if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
     // b == 0: the reference would divide 0/0 (pcg.h:313); we return x = 0 after 0 iterations instead
     solveIterations = (h.done == 1) ? h.iter : maxIt;
@@ -580,7 +691,7 @@ void Solver::recoverVelocityFromPressureStress() {
     exchange(haloX, x.p, nullptr);
     k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau)
     RowSet act;                                                      // the owned active face rows
-    for (int a = 0; a < 3; ++a) act.add(ownK.lo[a], ownK.lo[a] + (ownK.pre[a + 1] - ownK.pre[a]));
+    for (int a = 0; a < 3; ++a) act.add(C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank], C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank + 1]);
     k_recover_active(st, g, act, w.p, mcInv.p, rhsU.p, velSol.p);
     if (RG.regHi > RG.regLo) {
         reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr);

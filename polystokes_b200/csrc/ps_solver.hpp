@@ -5,6 +5,7 @@
 #include "ps_grid.hpp"
 #include "ps_part.hpp"
 #include "ps_comm.hpp"
+#include "ps_peer.hpp"
 #include "../../include/polystokes_b200.h"
 
 namespace ps {
@@ -68,7 +69,8 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     double rsold, pAp, alpha, beta, rsnew, xmag, rre;
     int iter, done, maxIter, pad;
     double tol2;
-    unsigned int ticket[4];   // last-CTA-done tickets of the fused dot products
+    unsigned int ticket[8];   // last-CTA-done tickets: 0 pass 2, 1 x/r update, 2 init, 3 p update, 4/5 halo push of p / w
+    int peerError, pad2;      // sticky: a peer-memory wait timed out (ps_peer.hpp)
     double red[4];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.x, [3] b.b
 };
 
@@ -117,7 +119,11 @@ public:
     void computeOwnership();            // owned row / DOF ranges of every rank from the replicated numbering
     void buildHalos();                  // send / receive index lists of p (system vector) and w (K_ext rows)
     void exchange(Halo& H, double* v, const PcgScalars* S);
-    void allreduce(double* devBuf, int n);
+    void allreduce(double* devBuf, int n);   // host-enqueued NCCL all-reduce; a no-op when the peer transport fuses it into the kernels
+    PeerLink peer;                      // NVLink peer-memory transport (ps_peer.hpp); off => NCCL for everything
+    void setupPeer();                   // collective: allocate + exchange + map the symmetric blocks
+    void closePeer();
+    PeerCtx reduceCtx(int slotIn, int slotOut);   // sequence numbers of the reductions one kernel consumes / produces
     RowSet rowsK(int rank) const, rowsP(int rank) const, rowsC(int rank) const, rowsE(int rank) const;
     RangeSet rowsSys(int rank) const;
     RowSet ownK, ownP, ownC, ownE;
@@ -205,14 +211,20 @@ struct OpArgs {   // everything one operator apply touches
     const double* mcInv; const double* uInv;
 };
 void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal);
-void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, int nPartials, PcgScalars* scal, int mode);
+void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode);
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal);
-void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* scal);
-void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter);
-void k_cg_begin(cudaStream_t, PcgScalars* scal);
+void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
+void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* scal, const PeerCtx& P);
+void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
+void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);
+#ifndef PS_EMULATE
+void k_halo_push_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
+                      unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket);
+void k_halo_unpack_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* src0, const double* src1, const unsigned long long* flag0, const unsigned long long* flag1,
+                        unsigned long long seq, double* v, PcgScalars* S, bool respectDone);
+#endif
 void k_recover_active(cudaStream_t, const Geom&, const RowSet& rows, const double* wAct, const double* mcInv, const double* rhsU, double* velSol);
 // faces this rank writes: active faces with index in [aLo, aHi), reduced faces of regions [regLo, regHi), every face without a DOF
 struct FaceOwner { int32_t aLo, aHi, regLo, regHi; };

@@ -15,8 +15,9 @@ from oracle.oracle import Oracle
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def launch(case, world, outdir, port, gpu=False):
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), OMP_NUM_THREADS="2")
+def launch(case, world, outdir, port, gpu=False, extra_env=None):
+    env = dict(os.environ, **(extra_env or {}))
+    env = dict(env, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), OMP_NUM_THREADS="2")
     procs = []
     for r in range(world):
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), case, str(outdir)] + (["gpu"] if gpu else []),

@@ -15,10 +15,13 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("case,world", [("blob48_tile8", 2), ("box48_uniform", 2), ("blob64_tile16", 2), ("blob64_tile16", 4)])
-def test_gpu_slab_decomposed_step_matches_oracle(built, tmp_path, case, world):
+def test_gpu_slab_decomposed_step_matches_oracle(built, tmp_path, case, world, transport):
+    """transport "peer": halo stores + fused all-reduce over NVLink peer memory (ps_peer.hpp); "nccl": the fallback."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29700 + (os.getpid() + hash(case) + world) % 200
-    ranks = launch(case, world, tmp_path, port, gpu=True)
+    port = 29700 + (os.getpid() + hash(case) + world + (7 if transport == "nccl" else 0)) % 200
+    ranks = launch(case, world, tmp_path, port, gpu=True, extra_env={"PS_COMM": "nccl"} if transport == "nccl" else {"PS_COMM": ""})
+    assert all(int(r["peer"]) == (1 if transport == "peer" else 0) for r in ranks), "requested transport not in use"
     parity.check_distributed(case, ranks)
