@@ -43,8 +43,20 @@ HostCsr blockdiag_csr(const std::vector<double>& blocks, int R) {
 HostCsr k_block(Solver& S, const std::string& name) {
     const Counts& C = S.C;
     const int64_t nRows = C.nRowsExt, nP = C.nPressures, nT = C.nStresses;
-    std::vector<double> kv = S.K.val.to_host(S.st, (size_t)8 * nRows);
-    std::vector<int32_t> kc = S.K.col.to_host(S.st, (size_t)8 * nRows);
+    // expand the compact operator (CompactOp, ps_solver.hpp) into 8 (value, column) slots per row
+    std::vector<double> kv((size_t)8 * nRows); std::vector<int32_t> kc((size_t)8 * nRows);
+    {
+        std::vector<uint64_t> code = S.Op.kcode.to_host(S.st, (size_t)nRows);
+        std::vector<int32_t> col = S.Op.kcol.to_host(S.st, (size_t)6 * nRows);
+        const double sc = S.g.invDx / 64.;
+        for (int64_t r = 0; r < nRows; ++r) {
+            const int32_t c0w = col[r];
+            const int64_t cOff = nP + (int64_t)((uint32_t)c0w >> 30) * C.nCenter;
+            const int64_t c0 = c0w & OP_COL_MASK, c1 = col[(size_t)nRows + r];
+            const int64_t cc[8] = {c0, c1, cOff + c0, cOff + c1, col[(size_t)2 * nRows + r], col[(size_t)3 * nRows + r], col[(size_t)4 * nRows + r], col[(size_t)5 * nRows + r]};
+            for (int k = 0; k < 8; ++k) { kv[(size_t)k * nRows + r] = (double)op_code(code[r], k) * sc; kc[(size_t)k * nRows + r] = (int32_t)cc[k]; }
+        }
+    }
     const bool pressure = (name == "G" || name == "JG");
     const int64_t colLo = pressure ? 0 : nP, colHi = pressure ? nP : nP + nT;
     HostCsr m; m.cols = colHi - colLo;
@@ -326,20 +338,27 @@ int ps_apply(ps_handle h, const double* x, double* y) {
 double ps_kernel_bytes(ps_handle h, const char* name) {
     if (!h || !name) return 0;
     const Solver& S = *h->S; const Counts& C = S.C; const std::string nm(name);
-    // ELL streams cost 12 B per stored slot, every vector is read / written once
+    // DESIGN.md section 5.  Compact operator: 8 B of codes + 6 x 4 B columns per face row (+ 1 B mass code on active rows),
+    // 8 + 24 B per cell (serves the pressure row and the 3 centre-stress rows), 4 + 16 B per edge; every vector is read /
+    // written once.  "csr_*" = the same passes priced as the CSR SpMV of SURVEY.md 8d (12 B per stored non-zero).
     const double nE = (double)(C.nEdge[0] + C.nEdge[1] + C.nEdge[2]);
-    const double kSlots = 8.0 * C.nRowsExt, ktSlots = 6.0 * C.nPressures + 2.0 * 3 * C.nCenter + 4.0 * nE;
     const double n = (double)C.nSystemSize;
     const double nRed = (double)S.RG.nRows;
-    const double pass1 = 12.0 * kSlots /*ELL slots*/ + 8.0 * n /*x*/ + 8.0 * C.nActiveVs /*Mc^-1*/ + 8.0 * C.nRowsExt /*w write*/;
-    const double pass2 = 12.0 * ktSlots + 8.0 * C.nRowsExt /*w read*/ + 8.0 * C.nStresses /*mu^-1*/ + 8.0 * C.nStresses /*x_tau*/ + 8.0 * n /*y*/;
+    const double pass1 = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs /*matrix*/ + 8.0 * n /*x*/ + 8.0 * C.nRowsExt /*w write*/;
+    const double pass2 = 32.0 * C.nCenter + 20.0 * nE /*matrix*/ + 8.0 * C.nRowsExt /*w read*/ + 8.0 * (C.nCenter + nE) /*mu^-1: once per cell / edge*/
+                       + 8.0 * n /*x (stress part: the mu term; pressure part: the fused dot)*/ + 8.0 * n /*y*/;
+    const double csrPass1 = 12.0 * 8.0 * C.nRowsExt + 8.0 * n + 8.0 * C.nActiveVs + 8.0 * C.nRowsExt;
+    const double csrPass2 = 12.0 * (6.0 * C.nPressures + 2.0 * 3 * C.nCenter + 4.0 * nE) + 8.0 * C.nRowsExt + 8.0 * C.nStresses + 8.0 * C.nStresses + 8.0 * n;
+    if (nm == "csr_pass1") return csrPass1;
+    if (nm == "csr_pass2") return csrPass2;
+    if (nm == "csr_apply") return csrPass1 + csrPass2 + nRed * 24.0 + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
     // reduced rows: w read + packed coordinates (moments), packed coordinates + w write (expand), B^-1 + t,s,sigma per region
     const double reduced = nRed * (8.0 + 4.0) + nRed * (4.0 + 8.0) + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
     if (nm == "pass1") return pass1;
     if (nm == "pass2") return pass2;
     if (nm == "reduced") return reduced;
     if (nm == "apply") return pass1 + pass2 + reduced;
-    if (nm == "cg_iteration") return pass1 + pass2 + reduced + 8.0 * n /*p for p.Ap*/ + 48.0 * n /*x,r update*/ + 24.0 * n /*p update*/;
+    if (nm == "cg_iteration") return pass1 + pass2 + reduced + 48.0 * n /*x,r update*/ + 24.0 * n /*p update*/;
     return 0;
 }
 

@@ -6,8 +6,9 @@
 //   K_ext  = [G D^T] on active face rows, followed by the same stencil on the *coupled reduced* face
 //            rows (the J = C * K_red factorisation: JG/JD^T entries are `contribution * c_f(n)`,
 //            S_CMB:443-456, 513-526, 601-614, i.e. a K-style row scaled by the basis row c_f)
-//   K_ext^T in three blocks: pressure rows (<= 6 faces), centre-stress rows (<= 2), edge-stress rows (<= 4)
-// Matrix values are products of <= 3 doubles formed exactly like the reference (S_CMB:362-380, 408-412).
+//   K_ext^T as cell rows (<= 6 faces: pressure + the three centre stresses) and edge rows (<= 4 faces)
+// Every value is +-(weight8 * weight8) / (64 dx): stored as the signed integer product (CompactOp, ps_solver.hpp) and
+// rebuilt in the kernels as (double)code * (invDx / 64) -- bit-equal to the reference's products (S_CMB:362-380, 408-412).
 #include "ps_solver.hpp"
 
 namespace ps {
@@ -35,11 +36,17 @@ PS_D double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi
 
 // coefficient of one (face, cell|edge) pair: faceFluidW * liquidW * invDx (S_CMB:408-411, 480-483, 568-571)
 PS_D double pair_coeff(int ffw8, int lw8, double invDx) { return mul_rn(mul_rn((double)ffw8 * 0.125, (double)lw8 * 0.125), invDx); }
+PS_D uint64_t pack_code(uint64_t word, int k, int code) { return word | ((uint64_t)(uint8_t)(int8_t)code << (8 * k)); }
 
 // K_ext rows: one thread per face of each axis.  Slots: 0,1 pressure of cell(-),cell(+); 2,3 centre stress;
 // 4..7 the two edge axes (ascending) x (dir 0, dir 1).  Empty slots carry value 0 and repeat a valid column.
-void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, double* kval, int32_t* kcol, double* mcInv, double* mc, double* rhsU, double* oldVs) {
-    const int64_t nRows = C.nRowsExt, nAct = C.nActiveVs, nP = C.nPressures, nC = C.nCenter;
+void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, CompactOp& Op, double* mcInv, double* mc, double* rhsU, double* oldVs) {
+    const int64_t nRows = C.nRowsExt, nAct = C.nActiveVs, nP = C.nPressures;
+    uint64_t* kcode = Op.kcode.p; int32_t* kcol = Op.kcol.p; uint8_t* kmc = Op.kmc.p;
+    {   // M_c^-1 by weight product (S_CMB:361-380): 1 / (rho * clamp(k / 64, MINWEIGHT^2, 1))
+        double* lut = Op.mcInvLut.p; const double density = g.density;
+        ps_for(st, 65, PS_LAMBDA(int64_t k) { const double volume = fmin(fmax((double)k * 0.125 * 0.125, 0.1 * 0.1), 1.0); lut[k] = 1. / mul_rn(volume, density); });
+    }
     for (int axis = 0; axis < 3; ++axis) {
         const int32_t* krow = F.krow[axis];
         const uint8_t* ffw = F.fluW[SL_FACE + axis]; const uint8_t* flw = F.liqW[SL_FACE + axis];
@@ -49,44 +56,43 @@ void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts&
         const int32_t* EA1 = F.aidx[SL_EDGE + e1]; const int32_t* EA2 = F.aidx[SL_EDGE + e2];
         const uint8_t* ew1 = F.liqW[SL_EDGE + e1]; const uint8_t* ew2 = F.liqW[SL_EDGE + e2];
         const int64_t eOff1 = nP + C.stressOff[3 + e1], eOff2 = nP + C.stressOff[3 + e2];
-        const int64_t cOff = nP + (int64_t)axis * nC;
         const float* vel = F.vel[axis];
-        const double density = g.density, invDx = g.invDx;
+        const double density = g.density;
         ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) {
             const int64_t row = krow[q];
             if (row < 0) return;
             const I3 f = delin(g, SL_FACE + axis, q);
             const int fw = ffw[q];
-            double v[8]; int32_t c[8];
-            for (int s = 0; s < 8; ++s) { v[s] = 0.; c[s] = -1; }
+            uint64_t word = 0; int32_t c[6] = {0, 0, 0, 0, 0, 0};
             for (int dir = 0; dir < 2; ++dir) {
                 const I3 cell = dir ? f : shifted(f, axis, -1);
                 if (!in_bounds(g, SL_CENTER, cell)) continue;
                 const int64_t qc = lin(g, SL_CENTER, cell);
                 const int ci = CA[qc];
                 if (ci < 0) continue;
-                const double coeff = pair_coeff(fw, clw[qc], invDx);
-                if (coeff <= 0.) continue;
-                v[dir] = dir ? coeff : -coeff;  c[dir] = ci;                               // G: gradientSign * coeff
-                v[2 + dir] = dir ? -coeff : coeff;  c[2 + dir] = (int32_t)(cOff + ci);       // D^T: -divergenceSign * coeff
+                const int prod = fw * (int)clw[qc];
+                if (prod <= 0) continue;
+                word = pack_code(word, dir, dir ? prod : -prod);          // G: gradientSign * coeff
+                word = pack_code(word, 2 + dir, dir ? -prod : prod);      // D^T: -divergenceSign * coeff (column = nP + axis nC + ci)
+                c[dir] = ci;
             }
             for (int dir = 0; dir < 2; ++dir) {
                 const I3 ed1 = dir ? shifted(f, 3 - axis - e1, 1) : f;
                 const int64_t q1 = lin(g, SL_EDGE + e1, ed1);
                 if (is_active(EL1[q1])) {
-                    const double coeff = pair_coeff(fw, ew1[q1], invDx);
-                    if (coeff > 0.) { v[4 + dir] = dir ? -coeff : coeff; c[4 + dir] = (int32_t)(eOff1 + EA1[q1]); }
+                    const int prod = fw * (int)ew1[q1];
+                    if (prod > 0) { word = pack_code(word, 4 + dir, dir ? -prod : prod); c[2 + dir] = (int32_t)(eOff1 + EA1[q1]); }
                 }
                 const I3 ed2 = dir ? shifted(f, 3 - axis - e2, 1) : f;
                 const int64_t q2 = lin(g, SL_EDGE + e2, ed2);
                 if (is_active(EL2[q2])) {
-                    const double coeff = pair_coeff(fw, ew2[q2], invDx);
-                    if (coeff > 0.) { v[6 + dir] = dir ? -coeff : coeff; c[6 + dir] = (int32_t)(eOff2 + EA2[q2]); }
+                    const int prod = fw * (int)ew2[q2];
+                    if (prod > 0) { word = pack_code(word, 6 + dir, dir ? -prod : prod); c[4 + dir] = (int32_t)(eOff2 + EA2[q2]); }
                 }
             }
-            int32_t fill = 0;
-            for (int s = 0; s < 8; ++s) if (c[s] >= 0) { fill = c[s]; break; }
-            for (int s = 0; s < 8; ++s) { kval[(int64_t)s * nRows + row] = v[s]; kcol[(int64_t)s * nRows + row] = c[s] >= 0 ? c[s] : fill; }
+            kcode[row] = word;
+            kcol[row] = c[0] | (int32_t)((uint32_t)axis << 30);
+            for (int s = 1; s < 6; ++s) kcol[(int64_t)s * nRows + row] = c[s];
             if (row < nAct) {
                 // M_c, M_c^-1, rhs_u, old velocities (S_CMB:361-391); MINWEIGHT = 0.1 (S.h:226)
                 const double MINWEIGHT = 0.1;
@@ -95,6 +101,7 @@ void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts&
                 const double m = mul_rn(volume, density);
                 const double lv = (double)vel[q];
                 mc[row] = m; mcInv[row] = 1. / m;
+                kmc[row] = (uint8_t)(fw * (int)flw[q]);
                 rhsU[row] = mul_rn(mul_rn(lv, volume), density);
                 oldVs[row] = lv;
             }
@@ -103,13 +110,12 @@ void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts&
 }
 
 // K_ext^T rows + the stress diagonal + the moving-solid right-hand sides, one thread per cell / edge.
-void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, Ell& KtP, Ell& KtC, Ell& KtE, double* uInv, double* uDiag, double* rhsPT) {
+void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, CompactOp& Op, double* uInv, double* uDiag, double* rhsPT) {
     const int64_t nP = C.nPressures, nC = C.nCenter;
     const double invDx = g.invDx;
     const double MINWEIGHT = 0.1;
     {
-        double* pv = KtP.val.p; int32_t* pc = KtP.col.p; double* cv = KtC.val.p; int32_t* cc = KtC.col.p;
-        const int64_t nCRows = 3 * nC;
+        uint64_t* ccode = Op.ccode.p; int32_t* ccol = Op.ccol.p;
         const int32_t* CA = F.aidx[SL_CENTER];
         const uint8_t* clw = F.liqW[SL_CENTER]; const uint8_t* cfw = F.fluW[SL_CENTER];
         const int32_t* kr0 = F.krow[0]; const int32_t* kr1 = F.krow[1]; const int32_t* kr2 = F.krow[2];
@@ -123,28 +129,26 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
             const I3 c = delin(g, SL_CENTER, q);
             const int lw = clw[q], fwc = cfw[q];
             double rhsP = 0.;
-            int32_t fillP = -1;
-            double pvals[6]; int32_t pcols[6];
+            uint64_t word = 0; int32_t pcols[6];
             for (int axis = 0; axis < 3; ++axis) {
                 const int32_t* kr = axis == 0 ? kr0 : axis == 1 ? kr1 : kr2;
                 const uint8_t* fwA = axis == 0 ? fw0 : axis == 1 ? fw1 : fw2;
                 const float* cvel = axis == 0 ? cv0 : axis == 1 ? cv1 : cv2;
                 double rhsT = 0.;
-                double tv[2] = {0., 0.}; int32_t tc[2] = {-1, -1};
                 for (int side = 0; side < 2; ++side) {
                     const I3 f = side ? shifted(c, axis, 1) : c;
                     const int64_t qf = lin(g, SL_FACE + axis, f);
                     const int slot = axis * 2 + side;
-                    pvals[slot] = 0.; pcols[slot] = -1;
+                    pcols[slot] = 0;
                     const int64_t row = kr[qf];
                     if (row < 0) continue;
+                    const int prod = (int)fwA[qf] * lw;
+                    if (prod <= 0) continue;
                     const double coeff = pair_coeff(fwA[qf], lw, invDx);
-                    if (coeff <= 0.) continue;
                     // low face: this cell is its (+) cell (dir 1); high face: its (-) cell (dir 0)
                     const double sign = side ? -1. : 1.;               // gradientSign = divergenceSign
-                    pvals[slot] = sign * coeff; pcols[slot] = (int32_t)row;
-                    tv[side] = -sign * coeff; tc[side] = (int32_t)row;
-                    if (fillP < 0) fillP = (int32_t)row;
+                    word = pack_code(word, slot, side ? -prod : prod);  // pressure row: sign * coeff; the stress row aa carries -sign * coeff
+                    pcols[slot] = (int32_t)row;
                     if (row < nAct) {   // moving-solid terms exist for active faces only (S_CMB:417-441, 489-511)
                         const double svel = (double)cvel[qf];
                         const double sc = sign * coeff;
@@ -153,12 +157,10 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
                     }
                 }
                 const int64_t trow = (int64_t)axis * nC + ci;
-                const int32_t fillT = tc[0] >= 0 ? tc[0] : (tc[1] >= 0 ? tc[1] : 0);
-                for (int s = 0; s < 2; ++s) { cv[(int64_t)s * nCRows + trow] = tv[s]; cc[(int64_t)s * nCRows + trow] = tc[s] >= 0 ? tc[s] : fillT; }
                 rhsPT[nP + trow] = rhsT;
             }
-            if (fillP < 0) fillP = 0;
-            for (int s = 0; s < 6; ++s) { pv[(int64_t)s * nP + ci] = pvals[s]; pc[(int64_t)s * nP + ci] = pcols[s] >= 0 ? pcols[s] : fillP; }
+            ccode[ci] = word;
+            for (int s = 0; s < 6; ++s) ccol[(int64_t)s * nC + ci] = pcols[s];
             rhsPT[ci] = rhsP;
             // centre stress diagonal (S_CMB:772-819)
             const double volumeWeight = clampd((double)fwc * 0.125, MINWEIGHT, 1.0) * ((double)lw * 0.125);
@@ -171,7 +173,7 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
     }
     const int64_t nERows = C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
     for (int e = 0; e < 3; ++e) {
-        double* ev = KtE.val.p; int32_t* ec = KtE.col.p;
+        uint32_t* ecode = Op.ecode.p; int32_t* ecol = Op.ecol.p;
         const int8_t* EL = F.label[SL_EDGE + e]; const int32_t* EA = F.aidx[SL_EDGE + e];
         const uint8_t* elw = F.liqW[SL_EDGE + e]; const uint8_t* efw = F.fluW[SL_EDGE + e];
         const int fa0 = (e == 0) ? 1 : 0, fa1 = (e == 2) ? 1 : 2;
@@ -187,7 +189,7 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
             const int ei = EA[q];
             const I3 ed = delin(g, SL_EDGE + e, q);
             const int lw = elw[q], fwe = efw[q];
-            double v[4] = {0., 0., 0., 0.}; int32_t cidx[4] = {-1, -1, -1, -1};
+            uint64_t word = 0; int32_t cidx[4] = {0, 0, 0, 0};
             double rhs = 0.;
             for (int k = 0; k < 4; ++k) {
                 const int fa = k < 2 ? fa0 : fa1;
@@ -198,10 +200,12 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
                 const int64_t row = (k < 2 ? krA : krB)[qf];
                 if (row < 0) continue;
                 const int ffw8 = (k < 2 ? fwA : fwB)[qf];
+                const int prod = ffw8 * lw;
+                if (prod <= 0) continue;
                 const double coeff = pair_coeff(ffw8, lw, invDx);
-                if (coeff <= 0.) continue;
                 const double divSign = back ? 1. : -1.;              // back face sees this edge at dir 1
-                v[k] = -divSign * coeff; cidx[k] = (int32_t)row;
+                word = pack_code(word, k, back ? -prod : prod);      // -divSign * coeff
+                cidx[k] = (int32_t)row;
                 if (row < nAct) {   // S_CMB:581-599
                     const double svel = (double)(k < 2 ? cvA : cvB)[qf];
                     const double sc = divSign * coeff;
@@ -209,10 +213,9 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
                     if (ffw8 < 8) rhs += sc * svel;
                 }
             }
-            int32_t fill = 0;
-            for (int k = 0; k < 4; ++k) if (cidx[k] >= 0) { fill = cidx[k]; break; }
             const int64_t erow = eRowOff + ei;
-            for (int k = 0; k < 4; ++k) { ev[(int64_t)k * nERows + erow] = v[k]; ec[(int64_t)k * nERows + erow] = cidx[k] >= 0 ? cidx[k] : fill; }
+            ecode[erow] = (uint32_t)word;
+            for (int k = 0; k < 4; ++k) ecol[(int64_t)k * nERows + erow] = cidx[k];
             rhsPT[nP + tOff + ei] = rhs;
             // edge stress diagonal (S_CMB:685-711)
             const double volumeWeight = clampd((double)fwe * 0.125, MINWEIGHT, 1.0) * ((double)lw * 0.125);

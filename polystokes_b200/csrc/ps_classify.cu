@@ -34,17 +34,36 @@ void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F) {
                     const int fl = (qq >= 0) ? (qq >> 2) : -((-qq + 3) >> 2);
                     base[a][s] = fl; fr[a][s] = (double)(qq - 4 * fl) * 0.25;
                 }
-            int nl = 0, nf = 0;
-            for (int sz = 0; sz < 2; ++sz) for (int sy = 0; sy < 2; ++sy) for (int sx = 0; sx < 2; ++sx) {
-                double accL = 0.0, accF = 0.0;
-                for (int dz = 0; dz < 2; ++dz) for (int dy = 0; dy < 2; ++dy) for (int dxx = 0; dxx < 2; ++dxx) {
-                    const double w = mul_rn(mul_rn(dxx ? fr[0][sx] : 1.0 - fr[0][sx], dy ? fr[1][sy] : 1.0 - fr[1][sy]), dz ? fr[2][sz] : 1.0 - fr[2][sz]);
-                    const I3 cc = clamped(g, SL_CENTER, I3{base[0][sx] + dxx, base[1][sy] + dy, base[2][sz] + dz});
-                    const int64_t l = lin(g, SL_CENTER, cc);
-                    accL = add_rn(accL, mul_rn(w, (double)surf[l]));
-                    accF = add_rn(accF, mul_rn(w, (double)coll[l]));
+            // Every sub-sample is a convex combination (all 8 trilinear weights are positive: fractions are 1/4 or 3/4)
+            // of the SDF values in the <= 3x3x3 cell block below, so away from the interfaces the count is decided
+            // by the signs alone -- exactly, rounding included -- and the fp64 interpolation is skipped.
+            float minS = 3.4e38f, maxS = -3.4e38f, minC = 3.4e38f, maxC = -3.4e38f;
+            {
+                int lo[3], hi[3];
+                for (int a = 0; a < 3; ++a) { lo[a] = min(base[a][0], base[a][1]); hi[a] = max(base[a][0], base[a][1]) + 1; }
+                for (int z = lo[2]; z <= hi[2]; ++z) for (int y = lo[1]; y <= hi[1]; ++y) for (int x = lo[0]; x <= hi[0]; ++x) {
+                    const int64_t l = lin(g, SL_CENTER, clamped(g, SL_CENTER, I3{x, y, z}));
+                    const float sv = surf[l], cv = coll[l];
+                    minS = fminf(minS, sv); maxS = fmaxf(maxS, sv); minC = fminf(minC, cv); maxC = fmaxf(maxC, cv);
                 }
-                nl += (accL < 0.0); nf += (accF >= 0.0);
+            }
+            const bool needL = !(minS >= 0.f || maxS < 0.f), needF = !(minC >= 0.f || maxC < 0.f);
+            int nl = (maxS < 0.f) ? 8 : 0, nf = (minC >= 0.f) ? 8 : 0;
+            if (needL || needF) {
+                int cl = 0, cf = 0;
+                for (int sz = 0; sz < 2; ++sz) for (int sy = 0; sy < 2; ++sy) for (int sx = 0; sx < 2; ++sx) {
+                    double accL = 0.0, accF = 0.0;
+                    for (int dz = 0; dz < 2; ++dz) for (int dy = 0; dy < 2; ++dy) for (int dxx = 0; dxx < 2; ++dxx) {
+                        const double w = mul_rn(mul_rn(dxx ? fr[0][sx] : 1.0 - fr[0][sx], dy ? fr[1][sy] : 1.0 - fr[1][sy]), dz ? fr[2][sz] : 1.0 - fr[2][sz]);
+                        const I3 cc = clamped(g, SL_CENTER, I3{base[0][sx] + dxx, base[1][sy] + dy, base[2][sz] + dz});
+                        const int64_t l = lin(g, SL_CENTER, cc);
+                        accL = add_rn(accL, mul_rn(w, (double)surf[l]));
+                        accF = add_rn(accF, mul_rn(w, (double)coll[l]));
+                    }
+                    cl += (accL < 0.0); cf += (accF >= 0.0);
+                }
+                if (needL) nl = cl;
+                if (needF) nf = cf;
             }
             lw[q] = (uint8_t)nl; fw[q] = (uint8_t)nf;
         });

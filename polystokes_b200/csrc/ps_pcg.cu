@@ -17,27 +17,33 @@
 
 namespace ps {
 
-// ---- row functors shared by the CUDA kernels and the emulation twins ----
+// ---- row functors (reference semantics of one row; the emulation twins call them directly) ----
+// face row r of K_ext: sum over the slots p-, p+, c-, c+, e0..e3 in this order (CompactOp, ps_solver.hpp)
 PS_D double k_row(const OpArgs& A, int64_t r, const double* __restrict__ x) {
+    const uint64_t word = A.kcode[r];
+    const int32_t c0w = A.kcol[r];
+    const int64_t cOff = A.nP + (int64_t)((uint32_t)c0w >> 30) * A.nC;
+    int64_t col[8];
+    col[0] = c0w & OP_COL_MASK; col[1] = A.kcol[A.nRowsExt + r]; col[2] = cOff + col[0]; col[3] = cOff + col[1];
+    for (int k = 0; k < 4; ++k) col[4 + k] = A.kcol[(int64_t)(2 + k) * A.nRowsExt + r];
     double s = 0.;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += A.kval[(int64_t)k * A.nRowsExt + r] * x[A.kcol[(int64_t)k * A.nRowsExt + r]];
+    for (int k = 0; k < 8; ++k) { const int code = op_code(word, k); if (code) s += ((double)code * A.valScale) * x[col[k]]; }
     return s;
 }
-PS_D double kt_row(const OpArgs& A, int64_t j, const double* __restrict__ w) {
+// cell ci: pressure row and the three centre-stress rows (same face columns, opposite sign); out[0] = (K^T w)_p, out[1+a] = (K^T w)_aa
+PS_D void kt_cell_rows(const OpArgs& A, int64_t ci, const double* __restrict__ w, double* out) {
+    const uint64_t word = A.ccode[ci];
+    double v[6], wv[6];
+    for (int k = 0; k < 6; ++k) { const int code = op_code(word, k); v[k] = (double)code * A.valScale; wv[k] = code ? w[A.ccol[(int64_t)k * A.nC + ci]] : 0.; }
     double s = 0.;
-    if (j < A.nP) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s += A.ktpVal[(int64_t)k * A.nP + j] * w[A.ktpCol[(int64_t)k * A.nP + j]];
-    } else if (j < A.nP + 3 * A.nC) {
-        const int64_t jj = j - A.nP, n = 3 * A.nC;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) s += A.ktcVal[(int64_t)k * n + jj] * w[A.ktcCol[(int64_t)k * n + jj]];
-    } else {
-        const int64_t jj = j - A.nP - 3 * A.nC;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s += A.kteVal[(int64_t)k * A.nE + jj] * w[A.kteCol[(int64_t)k * A.nE + jj]];
-    }
+    for (int k = 0; k < 6; ++k) s += v[k] * wv[k];
+    out[0] = s;
+    for (int a = 0; a < 3; ++a) { double t = 0.; t += (-v[2 * a]) * wv[2 * a]; t += (-v[2 * a + 1]) * wv[2 * a + 1]; out[1 + a] = t; }
+}
+PS_D double kt_edge_row(const OpArgs& A, int64_t e, const double* __restrict__ w) {
+    const uint64_t word = A.ecode[e];
+    double s = 0.;
+    for (int k = 0; k < 4; ++k) { const int code = op_code(word, k); if (code) s += ((double)code * A.valScale) * w[A.ecol[(int64_t)k * A.nE + e]]; }
     return s;
 }
 
@@ -102,26 +108,33 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
     return last;
 }
 
-// One ELL row (face row of K_ext or DOF row of K_ext^T) with a compile-time width: W coalesced value/column streams, W gathers of w.
-template <int W>
-__device__ __forceinline__ double kt_block_row(const double* __restrict__ val, const int32_t* __restrict__ col, int64_t rows, int64_t j, const double* __restrict__ w) {
-    double v[W]; int32_t c[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) { v[k] = __ldcs(val + (int64_t)k * rows + j); c[k] = __ldcs(col + (int64_t)k * rows + j); }
-    double s = 0.;
-#pragma unroll
-    for (int k = 0; k < W; ++k) s += v[k] * w[c[k]];
-    return s;
-}
-__global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
+// pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
+// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.
+__global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
+    __shared__ double lut[65];
     if (S && S->done) return;
+    if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
+    __syncthreads();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const double sc = A.valScale;
     // owned rows: one range on a single GPU; x, y, z faces + coupled reduced rows of the slab otherwise
 #pragma unroll 2
     for (RangeWalk<4> it(A.rowsK, tid); it.valid(A.rowsK); it.step(A.rowsK, stride)) {
         const int64_t r = it.j;
-        const double s = kt_block_row<8>(A.kval, A.kcol, A.nRowsExt, r, x);
-        w[r] = r < A.nActiveVs ? activeScale * __ldcs(A.mcInv + r) * s : s;     // coupled reduced rows keep the raw (K_red x)_f
+        const uint64_t word = __ldcs(A.kcode + r);
+        int32_t c[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c[k] = __ldcs(A.kcol + (int64_t)k * A.nRowsExt + r);
+        const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
+        const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
+        const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
+        double xv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xv[k] = ((word >> (8 * k)) & 0xffull) ? x[col[k]] : 0.;
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += ((double)op_code(word, k) * sc) * xv[k];
+        w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
     }
 }
 // last CTA of a producer: a, b are valid in thread 0; every rank's block receives this rank's partial sums
@@ -132,34 +145,68 @@ __device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, dou
     const double vals[2] = {pv[0], pv[1]};
     peer_reduce_push(P, slot, vals, nvals);
 }
-// one row block of K_ext^T (width W) over the owned row ranges; all pointers are pre-offset to the block so the
-// loop carries a single index.  Returns this thread's share of dot(x, y).
-template <int W, bool STRESS>
-__device__ __forceinline__ double kt_sweep(const double* __restrict__ val, const int32_t* __restrict__ col, int64_t ld, const RowSet& set, int64_t tid, int64_t stride,
-                                           const double* __restrict__ w, const double* __restrict__ xb, double* __restrict__ yb, const double* __restrict__ uInv,
-                                           double muScale, const double* __restrict__ addb, bool dot) {
-    double acc = 0.;
-#pragma unroll 2
-    for (RangeWalk<4> it(set, tid); it.valid(set); it.step(set, stride)) {
-        const int64_t j = it.j;
-        double v = -kt_block_row<W>(val, col, ld, j, w);
-        const double xj = (xb && (STRESS || dot)) ? xb[j] : 0.;
-        if (STRESS && muScale != 0.) v -= muScale * uInv[j] * xj;
-        if (addb) v += addb[j];
-        yb[j] = v;
-        acc += xj * v;
-    }
-    return acc;
-}
-__global__ void __launch_bounds__(HOT_THREADS, 6) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
+// y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) (p.Ap) -> S->red[0] / the peers.
+// Cell sweep: one thread computes the pressure row and the xx / yy / zz stress rows of its cell from ONE set of 6
+// columns, codes and w gathers (32 B of matrix per cell); edge sweep: 4 columns + 4 codes (20 B per edge).
+__global__ void __launch_bounds__(HOT_THREADS, 4) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
                                                               double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {
     if (S && S->done) return;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const bool dot = mode & 1;
-    const int64_t nCR = 3 * A.nC, oC = A.nP, oE = A.nP + nCR;
-    double acc = kt_sweep<6, false>(A.ktpVal, A.ktpCol, A.nP, A.rowsP, tid, stride, w, x, y, nullptr, 0., add, dot);
-    acc += kt_sweep<2, true>(A.ktcVal, A.ktcCol, nCR, A.rowsC, tid, stride, w, x ? x + oC : nullptr, y + oC, A.uInv, muScale, add ? add + oC : nullptr, dot);
-    acc += kt_sweep<4, true>(A.kteVal, A.kteCol, A.nE, A.rowsE, tid, stride, w, x ? x + oE : nullptr, y + oE, A.uInv + nCR, muScale, add ? add + oE : nullptr, dot);
+    const double sc = A.valScale;
+    const int64_t nC = A.nC, nP = A.nP, oE = A.nP + 3 * A.nC;
+    double acc = 0.;
+#pragma unroll 2
+    for (RangeWalk<4> it(A.rowsP, tid); it.valid(A.rowsP); it.step(A.rowsP, stride)) {
+        const int64_t ci = it.j;
+        const uint64_t word = __ldcs(A.ccode + ci);
+        double v[6], wv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int32_t c = __ldcs(A.ccol + (int64_t)k * nC + ci);
+            v[k] = (double)op_code(word, k) * sc;
+            wv[k] = ((word >> (8 * k)) & 0xffull) ? w[c] : 0.;
+        }
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += v[k] * wv[k];
+        double yp = -s;
+        if (add) yp += add[ci];
+        y[ci] = yp;
+        if (dot) acc += x[ci] * yp;
+        const double ui = muScale != 0. ? muScale * A.uInv[ci] : 0.;      // mu^-1 is the same for xx, yy, zz of a cell
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double t = 0.;
+            t += (-v[2 * a]) * wv[2 * a]; t += (-v[2 * a + 1]) * wv[2 * a + 1];
+            const int64_t jj = nP + a * nC + ci;
+            const double xj = x ? x[jj] : 0.;
+            double yt = -t;
+            if (muScale != 0.) yt -= ui * xj;
+            if (add) yt += add[jj];
+            y[jj] = yt;
+            acc += xj * yt;
+        }
+    }
+#pragma unroll 2
+    for (RangeWalk<4> it(A.rowsE, tid); it.valid(A.rowsE); it.step(A.rowsE, stride)) {
+        const int64_t e = it.j;
+        const uint32_t word = __ldcs(A.ecode + e);
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int32_t c = __ldcs(A.ecol + (int64_t)k * A.nE + e);
+            const double wv = ((word >> (8 * k)) & 0xffu) ? w[c] : 0.;
+            s += ((double)op_code(word, k) * sc) * wv;
+        }
+        const int64_t jj = oE + e;
+        const double xj = x ? x[jj] : 0.;
+        double yt = -s;
+        if (muScale != 0.) yt -= muScale * A.uInv[3 * nC + e] * xj;
+        if (add) yt += add[jj];
+        y[jj] = yt;
+        acc += xj * yt;
+    }
     if (dot) {
         const double bs = block_sum(acc);
         if (threadIdx.x == 0) dotPartial[blockIdx.x] = bs;
@@ -313,7 +360,7 @@ void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, doubl
     PS_CUDA(cudaGetLastError());
 }
 void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode) {
-    pass2_kernel<<<hot_blocks(pass2_kernel, A.rowsP.total() + A.rowsC.total() + A.rowsE.total()), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    pass2_kernel<<<hot_blocks(pass2_kernel, A.rowsP.total() + A.rowsE.total()), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -366,21 +413,26 @@ void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double*
 #else  // ---- serial twins ----
 void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
     if (S && S->done) return;
-    for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInv[r] * s : s; }
+    for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInvLut[A.kmc[r]] * s : s; }
 }
 void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode) {
     if (S && S->done) return;
     double acc = 0.;
-    auto row = [&](int64_t j) {
-        double v = -kt_row(A, j, w);
+    auto finish = [&](int64_t j, double ktw) {
+        double v = -ktw;
         const double xj = (mode & 1) || j >= A.nP ? (x ? x[j] : 0.) : 0.;
         if (j >= A.nP && muScale != 0.) v -= muScale * A.uInv[j - A.nP] * xj;
         if (add) v += add[j];
         y[j] = v; acc += xj * v;
     };
-    for (int64_t l = 0; l < A.rowsP.total(); ++l) row(A.rowsP.at(l));
-    for (int64_t l = 0; l < A.rowsC.total(); ++l) row(A.nP + A.rowsC.at(l));
-    for (int64_t l = 0; l < A.rowsE.total(); ++l) row(A.nP + 3 * A.nC + A.rowsE.at(l));
+    for (int64_t l = 0; l < A.rowsP.total(); ++l) {
+        const int64_t ci = A.rowsP.at(l);
+        double out[4];
+        kt_cell_rows(A, ci, w, out);
+        finish(ci, out[0]);
+        for (int a = 0; a < 3; ++a) finish(A.nP + a * A.nC + ci, out[1 + a]);
+    }
+    for (int64_t l = 0; l < A.rowsE.total(); ++l) { const int64_t e = A.rowsE.at(l); finish(A.nP + 3 * A.nC + e, kt_edge_row(A, e, w)); }
     if (mode & 1) S->red[0] = acc;
 }
 void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double*, PcgScalars* S, const PeerCtx&) {
@@ -408,17 +460,36 @@ void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, d
 void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) v[idx[i]] = buf[i]; }
 #endif
 
-// halo discovery: flag[c] = 1 for every column c of the given ELL rows that `colsOwned` contains
-template <class Owned>
-void k_mark_columns(cudaStream_t st, const int32_t* col, int width, int64_t ldRows, const RowSet& rows, const Owned& colsOwned, uint8_t* flag) {
-    const RowSet R = rows; const Owned Cs = colsOwned;
+// halo discovery: flag[c] = 1 for every column c of a non-empty slot of the given rows that `colsOwned` contains
+void k_mark_K_columns(cudaStream_t st, const OpArgs& A, const RowSet& rows, const RangeSet& colsOwned, uint8_t* flag) {
+    const RowSet R = rows; const RangeSet Cs = colsOwned;
+    const uint64_t* kcode = A.kcode; const int32_t* kcol = A.kcol; const int64_t nRows = A.nRowsExt, nP = A.nP, nC = A.nC;
     ps_for(st, R.total(), PS_LAMBDA(int64_t l) {
         const int64_t r = R.at(l);
-        for (int k = 0; k < width; ++k) { const int32_t c = col[(int64_t)k * ldRows + r]; if (Cs.has(c)) flag[c] = 1; }
+        const uint64_t word = kcode[r];
+        const int32_t c0w = kcol[r];
+        const int64_t cOff = nP + (int64_t)((uint32_t)c0w >> 30) * nC;
+        int64_t col[8];
+        col[0] = c0w & OP_COL_MASK; col[1] = kcol[nRows + r]; col[2] = cOff + col[0]; col[3] = cOff + col[1];
+        for (int k = 0; k < 4; ++k) col[4 + k] = kcol[(int64_t)(2 + k) * nRows + r];
+        for (int k = 0; k < 8; ++k) if (op_code(word, k) && Cs.has(col[k])) flag[col[k]] = 1;
     });
 }
-template void k_mark_columns<RangeSet>(cudaStream_t, const int32_t*, int, int64_t, const RowSet&, const RangeSet&, uint8_t*);
-template void k_mark_columns<RowSet>(cudaStream_t, const int32_t*, int, int64_t, const RowSet&, const RowSet&, uint8_t*);
+void k_mark_Kt_columns(cudaStream_t st, const OpArgs& A, const RowSet& cellRows, const RowSet& edgeRows, const RowSet& colsOwned, uint8_t* flag) {
+    const RowSet Rc = cellRows, Re = edgeRows, Cs = colsOwned;
+    const uint64_t* ccode = A.ccode; const int32_t* ccol = A.ccol; const uint32_t* ecode = A.ecode; const int32_t* ecol = A.ecol;
+    const int64_t nC = A.nC, nE = A.nE;
+    ps_for(st, Rc.total(), PS_LAMBDA(int64_t l) {
+        const int64_t ci = Rc.at(l);
+        const uint64_t word = ccode[ci];
+        for (int k = 0; k < 6; ++k) { const int32_t c = ccol[(int64_t)k * nC + ci]; if (op_code(word, k) && Cs.has(c)) flag[c] = 1; }
+    });
+    ps_for(st, Re.total(), PS_LAMBDA(int64_t l) {
+        const int64_t e = Re.at(l);
+        const uint64_t word = ecode[e];
+        for (int k = 0; k < 4; ++k) { const int32_t c = ecol[(int64_t)k * nE + e]; if (op_code(word, k) && Cs.has(c)) flag[c] = 1; }
+    });
+}
 
 // ---- reduced regions -------------------------------------------------------------------------------
 // t_r = J_r x = sum_f c_f (K_red x)_f ;  s_r = B_r^-1 (extraScale*extra_r + tScale*t_r) ;  w_f = scale * c_f . s_r

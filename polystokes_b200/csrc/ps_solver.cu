@@ -336,6 +336,7 @@ void Solver::constructActiveIndices() {
     if (C.nSystemSize >= INT32_MAX || C.nActiveVs + 26 >= INT32_MAX) throw Error("system too large for int32 column indices");
 }
 
+static OpArgs make_op(const Solver& S);
 static int key_bits(int64_t n) { int b = 1; while ((1ll << b) < n + 1 && b < 31) ++b; return b; }
 
 // builds (region, begin, end) chunk tables of at most `chunk` items for lists sorted by region
@@ -452,13 +453,12 @@ void Solver::constructMatrixBlocks() {
         RG.sigma.alloc((size_t)R * 30);
     }
     C.nRowsExt = C.nActiveVs + RG.nRows;
-    K.alloc(8, C.nRowsExt);
-    mcInv.alloc((size_t)C.nActiveVs); mc.alloc((size_t)C.nActiveVs); rhsU.alloc((size_t)C.nActiveVs); oldVs.alloc((size_t)C.nActiveVs);
-    k_assemble_K(st, g, F, C, K.val.p, K.col.p, mcInv.p, mc.p, rhsU.p, oldVs.p);
     const int64_t nE = C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
-    KtP.alloc(6, C.nPressures); KtC.alloc(2, 3 * C.nCenter); KtE.alloc(4, nE);
+    Op.alloc(C.nRowsExt, C.nActiveVs, C.nCenter, nE);
+    mcInv.alloc((size_t)C.nActiveVs); mc.alloc((size_t)C.nActiveVs); rhsU.alloc((size_t)C.nActiveVs); oldVs.alloc((size_t)C.nActiveVs);
+    k_assemble_K(st, g, F, C, Op, mcInv.p, mc.p, rhsU.p, oldVs.p);
     uInv.alloc((size_t)C.nStresses); uDiag.alloc((size_t)C.nStresses); rhsPT.alloc((size_t)C.nSystemSize);
-    k_assemble_Kt(st, g, F, C, KtP, KtC, KtE, uInv.p, uDiag.p, rhsPT.p);
+    k_assemble_Kt(st, g, F, C, Op, uInv.p, uDiag.p, rhsPT.p);
     const size_t n = (size_t)C.nSystemSize;
     b.alloc(n); x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); w.alloc((size_t)C.nRowsExt + 1);
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
@@ -505,22 +505,19 @@ void Solver::buildHalos() {
     haloX.reset(); haloW.reset();
     if (!part.multi()) return;
     const int64_t n = C.nSystemSize, nRows = C.nRowsExt;
-    const int64_t nE = C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
     static thread_local DBuf<uint8_t> flag;
     flag.alloc((size_t)std::max(n, nRows) + 1);
     const int me = part.rank;
     const int peers[2] = {me > 0 ? me - 1 : -1, me + 1 < part.nranks ? me + 1 : -1};
+    const OpArgs A = make_op(*this);
     auto listX = [&](int rowsOf, int colsOf, DBuf<int32_t>& out, int64_t off) {
         flag.zero(st, (size_t)n);
-        k_mark_columns(st, K.col.p, 8, nRows, rowsK(rowsOf), rowsSys(colsOf), flag.p);
+        k_mark_K_columns(st, A, rowsK(rowsOf), rowsSys(colsOf), flag.p);
         return select_flagged(st, n, flag.p, out, off);
     };
     auto listW = [&](int rowsOf, int colsOf, DBuf<int32_t>& out, int64_t off) {
         flag.zero(st, (size_t)nRows);
-        const RowSet owned = rowsK(colsOf);
-        k_mark_columns(st, KtP.col.p, 6, C.nPressures, rowsP(rowsOf), owned, flag.p);
-        k_mark_columns(st, KtC.col.p, 2, 3 * C.nCenter, rowsC(rowsOf), owned, flag.p);
-        k_mark_columns(st, KtE.col.p, 4, nE, rowsE(rowsOf), owned, flag.p);
+        k_mark_Kt_columns(st, A, rowsP(rowsOf), rowsE(rowsOf), rowsK(colsOf), flag.p);
         return select_flagged(st, nRows, flag.p, out, off);
     };
     for (int i = 0; i < 2; ++i) {
@@ -572,10 +569,10 @@ static OpArgs make_op(const Solver& S) {
     OpArgs A;
     A.nRowsExt = S.C.nRowsExt; A.nActiveVs = S.C.nActiveVs; A.nP = S.C.nPressures; A.nT = S.C.nStresses; A.nC = S.C.nCenter;
     A.nE = S.C.nEdge[0] + S.C.nEdge[1] + S.C.nEdge[2];
-    A.kval = S.K.val.p; A.kcol = S.K.col.p;
-    A.ktpVal = S.KtP.val.p; A.ktpCol = S.KtP.col.p; A.ktcVal = S.KtC.val.p; A.ktcCol = S.KtC.col.p; A.kteVal = S.KtE.val.p; A.kteCol = S.KtE.col.p;
-    A.mcInv = S.mcInv.p; A.uInv = S.uInv.p;
-    A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsC = S.ownC; A.rowsE = S.ownE;
+    A.kcode = S.Op.kcode.p; A.kcol = S.Op.kcol.p; A.kmc = S.Op.kmc.p; A.mcInvLut = S.Op.mcInvLut.p;
+    A.ccode = S.Op.ccode.p; A.ccol = S.Op.ccol.p; A.ecode = S.Op.ecode.p; A.ecol = S.Op.ecol.p;
+    A.uInv = S.uInv.p; A.valScale = S.g.invDx / 64.;
+    A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsE = S.ownE;
     return A;
 }
 

@@ -10,15 +10,35 @@
 
 namespace ps {
 
-// blocked-ELL storage of K_ext = [G D^T] (face rows) and of its transpose (DOF rows), slot-major so
-// that a warp reads 32 consecutive rows of one slot (coalesced 8 B values / 4 B columns).
-struct Ell {
-    int width = 0;
-    int64_t rows = 0;
-    DBuf<double> val;   // [width][rows]
-    DBuf<int32_t> col;  // [width][rows]
-    void alloc(int w, int64_t r) { width = w; rows = r; val.alloc((size_t)w * r); col.alloc((size_t)w * r); }
+// Compact slot-major storage of K_ext = [G D^T] (face rows) and of its transpose (DOF rows).  Every entry of G / D^T is
+// +-(faceFluidW * liquidW) / dx with both weights in eighths (S_CMB:408-411, 480-483, 568-571), i.e. an integer
+// code in [-64, 64] times the constant 1/(64 dx): the value is rebuilt in the kernel as (double)code * (invDx / 64),
+// which is the SAME double the reference forms (a power-of-two scaling commutes with the one rounding).  Columns:
+//   face row   : pressure of cell(-), cell(+) [bits 30-31 of slot 0 = face axis], then the 4 edge stresses; the two
+//                centre-stress columns are the pressure columns + nP + axis * nC and are not stored
+//   cell row   : the 6 face rows (-x +x -y +y -z +z) serve the pressure row AND the xx / yy / zz stress rows of the cell
+//                (same columns, opposite sign) -- one thread computes all four
+//   edge row   : 4 face rows
+// 33 B per face row, 32 B per cell, 20 B per edge instead of 96 / 144 / 48 B of fp64 + int32 ELL.  A slot with
+// code 0 is empty: its column is never dereferenced.
+struct CompactOp {
+    int64_t nRows = 0, nCells = 0, nEdges = 0;
+    DBuf<uint64_t> kcode;   // [nRows]   8 int8 codes: p-, p+, c-, c+, e0..e3
+    DBuf<int32_t> kcol;     // [6][nRows]
+    DBuf<uint8_t> kmc;      // [nActiveVs] faceFluidW * faceLiquidW (0..64): index of the M_c^-1 table
+    DBuf<double> mcInvLut;  // [65] 1 / (rho * clamp(k / 64, 0.01, 1))
+    DBuf<uint64_t> ccode;   // [nCells]  6 int8 codes of the pressure row
+    DBuf<int32_t> ccol;     // [6][nCells]
+    DBuf<uint32_t> ecode;   // [nEdges]  4 int8 codes
+    DBuf<int32_t> ecol;     // [4][nEdges]
+    void alloc(int64_t rows, int64_t nAct, int64_t cells, int64_t edges) {
+        nRows = rows; nCells = cells; nEdges = edges;
+        kcode.alloc((size_t)rows + 1); kcol.alloc((size_t)6 * rows + 1); kmc.alloc((size_t)nAct + 1); mcInvLut.alloc(65);
+        ccode.alloc((size_t)cells + 1); ccol.alloc((size_t)6 * cells + 1); ecode.alloc((size_t)edges + 1); ecol.alloc((size_t)4 * edges + 1);
+    }
 };
+PS_HD int op_code(uint64_t word, int k) { return (int)(int8_t)(uint8_t)(word >> (8 * k)); }
+constexpr int32_t OP_COL_MASK = 0x3fffffff;
 
 struct RegionData {
     int32_t count = 0;
@@ -146,8 +166,7 @@ public:
     DBuf<int> flags;             // small device flag / counter block
     RegionData RG;
     // matrices + vectors
-    Ell K;                        // rows = nRowsExt, width 8
-    Ell KtP, KtC, KtE;            // transpose blocks: pressure rows (6), centre-stress rows (2), edge-stress rows (4)
+    CompactOp Op;                 // K_ext and K_ext^T
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
     DBuf<double> x, r, p, Ap, w, velSol;
     DBuf<double> dotPartial;
@@ -199,16 +218,17 @@ void region_gram_finish(cudaStream_t, const Geom&, RegionData&, int nChunks);
 void k_flag_coupled_faces(cudaStream_t, const Geom&, const Fields&, int axis, uint8_t* flag);
 
 // ps_assemble.cu
-void k_assemble_K(cudaStream_t, const Geom&, const Fields&, const Counts&, double* kval, int32_t* kcol, double* mcInv, double* mc, double* rhsU, double* oldVs);
-void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, Ell& KtP, Ell& KtC, Ell& KtE, double* uInv, double* uDiag, double* rhsPT);
+void k_assemble_K(cudaStream_t, const Geom&, const Fields&, const Counts&, CompactOp& Op, double* mcInv, double* mc, double* rhsU, double* oldVs);
+void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, CompactOp& Op, double* uInv, double* uDiag, double* rhsPT);
 
 // ps_pcg.cu
 struct OpArgs {   // everything one operator apply touches
     int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
-    RowSet rowsK, rowsP, rowsC, rowsE;   // rows this rank computes (all rows on one GPU)
-    const double* kval; const int32_t* kcol;
-    const double* ktpVal; const int32_t* ktpCol; const double* ktcVal; const int32_t* ktcCol; const double* kteVal; const int32_t* kteCol;
-    const double* mcInv; const double* uInv;
+    RowSet rowsK, rowsP, rowsE;   // rows this rank computes (all rows on one GPU); the centre-stress rows follow rowsP
+    const uint64_t* kcode; const int32_t* kcol; const uint8_t* kmc; const double* mcInvLut;
+    const uint64_t* ccode; const int32_t* ccol; const uint32_t* ecode; const int32_t* ecol;
+    const double* uInv;
+    double valScale;              // invDx / 64
 };
 void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal);
 void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode);
@@ -233,7 +253,9 @@ void k_merge_face_plane(cudaStream_t, const Geom&, const Fields&, int axis, int 
 // halo plumbing
 void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* scal);
 void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* scal);
-template <class Owned> void k_mark_columns(cudaStream_t, const int32_t* col, int width, int64_t ldRows, const RowSet& rows, const Owned& colsOwned, uint8_t* flag);
+// halo discovery: flag[c] = 1 for every column c (of a non-empty slot) of the given rows that `colsOwned` contains
+void k_mark_K_columns(cudaStream_t, const OpArgs&, const RowSet& rows, const RangeSet& colsOwned, uint8_t* flag);
+void k_mark_Kt_columns(cudaStream_t, const OpArgs&, const RowSet& cellRows, const RowSet& edgeRows, const RowSet& colsOwned, uint8_t* flag);
 int64_t select_flagged(cudaStream_t, int64_t n, const uint8_t* flag, DBuf<int32_t>& out, int64_t outOffset);
 
 extern thread_local std::string g_lastError;

@@ -38,5 +38,7 @@ try: peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.
 except Exception: pass
 for k in ["pass1", "reduced", "pass2", "apply", "cg_iteration"]:
     ms = s.time_kernel(k, a.reps); by = s.kernel_bytes(k)
-    print(f"{k:13s} {ms:8.4f} ms  {by/1e9:7.3f} GB algorithmic  -> {by/ms/1e6:8.1f} GB/s  ({by/ms/1e6/peak*100:5.1f}% of {peak} GB/s measured peak)", flush=True)
+    csr = s.kernel_bytes("csr_" + k)
+    extra = f"   [as CSR SpMV (12 B/nnz): {csr/1e9:6.3f} GB -> {csr/ms/1e6:8.1f} GB/s]" if csr else ""
+    print(f"{k:13s} {ms:8.4f} ms  {by/1e9:7.3f} GB algorithmic  -> {by/ms/1e6:8.1f} GB/s  ({by/ms/1e6/peak*100:5.1f}% of {peak} GB/s measured peak){extra}", flush=True)
 print("velocity out max:", [float(v.abs().max()) for v in vout], "valid:", [int(v.sum()) for v in valid])
