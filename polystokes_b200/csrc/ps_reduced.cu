@@ -62,264 +62,390 @@ PS_D float local_viscosity(const Geom& g, const float* visc, int slot, const I3&
     return fadd_rn(cz[0], fmul_rn(t2, fsub_rn(cz[1], cz[0])));
 }
 
-struct FaceTerms { double wM, wN, u; bool visc; };
+// ---------------------------------------------------------------------------------------------------------------
+// Region matrices from polynomial moments.
+//
+// The reference accumulates  M_r = rho sum_f c_f c_f^T,  N_r = sum_surface c_f c_f^T,  rhs_r = sum_surface u_f c_f  and
+// (JD^T mu DJ^T)_r = sum_f c_f d_f^T  as 26x26 rank-1 updates per face (S.cpp:1330-1694): ~2000 FMAs per face.  But
+//   * c_f = S_a m(o_f): a fixed sparse 26x10 image S_a (per face axis a) of the 10 monomials m = {1,x,y,z,xx,xy,xz,yy,yz,zz}
+//     of the face offset o_f (buildConversionCoefficients, S.cpp:2107-2149), so  sum_f w_f c_f c_f^T = S_a Q_a S_a^T  with
+//     the 10x10 moment matrix  Q_a = sum_f w_f m m^T  (55 numbers per axis and weight);
+//   * the viscosity block is  sum over stress samples s of  kappa_s e_s e_s^T  where e_s = sum over the faces around s of
+//     +-c_f is the discrete strain rate of the basis at s (S.cpp:1537-1683 visits every (face, partner face) pair of a
+//     REDUCED cell / strictly REDUCED edge exactly once).  Central differences of quadratics are exact, so e_s is LINEAR
+//     in the sample position: e_s = dx A (1,x,y,z)^T with a constant 26x4 matrix A per sample type, and the block is
+//       sum_a A_a T^c A_a^T + 1/2 sum_e H_e T^e H_e^T,   T = sum_s mu_s (1,x,y,z)(1,x,y,z)^T   (10 numbers per type).
+// So a region needs 400 moments (2 x 3 x 55 + 3 x 10 + 10 + 3 x 10) accumulated over its cells in a FIXED order (chunks of
+// the (region, voxel order) sorted cell list, then chunk order): bit-reproducible, ~25x fewer flops and no 26x26
+// shared-memory traffic.  The tables S_a, A_a, H_e are generated from conversion_coefficients itself at integer points
+// (exact arithmetic), not typed in.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MOM_QM = 0, MOM_QN = 165, MOM_RHS = 330, MOM_TC = 360, MOM_TE = 370, MOM_COUNT = 400;
+constexpr int TAB_S = 0, TAB_A = 3 * RDOF * 10, TAB_H = TAB_A + 3 * RDOF * 4, TAB_COUNT = TAB_H + 3 * RDOF * 4;
+constexpr int GRAM_CELLS = 256;          // cells per chunk (build_chunks in ps_solver.cu)
+constexpr int STAGE_DOUBLES = 3 + 18 + 1 + 12;   // per cell: index (3), wM/wN/wN*u of 6 faces, mu, mu of the <= 12 owned REDUCED edges
 
-// Everything the three per-region sums need from one (reduced cell, axis, dir) face:
-//   c   = basis row of the face              (buildConversionCoefficients, S.cpp:2107-2149)
-//   wM  = rho if the face is counted by the mass matrix   (S.cpp:1442-1472)
-//   wN  = 1  if the opposite cell isActive (least-squares surface face, S.cpp:1369-1390), u = u*_face
-//   d   = sum of contribution * basis row over the viscous stencil partners of the face
-//         (centre terms S.cpp:1537-1603, edge terms S.cpp:1605-1683); valid when .visc is set
-PS_D FaceTerms face_terms(const Geom& g, const Fields& F, const double* com, const I3& cell, int axis, int dir, int region, double* c, double* d) {
-    FaceTerms t;
-    const I3 face = dir ? shifted(cell, axis, 1) : cell;
-    const I3 nbr = shifted(cell, axis, dir ? 1 : -1);
-    const int nbrLabel = label_at(g, F.label[SL_CENTER], SL_CENTER, nbr);
-    const bool nbrActive = is_active(nbrLabel);
-    double ox, oy, oz;
-    face_offset(g, face, axis, com + 3 * region, ox, oy, oz);
-    conversion_coefficients(ox, oy, oz, axis, c);
-    t.wM = (dir == 0 || nbrActive) ? g.density : 0.;
-    t.wN = nbrActive ? 1. : 0.;
-    t.u = (double)F.vel[axis][lin(g, SL_FACE + axis, face)];
-    // the face belongs to this cell's region (and is visited exactly once) iff it is the cell's low
-    // face, or its high face with a non-REDUCED cell behind it (findFaceReducedIndexFromCenter, S_Cls:1498-1528)
-    t.visc = (dir == 0) || (nbrLabel != L_REDUCED);
-    for (int n = 0; n < RDOF; ++n) d[n] = 0.;
-    if (!t.visc) return t;
-    const double dx2 = g.dx * g.dx;
-    double row[RDOF];
-    // cell-centred stress terms
-    for (int divDir = 0; divDir < 2; ++divDir) {
-        const I3 cc = divDir ? face : shifted(face, axis, -1);
-        if (!is_reduced(label_at(g, F.label[SL_CENTER], SL_CENTER, cc))) continue;
-        const double divSign = divDir ? 1. : -1.;
-        const double visc = (double)F.viscosity[lin(g, SL_CENTER, cc)];
-        for (int gradDir = 0; gradDir < 2; ++gradDir) {
-            const I3 adjFace = gradDir ? shifted(cc, axis, 1) : cc;
-            const double gradSign = gradDir ? 1. : -1.;
-            const double contribution = -1. * divSign * gradSign * visc / dx2;
-            const int adjR = F.ridx[SL_FACE + axis][lin(g, SL_FACE + axis, adjFace)];
-            if (adjR < 0) continue;
-            face_offset(g, adjFace, axis, com + 3 * adjR, ox, oy, oz);
-            conversion_coefficients(ox, oy, oz, axis, row);
-            for (int n = 0; n < RDOF; ++n) d[n] += contribution * row[n];
+PS_HD double monomial(int k, double x, double y, double z) {
+    switch (k) { case 0: return 1.; case 1: return x; case 2: return y; case 3: return z; case 4: return x * x; case 5: return x * y;
+                 case 6: return x * z; case 7: return y * y; case 8: return y * z; default: return z * z; }
+}
+// (k, l), k <= l, of the q-th entry of a symmetric n x n matrix stored row-wise upper triangle
+PS_HD void sym_pair(int n, int q, int& k, int& l) { k = 0; while (q >= n - k) { q -= n - k; ++k; } l = k + q; }
+PS_HD int sym_index(int n, int k, int l) { if (k > l) { const int t = k; k = l; l = t; } return k * n - k * (k - 1) / 2 + (l - k); }
+
+// host: S_a (26x10), A_a (26x4), H_e (26x4) from conversion_coefficients at small integer points (all values exact)
+static void build_region_tables(double* T) {
+    auto cc = [](double x, double y, double z, int axis, double* v) { conversion_coefficients(x, y, z, axis, v); };
+    for (int i = 0; i < TAB_COUNT; ++i) T[i] = 0.;
+    // S_a: column k = response to the k-th monomial; probe with points whose monomial vectors form an invertible system
+    // -- simpler: every entry of c is +-{1, 2, 1/2} times ONE monomial, so two probes identify (monomial, coefficient)
+    const double P[2][3] = {{2., 3., 5.}, {7., 11., 13.}};
+    for (int a = 0; a < 3; ++a) {
+        double v0[RDOF], v1[RDOF];
+        cc(P[0][0], P[0][1], P[0][2], a, v0); cc(P[1][0], P[1][1], P[1][2], a, v1);
+        for (int n = 0; n < RDOF; ++n) {
+            if (v0[n] == 0. && v1[n] == 0.) continue;
+            bool found = false;
+            for (int k = 0; k < 10 && !found; ++k) {
+                const double m0 = monomial(k, P[0][0], P[0][1], P[0][2]), m1 = monomial(k, P[1][0], P[1][1], P[1][2]);
+                const double c = v0[n] / m0;
+                if (c * m1 == v1[n]) { T[TAB_S + (a * RDOF + n) * 10 + k] = c; found = true; }
+            }
+            if (!found) throw Error("region tables: basis row is not a single monomial");
         }
     }
-    // edge-centred stress terms
-    for (int e = 0; e < 3; ++e) {
-        if (e == axis) continue;
-        for (int divDir = 0; divDir < 2; ++divDir) {
-            const double divSign = divDir ? 1. : -1.;
-            const I3 edge = divDir ? shifted(face, 3 - axis - e, 1) : face;
-            if (F.label[SL_EDGE + e][lin(g, SL_EDGE + e, edge)] != L_REDUCED) continue;   // isReducedButNotBoundary
-            const float visc = local_viscosity(g, F.viscosity, SL_EDGE + e, edge);
-            for (int gradAxis = 0; gradAxis < 3; ++gradAxis) {
-                if (gradAxis == e) continue;
-                const int adjAxis = 3 - gradAxis - e;
-                for (int gradDir = 0; gradDir < 2; ++gradDir) {
-                    const I3 adjFace = gradDir ? edge : shifted(edge, gradAxis, -1);   // edgeToFaceMap: -1 on axis 3-adjAxis-e = gradAxis
-                    const double gradSign = gradDir ? 1. : -1.;
-                    const double contribution = -0.5 * divSign * gradSign * (double)visc / dx2;
-                    const int adjR = index_at(g, F.ridx[SL_FACE + adjAxis], SL_FACE + adjAxis, adjFace);
-                    if (adjR < 0) continue;
-                    face_offset(g, adjFace, adjAxis, com + 3 * adjR, ox, oy, oz);
-                    conversion_coefficients(ox, oy, oz, adjAxis, row);
-                    for (int n = 0; n < RDOF; ++n) d[n] += contribution * row[n];
-                }
+    // A_a: (c_a(p + e_a) - c_a(p - e_a)) / 2 = d/da c_a, linear in p; H_e likewise for the two axes != e
+    auto strain = [&](int type, bool edge, double x, double y, double z, double* out) {
+        for (int n = 0; n < RDOF; ++n) out[n] = 0.;
+        double hi[RDOF], lo[RDOF];
+        if (!edge) {
+            const int a = type; double p[3] = {x, y, z}, q[3] = {x, y, z};
+            p[a] += 1.; q[a] -= 1.;
+            cc(p[0], p[1], p[2], a, hi); cc(q[0], q[1], q[2], a, lo);
+            for (int n = 0; n < RDOF; ++n) out[n] = (hi[n] - lo[n]) / 2.;
+        } else {
+            const int e = type;
+            for (int a = 0; a < 3; ++a) {
+                if (a == e) continue;
+                const int b = 3 - a - e;
+                double p[3] = {x, y, z}, q[3] = {x, y, z};
+                p[b] += 1.; q[b] -= 1.;
+                cc(p[0], p[1], p[2], a, hi); cc(q[0], q[1], q[2], a, lo);
+                for (int n = 0; n < RDOF; ++n) out[n] += (hi[n] - lo[n]) / 2.;
             }
         }
-    }
-    return t;
+    };
+    for (int pass = 0; pass < 2; ++pass)
+        for (int t = 0; t < 3; ++t) {
+            double f0[RDOF], f1[RDOF];
+            strain(t, pass == 1, 0., 0., 0., f0);
+            double* dst = T + (pass ? TAB_H : TAB_A) + t * RDOF * 4;
+            for (int n = 0; n < RDOF; ++n) dst[n * 4 + 0] = f0[n];
+            for (int d = 0; d < 3; ++d) {
+                strain(t, pass == 1, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., f1);
+                for (int n = 0; n < RDOF; ++n) dst[n * 4 + 1 + d] = f1[n] - f0[n];
+            }
+        }
 }
 
-// partial layout per chunk: [M 676][N 676][V 676][rhs 26]
-constexpr int GRAM_STRIDE = 3 * RDOF * RDOF + RDOF;
+// phase 1: everything the moments need from one REDUCED cell, staged as stage[field * GRAM_CELLS + slot]
+PS_D void stage_cell(const Geom& g, const Fields& F, int64_t cellQ, int slot, double* stage) {
+    const I3 c = delin(g, SL_CENTER, cellQ);
+    stage[0 * GRAM_CELLS + slot] = (double)c.x; stage[1 * GRAM_CELLS + slot] = (double)c.y; stage[2 * GRAM_CELLS + slot] = (double)c.z;
+    const int8_t* CL = F.label[SL_CENTER];
+    for (int axis = 0; axis < 3; ++axis)
+        for (int dir = 0; dir < 2; ++dir) {
+            const I3 face = dir ? shifted(c, axis, 1) : c;
+            const bool nbrActive = is_active(label_at(g, CL, SL_CENTER, shifted(c, axis, dir ? 1 : -1)));
+            const double wM = (dir == 0 || nbrActive) ? g.density : 0.;            // S.cpp:1442-1472
+            const double wN = nbrActive ? 1. : 0.;                                  // S.cpp:1369-1390
+            const double u = (double)F.vel[axis][lin(g, SL_FACE + axis, face)];
+            const int f = axis * 2 + dir;
+            stage[(3 + f) * GRAM_CELLS + slot] = wM; stage[(9 + f) * GRAM_CELLS + slot] = wN; stage[(15 + f) * GRAM_CELLS + slot] = wN * u;
+        }
+    stage[21 * GRAM_CELLS + slot] = (double)F.viscosity[cellQ];
+    // strictly REDUCED edges (S.cpp:1605-1683), each owned by the first REDUCED cell among its 4 cells in the order
+    // (0,0), (-a), (-b), (-a,-b) with a < b the axes across the edge
+    for (int e = 0; e < 3; ++e) {
+        const int a = e == 0 ? 1 : 0, b = e == 2 ? 1 : 2;
+        for (int db = 0; db < 2; ++db) for (int da = 0; da < 2; ++da) {
+            const I3 ed = shifted(shifted(c, a, da), b, db);
+            double mu = 0.;
+            if (F.label[SL_EDGE + e][lin(g, SL_EDGE + e, ed)] == L_REDUCED) {
+                // cells around the edge, in priority order; this cell is ed - (da, db)
+                bool owner = true;
+                const I3 cand[4] = {ed, shifted(ed, a, -1), shifted(ed, b, -1), shifted(shifted(ed, a, -1), b, -1)};
+                const int mine = da + 2 * db;                 // index of this cell in cand[]
+                for (int k = 0; k < mine; ++k) if (label_at(g, CL, SL_CENTER, cand[k]) == L_REDUCED) owner = false;
+                if (owner) mu = (double)local_viscosity(g, F.viscosity, SL_EDGE + e, ed);
+            }
+            stage[(22 + e * 4 + db * 2 + da) * GRAM_CELLS + slot] = mu;
+        }
+    }
+}
+// phase 2: moment `item` (0..234 work items, see the layout constants) over the staged cells, in cell order
+PS_D void accumulate_item(const Geom& g, const double* com, const double* stage, int nCells, int item, double* out) {
+    const double dx = g.dx;
+    if (item < 165) {                                    // Q^M_a, Q^N_a entry (k, l)
+        const int a = item / 55; int k, l; sym_pair(10, item % 55, k, l);
+        double accM = 0., accN = 0.;
+        for (int s = 0; s < nCells; ++s) {
+            double idx[3] = {stage[0 * GRAM_CELLS + s], stage[1 * GRAM_CELLS + s], stage[2 * GRAM_CELLS + s]};
+            for (int dir = 0; dir < 2; ++dir) {
+                const double wM = stage[(3 + 2 * a + dir) * GRAM_CELLS + s], wN = stage[(9 + 2 * a + dir) * GRAM_CELLS + s];
+                if (wM == 0. && wN == 0.) continue;
+                double o[3];
+                for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(d == a ? idx[d] + (dir ? 0.5 : -0.5) : idx[d], dx), com[d]);   // face_offset()
+                const double pr = monomial(k, o[0], o[1], o[2]) * monomial(l, o[0], o[1], o[2]);
+                accM += wM * pr; accN += wN * pr;
+            }
+        }
+        out[MOM_QM + item] = accM; out[MOM_QN + item] = accN;
+    } else if (item < 195) {                             // least-squares right-hand side moments
+        const int a = (item - 165) / 10, k = (item - 165) % 10;
+        double acc = 0.;
+        for (int s = 0; s < nCells; ++s) {
+            double idx[3] = {stage[0 * GRAM_CELLS + s], stage[1 * GRAM_CELLS + s], stage[2 * GRAM_CELLS + s]};
+            for (int dir = 0; dir < 2; ++dir) {
+                const double wu = stage[(15 + 2 * a + dir) * GRAM_CELLS + s];
+                if (wu == 0.) continue;
+                double o[3];
+                for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(d == a ? idx[d] + (dir ? 0.5 : -0.5) : idx[d], dx), com[d]);
+                acc += wu * monomial(k, o[0], o[1], o[2]);
+            }
+        }
+        out[MOM_RHS + (item - 165)] = acc;
+    } else if (item < 205) {                             // T^c: cell-centred stresses
+        int k, l; sym_pair(4, item - 195, k, l);
+        double acc = 0.;
+        for (int s = 0; s < nCells; ++s) {
+            double o[3];
+            for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(stage[d * GRAM_CELLS + s], dx), com[d]);
+            acc += stage[21 * GRAM_CELLS + s] * (monomial(k, o[0], o[1], o[2]) * monomial(l, o[0], o[1], o[2]));
+        }
+        out[MOM_TC + (item - 195)] = acc;
+    } else {                                             // T^e: edge-centred stresses of edge axis e
+        const int e = (item - 205) / 10; int k, l; sym_pair(4, (item - 205) % 10, k, l);
+        const int a = e == 0 ? 1 : 0, b = e == 2 ? 1 : 2;
+        double acc = 0.;
+        for (int s = 0; s < nCells; ++s)
+            for (int db = 0; db < 2; ++db) for (int da = 0; da < 2; ++da) {
+                const double mu = stage[(22 + e * 4 + db * 2 + da) * GRAM_CELLS + s];
+                if (mu == 0.) continue;
+                double idx[3] = {stage[0 * GRAM_CELLS + s], stage[1 * GRAM_CELLS + s], stage[2 * GRAM_CELLS + s]};
+                idx[a] += (double)da - 0.5; idx[b] += (double)db - 0.5;      // edge sample: -1/2 on the two axes across it
+                double o[3];
+                for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(idx[d], dx), com[d]);
+                acc += mu * (monomial(k, o[0], o[1], o[2]) * monomial(l, o[0], o[1], o[2]));
+            }
+        out[MOM_TE + (item - 205)] = acc;
+    }
+}
+constexpr int MOM_ITEMS = 235;
 
 #ifndef PS_EMULATE
-constexpr int GRAM_THREADS = 256;
-constexpr int GRAM_BATCH = 128;   // faces staged per pass (128 * (26+26+3) doubles = 56 KB smem)
-
-__global__ void __launch_bounds__(GRAM_THREADS) gram_partial_kernel(Geom g, Fields F, const double* __restrict__ com, const int32_t* __restrict__ cellList,
-                                                                   const int32_t* __restrict__ chunk, double* __restrict__ partial, int chunk0) {
-    extern __shared__ double sm[];
-    double* sc = sm;                              // [GRAM_BATCH][26]
-    double* sd = sc + GRAM_BATCH * RDOF;          // [GRAM_BATCH][26]
-    double* sw = sd + GRAM_BATCH * RDOF;          // [GRAM_BATCH][3]  wM, wN, u*wN
+__global__ void __launch_bounds__(GRAM_CELLS) gram_moments_kernel(Geom g, Fields F, const double* __restrict__ com, const int32_t* __restrict__ cellList,
+                                                                 const int32_t* __restrict__ chunk, double* __restrict__ partial, int chunk0) {
+    extern __shared__ double stage[];              // [STAGE_DOUBLES][GRAM_CELLS]
     const int ch = chunk0 + blockIdx.x;
     const int region = chunk[3 * ch + 0], begin = chunk[3 * ch + 1], end = chunk[3 * ch + 2];
-    const int nFaces = (end - begin) * 6;
-    // each thread owns up to 3 of the 676 (i,j) entries
-    double accM[3] = {0, 0, 0}, accN[3] = {0, 0, 0}, accV[3] = {0, 0, 0};
-    double accR = 0.;   // threads 0..25: rhs entry
-    for (int base = 0; base < nFaces; base += GRAM_BATCH) {
-        const int nb = min(GRAM_BATCH, nFaces - base);
-        __syncthreads();
-        if (threadIdx.x < nb) {
-            const int item = base + threadIdx.x;
-            const int cellQ = cellList[begin + item / 6];
-            const int fa = (item % 6) >> 1, dir = item & 1;
-            double c[RDOF], d[RDOF];
-            const FaceTerms t = face_terms(g, F, com, delin(g, SL_CENTER, cellQ), fa, dir, region, c, d);
-            for (int n = 0; n < RDOF; ++n) { sc[threadIdx.x * RDOF + n] = c[n]; sd[threadIdx.x * RDOF + n] = t.visc ? d[n] : 0.; }
-            sw[threadIdx.x * 3 + 0] = t.wM; sw[threadIdx.x * 3 + 1] = t.wN; sw[threadIdx.x * 3 + 2] = t.wN * t.u;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int e = threadIdx.x + k * GRAM_THREADS;
-            if (e < RDOF * RDOF) {
-                const int i = e / RDOF, j = e % RDOF;
-                double m = accM[k], nn = accN[k], v = accV[k];
-                for (int f = 0; f < nb; ++f) {
-                    const double ci = sc[f * RDOF + i], cj = sc[f * RDOF + j];
-                    m += (sw[f * 3 + 0] * ci) * cj;
-                    nn += (sw[f * 3 + 1] * ci) * cj;
-                    v += ci * sd[f * RDOF + j];
-                }
-                accM[k] = m; accN[k] = nn; accV[k] = v;
-            }
-        }
-        if (threadIdx.x < RDOF) {
-            double rr = accR;
-            for (int f = 0; f < nb; ++f) rr += sw[f * 3 + 2] * sc[f * RDOF + threadIdx.x];
-            accR = rr;
-        }
-    }
-    double* out = partial + (size_t)ch * GRAM_STRIDE;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int e = threadIdx.x + k * GRAM_THREADS;
-        if (e < RDOF * RDOF) { out[e] = accM[k]; out[RDOF * RDOF + e] = accN[k]; out[2 * RDOF * RDOF + e] = accV[k]; }
-    }
-    if (threadIdx.x < RDOF) out[3 * RDOF * RDOF + threadIdx.x] = accR;
+    const int nCells = end - begin;
+    if ((int)threadIdx.x < nCells) stage_cell(g, F, cellList[begin + threadIdx.x], threadIdx.x, stage);
+    __syncthreads();
+    if (threadIdx.x < MOM_ITEMS) accumulate_item(g, com + 3 * region, stage, nCells, threadIdx.x, partial + (size_t)ch * MOM_COUNT);
 }
-
 void region_gram_partials(cudaStream_t st, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
     if (RG.cellChunkHi <= RG.cellChunkLo) return;
-    const size_t smem = (size_t)GRAM_BATCH * (2 * RDOF + 3) * sizeof(double);
+    const size_t smem = (size_t)STAGE_DOUBLES * GRAM_CELLS * sizeof(double);
     static bool attr = false;
-    if (!attr) { PS_CUDA(cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    gram_partial_kernel<<<RG.cellChunkHi - RG.cellChunkLo, GRAM_THREADS, smem, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial, RG.cellChunkLo);
+    if (!attr) { PS_CUDA(cudaFuncSetAttribute(gram_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    gram_moments_kernel<<<RG.cellChunkHi - RG.cellChunkLo, GRAM_CELLS, smem, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial, RG.cellChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 #else
 void region_gram_partials(cudaStream_t, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
+    std::vector<double> stage((size_t)STAGE_DOUBLES * GRAM_CELLS);
     for (int ch = RG.cellChunkLo; ch < RG.cellChunkHi; ++ch) {
         const int region = RG.cellChunk.p[3 * ch], begin = RG.cellChunk.p[3 * ch + 1], end = RG.cellChunk.p[3 * ch + 2];
-        double* out = partial + (size_t)ch * GRAM_STRIDE;
-        for (int e = 0; e < GRAM_STRIDE; ++e) out[e] = 0.;
-        for (int ci = begin; ci < end; ++ci)
-            for (int item = 0; item < 6; ++item) {
-                double c[RDOF], d[RDOF];
-                const FaceTerms t = face_terms(g, F, RG.com.p, delin(g, SL_CENTER, RG.cellList.p[ci]), item >> 1, item & 1, region, c, d);
-                for (int i = 0; i < RDOF; ++i) {
-                    for (int j = 0; j < RDOF; ++j) {
-                        out[i * RDOF + j] += (t.wM * c[i]) * c[j];
-                        out[RDOF * RDOF + i * RDOF + j] += (t.wN * c[i]) * c[j];
-                        if (t.visc) out[2 * RDOF * RDOF + i * RDOF + j] += c[i] * d[j];
-                    }
-                    out[3 * RDOF * RDOF + i] += (t.wN * t.u) * c[i];
-                }
-            }
+        for (int i = begin; i < end; ++i) stage_cell(g, F, RG.cellList.p[i], i - begin, stage.data());
+        for (int item = 0; item < MOM_ITEMS; ++item) accumulate_item(g, RG.com.p + 3 * region, stage.data(), end - begin, item, partial + (size_t)ch * MOM_COUNT);
     }
 }
 #endif
 
-// dense 26x26 routines, one thread per region, matrices in a private global scratch slab.
-// S_AB:209 .inverse() -> PartialPivLU (extern/eigen/Eigen/src/LU/InverseImpl.h:25-31)
-PS_D void inverse_partial_piv(double* lu, double* inv, int* perm) {
+// dense 26x26 factorisations.  Same elimination order, pivot choice and per-element operations as the serial
+// algorithms (so the results are bit-identical to them), with the independent element updates spread over `nl` lanes.
+// PS_LANE_SYNC is a warp barrier in the CUDA build and nothing in the serial emulation (nl = 1).
+#ifndef PS_EMULATE
+#define PS_LANE_SYNC() __syncwarp()
+#else
+#define PS_LANE_SYNC()
+#endif
+// S_AB:209 .inverse() -> PartialPivLU (extern/eigen/Eigen/src/LU/InverseImpl.h:25-31).  lu, inv, perm live in shared / private memory.
+PS_D void inverse_partial_piv(double* lu, double* inv, int* perm, int lane, int nl) {
     const int n = RDOF;
-    for (int i = 0; i < n; ++i) perm[i] = i;
+    for (int i = lane; i < n; i += nl) perm[i] = i;
+    PS_LANE_SYNC();
     for (int k = 0; k < n; ++k) {
         int piv = k; double best = fabs(lu[k * n + k]);
-        for (int i = k + 1; i < n; ++i) { const double a = fabs(lu[i * n + k]); if (a > best) { best = a; piv = i; } }
-        if (piv != k) { for (int j = 0; j < n; ++j) { const double t = lu[k * n + j]; lu[k * n + j] = lu[piv * n + j]; lu[piv * n + j] = t; } const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+        for (int i = k + 1; i < n; ++i) { const double a = fabs(lu[i * n + k]); if (a > best) { best = a; piv = i; } }     // every lane, same answer
+        PS_LANE_SYNC();
+        if (piv != k) {
+            for (int j = lane; j < n; j += nl) { const double t = lu[k * n + j]; lu[k * n + j] = lu[piv * n + j]; lu[piv * n + j] = t; }
+            if (lane == 0) { const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+        }
+        PS_LANE_SYNC();
         const double dg = lu[k * n + k];
-        if (dg != 0.) for (int i = k + 1; i < n; ++i) lu[i * n + k] /= dg;
-        for (int i = k + 1; i < n; ++i) { const double l = lu[i * n + k]; for (int j = k + 1; j < n; ++j) lu[i * n + j] -= l * lu[k * n + j]; }
+        PS_LANE_SYNC();
+        if (dg != 0.) for (int i = k + 1 + lane; i < n; i += nl) lu[i * n + k] /= dg;
+        PS_LANE_SYNC();
+        const int m = n - k - 1;
+        for (int e = lane; e < m * m; e += nl) { const int i = k + 1 + e / m, j = k + 1 + e % m; lu[i * n + j] -= lu[i * n + k] * lu[k * n + j]; }
+        PS_LANE_SYNC();
     }
-    double col[RDOF];
-    for (int c = 0; c < n; ++c) {
+    for (int c = lane; c < n; c += nl) {          // one right-hand side (unit vector) per lane
+        double col[RDOF];
         for (int i = 0; i < n; ++i) col[i] = (perm[i] == c) ? 1. : 0.;
         for (int i = 0; i < n; ++i) { double s = col[i]; for (int j = 0; j < i; ++j) s -= lu[i * n + j] * col[j]; col[i] = s; }
         for (int i = n - 1; i >= 0; --i) { double s = col[i]; for (int j = i + 1; j < n; ++j) s -= lu[i * n + j] * col[j]; col[i] = s / lu[i * n + i]; }
         for (int i = 0; i < n; ++i) inv[i * n + c] = col[i];
     }
+    PS_LANE_SYNC();
 }
 // S.cpp:415 fullPivLu().solve(): complete pivoting, rank threshold maxPivot * eps * n, free variables 0
-PS_D void solve_full_piv(double* lu, const double* rhs, double* x, int* rowT, int* colT) {
+PS_D void solve_full_piv(double* lu, const double* rhs, double* x, int* rowT, int* colT, int lane, int nl) {
     const int n = RDOF;
     int nonzero = n; double maxPivot = 0.;
     for (int k = 0; k < n; ++k) {
-        int pr = k, pc = k; double best = 0.;
-        for (int i = k; i < n; ++i) for (int j = k; j < n; ++j) { const double a = fabs(lu[i * n + j]); if (a > best) { best = a; pr = i; pc = j; } }
-        if (best == 0.) { nonzero = k; for (int i = k; i < n; ++i) { rowT[i] = i; colT[i] = i; } break; }
+        // first maximum of |lu| over the trailing block in row-major order (the serial scan keeps the first on ties)
+        double best = 0.; int bestIdx = k * n + k;
+        const int m = n - k;
+        for (int e = lane; e < m * m; e += nl) { const int idx = (k + e / m) * n + (k + e % m); const double a = fabs(lu[idx]); if (a > best || (a == best && a > 0. && idx < bestIdx)) { best = a; bestIdx = idx; } }
+#ifndef PS_EMULATE
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+            if (ob > best || (ob == best && ob > 0. && oi < bestIdx)) { best = ob; bestIdx = oi; }
+        }
+#endif
+        const int pr = bestIdx / n, pc = bestIdx % n;
+        if (best == 0.) { nonzero = k; for (int i = k + lane; i < n; i += nl) { rowT[i] = i; colT[i] = i; } break; }
         if (best > maxPivot) maxPivot = best;
-        rowT[k] = pr; colT[k] = pc;
-        if (pr != k) for (int j = 0; j < n; ++j) { const double t = lu[k * n + j]; lu[k * n + j] = lu[pr * n + j]; lu[pr * n + j] = t; }
-        if (pc != k) for (int i = 0; i < n; ++i) { const double t = lu[i * n + k]; lu[i * n + k] = lu[i * n + pc]; lu[i * n + pc] = t; }
+        if (lane == 0) { rowT[k] = pr; colT[k] = pc; }
+        PS_LANE_SYNC();
+        if (pr != k) for (int j = lane; j < n; j += nl) { const double t = lu[k * n + j]; lu[k * n + j] = lu[pr * n + j]; lu[pr * n + j] = t; }
+        PS_LANE_SYNC();
+        if (pc != k) for (int i = lane; i < n; i += nl) { const double t = lu[i * n + k]; lu[i * n + k] = lu[i * n + pc]; lu[i * n + pc] = t; }
+        PS_LANE_SYNC();
         const double dg = lu[k * n + k];
-        for (int i = k + 1; i < n; ++i) lu[i * n + k] /= dg;
-        for (int i = k + 1; i < n; ++i) { const double l = lu[i * n + k]; for (int j = k + 1; j < n; ++j) lu[i * n + j] -= l * lu[k * n + j]; }
+        PS_LANE_SYNC();
+        for (int i = k + 1 + lane; i < n; i += nl) lu[i * n + k] /= dg;
+        PS_LANE_SYNC();
+        const int mm = n - k - 1;
+        for (int e = lane; e < mm * mm; e += nl) { const int i = k + 1 + e / mm, j = k + 1 + e % mm; lu[i * n + j] -= lu[i * n + k] * lu[k * n + j]; }
+        PS_LANE_SYNC();
     }
-    const double thr = maxPivot * (2.220446049250313e-16 * n);
-    int rank = 0;
-    for (int i = 0; i < nonzero; ++i) if (fabs(lu[i * n + i]) > thr) ++rank;
-    double c[RDOF];
-    for (int i = 0; i < n; ++i) c[i] = rhs[i];
-    for (int k = 0; k < n; ++k) if (rowT[k] != k) { const double t = c[k]; c[k] = c[rowT[k]]; c[rowT[k]] = t; }
-    for (int i = 0; i < n; ++i) { double s = c[i]; for (int j = 0; j < i; ++j) s -= lu[i * n + j] * c[j]; c[i] = s; }
-    for (int i = rank - 1; i >= 0; --i) { double s = c[i]; for (int j = i + 1; j < rank; ++j) s -= lu[i * n + j] * c[j]; c[i] = s / lu[i * n + i]; }
-    for (int i = rank; i < n; ++i) c[i] = 0.;
-    for (int k = n - 1; k >= 0; --k) if (colT[k] != k) { const double t = c[k]; c[k] = c[colT[k]]; c[colT[k]] = t; }
-    for (int i = 0; i < n; ++i) x[i] = c[i];
+    PS_LANE_SYNC();
+    if (lane == 0) {
+        const double thr = maxPivot * (2.220446049250313e-16 * n);
+        int rank = 0;
+        for (int i = 0; i < nonzero; ++i) if (fabs(lu[i * n + i]) > thr) ++rank;
+        double c[RDOF];
+        for (int i = 0; i < n; ++i) c[i] = rhs[i];
+        for (int k = 0; k < n; ++k) if (rowT[k] != k) { const double t = c[k]; c[k] = c[rowT[k]]; c[rowT[k]] = t; }
+        for (int i = 0; i < n; ++i) { double s = c[i]; for (int j = 0; j < i; ++j) s -= lu[i * n + j] * c[j]; c[i] = s; }
+        for (int i = rank - 1; i >= 0; --i) { double s = c[i]; for (int j = i + 1; j < rank; ++j) s -= lu[i * n + j] * c[j]; c[i] = s / lu[i * n + i]; }
+        for (int i = rank; i < n; ++i) c[i] = 0.;
+        for (int k = n - 1; k >= 0; --k) if (colT[k] != k) { const double t = c[k]; c[k] = c[colT[k]]; c[colT[k]] = t; }
+        for (int i = 0; i < n; ++i) x[i] = c[i];
+    }
+    PS_LANE_SYNC();
 }
 
-// sums the chunk partials of every region in chunk order, then per region:
-//   v* = fullPivLu(N).solve(rhs)                        (computeLeastSquaresFits, S.cpp:412-416)
-//   B  = M/dt + 2 V ; B^-1 = B.inverse()                (assembleReducedInvertedBlock, S_AB:195-244)
-//   rhs_r = M v*                                        (assembleReducedRHSVector, S_AB:356-367)
+// per region: v* = fullPivLu(N).solve(rhs) (S.cpp:412-416); B = M/dt + 2 V, B^-1 = B.inverse() (S_AB:195-244); rhs_r = M v* (S_AB:356-367)
+PS_D void region_factor(double invDt, const double* Mr, const double* Vi, const double* Nm, const double* lsq, double* fit, double* Binv, double* rhsR,
+                        double* a, double* b, int* piv, int lane, int nl) {
+    const int NN = RDOF * RDOF;
+    for (int e = lane; e < NN; e += nl) { a[e] = Nm[e]; b[e] = invDt * Mr[e] + 2. * Vi[e]; }
+    PS_LANE_SYNC();
+    solve_full_piv(a, lsq, fit, piv, piv + RDOF, lane, nl);
+    inverse_partial_piv(b, Binv, piv + 2 * RDOF, lane, nl);
+    for (int i = lane; i < RDOF; i += nl) { double s = 0.; for (int j = 0; j < RDOF; ++j) s += Mr[i * RDOF + j] * fit[j]; rhsR[i] = s; }
+}
+#ifndef PS_EMULATE
+__global__ void __launch_bounds__(32) region_factor_kernel(double invDt, int region0, const double* __restrict__ Mr, const double* __restrict__ Vi, const double* __restrict__ Nm,
+                                                          const double* __restrict__ lsq, double* fit, double* Binv, double* rhsR) {
+    __shared__ double a[RDOF * RDOF], b[RDOF * RDOF], inv[RDOF * RDOF], x[RDOF], out[RDOF];
+    __shared__ int piv[3 * RDOF];
+    const int r = region0 + blockIdx.x, NN = RDOF * RDOF;
+    region_factor(invDt, Mr + (size_t)r * NN, Vi + (size_t)r * NN, Nm + (size_t)r * NN, lsq + (size_t)r * RDOF, x, inv, out, a, b, piv, threadIdx.x, 32);
+    __syncwarp();
+    for (int e = threadIdx.x; e < NN; e += 32) Binv[(size_t)r * NN + e] = inv[e];
+    if (threadIdx.x < RDOF) { fit[(size_t)r * RDOF + threadIdx.x] = x[threadIdx.x]; rhsR[(size_t)r * RDOF + threadIdx.x] = out[threadIdx.x]; }
+}
+#endif
+
+// sums the chunk moments of every owned region in chunk order, expands them to M_r, N_r, (JD^T mu DJ^T)_r and the
+// least-squares right-hand side, then factorises
 void region_gram_finish(cudaStream_t st, const Geom& g, RegionData& RG, int nChunks) {
     // only the regions this rank owns [regLo, regHi) (all of them on one GPU)
     const int R0 = RG.regLo, R = RG.regHi - RG.regLo;
     if (R <= 0) return;
+    if (RG.tables.n < (size_t)TAB_COUNT) { std::vector<double> T(TAB_COUNT); build_region_tables(T.data()); RG.tables.from_host(st, T.data(), T.size()); }
+    RG.moments.alloc((size_t)RG.count * MOM_COUNT);
     const double* partial = RG.partial.p; const int32_t* chunkStart = RG.cellChunkStart.p;
+    double* mom = RG.moments.p; const double* T = RG.tables.p;
     double* Mr = RG.Mr.p; double* Vi = RG.Visc.p; double* Nm = RG.N.p; double* Binv = RG.Binv.p;
     double* lsq = RG.lsqRhs.p; double* fit = RG.bestFit.p; double* rhsR = RG.rhsR.p;
     const int NN = RDOF * RDOF;
+    ps_for(st, (int64_t)R * MOM_COUNT, PS_LAMBDA(int64_t ql) {
+        const int r = R0 + (int)(ql / MOM_COUNT), e = (int)(ql % MOM_COUNT);
+        double s = 0.;
+        for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) s += partial[(size_t)ch * MOM_COUNT + e];
+        mom[(size_t)r * MOM_COUNT + e] = s;
+    });
     ps_for(st, (int64_t)R * NN, PS_LAMBDA(int64_t ql) {
-        const int64_t q = ql + (int64_t)R0 * NN;
-        const int r = (int)(q / NN), e = (int)(q % NN);
-        double m = 0., n = 0., v = 0.;
-        for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) {
-            const double* p = partial + (size_t)ch * GRAM_STRIDE;
-            m += p[e]; n += p[NN + e]; v += p[2 * NN + e];
+        const int r = R0 + (int)(ql / NN), e = (int)(ql % NN), i = e / RDOF, j = e % RDOF;
+        const double* m = mom + (size_t)r * MOM_COUNT;
+        double M = 0., N = 0., V = 0.;
+        for (int a = 0; a < 3; ++a) {
+            const double* Si = T + TAB_S + (a * RDOF + i) * 10; const double* Sj = T + TAB_S + (a * RDOF + j) * 10;
+            for (int k = 0; k < 10; ++k) {
+                if (Si[k] == 0.) continue;
+                for (int l = 0; l < 10; ++l) {
+                    if (Sj[l] == 0.) continue;
+                    const int q = a * 55 + sym_index(10, k, l);
+                    M += Si[k] * Sj[l] * m[MOM_QM + q]; N += Si[k] * Sj[l] * m[MOM_QN + q];
+                }
+            }
+            const double* Ai = T + TAB_A + (a * RDOF + i) * 4; const double* Aj = T + TAB_A + (a * RDOF + j) * 4;
+            const double* Hi = T + TAB_H + (a * RDOF + i) * 4; const double* Hj = T + TAB_H + (a * RDOF + j) * 4;
+            for (int k = 0; k < 4; ++k) for (int l = 0; l < 4; ++l) {
+                const int q = sym_index(4, k, l);
+                V += Ai[k] * Aj[l] * m[MOM_TC + q] + 0.5 * (Hi[k] * Hj[l]) * m[MOM_TE + a * 10 + q];
+            }
         }
-        Mr[q] = m; Nm[q] = n; Vi[q] = v;
+        const size_t o = (size_t)r * NN + e;
+        Mr[o] = M; Nm[o] = N; Vi[o] = V;
     });
     ps_for(st, (int64_t)R * RDOF, PS_LAMBDA(int64_t ql) {
-        const int64_t q = ql + (int64_t)R0 * RDOF;
-        const int r = (int)(q / RDOF), e = (int)(q % RDOF);
+        const int r = R0 + (int)(ql / RDOF), i = (int)(ql % RDOF);
+        const double* m = mom + (size_t)r * MOM_COUNT;
         double s = 0.;
-        for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) s += partial[(size_t)ch * GRAM_STRIDE + 3 * NN + e];
-        lsq[q] = s;
+        for (int a = 0; a < 3; ++a) { const double* Si = T + TAB_S + (a * RDOF + i) * 10; for (int k = 0; k < 10; ++k) s += Si[k] * m[MOM_RHS + a * 10 + k]; }
+        lsq[(size_t)r * RDOF + i] = s;
     });
-    // scratch: reuse the partial buffer's head is unsafe (still read above on the same stream is fine, but keep it simple)
-    static thread_local DBuf<double> luA, luB;
-    static thread_local DBuf<int> piv;
-    luA.alloc((size_t)R * NN); luB.alloc((size_t)R * NN); piv.alloc((size_t)R * 3 * RDOF);
-    double* A = luA.p; double* B = luB.p; int* pv = piv.p;
-    const double invDt = g.invDt;
-    ps_for(st, R, PS_LAMBDA(int64_t rl) {
-        const int64_t r = rl + R0;
-        double* a = A + rl * NN; double* b = B + rl * NN; int* p3 = pv + rl * 3 * RDOF;
-        for (int e = 0; e < NN; ++e) { a[e] = Nm[r * NN + e]; b[e] = invDt * Mr[r * NN + e] + 2. * Vi[r * NN + e]; }
-        solve_full_piv(a, lsq + r * RDOF, fit + r * RDOF, p3, p3 + RDOF);
-        inverse_partial_piv(b, Binv + r * NN, p3 + 2 * RDOF);
-        for (int i = 0; i < RDOF; ++i) { double s = 0.; for (int j = 0; j < RDOF; ++j) s += Mr[r * NN + i * RDOF + j] * fit[r * RDOF + j]; rhsR[r * RDOF + i] = s; }
-    });
+#ifndef PS_EMULATE
+    region_factor_kernel<<<R, 32, 0, st>>>(g.invDt, R0, Mr, Vi, Nm, lsq, fit, Binv, rhsR);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+#else
+    for (int r = R0; r < R0 + R; ++r) {
+        double a[RDOF * RDOF], b[RDOF * RDOF]; int piv[3 * RDOF];
+        region_factor(g.invDt, Mr + (size_t)r * NN, Vi + (size_t)r * NN, Nm + (size_t)r * NN, lsq + (size_t)r * RDOF, fit + (size_t)r * RDOF, Binv + (size_t)r * NN,
+                      rhsR + (size_t)r * RDOF, a, b, piv, 0, 1);
+    }
+#endif
     (void)nChunks;
 }
 

@@ -396,7 +396,7 @@ void Solver::computeReducedRegionMatrices() {
     RG.cellChunk.from_host(st, table.data(), table.size());
     RG.cellChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
     const size_t NN = (size_t)RDOF * RDOF;
-    RG.partial.alloc((size_t)RG.nCellChunks * (3 * NN + RDOF));
+    RG.partial.alloc((size_t)RG.nCellChunks * 400);
     RG.Mr.alloc(R * NN); RG.Visc.alloc(R * NN); RG.N.alloc(R * NN); RG.Binv.alloc(R * NN);
     RG.lsqRhs.alloc((size_t)R * RDOF); RG.bestFit.alloc((size_t)R * RDOF); RG.rhsR.alloc((size_t)R * RDOF);
     RG.t.alloc((size_t)R * RDOF); RG.s.alloc((size_t)R * RDOF);

@@ -45,6 +45,8 @@ struct RegionData {
     DBuf<double> com;        // [R][3]
     DBuf<double> Mr, Visc, N, Binv;   // [R][26*26]
     DBuf<double> lsqRhs, bestFit, rhsR;  // [R][26]
+    DBuf<double> moments;    // [R][400] polynomial moments the region matrices are expanded from (ps_reduced.cu)
+    DBuf<double> tables;     // constant 26x10 / 26x4 images of the basis (generated once)
     DBuf<int32_t> cellList;  // REDUCED cells sorted by (region, tile order)
     DBuf<int32_t> cellStart; // [R+1]
     // coupled reduced face rows of K_ext, sorted by (region, axis, tile order)
