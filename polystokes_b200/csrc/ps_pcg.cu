@@ -110,7 +110,8 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
 
 // pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
 // streams, <= 8 gathers of x (L1 / L2), 8 B of w out.
-__global__ void __launch_bounds__(HOT_THREADS) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
+// (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
     __shared__ double lut[65];
     if (S && S->done) return;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
@@ -148,7 +149,8 @@ __device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, dou
 // y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) (p.Ap) -> S->red[0] / the peers.
 // Cell sweep: one thread computes the pressure row and the xx / yy / zz stress rows of its cell from ONE set of 6
 // columns, codes and w gathers (32 B of matrix per cell); edge sweep: 4 columns + 4 codes (20 B per edge).
-__global__ void __launch_bounds__(HOT_THREADS, 4) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
+template <int OCC>
+__global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
                                                               double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {
     if (S && S->done) return;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -360,7 +362,13 @@ void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, doubl
     PS_CUDA(cudaGetLastError());
 }
 void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode) {
-    pass2_kernel<<<hot_blocks(pass2_kernel, A.rowsP.total() + A.rowsE.total()), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    // resident CTAs per SM the kernel is compiled for.  Measured on S3 256^3 (profiles/r01_sweep_occupancy.log): 4 -> 0.148 ms, 5 -> 0.137 ms,
+    // 6 -> 0.132 ms, 7 / 8 spill and fall back to 0.137 ms
+    static const int occ = getenv("PS_PASS2_OCC") ? atoi(getenv("PS_PASS2_OCC")) : 6;
+    const int64_t rows = A.rowsP.total() + A.rowsE.total();
+    if (occ >= 6) pass2_kernel<6><<<hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    else if (occ == 5) pass2_kernel<5><<<hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    else pass2_kernel<4><<<hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }

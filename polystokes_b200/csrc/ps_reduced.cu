@@ -148,10 +148,28 @@ static void build_region_tables(double* T) {
         }
 }
 
-// phase 1: everything the moments need from one REDUCED cell, staged as stage[field * GRAM_CELLS + slot]
-PS_D void stage_cell(const Geom& g, const Fields& F, int64_t cellQ, int slot, double* stage) {
+// v^e for e in 0..4 without divergent control flow
+PS_HD double pow_small(double v, int e) {
+    const double v2 = v * v;
+    double r = (e & 1) ? v : 1.;
+    if (e & 2) r *= v2;
+    if (e & 4) r *= v2 * v2;
+    return r;
+}
+// exponents (ex, ey, ez) of monomial k of {1,x,y,z,xx,xy,xz,yy,yz,zz}, packed 4 bits each
+PS_HD int monomial_exps(int k) {
+    const int t[10] = {0x000, 0x001, 0x010, 0x100, 0x002, 0x011, 0x101, 0x020, 0x110, 0x200};
+    return t[k];
+}
+
+// phase 1: everything the moments need from one REDUCED cell, staged as stage[field * GRAM_CELLS + slot]:
+// fields 0-2 the cell-centre offset from the region's COM, 3-8 wM, 9-14 wN, 15-20 wN*u of the 6 faces, 21 mu, 22-33 mu of
+// the owned REDUCED edges
+PS_D void stage_cell(const Geom& g, const Fields& F, const double* com, int64_t cellQ, int slot, double* stage) {
     const I3 c = delin(g, SL_CENTER, cellQ);
-    stage[0 * GRAM_CELLS + slot] = (double)c.x; stage[1 * GRAM_CELLS + slot] = (double)c.y; stage[2 * GRAM_CELLS + slot] = (double)c.z;
+    stage[0 * GRAM_CELLS + slot] = sub_rn(mul_rn((double)c.x, g.dx), com[0]);
+    stage[1 * GRAM_CELLS + slot] = sub_rn(mul_rn((double)c.y, g.dx), com[1]);
+    stage[2 * GRAM_CELLS + slot] = sub_rn(mul_rn((double)c.z, g.dx), com[2]);
     const int8_t* CL = F.label[SL_CENTER];
     for (int axis = 0; axis < 3; ++axis)
         for (int dir = 0; dir < 2; ++dir) {
@@ -183,61 +201,56 @@ PS_D void stage_cell(const Geom& g, const Fields& F, int64_t cellQ, int slot, do
         }
     }
 }
-// phase 2: moment `item` (0..234 work items, see the layout constants) over the staged cells, in cell order
-PS_D void accumulate_item(const Geom& g, const double* com, const double* stage, int nCells, int item, double* out) {
-    const double dx = g.dx;
-    if (item < 165) {                                    // Q^M_a, Q^N_a entry (k, l)
-        const int a = item / 55; int k, l; sym_pair(10, item % 55, k, l);
-        double accM = 0., accN = 0.;
+// phase 2: moment `item` (0..234 work items, see the layout constants) over the staged cells, in cell order.
+// A face of axis a sits at the cell-centre offset -+ dx/2 on axis a; an edge of axis e at -+ dx/2 on the two other axes.
+PS_D void accumulate_item(const Geom& g, const double* stage, int nCells, int item, double* out) {
+    const double h = 0.5 * g.dx;
+    if (item < 195) {
+        const bool rhs = item >= 165;
+        const int a = rhs ? (item - 165) / 10 : item / 55;
+        int ex;
+        if (rhs) ex = monomial_exps((item - 165) % 10);
+        else { int k, l; sym_pair(10, item % 55, k, l); ex = monomial_exps(k) + monomial_exps(l); }
+        const int e[3] = {ex & 15, (ex >> 4) & 15, (ex >> 8) & 15};
+        const int b = (a + 1) % 3, c = (a + 2) % 3;
+        const double* pa = stage + a * GRAM_CELLS; const double* pb = stage + b * GRAM_CELLS; const double* pc = stage + c * GRAM_CELLS;
+        const double* w0 = stage + ((rhs ? 15 : 3) + 2 * a) * GRAM_CELLS;    // wM (or wN*u) of the two faces of axis a
+        const double* w1 = stage + (9 + 2 * a) * GRAM_CELLS;                  // wN
+        double acc0 = 0., acc1 = 0.;
         for (int s = 0; s < nCells; ++s) {
-            double idx[3] = {stage[0 * GRAM_CELLS + s], stage[1 * GRAM_CELLS + s], stage[2 * GRAM_CELLS + s]};
+            const double base = pow_small(pb[s], e[b]) * pow_small(pc[s], e[c]);
             for (int dir = 0; dir < 2; ++dir) {
-                const double wM = stage[(3 + 2 * a + dir) * GRAM_CELLS + s], wN = stage[(9 + 2 * a + dir) * GRAM_CELLS + s];
-                if (wM == 0. && wN == 0.) continue;
-                double o[3];
-                for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(d == a ? idx[d] + (dir ? 0.5 : -0.5) : idx[d], dx), com[d]);   // face_offset()
-                const double pr = monomial(k, o[0], o[1], o[2]) * monomial(l, o[0], o[1], o[2]);
-                accM += wM * pr; accN += wN * pr;
+                const double wa = w0[dir * GRAM_CELLS + s], wb = rhs ? 0. : w1[dir * GRAM_CELLS + s];
+                if (wa == 0. && wb == 0.) continue;
+                const double pr = base * pow_small(dir ? pa[s] + h : pa[s] - h, e[a]);
+                acc0 += wa * pr; acc1 += wb * pr;
             }
         }
-        out[MOM_QM + item] = accM; out[MOM_QN + item] = accN;
-    } else if (item < 195) {                             // least-squares right-hand side moments
-        const int a = (item - 165) / 10, k = (item - 165) % 10;
-        double acc = 0.;
-        for (int s = 0; s < nCells; ++s) {
-            double idx[3] = {stage[0 * GRAM_CELLS + s], stage[1 * GRAM_CELLS + s], stage[2 * GRAM_CELLS + s]};
-            for (int dir = 0; dir < 2; ++dir) {
-                const double wu = stage[(15 + 2 * a + dir) * GRAM_CELLS + s];
-                if (wu == 0.) continue;
-                double o[3];
-                for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(d == a ? idx[d] + (dir ? 0.5 : -0.5) : idx[d], dx), com[d]);
-                acc += wu * monomial(k, o[0], o[1], o[2]);
-            }
-        }
-        out[MOM_RHS + (item - 165)] = acc;
-    } else if (item < 205) {                             // T^c: cell-centred stresses
+        if (rhs) out[MOM_RHS + (item - 165)] = acc0;
+        else { out[MOM_QM + item] = acc0; out[MOM_QN + item] = acc1; }
+    } else if (item < 205) {                             // T^c: cell-centred stresses, sum mu (1,x,y,z)(1,x,y,z)^T
         int k, l; sym_pair(4, item - 195, k, l);
+        const int ex = monomial_exps(k) + monomial_exps(l);
+        const double* mu = stage + 21 * GRAM_CELLS;
         double acc = 0.;
-        for (int s = 0; s < nCells; ++s) {
-            double o[3];
-            for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(stage[d * GRAM_CELLS + s], dx), com[d]);
-            acc += stage[21 * GRAM_CELLS + s] * (monomial(k, o[0], o[1], o[2]) * monomial(l, o[0], o[1], o[2]));
-        }
+        for (int s = 0; s < nCells; ++s)
+            acc += mu[s] * (pow_small(stage[s], ex & 15) * pow_small(stage[GRAM_CELLS + s], (ex >> 4) & 15) * pow_small(stage[2 * GRAM_CELLS + s], (ex >> 8) & 15));
         out[MOM_TC + (item - 195)] = acc;
     } else {                                             // T^e: edge-centred stresses of edge axis e
         const int e = (item - 205) / 10; int k, l; sym_pair(4, (item - 205) % 10, k, l);
+        const int ex = monomial_exps(k) + monomial_exps(l);
+        const int ee[3] = {ex & 15, (ex >> 4) & 15, (ex >> 8) & 15};
         const int a = e == 0 ? 1 : 0, b = e == 2 ? 1 : 2;
+        const double* pe = stage + e * GRAM_CELLS; const double* pa = stage + a * GRAM_CELLS; const double* pb = stage + b * GRAM_CELLS;
         double acc = 0.;
-        for (int s = 0; s < nCells; ++s)
+        for (int s = 0; s < nCells; ++s) {
+            const double along = pow_small(pe[s], ee[e]);
             for (int db = 0; db < 2; ++db) for (int da = 0; da < 2; ++da) {
                 const double mu = stage[(22 + e * 4 + db * 2 + da) * GRAM_CELLS + s];
                 if (mu == 0.) continue;
-                double idx[3] = {stage[0 * GRAM_CELLS + s], stage[1 * GRAM_CELLS + s], stage[2 * GRAM_CELLS + s]};
-                idx[a] += (double)da - 0.5; idx[b] += (double)db - 0.5;      // edge sample: -1/2 on the two axes across it
-                double o[3];
-                for (int d = 0; d < 3; ++d) o[d] = sub_rn(mul_rn(idx[d], dx), com[d]);
-                acc += mu * (monomial(k, o[0], o[1], o[2]) * monomial(l, o[0], o[1], o[2]));
+                acc += mu * (along * pow_small(da ? pa[s] + h : pa[s] - h, ee[a]) * pow_small(db ? pb[s] + h : pb[s] - h, ee[b]));
             }
+        }
         out[MOM_TE + (item - 205)] = acc;
     }
 }
@@ -250,9 +263,9 @@ __global__ void __launch_bounds__(GRAM_CELLS) gram_moments_kernel(Geom g, Fields
     const int ch = chunk0 + blockIdx.x;
     const int region = chunk[3 * ch + 0], begin = chunk[3 * ch + 1], end = chunk[3 * ch + 2];
     const int nCells = end - begin;
-    if ((int)threadIdx.x < nCells) stage_cell(g, F, cellList[begin + threadIdx.x], threadIdx.x, stage);
+    if ((int)threadIdx.x < nCells) stage_cell(g, F, com + 3 * region, cellList[begin + threadIdx.x], threadIdx.x, stage);
     __syncthreads();
-    if (threadIdx.x < MOM_ITEMS) accumulate_item(g, com + 3 * region, stage, nCells, threadIdx.x, partial + (size_t)ch * MOM_COUNT);
+    if (threadIdx.x < MOM_ITEMS) accumulate_item(g, stage, nCells, threadIdx.x, partial + (size_t)ch * MOM_COUNT);
 }
 void region_gram_partials(cudaStream_t st, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
     if (RG.cellChunkHi <= RG.cellChunkLo) return;
@@ -268,8 +281,8 @@ void region_gram_partials(cudaStream_t, const Geom& g, const Fields& F, const Re
     std::vector<double> stage((size_t)STAGE_DOUBLES * GRAM_CELLS);
     for (int ch = RG.cellChunkLo; ch < RG.cellChunkHi; ++ch) {
         const int region = RG.cellChunk.p[3 * ch], begin = RG.cellChunk.p[3 * ch + 1], end = RG.cellChunk.p[3 * ch + 2];
-        for (int i = begin; i < end; ++i) stage_cell(g, F, RG.cellList.p[i], i - begin, stage.data());
-        for (int item = 0; item < MOM_ITEMS; ++item) accumulate_item(g, RG.com.p + 3 * region, stage.data(), end - begin, item, partial + (size_t)ch * MOM_COUNT);
+        for (int i = begin; i < end; ++i) stage_cell(g, F, RG.com.p + 3 * region, RG.cellList.p[i], i - begin, stage.data());
+        for (int item = 0; item < MOM_ITEMS; ++item) accumulate_item(g, stage.data(), end - begin, item, partial + (size_t)ch * MOM_COUNT);
     }
 }
 #endif
