@@ -72,6 +72,7 @@ PS_D void cg_advance(PcgScalars* S) {
 #ifndef PS_EMULATE
 constexpr int HOT_THREADS = 256;
 constexpr int HOT_MAX_BLOCKS = 148 * 8;
+static_assert(HOT_THREADS == SCHED_BLOCK, "one schedule block per CTA iteration");
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -116,25 +117,27 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_cons
     if (S && S->done) return;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
     __syncthreads();
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const double sc = A.valScale;
-    // owned rows: one range on a single GPU; x, y, z faces + coupled reduced rows of the slab otherwise
+    // owned rows in the merged block order of the four ranges (SchedRanges, ps_solver.hpp)
 #pragma unroll 2
-    for (RangeWalk<4> it(A.rowsK, tid); it.valid(A.rowsK); it.step(A.rowsK, stride)) {
-        const int64_t r = it.j;
+    for (int g = blockIdx.x; g < A.nSched1; g += gridDim.x) {
+        const int32_t e = __ldg(A.sched1 + g);
+        const int k = (int)((uint32_t)e >> 28);
+        const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
+        if (r >= A.s1.hi[k]) continue;
         const uint64_t word = __ldcs(A.kcode + r);
         int32_t c[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c[k] = __ldcs(A.kcol + (int64_t)k * A.nRowsExt + r);
+        for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
         const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
         const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
         const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
         double xv[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xv[k] = ((word >> (8 * k)) & 0xffull) ? x[col[k]] : 0.;
+        for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
         double s = 0.;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += ((double)op_code(word, k) * sc) * xv[k];
+        for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
         w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
     }
 }
@@ -153,61 +156,65 @@ template <int OCC>
 __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
                                                               double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {
     if (S && S->done) return;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const bool dot = mode & 1;
     const double sc = A.valScale;
     const int64_t nC = A.nC, nP = A.nP, oE = A.nP + 3 * A.nC;
     double acc = 0.;
-#pragma unroll 2
-    for (RangeWalk<4> it(A.rowsP, tid); it.valid(A.rowsP); it.step(A.rowsP, stride)) {
-        const int64_t ci = it.j;
-        const uint64_t word = __ldcs(A.ccode + ci);
-        double v[6], wv[6];
+    // owned rows in the merged block order: range 0 = cells, 1..3 = yz / xz / xy edges (SchedRanges, ps_solver.hpp)
+#pragma unroll 1
+    for (int g = blockIdx.x; g < A.nSched2; g += gridDim.x) {
+        const int32_t se = __ldg(A.sched2 + g);
+        const int k = (int)((uint32_t)se >> 28);
+        const int64_t row = A.s2.lo[k] + (int64_t)(se & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
+        if (row >= A.s2.hi[k]) continue;
+        if (k == 0) {
+            const int64_t ci = row;
+            const uint64_t word = __ldcs(A.ccode + ci);
+            double v[6], wv[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int32_t c = __ldcs(A.ccol + (int64_t)k * nC + ci);
-            v[k] = (double)op_code(word, k) * sc;
-            wv[k] = ((word >> (8 * k)) & 0xffull) ? w[c] : 0.;
-        }
-        double s = 0.;
+            for (int q = 0; q < 6; ++q) {
+                const int32_t c = __ldcs(A.ccol + (int64_t)q * nC + ci);
+                v[q] = (double)op_code(word, q) * sc;
+                wv[q] = ((word >> (8 * q)) & 0xffull) ? w[c] : 0.;
+            }
+            double s = 0.;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) s += v[k] * wv[k];
-        double yp = -s;
-        if (add) yp += add[ci];
-        y[ci] = yp;
-        if (dot) acc += x[ci] * yp;
-        const double ui = muScale != 0. ? muScale * A.uInv[ci] : 0.;      // mu^-1 is the same for xx, yy, zz of a cell
+            for (int q = 0; q < 6; ++q) s += v[q] * wv[q];
+            double yp = -s;
+            if (add) yp += add[ci];
+            y[ci] = yp;
+            if (dot) acc += x[ci] * yp;
+            const double ui = muScale != 0. ? muScale * A.uInv[ci] : 0.;      // mu^-1 is the same for xx, yy, zz of a cell
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            double t = 0.;
-            t += (-v[2 * a]) * wv[2 * a]; t += (-v[2 * a + 1]) * wv[2 * a + 1];
-            const int64_t jj = nP + a * nC + ci;
+            for (int a = 0; a < 3; ++a) {
+                double t = 0.;
+                t += (-v[2 * a]) * wv[2 * a]; t += (-v[2 * a + 1]) * wv[2 * a + 1];
+                const int64_t jj = nP + a * nC + ci;
+                const double xj = x ? x[jj] : 0.;
+                double yt = -t;
+                if (muScale != 0.) yt -= ui * xj;
+                if (add) yt += add[jj];
+                y[jj] = yt;
+                acc += xj * yt;
+            }
+        } else {
+            const int64_t e = row;
+            const uint32_t word = __ldcs(A.ecode + e);
+            double s = 0.;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int32_t c = __ldcs(A.ecol + (int64_t)q * A.nE + e);
+                const double wv = ((word >> (8 * q)) & 0xffu) ? w[c] : 0.;
+                s += ((double)op_code(word, q) * sc) * wv;
+            }
+            const int64_t jj = oE + e;
             const double xj = x ? x[jj] : 0.;
-            double yt = -t;
-            if (muScale != 0.) yt -= ui * xj;
+            double yt = -s;
+            if (muScale != 0.) yt -= muScale * A.uInv[3 * nC + e] * xj;
             if (add) yt += add[jj];
             y[jj] = yt;
             acc += xj * yt;
         }
-    }
-#pragma unroll 2
-    for (RangeWalk<4> it(A.rowsE, tid); it.valid(A.rowsE); it.step(A.rowsE, stride)) {
-        const int64_t e = it.j;
-        const uint32_t word = __ldcs(A.ecode + e);
-        double s = 0.;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int32_t c = __ldcs(A.ecol + (int64_t)k * A.nE + e);
-            const double wv = ((word >> (8 * k)) & 0xffu) ? w[c] : 0.;
-            s += ((double)op_code(word, k) * sc) * wv;
-        }
-        const int64_t jj = oE + e;
-        const double xj = x ? x[jj] : 0.;
-        double yt = -s;
-        if (muScale != 0.) yt -= muScale * A.uInv[3 * nC + e] * xj;
-        if (add) yt += add[jj];
-        y[jj] = yt;
-        acc += xj * yt;
     }
     if (dot) {
         const double bs = block_sum(acc);

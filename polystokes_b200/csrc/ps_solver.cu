@@ -464,6 +464,7 @@ void Solver::constructMatrixBlocks() {
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
     dotPartial.alloc(4096);
     computeOwnership();
+    buildSchedules();
     buildHalos();
 }
 
@@ -492,6 +493,37 @@ RangeSet Solver::rowsSys(int k) const {  // x = [p | xx | yy | zz | yz | xz | xy
     for (int i = 0; i < c.n; ++i) r.add(C.nPressures + c.lo[i], C.nPressures + c.lo[i] + c.count(i));
     for (int i = 0; i < e.n; ++i) r.add(C.nPressures + 3 * C.nCenter + e.lo[i], C.nPressures + 3 * C.nCenter + e.lo[i] + e.count(i));
     return r;
+}
+// K-way merge of the ranges' 256-row blocks by fractional position (j + 1/2) / blocks(k); ties go to the lower range
+std::vector<int32_t> merge_schedule(const SchedRanges& R) {
+    int64_t nb[4] = {0, 0, 0, 0}, next[4] = {0, 0, 0, 0}, total = 0;
+    for (int k = 0; k < R.n; ++k) { nb[k] = R.blocks(k); total += nb[k]; }
+    std::vector<int32_t> out;
+    out.reserve((size_t)total);
+    for (int64_t i = 0; i < total; ++i) {
+        int best = -1;
+        for (int k = 0; k < R.n; ++k) {
+            if (next[k] >= nb[k]) continue;
+            // (2 next[k] + 1) / nb[k] < (2 next[best] + 1) / nb[best], in integers
+            if (best < 0 || (2 * next[k] + 1) * nb[best] < (2 * next[best] + 1) * nb[k]) best = k;
+        }
+        if (nb[best] >= (1ll << 28)) throw Error("merge_schedule: range too long for 28-bit block indices");
+        out.push_back((int32_t)((uint32_t)best << 28 | (uint32_t)next[best]));
+        ++next[best];
+    }
+    return out;
+}
+void Solver::buildSchedules() {
+    const int k = part.rank;
+    sr1 = SchedRanges(); sr2 = SchedRanges();
+    for (int a = 0; a < 3; ++a) sr1.add(C.faceOff[a] + part.slotCut[SL_FACE + a][k], C.faceOff[a] + part.slotCut[SL_FACE + a][k + 1]);
+    sr1.add(C.nActiveVs + part.redRowCut[k], C.nActiveVs + part.redRowCut[k + 1]);
+    sr2.add(part.slotCut[SL_CENTER][k], part.slotCut[SL_CENTER][k + 1]);
+    for (int e = 0; e < 3; ++e) { const int64_t off = C.stressOff[3 + e] - 3 * C.nCenter; sr2.add(off + part.slotCut[SL_EDGE + e][k], off + part.slotCut[SL_EDGE + e][k + 1]); }
+    const std::vector<int32_t> a = merge_schedule(sr1), b = merge_schedule(sr2);
+    nSched1 = (int)a.size(); nSched2 = (int)b.size();
+    sched1.from_host(st, a.data(), a.size()); sched2.from_host(st, b.data(), b.size());
+    stream_sync(st);    // the vectors die here
 }
 void Solver::computeOwnership() {
     if (part.regionCut.size() != (size_t)part.nranks + 1) part.regionCut.assign((size_t)part.nranks + 1, 0);   // no reduced regions
@@ -573,6 +605,7 @@ static OpArgs make_op(const Solver& S) {
     A.ccode = S.Op.ccode.p; A.ccol = S.Op.ccol.p; A.ecode = S.Op.ecode.p; A.ecol = S.Op.ecol.p;
     A.uInv = S.uInv.p; A.valScale = S.g.invDx / 64.;
     A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsE = S.ownE;
+    A.s1 = S.sr1; A.s2 = S.sr2; A.sched1 = S.sched1.p; A.sched2 = S.sched2.p; A.nSched1 = S.nSched1; A.nSched2 = S.nSched2;
     return A;
 }
 

@@ -40,6 +40,21 @@ struct CompactOp {
 PS_HD int op_code(uint64_t word, int k) { return (int)(int8_t)(uint8_t)(word >> (8 * k)); }
 constexpr int32_t OP_COL_MASK = 0x3fffffff;
 
+// Block schedule of a hot sweep.  The rows of K_ext come in four index ranges (x / y / z faces, coupled reduced rows),
+// those of K_ext^T in four as well (cells, yz / xz / xy edges); each range is numbered in the reference's tile order, so
+// equal FRACTIONS of two ranges cover the same part of the grid.  Sweeping range after range streams the gathered
+// vector (132 MB at 256^3, more than the L2 holds) once per range; instead the 256-row blocks of all ranges are merged
+// by fractional position, so that the blocks in flight at any moment gather from the same few MB of the vector.
+//   entry = range << 28 | block index inside the range
+constexpr int SCHED_BLOCK = 256;
+struct SchedRanges {
+    int n = 0;
+    int64_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    void add(int64_t a, int64_t b) { lo[n] = a; hi[n] = b > a ? b : a; ++n; }
+    int64_t blocks(int k) const { return (hi[k] - lo[k] + SCHED_BLOCK - 1) / SCHED_BLOCK; }
+};
+std::vector<int32_t> merge_schedule(const SchedRanges& R);
+
 struct RegionData {
     int32_t count = 0;
     DBuf<double> com;        // [R][3]
@@ -169,6 +184,10 @@ public:
     RegionData RG;
     // matrices + vectors
     CompactOp Op;                 // K_ext and K_ext^T
+    SchedRanges sr1, sr2;         // block schedules of pass 1 / pass 2 over the owned rows (merge_schedule)
+    DBuf<int32_t> sched1, sched2;
+    int nSched1 = 0, nSched2 = 0;
+    void buildSchedules();
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
     DBuf<double> x, r, p, Ap, w, velSol;
     DBuf<double> dotPartial;
@@ -226,6 +245,8 @@ void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, Comp
 // ps_pcg.cu
 struct OpArgs {   // everything one operator apply touches
     int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
+    SchedRanges s1, s2;           // pass 1: face rows x, y, z, coupled reduced rows; pass 2: cells, edges yz, xz, xy (edge numbering)
+    const int32_t* sched1; const int32_t* sched2; int nSched1, nSched2;
     RowSet rowsK, rowsP, rowsE;   // rows this rank computes (all rows on one GPU); the centre-stress rows follow rowsP
     const uint64_t* kcode; const int32_t* kcol; const uint8_t* kmc; const double* mcInvLut;
     const uint64_t* ccode; const int32_t* ccol; const uint32_t* ecode; const int32_t* ecol;

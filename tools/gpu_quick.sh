@@ -1,0 +1,6 @@
+# quick single-GPU iteration: parity subset + probe (kernel rooflines)
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout -k 10 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_quick.log
+timeout -k 10 600 python tools/probe.py --scene S3 --n 256 --steps 2 2>&1 | tail -12 | tee gpurun_out/probe_s3_256.log
