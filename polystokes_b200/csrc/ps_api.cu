@@ -372,7 +372,9 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
             const int savedMax = S.P.maxSolverIterations, savedEvery = S.P.checkEvery; const double savedTol = S.P.tolerance;
             S.P.maxSolverIterations = reps; S.P.checkEvery = reps; S.P.tolerance = 0.0;   // never converges: exactly `reps` iterations
             S.stageMs[PS_STAGE_SOLVE] = 0;
-            S.solve();
+            S.cgOnly = true;
+            try { S.solve(); } catch (...) { S.cgOnly = false; throw; }
+            S.cgOnly = false;
             ms = S.stageMs[PS_STAGE_SOLVE] / reps;
             S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
             return 0;

@@ -475,6 +475,96 @@ void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, d
 void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) v[idx[i]] = buf[i]; }
 #endif
 
+// ---- BiCGSTAB fallback (bicgstab_external_matrix_A, lib/include/pcg.h:134-200) ---------------------------------
+// One generic sweep: f(i, a, b) updates element i and may add to two running sums; the sums end up rank-local in
+// S->bred[0..1] (CTA partials summed by the last CTA in fixed order).  The fallback runs only after CG has used
+// up maxSolverIterations, so these kernels favour clarity; each is still one coalesced pass over the vectors.
+// scalar bookkeeping of one iteration, in the reference's statement order
+PS_D void bicg_stage(PcgScalars* S, int stage) {
+    if (S->done) return;
+    if (stage == 0) {            // pcg.h:171-173
+        S->rhoOld = S->rhoCurr; S->rhoCurr = S->bred[0];
+        S->beta = (S->rhoCurr / S->rhoOld) * (S->alpha / S->omega);
+    } else if (stage == 1) {     // pcg.h:176
+        S->alpha = S->rhoCurr / S->bred[0];
+    } else if (stage == 2) {     // pcg.h:181
+        S->omega = S->bred[0] / S->bred[1];
+    } else {                     // pcg.h:185-193: the reference compares rre with tol (not tol^2) here
+        const double xmag = sqrt(S->bred[0]), rsnew = S->bred[1];
+        double rre = rsnew;
+        if (sqrt(rsnew) / xmag < rre) rre = sqrt(rsnew) / xmag;
+        S->xmag = xmag; S->rsnew = rsnew; S->rre = rre;
+        if (rre < S->tol) { S->done = 1; return; }
+        S->iter += 1;
+        if (S->iter >= S->maxIter) S->done = 2;
+    }
+}
+#ifndef PS_EMULATE
+template <class F>
+__global__ void __launch_bounds__(HOT_THREADS) vec_sweep_kernel(RangeSet own, double* dotPartial, PcgScalars* S, int nred, int slot, bool respectDone, F f) {
+    if (respectDone && S->done) return;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    double a = 0., b = 0.;
+    for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) f(it.j, a, b);
+    if (nred > 0) {
+        const double ba = block_sum(a), bb = block_sum(b);
+        if (threadIdx.x == 0) { dotPartial[blockIdx.x] = ba; dotPartial[gridDim.x + blockIdx.x] = bb; }
+        if (last_block(&S->ticket[6])) {
+            const double ta = block_sum_partials(dotPartial, gridDim.x), tb = block_sum_partials(dotPartial + gridDim.x, gridDim.x);
+            if (threadIdx.x == 0) { S->bred[slot] = ta; if (nred > 1) S->bred[slot + 1] = tb; }
+        }
+    }
+}
+template <class F>
+static void vec_sweep(cudaStream_t st, const RangeSet& own, double* dotPartial, PcgScalars* S, int nred, int slot, bool respectDone, F f) {
+    vec_sweep_kernel<<<hot_blocks(vec_sweep_kernel<F>, own.total()), HOT_THREADS, 0, st>>>(own, dotPartial, S, nred, slot, respectDone, f);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+#else
+template <class F>
+static void vec_sweep(cudaStream_t, const RangeSet& own, double*, PcgScalars* S, int nred, int slot, bool respectDone, F f) {
+    if (respectDone && S->done) return;
+    double a = 0., b = 0.;
+    for (int64_t l = 0; l < own.total(); ++l) f(own.at(l), a, b);
+    if (nred > 0) { S->bred[slot] = a; if (nred > 1) S->bred[slot + 1] = b; }
+}
+#endif
+// pcg.h:149-168: x = 0 => r = b - A 0 = b, rhat = r, p = v = 0, rho = alpha = omega = 1
+void k_bicg_init(cudaStream_t st, const RangeSet& own, const double* b, double* x, double* r, double* rhat, double* p, double* v, PcgScalars* S, double tol, int maxIter) {
+    vec_sweep(st, own, nullptr, S, 0, 0, false, PS_LAMBDA(int64_t i, double&, double&) { const double bi = b[i]; x[i] = 0.; r[i] = bi; rhat[i] = bi; p[i] = 0.; v[i] = 0.; });
+    ps_for(st, 1, PS_LAMBDA(int64_t) {
+        S->rhoCurr = 1.; S->rhoOld = 1.; S->alpha = 1.; S->beta = 0.; S->omega = 1.; S->xmag = 0.; S->rsnew = 0.; S->rre = 0.;
+        S->bred[0] = 0.; S->bred[1] = 0.; S->tol = tol; S->tol2 = tol * tol; S->iter = 0; S->maxIter = maxIter; S->done = maxIter > 0 ? 0 : 2;
+        S->ticket[6] = 0;
+    });
+}
+void k_bicg_dot(cudaStream_t st, const RangeSet& own, const double* a0, const double* b0, const double* a1, const double* b1, double* dotPartial, PcgScalars* S) {
+    if (a1) vec_sweep(st, own, dotPartial, S, 2, 0, true, PS_LAMBDA(int64_t i, double& a, double& b) { a += a0[i] * b0[i]; b += a1[i] * b1[i]; });
+    else vec_sweep(st, own, dotPartial, S, 1, 0, true, PS_LAMBDA(int64_t i, double& a, double&) { a += a0[i] * b0[i]; });
+}
+void k_bicg_stage(cudaStream_t st, PcgScalars* S, int stage) { ps_for(st, 1, PS_LAMBDA(int64_t) { bicg_stage(S, stage); }); }
+// pcg.h:174  p = r + beta (p - omega v)
+void k_bicg_update_p(cudaStream_t st, const RangeSet& own, double* p, const double* r, const double* v, const PcgScalars* S) {
+    vec_sweep(st, own, nullptr, const_cast<PcgScalars*>(S), 0, 0, true, PS_LAMBDA(int64_t i, double&, double&) { p[i] = r[i] + S->beta * (p[i] - S->omega * v[i]); });
+}
+// pcg.h:177-179  h = x + alpha p (kept in x),  s = r - alpha v
+void k_bicg_update_hs(cudaStream_t st, const RangeSet& own, double* x, double* s, const double* r, const double* p, const double* v, const PcgScalars* S) {
+    vec_sweep(st, own, nullptr, const_cast<PcgScalars*>(S), 0, 0, true, PS_LAMBDA(int64_t i, double&, double&) { const double al = S->alpha; x[i] = x[i] + al * p[i]; s[i] = r[i] - al * v[i]; });
+}
+// pcg.h:182-185  x = h + omega s, fused x.x
+void k_bicg_update_x(cudaStream_t st, const RangeSet& own, double* x, const double* s, double* dotPartial, PcgScalars* S) {
+    vec_sweep(st, own, dotPartial, S, 1, 0, true, PS_LAMBDA(int64_t i, double& a, double&) { const double xi = x[i] + S->omega * s[i]; x[i] = xi; a += xi * xi; });
+}
+// pcg.h:186-187  err = b - A x, rsnew = err.err  (into bred[1]; bred[0] keeps x.x)
+void k_bicg_err(cudaStream_t st, const RangeSet& own, const double* b, const double* Ax, double* dotPartial, PcgScalars* S) {
+    vec_sweep(st, own, dotPartial, S, 1, 1, true, PS_LAMBDA(int64_t i, double& a, double&) { const double e = b[i] - Ax[i]; a += e * e; });
+}
+// pcg.h:195  r = s - omega t
+void k_bicg_update_r(cudaStream_t st, const RangeSet& own, double* r, const double* s, const double* t, const PcgScalars* S) {
+    vec_sweep(st, own, nullptr, const_cast<PcgScalars*>(S), 0, 0, true, PS_LAMBDA(int64_t i, double&, double&) { r[i] = s[i] - S->omega * t[i]; });
+}
+
 // halo discovery: flag[c] = 1 for every column c of a non-empty slot of the given rows that `colsOwned` contains
 void k_mark_K_columns(cudaStream_t st, const OpArgs& A, const RowSet& rows, const RangeSet& colsOwned, uint8_t* flag) {
     const RowSet R = rows; const RangeSet Cs = colsOwned;

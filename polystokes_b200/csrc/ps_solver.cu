@@ -630,8 +630,7 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
     k_pass1(st, A, xin, w.p, g.dt, nullptr);
     if (RG.count > 0) {
         reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr);
-        reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr);
-        reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
+        reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     }
     exchange(haloW, w.p, nullptr);
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, PeerCtx(), nullptr, 0);
@@ -679,8 +678,7 @@ int Solver::solve() {
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);             mark(tr, "pass1");
             if (RG.count > 0) {
                 reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p);
-                reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p);
-                reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
+                reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
             }
             mark(tr, "reduced x3");
             exchange(haloW, w.p, scal.p);                       mark(tr, "halo w");
@@ -711,6 +709,62 @@ int Solver::solve() {
     // b == 0: the reference would divide 0/0 (pcg.h:313); we return x = 0 after 0 iterations instead
     solveIterations = (h.done == 1) ? h.iter : maxIt;
     solveError = std::sqrt(h.rre);
+    // "have minres as a backup" (S.cpp:784-799): CG used up its iterations -> restart from x = 0 with BiCGSTAB
+    if (solveIterations == maxIt && !cgOnly) return solveBiCGStab();
+    result = (solveIterations == maxIt) ? R_NOCONVERGE : R_SUCCESS;
+    return result;
+}
+
+// bicgstab_external_matrix_A (pcg.h:134-200) on the factored operator: three applies per iteration (v = A p, t = A s and
+// the explicit residual b - A x of the stop test), identity preconditioner, the reference's stop rule
+// min(|err|^2, |err| / |x|) < tol.  Scalars stay on the device; the host polls the flag like the CG loop does.
+int Solver::solveBiCGStab() {
+    const OpArgs A = make_op(*this);
+    const size_t n = (size_t)C.nSystemSize;
+    const int maxIt = P.maxSolverIterations;
+    const int every = P.checkEvery > 0 ? P.checkEvery : 25;
+    usedBiCGStab = 1;
+    bRhat.alloc(n); bV.alloc(n); bS.alloc(n); bT.alloc(n);
+    auto applyTo = [&](double* xin, double* y) {
+        exchange(haloX, xin, scal.p);
+        k_pass1(st, A, xin, w.p, g.dt, scal.p);
+        if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+        exchange(haloW, w.p, scal.p);
+        k_pass2(st, A, w.p, xin, y, 0.5, nullptr, nullptr, PeerCtx(), scal.p, 0);
+    };
+    auto reduce = [&](int count) { if (part.multi() && comm) comm->allreduce_sum(scal.p->bred, count, st); };
+    k_bicg_init(st, ownSys, b.p, x.p, r.p, bRhat.p, p.p, bV.p, scal.p, P.tolerance, maxIt);
+    PcgScalars h; memset(&h, 0, sizeof h);
+    bool cancelled = false;
+    for (int it = 0; it < maxIt;) {
+        const int batch = std::min(every, maxIt - it);
+        for (int k = 0; k < batch; ++k) {
+            k_bicg_dot(st, ownSys, bRhat.p, r.p, nullptr, nullptr, dotPartial.p, scal.p); reduce(1);      // rho = rhat . r
+            k_bicg_stage(st, scal.p, 0);
+            k_bicg_update_p(st, ownSys, p.p, r.p, bV.p, scal.p);
+            applyTo(p.p, bV.p);                                                                           // v = A p
+            k_bicg_dot(st, ownSys, bRhat.p, bV.p, nullptr, nullptr, dotPartial.p, scal.p); reduce(1);     // rhat . v
+            k_bicg_stage(st, scal.p, 1);
+            k_bicg_update_hs(st, ownSys, x.p, bS.p, r.p, p.p, bV.p, scal.p);
+            applyTo(bS.p, bT.p);                                                                          // t = A s
+            k_bicg_dot(st, ownSys, bT.p, bS.p, bT.p, bT.p, dotPartial.p, scal.p); reduce(2);              // t . s, t . t
+            k_bicg_stage(st, scal.p, 2);
+            k_bicg_update_x(st, ownSys, x.p, bS.p, dotPartial.p, scal.p);                                 // + x . x
+            applyTo(x.p, Ap.p);
+            k_bicg_err(st, ownSys, b.p, Ap.p, dotPartial.p, scal.p); reduce(2);                           // |b - A x|^2
+            k_bicg_stage(st, scal.p, 3);
+            k_bicg_update_r(st, ownSys, r.p, bS.p, bT.p, scal.p);
+        }
+        it += batch;
+        copy_d2h(&h, scal.p, sizeof h, st);
+        if (h.done) break;
+        if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
+    }
+    copy_d2h(&h, scal.p, sizeof h, st);
+    if (h.peerError) { result = R_FAILED; throw Error("a peer-memory wait timed out (another rank died or fell out of step)"); }
+    if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
+    solveIterations = (h.done == 1) ? h.iter : maxIt;
+    solveError = h.rre;                          // pcg.h:188-190: no square root on this path
     result = (solveIterations == maxIt) ? R_NOCONVERGE : R_SUCCESS;
     return result;
 }

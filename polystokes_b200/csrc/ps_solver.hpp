@@ -109,6 +109,8 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     unsigned int ticket[8];   // last-CTA-done tickets: 0 pass 2, 1 x/r update, 2 init, 3 p update, 4/5 halo push of p / w
     int peerError, pad2;      // sticky: a peer-memory wait timed out (ps_peer.hpp)
     double red[4];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.x, [3] b.b
+    // BiCGSTAB fallback (pcg.h:134-200): its own scalars; bred[] = rank-local dot products of the current stage
+    double rhoCurr, rhoOld, omega, tol, bred[2];
 };
 
 class Solver {
@@ -123,6 +125,7 @@ public:
     int solveIterations = -1;
     double solveError = -1;
     int usedBiCGStab = 0;
+    bool cgOnly = false;                // ps_time_kernel("cg_iteration"): run exactly maxSolverIterations CG iterations, no fallback
     int fixLoops = 0;
     double stageMs[PS_NUM_STAGES] = {0};
 
@@ -141,6 +144,7 @@ public:
     void constructMatrixBlocks();
     void assemble();                    // assembleSystemPressureStressFactored
     int solve();                        // solveSPDwithMatrixVectorPCG
+    int solveBiCGStab();                // its fallback when CG hits maxSolverIterations (S.cpp:784-799 -> pcg.h:134-200)
     void buildValidFaces(const ps_fields_out& out);
     void recoverVelocityFromPressureStress();
     void applySolutionToVelocity(const ps_fields_out& out);
@@ -190,6 +194,7 @@ public:
     void buildSchedules();
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
     DBuf<double> x, r, p, Ap, w, velSol;
+    DBuf<double> bRhat, bV, bS, bT;     // BiCGSTAB work vectors, allocated when the fallback first fires
     DBuf<double> dotPartial;
     DBuf<PcgScalars> scal;
     bool inputsOnDevice = false;
@@ -262,6 +267,16 @@ void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, con
 void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* scal, const PeerCtx& P);
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
 void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);
+// BiCGSTAB fallback (pcg.h:134-200).  Dot products land rank-local in scal->bred[], the host enqueues the all-reduce
+// (NCCL) when there are several ranks, k_bicg_stage then advances the scalars exactly in the reference's order.
+void k_bicg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* rhat, double* p, double* v, PcgScalars* scal, double tol, int maxIter);
+void k_bicg_dot(cudaStream_t, const RangeSet& own, const double* a0, const double* b0, const double* a1, const double* b1, double* dotPartial, PcgScalars* scal);
+void k_bicg_stage(cudaStream_t, PcgScalars* scal, int stage);
+void k_bicg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, const double* v, const PcgScalars* scal);
+void k_bicg_update_hs(cudaStream_t, const RangeSet& own, double* x, double* s, const double* r, const double* p, const double* v, const PcgScalars* scal);
+void k_bicg_update_x(cudaStream_t, const RangeSet& own, double* x, const double* s, double* dotPartial, PcgScalars* scal);
+void k_bicg_err(cudaStream_t, const RangeSet& own, const double* b, const double* Ax, double* dotPartial, PcgScalars* scal);
+void k_bicg_update_r(cudaStream_t, const RangeSet& own, double* r, const double* s, const double* t, const PcgScalars* scal);
 #ifndef PS_EMULATE
 void k_halo_push_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
                       unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket);

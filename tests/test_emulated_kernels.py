@@ -9,3 +9,7 @@ import parity
 @pytest.mark.parametrize("case", list(parity.SCENE_CASES))
 def test_emulated_step_matches_oracle(built, case):
     parity.run_case(case, lib_path=parity.EMUL_LIB)
+
+
+def test_emulated_bicgstab_fallback(built):
+    parity.check_bicgstab_fallback(lib_path=parity.EMUL_LIB)

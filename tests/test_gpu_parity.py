@@ -54,3 +54,9 @@ def test_gpu_repeated_steps_are_deterministic(built):
     assert rc1 == rc2 and it1 == s.count("iterations")
     for a in range(3):
         assert np.array_equal(v1[a], v2[a])
+
+
+def test_gpu_bicgstab_fallback(built):
+    """CG out of iterations -> BiCGSTAB (S.cpp:784-799), against the oracle's restatement of pcg.h:134-200."""
+    parity.check_bicgstab_fallback()
+
