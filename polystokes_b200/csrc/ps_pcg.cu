@@ -258,9 +258,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, 
     const double beta = rx[0] / S->rsold;
     if (!converged) {
         const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-    #pragma unroll 1
-    for (int k = 0; k < own.n; ++k)
-            for (int64_t i = own.lo[k] + tid, end = own.lo[k] + own.count(k); i < end; i += stride) p[i] = r[i] + beta * p[i];
+#pragma unroll 4
+        for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) { const int64_t i = it.j; p[i] = r[i] + beta * p[i]; }
     }
     if (last_block(&S->ticket[3]) && threadIdx.x == 0) { S->red[1] = rx[0]; S->red[2] = rx[1]; cg_advance(S); }
 }
@@ -630,22 +629,59 @@ PS_D void s_to_sigma(const double* s, double* sg) {
 
 #ifndef PS_EMULATE
 constexpr int RED_THREADS = 256;
-// one CTA per (region, axis) chunk of coupled reduced rows: 10 monomial moments of w_f = (K_red x)_f (written by pass 1)
-__global__ void __launch_bounds__(RED_THREADS) reduced_moments_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk,
-                                                                     const double* __restrict__ com, const double* __restrict__ wRows, double* __restrict__ partial, const PcgScalars* S, int chunk0) {
+constexpr int MOM_THREADS = 64;
+// the small solve of one region, shared by reduced_finish_kernel and the fused tail of reduced_moments_kernel (lane = thread
+// index, at least 32 threads, all of them call): ordered sum of the chunk partials -> t -> s = B^-1 t -> sigma
+__device__ __forceinline__ void region_solve(int r, int lane, const int32_t* __restrict__ chunkStart, const int32_t* __restrict__ chunk, const double* partial,
+                                             const double* __restrict__ Binv, const double* __restrict__ extra, double extraScale, double tScale,
+                                             double* tOut, double* sOut, double* __restrict__ sigma, double* M, double* t, double* sv) {
+    if (lane < 30) {
+        const int axis = lane / 10, k = lane % 10;
+        double s = 0.;
+        if (tScale != 0.)
+            for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) if (chunk[4 * ch + 3] == axis) s += __ldcg(partial + (size_t)ch * 10 + k);
+        M[lane] = s;
+    }
+    __syncthreads();
+    if (lane == 0) moments_to_t(M, t);
+    __syncthreads();
+    if (lane < RDOF) {
+        double v = tScale * t[lane];
+        if (extra) v += extraScale * extra[(size_t)r * RDOF + lane];
+        t[lane] = v; if (tOut) tOut[(size_t)r * RDOF + lane] = v;
+    }
+    __syncthreads();
+    if (lane < RDOF) {
+        const double* B = Binv + (size_t)r * RDOF * RDOF + lane * RDOF;
+        double s = 0.;
+#pragma unroll
+        for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
+        sv[lane] = s; if (sOut) sOut[(size_t)r * RDOF + lane] = s;
+    }
+    __syncthreads();
+    if (lane == 0) { double sg[30]; s_to_sigma(sv, sg); for (int k = 0; k < 30; ++k) sigma[(size_t)r * 30 + k] = sg[k]; }
+}
+// one small CTA per (region, axis) chunk of coupled reduced rows: 10 monomial moments of w_f = (K_red x)_f (written by pass 1).
+// With `regionTicket` the LAST chunk of a region to finish also runs the region's small solve (t -> s = B^-1 t -> sigma):
+// the sums are taken in chunk order whoever comes last, so the result does not depend on the schedule.
+__global__ void __launch_bounds__(MOM_THREADS) reduced_moments_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk, const int32_t* __restrict__ chunkStart,
+                                                                     const double* __restrict__ com, const double* __restrict__ wRows, double* partial, const double* __restrict__ Binv,
+                                                                     double* __restrict__ sigma, unsigned int* regionTicket, const PcgScalars* S, int chunk0) {
     if (S && S->done) return;
-    __shared__ double red[RED_THREADS / 32][10];
+    __shared__ double red[MOM_THREADS / 32][10];
+    __shared__ double M[30], t[RDOF], sv[RDOF];
+    __shared__ bool last;
     const int ch = chunk0 + blockIdx.x;
     const int region = chunk[4 * ch], begin = chunk[4 * ch + 1], end = chunk[4 * ch + 2];
-    const double c0 = com[3 * region], c1 = com[3 * region + 1], c2 = com[3 * region + 2];
-    const double cm[3] = {c0, c1, c2};
+    const double cm[3] = {com[3 * region], com[3 * region + 1], com[3 * region + 2]};
     double acc[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) acc[k] = 0.;
-    for (int row = begin + threadIdx.x; row < end; row += RED_THREADS) {
-        const double gk = wRows[row];
+#pragma unroll 4
+    for (int row = begin + threadIdx.x; row < end; row += MOM_THREADS) {
+        const double gk = __ldcs(wRows + row);
         double m[10];
-        row_monomials(dx, rowXYZ[row], cm, m);
+        row_monomials(dx, __ldcs(rowXYZ + row), cm, m);
 #pragma unroll
         for (int k = 0; k < 10; ++k) acc[k] += m[k] * gk;
     }
@@ -658,9 +694,20 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_moments_kernel(double dx,
     if (threadIdx.x < 10) {
         double s = 0.;
 #pragma unroll
-        for (int wI = 0; wI < RED_THREADS / 32; ++wI) s += red[wI][threadIdx.x];
+        for (int wI = 0; wI < MOM_THREADS / 32; ++wI) s += red[wI][threadIdx.x];
         partial[(size_t)ch * 10 + threadIdx.x] = s;
     }
+    if (!regionTicket) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned nch = (unsigned)(chunkStart[region + 1] - chunkStart[region]);
+        const unsigned tk = atomicInc(regionTicket + region, nch - 1);
+        last = (tk == nch - 1);
+        if (last) __threadfence();
+    }
+    __syncthreads();
+    if (last) region_solve(region, threadIdx.x, chunkStart, chunk, partial, Binv, nullptr, 0., 1., nullptr, nullptr, sigma, M, t, sv);
 }
 // one warp per region: ordered sum of the chunk partials -> t -> s = B^-1 t -> sigma
 __global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __restrict__ chunkStart, const int32_t* __restrict__ chunk, const double* __restrict__ partial,
@@ -668,55 +715,30 @@ __global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __res
                                                            double* __restrict__ tOut, double* __restrict__ sOut, double* __restrict__ sigma, const PcgScalars* S, int region0) {
     if (S && S->done) return;
     __shared__ double M[30], t[RDOF], sv[RDOF];
-    const int r = region0 + blockIdx.x, lane = threadIdx.x;
-    if (lane < 30) {
-        const int axis = lane / 10, k = lane % 10;
-        double s = 0.;
-        if (tScale != 0.)
-            for (int ch = chunkStart[r]; ch < chunkStart[r + 1]; ++ch) if (chunk[4 * ch + 3] == axis) s += partial[(size_t)ch * 10 + k];
-        M[lane] = s;
-    }
-    __syncwarp();
-    if (lane == 0) moments_to_t(M, t);
-    __syncwarp();
-    if (lane < RDOF) {
-        double v = tScale * t[lane];
-        if (extra) v += extraScale * extra[(size_t)r * RDOF + lane];
-        t[lane] = v; tOut[(size_t)r * RDOF + lane] = v;
-    }
-    __syncwarp();
-    if (lane < RDOF) {
-        const double* B = Binv + (size_t)r * RDOF * RDOF + lane * RDOF;
-        double s = 0.;
-#pragma unroll
-        for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
-        sv[lane] = s; sOut[(size_t)r * RDOF + lane] = s;
-    }
-    __syncwarp();
-    if (lane == 0) { double sg[30]; s_to_sigma(sv, sg); for (int k = 0; k < 30; ++k) sigma[(size_t)r * 30 + k] = sg[k]; }
+    region_solve(region0 + blockIdx.x, threadIdx.x, chunkStart, chunk, partial, Binv, extra, extraScale, tScale, tOut, sOut, sigma, M, t, sv);
 }
-// one CTA per chunk: w_f = scale * sigma[region][axis] . monomials(f)
-__global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk, const double* __restrict__ com,
-                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S, int chunk0) {
+// w_f = scale * sigma[region][axis] . monomials(f): one thread per coupled reduced row (sigma / com of a region are shared by
+// neighbouring rows and come through L1)
+__global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ rowRegion, const double* __restrict__ com,
+                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S, int rowLo, int rowHi) {
     if (S && S->done) return;
-    const int ch = chunk0 + blockIdx.x;
-    const int region = chunk[4 * ch], begin = chunk[4 * ch + 1], end = chunk[4 * ch + 2], axis = chunk[4 * ch + 3];
-    const double cm[3] = {com[3 * region], com[3 * region + 1], com[3 * region + 2]};
-    double sg[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) sg[k] = sigma[(size_t)region * 30 + axis * 10 + k];
-    for (int row = begin + threadIdx.x; row < end; row += RED_THREADS) {
+    for (int row = rowLo + blockIdx.x * RED_THREADS + threadIdx.x; row < rowHi; row += gridDim.x * RED_THREADS) {
+        const uint32_t xyz = __ldcs(rowXYZ + row);
+        const int region = __ldcs(rowRegion + row), axis = (int)(xyz >> 30);
+        const double cm[3] = {__ldg(com + 3 * region), __ldg(com + 3 * region + 1), __ldg(com + 3 * region + 2)};
+        const double* sg = sigma + (size_t)region * 30 + axis * 10;
         double m[10];
-        row_monomials(dx, rowXYZ[row], cm, m);
+        row_monomials(dx, xyz, cm, m);
         double v = 0.;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v += sg[k] * m[k];
+        for (int k = 0; k < 10; ++k) v += __ldg(sg + k) * m[k];
         wRows[row] = scale * v;
     }
 }
-void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S) {
+void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S, bool solve) {
     if (RG.rowChunkHi <= RG.rowChunkLo) return;
-    reduced_moments_kernel<<<RG.rowChunkHi - RG.rowChunkLo, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, wRows, RG.partial.p, S, RG.rowChunkLo);
+    reduced_moments_kernel<<<RG.rowChunkHi - RG.rowChunkLo, MOM_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.rowChunkStart.p, RG.com.p, wRows, RG.partial.p, RG.Binv.p, RG.sigma.p,
+                                                                                 solve ? RG.regionTicket.p : nullptr, S, RG.rowChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -727,13 +749,15 @@ void reduced_finish(cudaStream_t st, const Geom&, const RegionData& RG, const do
     PS_CUDA(cudaGetLastError());
 }
 void reduced_expand(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
-    if (RG.rowChunkHi <= RG.rowChunkLo) return;
-    reduced_expand_kernel<<<RG.rowChunkHi - RG.rowChunkLo, RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.rowChunkLo);
+    if (RG.ownRowHi <= RG.ownRowLo) return;
+    const int n = RG.ownRowHi - RG.ownRowLo;
+    reduced_expand_kernel<<<std::min((n + RED_THREADS - 1) / RED_THREADS, 148 * 8), RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowRegion.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.ownRowLo, RG.ownRowHi);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 #else
-void reduced_moments(cudaStream_t, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S) {
+void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S);
+void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S, bool solve) {
     if (S && S->done) return;
     for (int ch = RG.rowChunkLo; ch < RG.rowChunkHi; ++ch) {
         const int region = RG.rowChunk.p[4 * ch], begin = RG.rowChunk.p[4 * ch + 1], end = RG.rowChunk.p[4 * ch + 2];
@@ -745,6 +769,7 @@ void reduced_moments(cudaStream_t, const Geom& g, const RegionData& RG, const do
         }
         for (int k = 0; k < 10; ++k) RG.partial.p[(size_t)ch * 10 + k] = acc[k];
     }
+    if (solve) reduced_finish(st, g, RG, nullptr, 0.0, 1.0, S);
 }
 void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S) {
     if (S && S->done) return;

@@ -408,7 +408,7 @@ void Solver::computeReducedRegionMatrices() {
 void Solver::constructMatrixBlocks() {
     const int R = RG.count;
     for (int a = 0; a < 3; ++a) k_krow_active(st, g.n[SL_FACE + a], F.aidx[SL_FACE + a], (int32_t)C.faceOff[a], F.krow[a]);
-    RG.nRows = 0; RG.nRowChunks = 0; RG.rowChunkLo = RG.rowChunkHi = 0;
+    RG.nRows = 0; RG.nRowChunks = 0; RG.rowChunkLo = RG.rowChunkHi = 0; RG.ownRowLo = RG.ownRowHi = 0;
     part.redRowCut.assign((size_t)part.nranks + 1, 0);
     if (R > 0) {
         int64_t cnt[3], off[3];
@@ -445,6 +445,8 @@ void Solver::constructMatrixBlocks() {
         start[R] = pos; chunkStart[R] = (int32_t)(table.size() / 4);
         RG.nRowChunks = (int32_t)(table.size() / 4);
         RG.rowChunkLo = chunkStart[RG.regLo]; RG.rowChunkHi = chunkStart[RG.regHi];
+        RG.ownRowLo = start[RG.regLo]; RG.ownRowHi = start[RG.regHi];
+        RG.regionTicket.alloc((size_t)R + 1); RG.regionTicket.zero(st, (size_t)R + 1);
         for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
         RG.rowStart.from_host(st, start.data(), start.size());
         RG.rowChunk.from_host(st, table.data(), table.size());
@@ -629,8 +631,8 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
     const OpArgs A = make_op(*this);
     k_pass1(st, A, xin, w.p, g.dt, nullptr);
     if (RG.count > 0) {
-        reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr);
-        reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
+        reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr, true);
+        reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     }
     exchange(haloW, w.p, nullptr);
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, PeerCtx(), nullptr, 0);
@@ -640,7 +642,7 @@ void Solver::timedOperator(int which) {
     const OpArgs A = make_op(*this);
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
     if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
-    else if (which == 3 && RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, nullptr); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
+    else if (which == 3 && RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
     else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, PeerCtx(), nullptr, 0);
 }
 
@@ -677,8 +679,8 @@ int Solver::solve() {
             exchange(haloX, p.p, scal.p);                       mark(tr, "halo p");
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);             mark(tr, "pass1");
             if (RG.count > 0) {
-                reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p);
-                reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
+                reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p, true);      // + B^-1 per region by its last chunk
+                reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
             }
             mark(tr, "reduced x3");
             exchange(haloW, w.p, scal.p);                       mark(tr, "halo w");
@@ -728,7 +730,7 @@ int Solver::solveBiCGStab() {
     auto applyTo = [&](double* xin, double* y) {
         exchange(haloX, xin, scal.p);
         k_pass1(st, A, xin, w.p, g.dt, scal.p);
-        if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p); reduced_finish(st, g, RG, nullptr, 0.0, 1.0, scal.p); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+        if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
         exchange(haloW, w.p, scal.p);
         k_pass2(st, A, w.p, xin, y, 0.5, nullptr, nullptr, PeerCtx(), scal.p, 0);
     };
