@@ -263,7 +263,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("pass2_kernel")
+            tj = json.load(f)
+            traffic = next((v for k, v in tj.items() if "pass2_kernel" in k), None)
     except Exception:
         pass
     roofline = {"kernel": "pass2_kernel (y = -K_ext^T w - 1/2 mu^-1 x, fused p.Ap)", "bound": "hbm", "achieved": kern["pass2"]["gbs"], "peak": peak,
