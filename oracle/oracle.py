@@ -57,10 +57,12 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.orc_set_inputs.argtypes = [C.c_void_p] + [fp] * 9
         L.orc_set_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
-        for f in ("orc_setup", "orc_build_weights", "orc_classify", "orc_assemble_explicit_A"):
+        for f in ("orc_setup", "orc_build_weights", "orc_classify", "orc_assemble_explicit_A", "orc_construct_guess"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_solve.argtypes = [C.c_void_p]
         L.orc_solve.restype = C.c_int
+        L.orc_solve_eigen_cg.argtypes = [C.c_void_p]
+        L.orc_solve_eigen_cg.restype = C.c_int
         L.orc_apply.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_writeback.argtypes = [C.c_void_p] + [fp] * 6
         L.orc_count.argtypes = [C.c_void_p, C.c_char_p]
@@ -137,6 +139,14 @@ class Oracle:
 
     def solve(self):
         return self.L.orc_solve(self.h)
+
+    def construct_guess(self):
+        """useWarmStart branch (PS.C:465-467): fills the vector "guess"."""
+        self.L.orc_construct_guess(self.h)
+
+    def solve_eigen_cg(self):
+        """solverType EIGEN (S.cpp:814-862): Jacobi-preconditioned Eigen CG on the explicit A, started from "guess"."""
+        return self.L.orc_solve_eigen_cg(self.h)
 
     def apply(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

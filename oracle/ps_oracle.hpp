@@ -152,6 +152,7 @@ struct Oracle {
     Csr Mc, McInv, uInv, uMat, G, Dt, JG, JDt, MrMat, Bmat, BinvMat, A;
     std::vector<Real> activeRHS, reducedRHS, pressureRHS, stressRHS, oldActiveVs;
     std::vector<Real> b, solution, velSolution;
+    std::vector<Real> guess;                    // guessVector (S_AS:413-419); zero unless constructGuessVectors ran
     // derived operator factors (Apply.h:24-68)
     Csr Gt, D, JGt, DJt, McInvG, McInvDt;
     std::vector<Real> mcInvDiag, uInvDiag;
@@ -184,6 +185,8 @@ struct Oracle {
     void setupMatrixVectorProducts();           // Apply.h:24-68
     void applyMatrixVectorProducts(const Real* x, Real* y);  // Apply.h:102-179
     int solveSPDwithMatrixVectorPCG();          // S.cpp:734-812 (+ pcg.h:268-340, 134-200)
+    void constructGuessVectors();               // S.cpp:512-531 (+ S_AS:413-419), the useWarmStart branch of PS.C:465-467
+    int solveEigenCG();                         // S.cpp:814-862: Eigen::ConjugateGradient<Lower|Upper> + DiagonalPreconditioner on explicit A
     void buildValidFaces(float* const valid[3]);// S_Cls:4-54
     void recoverVelocityFromPressureStress();   // S.cpp:492-510
     void applySolutionToVelocity(float* velOut, const float* valid, int axis); // S.cpp:937-1028

@@ -50,6 +50,8 @@ void orc_classify(void* h) {
     o->constructActiveIndices();
 }
 void orc_assemble_explicit_A(void* h) { ((Oracle*)h)->assembleExplicitA(); }
+void orc_construct_guess(void* h) { ((Oracle*)h)->constructGuessVectors(); }
+int orc_solve_eigen_cg(void* h) { Oracle* o = (Oracle*)h; if (o->A.rows != o->nSystemSize || o->A.nnz() == 0) o->assembleExplicitA(); return o->solveEigenCG(); }
 int orc_solve(void* h) { return ((Oracle*)h)->solveSPDwithMatrixVectorPCG(); }
 void orc_apply(void* h, const double* x, double* y) { Oracle* o = (Oracle*)h; if (o->McInvG.rows != o->nActiveVs || o->McInvG.nnz() != o->G.nnz()) o->setupMatrixVectorProducts(); o->applyMatrixVectorProducts(x, y); }
 void orc_writeback(void* h, float* vx, float* vy, float* vz, float* valx, float* valy, float* valz) {
@@ -117,7 +119,7 @@ static std::vector<Real>* findVec(Oracle* o, const std::string& n) {
     if (n == "activeRHS") return &o->activeRHS; if (n == "reducedRHS") return &o->reducedRHS;
     if (n == "pressureRHS") return &o->pressureRHS; if (n == "stressRHS") return &o->stressRHS;
     if (n == "b") return &o->b; if (n == "solution") return &o->solution; if (n == "velSolution") return &o->velSolution;
-    if (n == "oldActiveVs") return &o->oldActiveVs;
+    if (n == "oldActiveVs") return &o->oldActiveVs; if (n == "guess") return &o->guess;
     return nullptr;
 }
 int64_t orc_vector(void* h, const char* name, double* out) {

@@ -2,6 +2,8 @@
 // Factored operator apply, the Krylov loops, velocity recovery and write-back, restated.
 #include "ps_oracle.hpp"
 #include <chrono>
+#include <limits>
+#include <algorithm>
 #include <cstdio>
 
 namespace orc {
@@ -130,6 +132,73 @@ int Oracle::solveSPDwithMatrixVectorPCG() {
     solveMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     solverResult = (solveIterations == maxIt) ? NOCONVERGE : SUCCESS;
     return solverResult;
+}
+
+// S.cpp:521-531: pressureGuess = -G^T u_old - JG^T v*;  stressGuess = -2 uInv (-D u_old - DJ^T v*)
+// (the reference multiplies by uInv_Matrix here, not u_Matrix -- restated as written), then S_AS:413-419.
+void Oracle::constructGuessVectors() {
+    const exint np = nPressures, nt = nStresses, nr = nReducedVs;
+    std::vector<Real> red(nr, 0.);
+    for (exint r = 0; r < regionCount; ++r) for (int j = 0; j < RDOF; ++j) red[r * RDOF + j] = bestFit[r][j];
+    std::vector<Real> g1(np, 0.), g2(np, 0.), d1(nt, 0.), d2(nt, 0.);
+    Gt.mulVec(oldActiveVs.data(), g1.data()); D.mulVec(oldActiveVs.data(), d1.data());
+    if (nr > 0) { JGt.mulVec(red.data(), g2.data()); DJt.mulVec(red.data(), d2.data()); }
+    guess.assign(nSystemSize, 0.);
+    for (exint i = 0; i < np; ++i) guess[i] = -g1[i] - g2[i];
+    for (exint i = 0; i < nt; ++i) guess[np + i] = (-2. * uInvDiag[i]) * (-d1[i] - d2[i]);
+}
+
+// S.cpp:814-862.  Eigen::ConjugateGradient<SparseMatrix, Lower|Upper> with the default DiagonalPreconditioner:
+// extern/eigen/Eigen/src/IterativeLinearSolvers/ConjugateGradient.h:28-93 (the loop restated statement by statement),
+// BasicPreconditioners.h:66-94 (invdiag = 1/A_jj, 1 where the diagonal entry is absent or zero),
+// solveWithGuess(b, guessVector).  Needs assembleExplicitA().
+int Oracle::solveEigenCG() {
+    auto t0 = std::chrono::steady_clock::now();
+    const exint n = nSystemSize;
+    std::vector<Real> invdiag(n, 1.);
+    for (exint j = 0; j < n; ++j)
+        for (exint q = A.ptr[j]; q < A.ptr[j + 1]; ++q)
+            if (A.idx[q] == j) { if (A.val[q] != 0.) invdiag[j] = 1. / A.val[q]; break; }
+    std::vector<Real>& x = solution;
+    x = guess; x.resize(n, 0.);
+    std::vector<Real> residual(n), p(n), z(n), tmp(n);
+    const Real tol = P.tolerance; const int maxIters = P.maxIterations;
+    int iters = maxIters; Real tol_error = tol;
+    auto finish = [&]() {
+        solveIterations = iters; solveError = tol_error;
+        solveMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        solverResult = (tol_error <= tol) ? SUCCESS : NOCONVERGE;     // m_info, S.cpp:853-859
+        return solverResult;
+    };
+    A.mulVec(x.data(), tmp.data());
+    for (exint i = 0; i < n; ++i) residual[i] = b[i] - tmp[i];
+    const Real rhsNorm2 = dot(b, b);
+    if (rhsNorm2 == 0) { std::fill(x.begin(), x.end(), 0.); iters = 0; tol_error = 0; return finish(); }
+    const Real considerAsZero = std::numeric_limits<Real>::min();
+    const Real threshold = std::max(tol * tol * rhsNorm2, considerAsZero);
+    Real residualNorm2 = dot(residual, residual);
+    if (residualNorm2 < threshold) { iters = 0; tol_error = std::sqrt(residualNorm2 / rhsNorm2); return finish(); }
+    for (exint i = 0; i < n; ++i) p[i] = invdiag[i] * residual[i];
+    Real absNew = dot(residual, p);
+    int i = 0;
+    while (i < maxIters) {
+        A.mulVec(p.data(), tmp.data());
+        const Real alpha = absNew / dot(p, tmp);
+#pragma omp parallel for schedule(static)
+        for (exint k = 0; k < n; ++k) { x[k] += alpha * p[k]; residual[k] -= alpha * tmp[k]; }
+        residualNorm2 = dot(residual, residual);
+        if (residualNorm2 < threshold) break;
+        for (exint k = 0; k < n; ++k) z[k] = invdiag[k] * residual[k];
+        const Real absOld = absNew;
+        absNew = dot(residual, z);
+        const Real beta = absNew / absOld;
+#pragma omp parallel for schedule(static)
+        for (exint k = 0; k < n; ++k) p[k] = z[k] + beta * p[k];
+        i++;
+    }
+    tol_error = std::sqrt(residualNorm2 / rhsNorm2);
+    iters = i;
+    return finish();
 }
 
 // S.cpp:492-510

@@ -238,7 +238,10 @@ int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* s
 }
 int ps_setup(ps_handle h, const ps_fields_in* in) {
     if (!h || !in) { g_lastError = "ps_setup: null argument"; return PS_INVALID; }
-    return guarded([&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; S.setInputs(*in); S.setup(); return (int)PS_SUCCESS; });
+    return guarded([&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; 
+        try { S.setInputs(*in); S.setup(); }
+        catch (...) { stream_sync(S.stIn); S.lateInputsPending = false; throw; }   // no copy may outlive the error return
+        return (int)PS_SUCCESS; });
 }
 int ps_solve(ps_handle h, ps_fields_out* out, ps_stats* stats) {
     if (!h) { g_lastError = "ps_solve: null handle"; return PS_INVALID; }

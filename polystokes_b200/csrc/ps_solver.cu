@@ -65,6 +65,8 @@ Solver::Solver(const ps_params& p) : P(p) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error("ps_create: no CUDA device (this library has no CPU path)");
     PS_CUDA(cudaSetDevice(p.device));
     PS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    PS_CUDA(cudaStreamCreateWithFlags(&stIn, cudaStreamNonBlocking));
+    PS_CUDA(cudaStreamCreateWithFlags(&stOut, cudaStreamNonBlocking));
 #endif
     flags.alloc(64);
     scal.alloc(1);
@@ -169,6 +171,8 @@ Solver::~Solver() {
     delete comm;
 #ifndef PS_EMULATE
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (stIn) { cudaStreamSynchronize(stIn); cudaStreamDestroy(stIn); }
+    if (stOut) { cudaStreamSynchronize(stOut); cudaStreamDestroy(stOut); }
 #endif
 }
 
@@ -181,14 +185,26 @@ void Solver::setInputs(const ps_fields_in& in) {
     dSurface.alloc(nc); dCollision.alloc(nc); dViscosity.alloc(nc);
     copy_any2d(dSurface.p, in.surface, nc * sizeof(float), dev, st);
     copy_any2d(dCollision.p, in.collision, nc * sizeof(float), dev, st);
-    copy_any2d(dViscosity.p, in.viscosity, nc * sizeof(float), dev, st);
+    // host inputs: only the two SDFs are needed at once (weights); the other seven fields are first read by the region
+    // matrices, so they cross PCIe on the copy stream while weights / classification / numbering run (waitLateInputs)
+    cudaStream_t sLate = st;
+#ifndef PS_EMULATE
+    if (!dev) {
+        sLate = stIn;
+        cudaEvent_t e; PS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        PS_CUDA(cudaEventRecord(e, st)); PS_CUDA(cudaStreamWaitEvent(stIn, e, 0)); PS_CUDA(cudaEventDestroy(e));   // earlier readers of the old fields
+        lateInputsPending = true;
+    }
+#endif
+    copy_any2d(dViscosity.p, in.viscosity, nc * sizeof(float), dev, sLate);
     for (int a = 0; a < 3; ++a) {
         const size_t nf = (size_t)g.n[SL_FACE + a];
         dVel[a].alloc(nf); dColVel[a].alloc(nf);
-        copy_any2d(dVel[a].p, in.velocity[a], nf * sizeof(float), dev, st);
-        copy_any2d(dColVel[a].p, in.collisionvel[a], nf * sizeof(float), dev, st);
+        copy_any2d(dVel[a].p, in.velocity[a], nf * sizeof(float), dev, sLate);
+        copy_any2d(dColVel[a].p, in.collisionvel[a], nf * sizeof(float), dev, sLate);
         F.vel[a] = dVel[a].p; F.colvel[a] = dColVel[a].p;
     }
+    validSent = false;
     F.surface = dSurface.p; F.collision = dCollision.p; F.viscosity = dViscosity.p;
     // labels / indices start UNASSIGNED (S.cpp:94-152); byte 0xFF = -1 for int8 and int32 alike
     for (int s = 0; s < N_SLOTS; ++s) {
@@ -203,6 +219,32 @@ void Solver::setInputs(const ps_fields_in& in) {
     for (auto& b : scratch8) b.alloc(nmax);
     for (auto& b : scratch32) b.alloc(nmax);
     haveSetup = false;
+}
+
+// the compute stream joins the copy stream: from here on viscosity / velocity / collision velocity are read
+void Solver::waitLateInputs() {
+#ifndef PS_EMULATE
+    if (!lateInputsPending) return;
+    StageTimer T(st, &stageMs[PS_STAGE_UPLOAD]);
+    cudaEvent_t e; PS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PS_CUDA(cudaEventRecord(e, stIn)); PS_CUDA(cudaStreamWaitEvent(st, e, 0)); PS_CUDA(cudaEventDestroy(e));
+    lateInputsPending = false;
+#endif
+}
+
+// `valid` depends on the face labels only (S_Cls:4-54), which are final after setup: a host caller's three valid fields
+// are produced now and cross PCIe on the output stream while the CG loop runs
+void Solver::sendValidEarly(const ps_fields_out& out) {
+#ifndef PS_EMULATE
+    if (out.memory == PS_MEM_DEVICE || !(out.valid[0] && out.valid[1] && out.valid[2])) return;
+    float* v[3];
+    for (int a = 0; a < 3; ++a) { outStage[3 + a].alloc((size_t)g.n[SL_FACE + a]); v[a] = outStage[3 + a].p; }
+    k_valid_faces(st, g, F, v);
+    cudaEvent_t e; PS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PS_CUDA(cudaEventRecord(e, st)); PS_CUDA(cudaStreamWaitEvent(stOut, e, 0)); PS_CUDA(cudaEventDestroy(e));
+    for (int a = 0; a < 3; ++a) copy_d2any(out.valid[a], v[a], (size_t)g.n[SL_FACE + a] * sizeof(float), false, stOut);
+    validSent = true;
+#endif
 }
 
 void Solver::buildIntegrationWeightsAlt() {
@@ -790,15 +832,20 @@ void Solver::recoverVelocityFromPressureStress() {
 void Solver::applySolutionToVelocity(const ps_fields_out& out) {
     const bool dev = out.memory == PS_MEM_DEVICE;
     const bool writeVel = (result == R_SUCCESS || P.keepNonConvergedResults);
+#ifndef PS_EMULATE
+    cudaEvent_t evLast = nullptr, evDone = nullptr;
+#endif
     for (int a = 0; a < 3; ++a) {
         const size_t nf = (size_t)g.n[SL_FACE + a];
         float* velDev = nullptr; float* validDev = nullptr;
         // velocity staging starts as the input velocity: invalid faces are left untouched (S.cpp:975-978)
         if (out.velocity[a] && writeVel) {
             if (dev) { velDev = out.velocity[a]; if (velDev != dVel[a].p) copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
-            else { velDev = (float*)scratch32[0].p; copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
+            else { outStage[a].alloc(nf); velDev = outStage[a].p; copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
         }
-        if (out.valid[a]) validDev = dev ? out.valid[a] : (float*)scratch32[1].p;
+        if (out.valid[a] && !(validSent && !dev)) {
+            if (dev) validDev = out.valid[a]; else { outStage[3 + a].alloc(nf); validDev = outStage[3 + a].p; }
+        }
         const FaceOwner own = {(int32_t)part.slotCut[SL_FACE + a][part.rank], (int32_t)part.slotCut[SL_FACE + a][part.rank + 1], RG.regLo, RG.regHi};
         k_writeback_velocity(st, g, F, C, RG, velSol.p, a, velDev, validDev != nullptr, validDev, own);
         if (a == 2 && part.multi() && comm && velDev) {
@@ -815,12 +862,29 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
             for (int i = 0; i < 2; ++i) if (peers[i] >= 0) k_merge_face_plane(st, g, F, a, kz[i], planes.p + plane * i, velDev, own);
         }
         if (!dev) {
+#ifndef PS_EMULATE
+            // this axis crosses PCIe on the output stream while the next axis' kernel runs
+            cudaEvent_t e; PS_CUDA(cudaEventCreate(&e));
+            PS_CUDA(cudaEventRecord(e, st)); PS_CUDA(cudaStreamWaitEvent(stOut, e, 0));
+            if (a == 2) evLast = e; else PS_CUDA(cudaEventDestroy(e));
+            if (velDev) copy_d2any(out.velocity[a], velDev, nf * sizeof(float), false, stOut);
+            if (validDev) copy_d2any(out.valid[a], validDev, nf * sizeof(float), false, stOut);
+#else
             if (velDev) copy_d2any(out.velocity[a], velDev, nf * sizeof(float), false, st);
             if (validDev) copy_d2any(out.valid[a], validDev, nf * sizeof(float), false, st);
-            stream_sync(st);
+#endif
         }
     }
     stream_sync(st);
+#ifndef PS_EMULATE
+    if (!dev) {
+        PS_CUDA(cudaEventCreate(&evDone)); PS_CUDA(cudaEventRecord(evDone, stOut));
+        PS_CUDA(cudaEventSynchronize(evDone));
+        float ms = 0; cudaEventElapsedTime(&ms, evLast, evDone); stageMs[PS_STAGE_DOWNLOAD] += ms;   // PCIe tail not hidden under kernels
+        cudaEventDestroy(evLast); cudaEventDestroy(evDone);
+    }
+#endif
+    validSent = false;
 }
 
 void Solver::setup() {
@@ -839,6 +903,7 @@ void Solver::setup() {
         if (P.doReducedRegions) { constructCenterReducedIndices(); constructFacesReducedIndices(); constructEdgesReducedIndices(); }
     }
     { StageTimer T(st, &stageMs[PS_STAGE_INDICES]); constructActiveIndices(); }
+    waitLateInputs();
     { StageTimer T(st, &stageMs[PS_STAGE_REGION_MATRICES]); if (P.doReducedRegions) computeReducedRegionMatrices(); }
     { StageTimer T(st, &stageMs[PS_STAGE_MATRIX_BLOCKS]); constructMatrixBlocks(); }
     { StageTimer T(st, &stageMs[PS_STAGE_ASSEMBLE]); assemble(); }
@@ -849,15 +914,26 @@ void Solver::setup() {
 int Solver::step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* stats) {
     for (double& m : stageMs) m = 0;
     g_launches = 0;
-    setInputs(in);
-    setup();
     int res = R_INCOMPLETE;
-    if (P.doSolve) res = solve();
-    if (res == R_UNSUPPORTED_SOLVER) { if (stats) fillStats(stats); return res; }
-    if (out) {
-        StageTimer T(st, &stageMs[PS_STAGE_WRITEBACK]);
-        if (P.doSolve && (res == R_SUCCESS || P.keepNonConvergedResults)) recoverVelocityFromPressureStress();
-        applySolutionToVelocity(*out);
+    try {
+        setInputs(in);
+        setup();
+        if (out) sendValidEarly(*out);
+        if (P.doSolve) res = solve();
+        if (res == R_UNSUPPORTED_SOLVER) { stream_sync(stOut); validSent = false; if (stats) fillStats(stats); return res; }
+        if (out) {
+            {
+                StageTimer T(st, &stageMs[PS_STAGE_WRITEBACK]);
+                if (P.doSolve && (res == R_SUCCESS || P.keepNonConvergedResults)) recoverVelocityFromPressureStress();
+                applySolutionToVelocity(*out);
+            }
+            stageMs[PS_STAGE_WRITEBACK] = std::max(0., stageMs[PS_STAGE_WRITEBACK] - stageMs[PS_STAGE_DOWNLOAD]);   // the PCIe tail is its own stage
+        }
+    } catch (...) {
+        // no copy may still be reading / writing the caller's host buffers once the error is reported
+        stream_sync(stIn); stream_sync(stOut);
+        lateInputsPending = false; validSent = false;
+        throw;
     }
     if (stats) fillStats(stats);
     return res;

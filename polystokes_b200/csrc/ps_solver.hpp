@@ -122,6 +122,15 @@ public:
     ps_params P;
     Geom g;
     cudaStream_t st = nullptr;
+    // host-memory callers (ps_fields_in/out::memory == PS_MEM_HOST): the PCIe copies run on their own streams underneath
+    // the compute stream -- late inputs (viscosity, velocity, collision velocity: first read by the region matrices)
+    // under weights + classification + numbering, the `valid` field (final once the faces are classified) under the CG
+    // loop, each velocity axis under the write-back kernel of the next one
+    cudaStream_t stIn = nullptr, stOut = nullptr;
+    bool lateInputsPending = false, validSent = false;
+    DBuf<float> outStage[6];            // device staging of velocity[3] / valid[3] for host outputs
+    void waitLateInputs();
+    void sendValidEarly(const ps_fields_out& out);
     Counts C;
     int result = R_INCOMPLETE;
     int solveIterations = -1;
