@@ -144,6 +144,8 @@ bool get_vector(Solver& S, const std::string& n, std::vector<double>& out) {
     else if (n == "MrDense") out = R ? S.RG.Mr.to_host(S.st, R * NN) : std::vector<double>();
     else if (n == "ViscDense") out = R ? S.RG.Visc.to_host(S.st, R * NN) : std::vector<double>();
     else if (n == "BinvDense") out = R ? S.RG.Binv.to_host(S.st, R * NN) : std::vector<double>();
+    else if (n == "guess") { if (S.guess.n < (size_t)C.nSystemSize) out.assign((size_t)C.nSystemSize, 0.); else out = S.guess.to_host(S.st, (size_t)C.nSystemSize); }
+    else if (n == "diagA") { if (S.part.multi()) return false; S.computeDiagonal(); out = S.diagA.to_host(S.st, (size_t)C.nSystemSize); }
     else return false;
     // several ranks: keep only this rank's share (the sum over ranks is the global vector)
     if (S.part.multi()) {
@@ -408,6 +410,7 @@ int ps_export(ps_handle h, const char* prefix, int what) {
         std::vector<double> v;
         if (what & 1) {   // exportMatrices / exportMatricesPostSolve (S.cpp:533-541, 568-572); A is implicit on this path
             if (get_vector(S, "b", v)) ok &= save_market_vector(v, pre + "Vec_b.mtx");
+            if (get_vector(S, "guess", v)) ok &= save_market_vector(v, pre + "Vec_guess.mtx");
             if (get_vector(S, "solution", v)) ok &= save_market_vector(v, pre + "solutionVector.mtx");
         }
         if (what & 2) {   // exportComponentMatrices (S.cpp:543-566)

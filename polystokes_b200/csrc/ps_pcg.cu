@@ -799,6 +799,123 @@ void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* w
 }
 #endif
 
+// ---- solverType EIGEN (exec/HDK_PolyStokesSolver.cpp:814-862) ---------------------------------------------------
+// The reference hands the explicit A to Eigen::ConjugateGradient<SparseMatrix, Lower|Upper> (default
+// DiagonalPreconditioner) and starts from guessVector.  Here the operator stays factored (same A up to rounding) and only
+// diag(A) is formed, row by row, from the factors:
+//   A_ii = -dt sum_{active f} K_fi^2 / Mc_f  -  v_i^T B_r^-1 v_i  -  1/2 mu^-1_i [stress rows],   v_i = sum_{f in region r} K_fi c_f
+// (column i of J_r = C_r K_red; the coupled reduced faces of one DOF belong to one region after C6, several are handled anyway).
+struct DiagCtx { const int32_t* rowRegion; const uint32_t* rowXYZ; const double* com; const double* Binv; double dx, dt; };
+template <int NS>
+PS_D double diag_row(const OpArgs& A, const DiagCtx& D, const int64_t* f, const double* val) {
+    double uni = 0., red = 0.;
+    bool used[NS];
+    for (int k = 0; k < NS; ++k) {
+        used[k] = (val[k] == 0.) || f[k] < A.nActiveVs;
+        if (val[k] != 0. && f[k] < A.nActiveVs) uni += val[k] * val[k] * A.mcInvLut[A.kmc[f[k]]];
+    }
+    for (int k = 0; k < NS; ++k) {
+        if (used[k]) continue;
+        const int region = D.rowRegion[f[k] - A.nActiveVs];
+        double V[RDOF], c[RDOF], m[10];
+        for (int n = 0; n < RDOF; ++n) V[n] = 0.;
+        for (int q = k; q < NS; ++q) {
+            if (used[q] || D.rowRegion[f[q] - A.nActiveVs] != region) continue;
+            used[q] = true;
+            const uint32_t packed = D.rowXYZ[f[q] - A.nActiveVs];
+            row_monomials(D.dx, packed, D.com + 3 * region, m);
+            conversion_coefficients(m[1], m[2], m[3], (int)(packed >> 30), c);
+            for (int n = 0; n < RDOF; ++n) V[n] += val[q] * c[n];
+        }
+        const double* B = D.Binv + (size_t)region * RDOF * RDOF;
+        for (int i = 0; i < RDOF; ++i) { double t = 0.; for (int j = 0; j < RDOF; ++j) t += B[i * RDOF + j] * V[j]; red += V[i] * t; }
+    }
+    return -D.dt * uni - red;
+}
+void k_diag_A(cudaStream_t st, const Geom& g, const OpArgs& A, const RegionData& RG, double* diag) {
+    const DiagCtx D = {RG.rowRegion.p, RG.rowXYZ.p, RG.com.p, RG.Binv.p, g.dx, g.dt};
+    ps_for(st, A.nC, PS_LAMBDA(int64_t ci) {
+        const uint64_t word = A.ccode[ci];
+        int64_t f[6]; double v[6];
+        for (int k = 0; k < 6; ++k) { const int code = op_code(word, k); v[k] = (double)code * A.valScale; f[k] = code ? A.ccol[(int64_t)k * A.nC + ci] : 0; }
+        diag[ci] = diag_row<6>(A, D, f, v);
+        for (int a = 0; a < 3; ++a) {
+            const double va[2] = {-v[2 * a], -v[2 * a + 1]};
+            const int64_t j = (int64_t)a * A.nC + ci;
+            diag[A.nP + j] = diag_row<2>(A, D, f + 2 * a, va) - 0.5 * A.uInv[j];
+        }
+    });
+    ps_for(st, A.nE, PS_LAMBDA(int64_t e) {
+        const uint32_t word = A.ecode[e];
+        int64_t f[4]; double v[4];
+        for (int k = 0; k < 4; ++k) { const int code = op_code(word, k); v[k] = (double)code * A.valScale; f[k] = code ? A.ecol[(int64_t)k * A.nE + e] : 0; }
+        const int64_t j = 3 * A.nC + e;
+        diag[A.nP + j] = diag_row<4>(A, D, f, v) - 0.5 * A.uInv[j];
+    });
+}
+// warm start (S.cpp:521-531): sigma of v*_r without the B^-1 solve, so that expand gives w_f = c_f . v*_r
+void k_sigma_from_s(cudaStream_t st, int32_t R, const double* s, double* sigma) {
+    ps_for(st, R, PS_LAMBDA(int64_t r) { double sg[30]; s_to_sigma(s + r * RDOF, sg); for (int k = 0; k < 30; ++k) sigma[r * 30 + k] = sg[k]; });
+}
+// guess holds -K_ext^T w; the stress part becomes -2 mu^-1 (-D u - DJ^T v*) (S.cpp:530, uInv_Matrix as written there)
+void k_guess_finish(cudaStream_t st, const OpArgs& A, double* guess) {
+    ps_for(st, A.nT, PS_LAMBDA(int64_t i) { guess[A.nP + i] = (-2. * A.uInv[i]) * guess[A.nP + i]; });
+}
+// Eigen's m_invdiag: 1 / A_jj, 1 where the diagonal entry is absent or zero (BasicPreconditioners.h:75-84)
+PS_D double eig_invdiag(double d) { return d != 0. ? 1. / d : 1.; }
+// scalar bookkeeping in the statement order of ConjugateGradient.h:44-90
+PS_D void eig_stage(PcgScalars* S, int stage) {
+    if (S->done) return;
+    if (stage == 0) {            // :46-61  bred = {b.b, r.r}
+        const double rhsNorm2 = S->bred[0], residualNorm2 = S->bred[1];
+        S->eigRhsNorm2 = rhsNorm2;
+        if (rhsNorm2 == 0.) { S->rre = 0.; S->done = 3; return; }                      // x.setZero(), 0 iterations
+        const double t = S->tol * S->tol * rhsNorm2;
+        S->eigThreshold = t > 2.2250738585072014e-308 ? t : 2.2250738585072014e-308;
+        S->rre = sqrt(residualNorm2 / rhsNorm2);
+        if (residualNorm2 < S->eigThreshold) S->done = 1;
+        else if (S->maxIter <= 0) S->done = 2;
+    } else if (stage == 1) {     // :67  absNew = r.p
+        S->eigAbsNew = S->bred[0];
+    } else {                     // :78-88  bred = {r.r, r.z}
+        const double residualNorm2 = S->bred[0];
+        S->rsnew = residualNorm2; S->rre = sqrt(residualNorm2 / S->eigRhsNorm2);
+        if (residualNorm2 < S->eigThreshold) { S->done = 1; return; }
+        const double absOld = S->eigAbsNew;
+        S->eigAbsNew = S->bred[1];
+        S->beta = S->eigAbsNew / absOld;
+        S->iter += 1;
+        if (S->iter >= S->maxIter) S->done = 2;
+    }
+}
+void k_eig_stage(cudaStream_t st, PcgScalars* S, int stage) { ps_for(st, 1, PS_LAMBDA(int64_t) { eig_stage(S, stage); }); }
+// :40-48  residual = rhs - mat * x, |rhs|^2, |residual|^2
+void k_eig_init(cudaStream_t st, const RangeSet& own, const double* b, const double* Ax, double* r, double* dotPartial, PcgScalars* S, double tol, int maxIter) {
+    ps_for(st, 1, PS_LAMBDA(int64_t) {
+        S->alpha = 0.; S->beta = 0.; S->rsnew = 0.; S->rre = 0.; S->red[0] = 0.; S->bred[0] = 0.; S->bred[1] = 0.;
+        S->tol = tol; S->tol2 = tol * tol; S->iter = 0; S->maxIter = maxIter; S->done = 0;
+        S->ticket[0] = 0; S->ticket[6] = 0;
+    });
+    vec_sweep(st, own, dotPartial, S, 2, 0, false, PS_LAMBDA(int64_t i, double& a, double& c) { const double bi = b[i], ri = bi - Ax[i]; r[i] = ri; a += bi * bi; c += ri * ri; });
+}
+// :64-67  p = precond.solve(residual), absNew = residual . p
+void k_eig_first_p(cudaStream_t st, const RangeSet& own, const double* diag, const double* r, double* p, double* dotPartial, PcgScalars* S) {
+    vec_sweep(st, own, dotPartial, S, 1, 0, true, PS_LAMBDA(int64_t i, double& a, double&) { const double ri = r[i], pi = eig_invdiag(diag[i]) * ri; p[i] = pi; a += ri * pi; });
+}
+// :73-84  alpha = absNew / p.tmp (p.tmp left in red[0] by pass 2), x += alpha p, residual -= alpha tmp, |residual|^2, residual . z
+void k_eig_update_xr(cudaStream_t st, const RangeSet& own, const double* diag, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* S) {
+    vec_sweep(st, own, dotPartial, S, 2, 0, true, PS_LAMBDA(int64_t i, double& a, double& c) {
+        const double alpha = S->eigAbsNew / S->red[0];
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap[i];
+        r[i] = ri; a += ri * ri; c += ri * (eig_invdiag(diag[i]) * ri);
+    });
+}
+// :81, :87  p = z + beta p
+void k_eig_update_p(cudaStream_t st, const RangeSet& own, const double* diag, double* p, const double* r, const PcgScalars* S) {
+    vec_sweep(st, own, nullptr, const_cast<PcgScalars*>(S), 0, 0, true, PS_LAMBDA(int64_t i, double&, double&) { p[i] = eig_invdiag(diag[i]) * r[i] + S->beta * p[i]; });
+}
+
 // W1 recoverVelocityFromPressureStress, active part (S.cpp:507): u = dt Mc^-1 (rhs_u/dt - G p - D^T tau)
 // (wAct already holds dt Mc^-1 K x from pass 1)
 void k_recover_active(cudaStream_t st, const Geom& g, const RowSet& rows, const double* wAct, const double* mcInv, const double* rhsU, double* velSol) {

@@ -692,7 +692,9 @@ void Solver::timedOperator(int which) {
 // preconditioner (Preconditioner.cpp:271-274), zero start, stop test min(rr, rr/xx) < tol^2.
 int Solver::solve() {
     StageTimer T(st, &stageMs[PS_STAGE_SOLVE]);
-    if (P.matrixSetup != 0 || P.solverType != 0) { result = R_UNSUPPORTED_SOLVER; return result; }
+    // units.h:76-94: matrixSetup 0 = PRESSURE_STRESS; solverType 0 = PCG_MATRIX_VECTOR_PRODUCTS, 1 = EIGEN
+    if (P.matrixSetup != 0 || (P.solverType != 0 && P.solverType != 1)) { result = R_UNSUPPORTED_SOLVER; return result; }
+    if (P.solverType == 1) return solveEigenCG();
     const OpArgs A = make_op(*this);
     const int64_t n = C.nSystemSize;
     const int maxIt = P.maxSolverIterations;
@@ -756,6 +758,81 @@ int Solver::solve() {
     // "have minres as a backup" (S.cpp:784-799): CG used up its iterations -> restart from x = 0 with BiCGSTAB
     if (solveIterations == maxIt && !cgOnly) return solveBiCGStab();
     result = (solveIterations == maxIt) ? R_NOCONVERGE : R_SUCCESS;
+    return result;
+}
+
+// useWarmStart (PS.C:465-467): constructGuessVectors (S.cpp:521-531) + the copy into guessVector (S_AS:413-419)
+//   pressureGuess = -G^T u_old - JG^T v*  = (-K_ext^T w)_p,   stressGuess = -2 mu^-1 (-D u_old - DJ^T v*) = -2 mu^-1 (-K_ext^T w)_tau
+//   with w_active = u_old, w_f = c_f . v*_r on the coupled reduced rows.  Single GPU only (the live solver never reads it).
+void Solver::constructGuessVectors() {
+    haveGuess = false;
+    const int64_t n = C.nSystemSize;
+    guess.alloc((size_t)std::max<int64_t>(n, 1));
+    guess.zero(st, (size_t)n);
+    if (!P.useWarmStart || part.multi() || n == 0) return;
+    const OpArgs A = make_op(*this);
+    w.zero(st, (size_t)C.nRowsExt);
+    copy_d2d(w.p, oldVs.p, (size_t)C.nActiveVs * sizeof(double), st);
+    if (RG.count > 0) {
+        k_sigma_from_s(st, RG.count, RG.bestFit.p, RG.sigma.p);
+        reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
+    }
+    k_pass2(st, A, w.p, nullptr, guess.p, 0.0, nullptr, nullptr, PeerCtx(), nullptr, 0);
+    k_guess_finish(st, A, guess.p);
+    haveGuess = true;
+}
+
+// diag(A) from the factors (ps_pcg.cu, k_diag_A)
+void Solver::computeDiagonal() {
+    if (haveDiag) return;
+    diagA.alloc((size_t)std::max<int64_t>(C.nSystemSize, 1));
+    diagA.zero(st, (size_t)C.nSystemSize);
+    k_diag_A(st, g, make_op(*this), RG, diagA.p);
+    haveDiag = true;
+}
+
+// solveEigenCG (S.cpp:814-862): Eigen::ConjugateGradient<SparseMatrix, Lower|Upper>, DiagonalPreconditioner,
+// solveWithGuess(b, guessVector); iterations / error / Success as Eigen reports them (ConjugateGradient.h:28-93, :217-222).
+// The reference needs the explicit A for this solver; here A stays factored and only its diagonal is formed, so the
+// path also runs at sizes where the explicit matrix (dense region blocks) could not be stored.
+int Solver::solveEigenCG() {
+    if (part.multi()) { result = R_UNSUPPORTED_SOLVER; g_lastError = "solverType EIGEN runs on one GPU (diag(A) needs the neighbour's region blocks)"; return result; }
+    const OpArgs A = make_op(*this);
+    const int64_t n = C.nSystemSize;
+    const int maxIt = P.maxSolverIterations;
+    const int every = P.checkEvery > 0 ? P.checkEvery : 25;
+    usedBiCGStab = 0;
+    if (n == 0) { solveIterations = 0; solveError = 0; result = R_SUCCESS; return result; }
+    computeDiagonal();
+    if (haveGuess) copy_d2d(x.p, guess.p, (size_t)n * sizeof(double), st); else x.zero(st, (size_t)n);
+    applyOperator(x.p, Ap.p, nullptr);
+    k_eig_init(st, ownSys, b.p, Ap.p, r.p, dotPartial.p, scal.p, P.tolerance, maxIt);
+    k_eig_stage(st, scal.p, 0);
+    k_eig_first_p(st, ownSys, diagA.p, r.p, p.p, dotPartial.p, scal.p);
+    k_eig_stage(st, scal.p, 1);
+    PcgScalars h; memset(&h, 0, sizeof h);
+    bool cancelled = false;
+    for (int it = 0; it < maxIt;) {
+        const int batch = std::min(every, maxIt - it);
+        for (int k = 0; k < batch; ++k) {
+            k_pass1(st, A, p.p, w.p, g.dt, scal.p);
+            if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, PeerCtx(), scal.p, 1);          // tmp = A p, p.tmp -> red[0]
+            k_eig_update_xr(st, ownSys, diagA.p, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p);
+            k_eig_stage(st, scal.p, 2);
+            k_eig_update_p(st, ownSys, diagA.p, p.p, r.p, scal.p);
+        }
+        it += batch;
+        copy_d2h(&h, scal.p, sizeof h, st);
+        if (h.done) break;
+        if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
+    }
+    copy_d2h(&h, scal.p, sizeof h, st);
+    if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
+    if (h.done == 3) x.zero(st, (size_t)n);                 // rhs == 0: x.setZero() (ConjugateGradient.h:47-53)
+    solveIterations = h.iter;
+    solveError = h.rre;
+    result = (solveError <= P.tolerance) ? R_SUCCESS : R_NOCONVERGE;      // m_info (ConjugateGradient.h:222), S.cpp:853-859
     return result;
 }
 
@@ -906,7 +983,8 @@ void Solver::setup() {
     waitLateInputs();
     { StageTimer T(st, &stageMs[PS_STAGE_REGION_MATRICES]); if (P.doReducedRegions) computeReducedRegionMatrices(); }
     { StageTimer T(st, &stageMs[PS_STAGE_MATRIX_BLOCKS]); constructMatrixBlocks(); }
-    { StageTimer T(st, &stageMs[PS_STAGE_ASSEMBLE]); assemble(); }
+    haveDiag = false;
+    { StageTimer T(st, &stageMs[PS_STAGE_ASSEMBLE]); constructGuessVectors(); assemble(); }
     haveSetup = true;
     result = R_INCOMPLETE;
 }

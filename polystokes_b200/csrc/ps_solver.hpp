@@ -113,6 +113,8 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     double red[4];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.x, [3] b.b
     // BiCGSTAB fallback (pcg.h:134-200): its own scalars; bred[] = rank-local dot products of the current stage
     double rhoCurr, rhoOld, omega, tol, bred[2];
+    // solverType EIGEN (Eigen::ConjugateGradient, ConjugateGradient.h:28-93): |b|^2, max(tol^2 |b|^2, DBL_MIN), r.z
+    double eigRhsNorm2, eigThreshold, eigAbsNew;
 };
 
 class Solver {
@@ -156,6 +158,9 @@ public:
     void assemble();                    // assembleSystemPressureStressFactored
     int solve();                        // solveSPDwithMatrixVectorPCG
     int solveBiCGStab();                // its fallback when CG hits maxSolverIterations (S.cpp:784-799 -> pcg.h:134-200)
+    int solveEigenCG();                 // solverType EIGEN (S.cpp:814-862): Jacobi-preconditioned Eigen CG from guessVector, on the factored operator
+    void constructGuessVectors();       // useWarmStart (PS.C:465-467 -> S.cpp:521-531, S_AS:413-419)
+    void computeDiagonal();             // diag(A) for Eigen's DiagonalPreconditioner (BasicPreconditioners.h:66-94), matrix free
     void buildValidFaces(const ps_fields_out& out);
     void recoverVelocityFromPressureStress();
     void applySolutionToVelocity(const ps_fields_out& out);
@@ -206,6 +211,8 @@ public:
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
     DBuf<double> x, r, p, Ap, w, velSol;
     DBuf<double> bRhat, bV, bS, bT;     // BiCGSTAB work vectors, allocated when the fallback first fires
+    DBuf<double> guess, diagA;          // guessVector (zero unless useWarmStart) and diag(A), built on demand
+    bool haveGuess = false, haveDiag = false;
     DBuf<double> dotPartial;
     DBuf<PcgScalars> scal;
     bool inputsOnDevice = false;
@@ -289,6 +296,15 @@ void k_bicg_update_hs(cudaStream_t, const RangeSet& own, double* x, double* s, c
 void k_bicg_update_x(cudaStream_t, const RangeSet& own, double* x, const double* s, double* dotPartial, PcgScalars* scal);
 void k_bicg_err(cudaStream_t, const RangeSet& own, const double* b, const double* Ax, double* dotPartial, PcgScalars* scal);
 void k_bicg_update_r(cudaStream_t, const RangeSet& own, double* r, const double* s, const double* t, const PcgScalars* scal);
+// solverType EIGEN (S.cpp:814-862): Eigen's CG loop with the Jacobi preconditioner, scalars on the device
+void k_diag_A(cudaStream_t, const Geom&, const OpArgs&, const RegionData&, double* diag);
+void k_sigma_from_s(cudaStream_t, int32_t R, const double* s, double* sigma);
+void k_guess_finish(cudaStream_t, const OpArgs&, double* guess);
+void k_eig_init(cudaStream_t, const RangeSet& own, const double* b, const double* Ax, double* r, double* dotPartial, PcgScalars* scal, double tol, int maxIter);
+void k_eig_stage(cudaStream_t, PcgScalars* scal, int stage);
+void k_eig_first_p(cudaStream_t, const RangeSet& own, const double* diag, const double* r, double* p, double* dotPartial, PcgScalars* scal);
+void k_eig_update_xr(cudaStream_t, const RangeSet& own, const double* diag, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal);
+void k_eig_update_p(cudaStream_t, const RangeSet& own, const double* diag, double* p, const double* r, const PcgScalars* scal);
 #ifndef PS_EMULATE
 void k_halo_push_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
                       unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket);

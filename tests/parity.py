@@ -140,6 +140,40 @@ def check_bicgstab_fallback(lib_path=None):
     s.close()
 
 
+def check_eigen_cg(lib_path=None, warm=1, scene=None):
+    """solverType EIGEN (S.cpp:814-862): Eigen's CG with the Jacobi preconditioner, started from guessVector
+    (useWarmStart, S.cpp:521-531).  The oracle runs it on the explicit A (S_AS:381-397); the library keeps A factored
+    and forms only diag(A).  Gates: guess <= 1e-10, diag(A) <= 1e-10 against the explicit matrix, same result code,
+    iterations within max(2, 1 %), Eigen's error estimate within 5 %, velocity within 10 * tol."""
+    sc = scene or scenes.blob_scene(32, seed=6, tile=8, pad=1, tolerance=1e-5)
+    o = Oracle(sc).setup()
+    o.assemble_explicit_A()
+    if warm:
+        o.construct_guess()
+    s = PolyStokesSolver.from_scene(sc, lib_path=lib_path, solverType=1, useWarmStart=warm)
+    s.setup_scene(sc)
+    n = o.count("nSystemSize")
+    og = o.vector("guess") if warm else np.zeros(n)
+    assert rel(og, s.vector("guess")) <= 1e-10, f"guess rel {rel(og, s.vector('guess')):.2e}"
+    assert (np.abs(og).max() > 0) == bool(warm)
+    A = o.scipy_csr("A")
+    assert rel(A.diagonal(), s.vector("diagA")) <= 1e-10, f"diag(A) rel {rel(A.diagonal(), s.vector('diagA')):.2e}"
+    ro = o.solve_eigen_cg()
+    ovel, ovalid = o.writeback()
+    rs, vel, valid = s.step_scene(sc)
+    assert ro == rs == 1, f"solver result oracle {ro} vs {rs}"
+    io, is_ = o.count("iterations"), s.count("iterations")
+    assert abs(io - is_) <= max(2, int(0.01 * io)), f"iterations oracle {io} vs {is_}"
+    assert abs(o.real("solveError") - s.real("solveError")) <= 0.05 * o.real("solveError"), f"error {o.real('solveError')} vs {s.real('solveError')}"
+    tol = max(10 * sc.params["tolerance"], 4e-7)
+    for a in range(3):
+        assert np.array_equal(ovalid[a], valid[a])
+        scale = max(float(np.abs(ovel[a]).max()), 1e-30)
+        assert float(np.abs(ovel[a] - vel[a]).max()) <= tol * scale, f"velocity axis {a}: {float(np.abs(ovel[a] - vel[a]).max()) / scale:.2e}"
+    s.close()
+    return io, is_
+
+
 def run_case(name, lib_path=None, solve=True):
     sc, ov = SCENE_CASES[name]()
     o = Oracle(sc, **ov).setup()

@@ -13,3 +13,13 @@ def test_emulated_step_matches_oracle(built, case):
 
 def test_emulated_bicgstab_fallback(built):
     parity.check_bicgstab_fallback(lib_path=parity.EMUL_LIB)
+
+
+@pytest.mark.parametrize("warm", [1, 0])
+def test_emulated_eigen_cg(built, warm):
+    parity.check_eigen_cg(lib_path=parity.EMUL_LIB, warm=warm)
+
+
+def test_emulated_eigen_cg_uniform(built):
+    from polystokes_b200 import scenes
+    parity.check_eigen_cg(lib_path=parity.EMUL_LIB, scene=scenes.box_scene(20, doReduced=0, tolerance=1e-6))

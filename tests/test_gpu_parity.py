@@ -60,3 +60,42 @@ def test_gpu_bicgstab_fallback(built):
     """CG out of iterations -> BiCGSTAB (S.cpp:784-799), against the oracle's restatement of pcg.h:134-200."""
     parity.check_bicgstab_fallback()
 
+
+
+@pytest.mark.parametrize("warm", [1, 0])
+def test_gpu_eigen_cg(built, warm):
+    """solverType EIGEN: Jacobi-preconditioned Eigen CG from the warm-start guess (S.cpp:814-862, 521-531) against the
+    oracle's run on the explicit A."""
+    parity.check_eigen_cg(warm=warm)
+
+
+def test_gpu_eigen_cg_s2_beam(built):
+    """The same path on the 128^3-style cantilever (BASELINE.json configs[1]) at 64^3: reduced tiles 8 pad 1, C6 widening."""
+    from polystokes_b200 import scenes
+    parity.check_eigen_cg(warm=1, scene=scenes.scene_s2(64))
+
+
+def test_gpu_host_io_pinned_and_pageable(built):
+    """Host callers: the overlapped PCIe path (copy streams) gives the same fields from pageable and from pinned buffers,
+    with and without the valid outputs, and equals the device-resident result."""
+    import torch
+    from polystokes_b200 import PolyStokesSolver, scenes
+    sc = scenes.blob_scene(36, seed=2)
+    s = PolyStokesSolver.from_scene(sc)
+    rc, vel, valid = s.step_scene(sc)                      # pageable numpy
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    ins = [pin(sc.surface), pin(sc.collision), pin(sc.viscosity)]
+    pv, pc = [pin(v) for v in sc.vel], [pin(v) for v in sc.colvel]
+    out = [torch.empty_like(v).pin_memory() for v in pv]
+    val = [torch.empty_like(v).pin_memory() for v in pv]
+    npv = lambda ts: [t.numpy() for t in ts]
+    for _ in range(2):
+        rc2 = s.step(ins[0].numpy(), ins[1].numpy(), ins[2].numpy(), npv(pv), npv(pc), npv(out), npv(val))
+        assert rc == rc2
+        for a in range(3):
+            assert np.array_equal(vel[a], out[a].numpy()) and np.array_equal(valid[a], val[a].numpy())
+    out2 = [np.zeros_like(v) for v in sc.vel]
+    rc3 = s.step(sc.surface, sc.collision, sc.viscosity, sc.vel, sc.colvel, out2, None)     # velocity only
+    assert rc3 == rc
+    for a in range(3):
+        assert np.array_equal(vel[a], out2[a])
