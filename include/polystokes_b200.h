@@ -52,9 +52,12 @@ typedef struct ps_params {
     char exportDataPrefix[256];
     int32_t doSolve;
     int32_t keepNonConvergedResults;
-    int32_t useWarmStart;             /* accepted; the live reference solver discards the guess (S.cpp:768) */
+    int32_t useWarmStart;             /* guessVector = constructGuessVectors (S.cpp:521-531); read by solverType 1 only --
+                                       * the live solver (type 0) starts from zero whatever the guess (S.cpp:768) */
     int32_t matrixSetup;              /* 0 = pressurestress (units.h:76-83); others -> PS_UNSUPPORTED_SOLVER */
-    int32_t solverType;               /* 0 = pcg_matrix_vector_products (units.h:85-94) */
+    int32_t solverType;               /* units.h:85-94: 0 = pcg_matrix_vector_products (solveSPDwithMatrixVectorPCG, S.cpp:734-812),
+                                       * 1 = eigen (solveEigenCG, S.cpp:814-862: Eigen CG + Jacobi from guessVector; one GPU);
+                                       * others -> PS_UNSUPPORTED_SOLVER */
     int32_t useInputSurfaceWeights;   /* validated, ignored by the live weights builder (PS.C:351-352) */
     int32_t useInputCollisionWeights;
     double minDensity, maxDensity;    /* stored, never used by the reference (S.cpp:55-56) */
@@ -109,7 +112,9 @@ int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* s
 int ps_setup(ps_handle h, const ps_fields_in* in);
 int ps_solve(ps_handle h, ps_fields_out* out, ps_stats* stats);
 /* exportMatrices / exportComponentMatrices / exportStats (S.cpp:533-606): MatrixMarket files written with
- * Eigen's saveMarket format.  `what` is a bit mask: 1 = b + solution, 2 = component matrices, 4 = stats. */
+ * Eigen's saveMarket format.  `what` is a bit mask: 1 = Mat_A + Vec_b + Vec_guess + solutionVector (Mat_A is the explicit
+ * matrix with solverType 1 and the empty nSystemSize x nSystemSize matrix of the factored path otherwise, as in the
+ * reference), 2 = component matrices, 4 = stats. */
 int ps_export(ps_handle h, const char* prefix, int what);
 /* thread-local description of the last PS_FAILED / PS_INVALID */
 const char* ps_last_error(void);
@@ -140,11 +145,13 @@ double ps_get_real(ps_handle h, const char* name);     /* solveError */
 int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out);
 /* liquid != 0: liquid weights, else fluid weights; values k/8 as float */
 int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out);
-/* CSR export of a block by name (G Dt JG JDt Mc McInv uInv u Mr B BInv): call once with NULL arrays for
- * the sizes, then with arrays.  Column indices sorted per row, explicit zeros kept (Eigen semantics). */
+/* CSR export of a block by name (G Dt JG JDt Mc McInv uInv u Mr B BInv A): call once with NULL arrays for
+ * the sizes, then with arrays.  Column indices sorted per row, explicit zeros kept (Eigen semantics).  "A" is the explicit
+ * system matrix of assembleSystemPressureStress (S_AS:351-430), built on the device on first request (one GPU; its region
+ * blocks are dense, so it only fits for small / medium grids -- PS_FAILED beyond 2^31-1 entries or device memory). */
 int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz, int64_t* rowptr, int32_t* colidx, double* vals);
-/* dense vectors by name (activeRHS reducedRHS pressureRHS stressRHS b solution velSolution com bestFit
- * MrDense ViscDense BinvDense); returns the length.  With several ranks b / solution / region data are zero
+/* dense vectors by name (activeRHS reducedRHS pressureRHS stressRHS b guess diagA solution velSolution com bestFit
+ * MrDense ViscDense BinvDense); returns the length.  diagA = diag(A) formed from the factors (one GPU).  With several ranks b / solution / region data are zero
  * outside the calling rank's share, so the sum over ranks is the global vector. */
 int64_t ps_get_vector(ps_handle h, const char* name, double* out);
 /* y = A x with host vectors of length nSystemSize (ApplyPressureStressMatrix::apply, Apply.h:182-184) */

@@ -108,6 +108,14 @@ bool get_matrix(Solver& S, const std::string& name, HostCsr& out) {
     const Counts& C = S.C;
     const int R = S.RG.count;
     if (name == "G" || name == "Dt" || name == "JG" || name == "JDt") { out = k_block(S, name); return true; }
+    if (name == "A") {     // explicit system matrix, built on the device (ps_explicit.cu)
+        S.buildExplicitA();
+        out.rows = out.cols = S.Aexp.n;
+        out.ptr = S.Aexp.ptr.to_host(S.st, (size_t)S.Aexp.n + 1);
+        out.idx = S.Aexp.nnz ? S.Aexp.idx.to_host(S.st, (size_t)S.Aexp.nnz) : std::vector<int32_t>();
+        out.val = S.Aexp.nnz ? S.Aexp.val.to_host(S.st, (size_t)S.Aexp.nnz) : std::vector<double>();
+        return true;
+    }
     if (name == "Mc") { out = diag_csr(S.mc.to_host(S.st, (size_t)C.nActiveVs)); return true; }
     if (name == "McInv") { out = diag_csr(S.mcInv.to_host(S.st, (size_t)C.nActiveVs)); return true; }
     if (name == "uInv") { out = diag_csr(S.uInv.to_host(S.st, (size_t)C.nStresses)); return true; }
@@ -411,6 +419,12 @@ int ps_export(ps_handle h, const char* prefix, int what) {
         if (what & 1) {   // exportMatrices / exportMatricesPostSolve (S.cpp:533-541, 568-572); A is implicit on this path
             if (get_vector(S, "b", v)) ok &= save_market_vector(v, pre + "Vec_b.mtx");
             if (get_vector(S, "guess", v)) ok &= save_market_vector(v, pre + "Vec_guess.mtx");
+            // Mat_A.mtx: the explicit matrix exists only for solverType EIGEN (S_AS:7-27); the factored path leaves A an
+            // empty nSystemSize x nSystemSize matrix (A.resize only, S_AS:446) and that is what the reference writes
+            HostCsr Am;
+            if (S.P.solverType == 1 && !S.part.multi()) get_matrix(S, "A", Am);
+            else { Am.rows = Am.cols = S.C.nSystemSize; Am.ptr.assign((size_t)Am.rows + 1, 0); }
+            ok &= save_market(Am, pre + "Mat_A.mtx");
             if (get_vector(S, "solution", v)) ok &= save_market_vector(v, pre + "solutionVector.mtx");
         }
         if (what & 2) {   // exportComponentMatrices (S.cpp:543-566)

@@ -120,5 +120,14 @@ PS_D void face_offset(const Geom& g, const I3& f, int axis, const double* com, d
     if (axis == 0) px -= 0.5; else if (axis == 1) py -= 0.5; else pz -= 0.5;
     ox = sub_rn(mul_rn(px, g.dx), com[0]); oy = sub_rn(mul_rn(py, g.dx), com[1]); oz = sub_rn(mul_rn(pz, g.dx), com[2]);
 }
+// the 10 monomials {1,x,y,z,xx,xy,xz,yy,yz,zz} of a coupled reduced face row's offset from its region's centre of mass;
+// `packed` = x | y<<10 | z<<20 | axis<<30 (RegionData::rowXYZ)
+PS_D void row_monomials(double dx, uint32_t packed, const double* com, double* m) {
+    const int axis = (int)(packed >> 30);
+    double px = (double)(packed & 1023u), py = (double)((packed >> 10) & 1023u), pz = (double)((packed >> 20) & 1023u);
+    if (axis == 0) px -= 0.5; else if (axis == 1) py -= 0.5; else pz -= 0.5;
+    const double ox = sub_rn(mul_rn(px, dx), com[0]), oy = sub_rn(mul_rn(py, dx), com[1]), oz = sub_rn(mul_rn(pz, dx), com[2]);
+    m[0] = 1.; m[1] = ox; m[2] = oy; m[3] = oz; m[4] = ox * ox; m[5] = ox * oy; m[6] = ox * oz; m[7] = oy * oy; m[8] = oy * oz; m[9] = oz * oz;
+}
 
 }  // namespace ps

@@ -601,13 +601,6 @@ void k_mark_Kt_columns(cudaStream_t st, const OpArgs& A, const RowSet& cellRows,
 // offset (S.cpp:2107-2149), so a chunk of same-axis rows only accumulates 10 moments per row; the 26-vector
 // t_r is a fixed sparse image of the 3x10 moments, and w_f is a 10-term polynomial with coefficients
 // sigma[axis] = (that image)^T s_r.
-PS_D void row_monomials(double dx, uint32_t packed, const double* com, double* m) {
-    const int axis = (int)(packed >> 30);
-    double px = (double)(packed & 1023u), py = (double)((packed >> 10) & 1023u), pz = (double)((packed >> 20) & 1023u);
-    if (axis == 0) px -= 0.5; else if (axis == 1) py -= 0.5; else pz -= 0.5;
-    const double ox = sub_rn(mul_rn(px, dx), com[0]), oy = sub_rn(mul_rn(py, dx), com[1]), oz = sub_rn(mul_rn(pz, dx), com[2]);
-    m[0] = 1.; m[1] = ox; m[2] = oy; m[3] = oz; m[4] = ox * ox; m[5] = ox * oy; m[6] = ox * oz; m[7] = oy * oy; m[8] = oy * oz; m[9] = oz * oz;
-}
 // t (26) from the per-axis moments M[3][10]
 PS_D void moments_to_t(const double* M, double* t) {
     for (int n = 0; n < RDOF; ++n) t[n] = 0.;

@@ -9,6 +9,7 @@
 #ifndef PS_EMULATE
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #endif
 
@@ -161,7 +162,26 @@ void sort_pairs_by_key(cudaStream_t st, int64_t n, int keyBits, DBuf<int32_t>& k
     copy_d2d(vals.p, valsTmp.p, (size_t)n * sizeof(int32_t), st);
 }
 
+int64_t exclusive_scan_i64(cudaStream_t st, int64_t n, const int64_t* in, int64_t* out) {
+    if (n <= 0) return 0;
+    size_t tmpBytes = 0;
+    PS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, in, out, (int)n, st));
+    static thread_local DBuf<uint8_t> tmp;
+    tmp.alloc(tmpBytes);
+    PS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, in, out, (int)n, st));
+    int64_t last[2] = {0, 0};
+    copy_d2h(&last[0], out + (n - 1), sizeof(int64_t), st);
+    copy_d2h(&last[1], in + (n - 1), sizeof(int64_t), st);
+    return last[0] + last[1];
+}
+
 #else  // ---- PS_EMULATE: serial twins (test-only build) ----
+
+int64_t exclusive_scan_i64(cudaStream_t, int64_t n, const int64_t* in, int64_t* out) {
+    int64_t s = 0;
+    for (int64_t i = 0; i < n; ++i) { const int64_t v = in[i]; out[i] = s; s += v; }
+    return s;
+}
 
 int64_t tile_order_scan(cudaStream_t, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>&,
                         const std::vector<int>* zCut, std::vector<int64_t>* cuts) {

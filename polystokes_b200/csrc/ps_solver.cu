@@ -653,6 +653,8 @@ static OpArgs make_op(const Solver& S) {
     return A;
 }
 
+OpArgs Solver::make_op_args() const { return make_op(*this); }
+
 // assembleSystemPressureStressFactored (S_AS:432-470):
 //   b = -[G^T; D] Mc^-1 rhs_u - (1/dt) [JG^T; DJ^T] B^-1 rhs_r + [rhs_p; rhs_tau]  =  -K_ext^T w + rhs_pt
 //   with  w_active = Mc^-1 rhs_u,  w_reduced(f) = (1/dt) c_f . (B^-1 rhs_r)
@@ -983,7 +985,7 @@ void Solver::setup() {
     waitLateInputs();
     { StageTimer T(st, &stageMs[PS_STAGE_REGION_MATRICES]); if (P.doReducedRegions) computeReducedRegionMatrices(); }
     { StageTimer T(st, &stageMs[PS_STAGE_MATRIX_BLOCKS]); constructMatrixBlocks(); }
-    haveDiag = false;
+    haveDiag = false; haveA = false;
     { StageTimer T(st, &stageMs[PS_STAGE_ASSEMBLE]); constructGuessVectors(); assemble(); }
     haveSetup = true;
     result = R_INCOMPLETE;

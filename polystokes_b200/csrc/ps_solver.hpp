@@ -117,6 +117,15 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     double eigRhsNorm2, eigThreshold, eigAbsNew;
 };
 
+// explicit A of assembleSystemPressureStress (S_AS:351-430) as device CSR: export / parity only (ps_explicit.cu)
+struct ExplicitA {
+    int64_t n = 0, nnz = 0;
+    DBuf<int64_t> ptr;      // [n+1]
+    DBuf<int32_t> idx;      // sorted per row, explicit zeros kept
+    DBuf<double> val;
+};
+struct OpArgs;
+
 class Solver {
 public:
     explicit Solver(const ps_params& p);
@@ -213,6 +222,10 @@ public:
     DBuf<double> bRhat, bV, bS, bT;     // BiCGSTAB work vectors, allocated when the fallback first fires
     DBuf<double> guess, diagA;          // guessVector (zero unless useWarmStart) and diag(A), built on demand
     bool haveGuess = false, haveDiag = false;
+    ExplicitA Aexp;                     // built on demand by buildExplicitA (ps_get_csr("A"), Mat_A.mtx with solverType EIGEN)
+    bool haveA = false;
+    void buildExplicitA();
+    OpArgs make_op_args() const;
     DBuf<double> dotPartial;
     DBuf<PcgScalars> scal;
     bool inputsOnDevice = false;
@@ -251,6 +264,8 @@ void k_valid_faces(cudaStream_t, const Geom&, const Fields&, float* const valid[
 // If `zCut` is given, cuts[k] receives the rank of the first flagged voxel with z >= zCut[k] (cuts multiple of 16).
 int64_t tile_order_scan(cudaStream_t, const Geom&, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts,
                         const std::vector<int>* zCut = nullptr, std::vector<int64_t>* cuts = nullptr);
+// out[k] = in[0] + ... + in[k-1] for k < n; returns the total (host sync)
+int64_t exclusive_scan_i64(cudaStream_t, int64_t n, const int64_t* in, int64_t* out);
 // stable sort of (key, value) pairs by key (keys < 2^keyBits)
 void sort_pairs_by_key(cudaStream_t, int64_t n, int keyBits, DBuf<int32_t>& keys, DBuf<int32_t>& vals, DBuf<int32_t>& keysTmp, DBuf<int32_t>& valsTmp);
 

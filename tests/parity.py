@@ -140,6 +140,43 @@ def check_bicgstab_fallback(lib_path=None):
     s.close()
 
 
+EXPLICIT_CASES = {
+    "blob32_tile8": lambda: scenes.blob_scene(32, seed=6, tile=8, pad=1),
+    "box20_uniform": lambda: scenes.box_scene(20, doReduced=0),
+    "blob20_notile": lambda: scenes.blob_scene(20, seed=3, doTile=0),
+    "ragged_30x26x22": lambda: scenes.blob_scene((30, 26, 22), seed=5, tile=8, pad=2),
+}
+
+
+def check_explicit_A(case, lib_path=None, tmpdir=None):
+    """Explicit A of assembleSystemPressureStress (S_AS:351-430), built on the device from the factors, against the
+    oracle's sparse triple products: sparsity pattern bit-exact (Eigen's structural union incl. the explicit zeros of the
+    dense region blocks), values <= 1e-8 (measured ~1e-16), symmetric to rounding, and A x equal to the factored operator."""
+    sc = EXPLICIT_CASES[case]()
+    o = Oracle(sc).setup()
+    o.assemble_explicit_A()
+    s = PolyStokesSolver.from_scene(sc, lib_path=lib_path, solverType=1)
+    s.setup_scene(sc)
+    so, po, io, vo = o.csr("A")
+    ss, ps_, is_, vs = s.csr("A")
+    assert tuple(so) == tuple(ss)
+    assert np.array_equal(po, ps_) and np.array_equal(io, is_), "explicit A: sparsity pattern differs"
+    assert rel(vo, vs) <= 1e-8, f"explicit A values rel {rel(vo, vs):.2e}"
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vs, is_, ps_), shape=ss)
+    assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
+    x = np.random.default_rng(1).standard_normal(ss[0])
+    assert rel(A @ x, s.apply(x)) <= 1e-11, f"explicit A x vs factored apply: {rel(A @ x, s.apply(x)):.2e}"
+    if tmpdir is not None and vs.size < 3_000_000:     # exportMatrices with solverType EIGEN writes the explicit matrix (S.cpp:533-541)
+        pre = os.path.join(str(tmpdir), "e_")
+        s.export(pre, 1)
+        o.save_csr("A", pre + "oracle_A.mtx")
+        ha, hb = open(pre + "Mat_A.mtx").readlines(), open(pre + "oracle_A.mtx").readlines()
+        assert ha[:2] == hb[:2] and len(ha) == len(hb), "Mat_A.mtx header / entry count"
+        assert [l.split()[:2] for l in ha[2:200]] == [l.split()[:2] for l in hb[2:200]]
+    s.close()
+
+
 def check_eigen_cg(lib_path=None, warm=1, scene=None):
     """solverType EIGEN (S.cpp:814-862): Eigen's CG with the Jacobi preconditioner, started from guessVector
     (useWarmStart, S.cpp:521-531).  The oracle runs it on the explicit A (S_AS:381-397); the library keeps A factored

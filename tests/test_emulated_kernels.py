@@ -23,3 +23,8 @@ def test_emulated_eigen_cg(built, warm):
 def test_emulated_eigen_cg_uniform(built):
     from polystokes_b200 import scenes
     parity.check_eigen_cg(lib_path=parity.EMUL_LIB, scene=scenes.box_scene(20, doReduced=0, tolerance=1e-6))
+
+
+@pytest.mark.parametrize("case", list(parity.EXPLICIT_CASES))
+def test_emulated_explicit_A(built, case, tmp_path):
+    parity.check_explicit_A(case, lib_path=parity.EMUL_LIB, tmpdir=tmp_path)

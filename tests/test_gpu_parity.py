@@ -99,3 +99,9 @@ def test_gpu_host_io_pinned_and_pageable(built):
     assert rc3 == rc
     for a in range(3):
         assert np.array_equal(vel[a], out2[a])
+
+
+@pytest.mark.parametrize("case", list(parity.EXPLICIT_CASES))
+def test_gpu_explicit_A(built, case, tmp_path):
+    """A2: the explicit system matrix built on the device against the oracle's sparse triple products."""
+    parity.check_explicit_A(case, tmpdir=tmp_path)
