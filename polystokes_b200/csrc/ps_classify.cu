@@ -14,7 +14,33 @@ namespace ps {
 // evaluated in double (all products exact), liquid counts sdf < 0, fluid counts collision >= 0.
 // One thread per sample computes BOTH weights of its slot (the 8 sub-sample stencils are shared).
 // ---------------------------------------------------------------------------------------------
-void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F) {
+void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* signX, uint8_t* signBox) {
+    // Pre-pass: signBox[c] = OR over the (clamped) 3x3x3 cell block around c of {1: surface < 0, 2: surface >= 0,
+    // 4: collision < 0, 8: collision >= 0}, separably (x taps from the SDFs, then the 3x3 y/z taps of the x result).
+    // Every slot's sub-sample stencil at index c lies inside that block (base cells c-1..c per axis, +1 for the upper
+    // trilinear corner; an index one past the centre range clamps into the block of the last cell), so where the block
+    // has one sign the eighth-counts are 0 or 8 without touching the SDFs again; the exact per-slot test below only
+    // runs near the interfaces.
+    {
+        const float* surf = F.surface; const float* coll = F.collision;
+        ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+            const I3 c = delin(g, SL_CENTER, q);
+            int code = 0;
+            for (int d = -1; d <= 1; ++d) {
+                const int64_t l = lin(g, SL_CENTER, clamped(g, SL_CENTER, I3{c.x + d, c.y, c.z}));
+                const float sv = surf[l], cv = coll[l];
+                code |= (sv < 0.f ? 1 : 0) | (sv >= 0.f ? 2 : 0) | (cv < 0.f ? 4 : 0) | (cv >= 0.f ? 8 : 0);
+            }
+            signX[q] = (uint8_t)code;
+        });
+        ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+            const I3 c = delin(g, SL_CENTER, q);
+            int code = 0;
+            for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy)
+                code |= signX[lin(g, SL_CENTER, clamped(g, SL_CENTER, I3{c.x, c.y + dy, c.z + dz}))];
+            signBox[q] = (uint8_t)code;
+        });
+    }
     for (int slot = 0; slot < N_SLOTS; ++slot) {
         int off2[3] = {1, 1, 1};   // 2 * SamplingOffset (exec/HDK_PolyStokesSolver.h:193-222)
         if (slot >= SL_FACE && slot < SL_EDGE) off2[slot - SL_FACE] = 0;
@@ -24,6 +50,13 @@ void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F) {
         uint8_t* lw = F.liqW[slot]; uint8_t* fw = F.fluW[slot];
         ps_for(st, g.n[slot], PS_LAMBDA(int64_t q) {
             const I3 c = delin(g, slot, q);
+            {
+                const int box = signBox[lin(g, SL_CENTER, clamped(g, SL_CENTER, c))];
+                if ((box & 3) != 3 && (box & 12) != 12) {      // one sign each (a NaN-only block has neither bit: 8 / 8 as below)
+                    lw[q] = (uint8_t)((box & 3) != 2 ? 8 : 0); fw[q] = (uint8_t)((box & 12) != 4 ? 8 : 0);
+                    return;
+                }
+            }
             const int idx[3] = {c.x, c.y, c.z};
             const int o[3] = {o0, o1, o2};
             // per axis: two sub-sample positions -> base cell and fraction (1/4 or 3/4)

@@ -74,6 +74,25 @@ constexpr int HOT_THREADS = 256;
 constexpr int HOT_MAX_BLOCKS = 148 * 8;
 static_assert(HOT_THREADS == SCHED_BLOCK, "one schedule block per CTA iteration");
 
+// Programmatic dependent launch (PDL): the kernels of the CG loop form one dependency chain on one stream, ~10 launches
+// per iteration of 20-120 us each.  Every kernel of the chain is launched with programmatic stream serialization and
+// starts with pdl_sync(): "launch_dependents" lets the NEXT kernel's CTAs take SM slots as soon as this kernel's CTAs
+// drain (their launch latency and prologue hide under this kernel's tail), "wait" blocks until the PREVIOUS kernel has
+// completed and flushed -- so nothing that reads or writes global memory may precede it (kernel parameters are fine).
+// PS_PDL=0 launches the same kernels with plain stream order (the instructions are no-ops then).
+__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
+static inline bool pdl_enabled() { static const bool on = !(getenv("PS_PDL") && atoi(getenv("PS_PDL")) == 0); return on; }
+template <class... KA, class... AA>
+static inline void launch_chain(void (*kernel)(KA...), unsigned grid, unsigned block, cudaStream_t st, AA&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    PS_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<AA>(args)...));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -112,7 +131,8 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
 // pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
 // streams, <= 8 gathers of x (L1 / L2), 8 B of w out.
 // (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
-__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {    pdl_sync();
+
     __shared__ double lut[65];
     if (S && S->done) return;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
@@ -154,7 +174,8 @@ __device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, dou
 // columns, codes and w gathers (32 B of matrix per cell); edge sweep: 4 columns + 4 codes (20 B per edge).
 template <int OCC>
 __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
-                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {
+                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {    pdl_sync();
+
     if (S && S->done) return;
     const bool dot = mode & 1;
     const double sc = A.valScale;
@@ -227,7 +248,8 @@ __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_co
     }
 }
 __global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(RangeSet own, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap,
-                                                                  double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P) {
+                                                                  double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P) {    pdl_sync();
+
     if (S->done) return;
     double pAp = S->red[0];
     if (P.nranks > 1 && !peer_reduce_wait(P, 0, &pAp, 1)) { if (threadIdx.x == 0) S->peerError = 1; return; }    // fused all-reduce, consumer side
@@ -250,7 +272,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_xr_kernel(RangeSet own,
     }
 }
 // p = r + beta p unless the stop test fired; the last CTA then advances the CG state (every CTA has read rsold by then)
-__global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, double* __restrict__ p, const double* __restrict__ r, PcgScalars* S, const __grid_constant__ PeerCtx P) {
+__global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, double* __restrict__ p, const double* __restrict__ r, PcgScalars* S, const __grid_constant__ PeerCtx P) {    pdl_sync();
+
     if (S->done) return;
     double rx[2] = {S->red[1], S->red[2]};
     if (P.nranks > 1 && !peer_reduce_wait(P, 1, rx, 2)) { if (threadIdx.x == 0) S->peerError = 1; return; }
@@ -264,7 +287,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_p_kernel(RangeSet own, 
     if (last_block(&S->ticket[3]) && threadIdx.x == 0) { S->red[1] = rx[0]; S->red[2] = rx[1]; cg_advance(S); }
 }
 __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, const double* __restrict__ b, double* x, double* r, double* p, double* dotPartial, PcgScalars* S, double tol, int maxIter,
-                                                             const __grid_constant__ PeerCtx P) {
+                                                             const __grid_constant__ PeerCtx P) {    pdl_sync();
+
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     double rr = 0.;
     for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) {
@@ -286,7 +310,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, cons
     }
 }
 // after the all-reduce of b.b: rsold, and the b == 0 early out
-__global__ void cg_begin_kernel(PcgScalars* S, const __grid_constant__ PeerCtx P) {
+__global__ void cg_begin_kernel(PcgScalars* S, const __grid_constant__ PeerCtx P) {    pdl_sync();
+
     double bb = S->red[3];
     if (P.nranks > 1 && !peer_reduce_wait(P, 2, &bb, 1)) { if (threadIdx.x == 0) { S->peerError = 1; S->done = 1; } return; }
     if (threadIdx.x == 0) { S->red[3] = bb; S->rsold = bb; S->done = (bb == 0.) ? 1 : 0; }
@@ -295,7 +320,8 @@ __global__ void cg_begin_kernel(PcgScalars* S, const __grid_constant__ PeerCtx P
 // neighbours' receive buffers (NVLink), then raise their sequence flags once every CTA's stores are fenced
 __global__ void __launch_bounds__(256) halo_push_kernel(int64_t n0, int64_t n1, const int32_t* __restrict__ idx, const double* __restrict__ v,
                                                        double* __restrict__ dst0, double* __restrict__ dst1, unsigned long long* flag0, unsigned long long* flag1,
-                                                       unsigned long long seq, PcgScalars* S, int respectDone, unsigned int* ticket) {
+                                                       unsigned long long seq, PcgScalars* S, int respectDone, unsigned int* ticket) {    pdl_sync();
+
     if (respectDone && S->done) return;
     const int64_t n = n0 + n1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -319,7 +345,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int64_t n0, int64_t n1, 
 // receiver side: wait for the neighbours' flags, then scatter the received entries into the global-length vector
 __global__ void __launch_bounds__(256) halo_wait_unpack_kernel(int64_t n0, int64_t n1, const int32_t* __restrict__ idx, const double* src0, const double* src1,
                                                               const unsigned long long* flag0, const unsigned long long* flag1, unsigned long long seq,
-                                                              double* __restrict__ v, PcgScalars* S, int respectDone) {
+                                                              double* __restrict__ v, PcgScalars* S, int respectDone) {    pdl_sync();
+
     if (respectDone && S->done) return;
     __shared__ int ok;
     if (threadIdx.x == 0) {
@@ -334,11 +361,48 @@ __global__ void __launch_bounds__(256) halo_wait_unpack_kernel(int64_t n0, int64
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         v[idx[i]] = __ldcg(i < n0 ? src0 + i : src1 + (i - n0));
 }
-__global__ void __launch_bounds__(256) halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf, const PcgScalars* S) {
+// Both sides in ONE launch (<= one CTA per SM, so every CTA is resident): each CTA first pushes its share of my boundary
+// entries, the last CTA to finish raises the neighbours' flags, then every CTA waits for MY flags and scatters its share of
+// what the neighbours stored here.  No CTA waits before it has pushed, so two ranks can never wait on each other.
+__global__ void __launch_bounds__(256) halo_exchange_kernel(int64_t ns0, int64_t ns1, const int32_t* __restrict__ sendIdx, double* __restrict__ dst0, double* __restrict__ dst1,
+                                                           unsigned long long* dflag0, unsigned long long* dflag1,
+                                                           int64_t nr0, int64_t nr1, const int32_t* __restrict__ recvIdx, const double* src0, const double* src1,
+                                                           const unsigned long long* sflag0, const unsigned long long* sflag1,
+                                                           unsigned long long seq, double* v, PcgScalars* S, int respectDone, unsigned int* ticket) {
+    pdl_sync();
+    if (respectDone && S->done) return;
+    const int64_t ns = ns0 + ns1, nr = nr0 + nr1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += (int64_t)gridDim.x * blockDim.x) {
+        const double val = v[sendIdx[i]];
+        if (i < ns0) dst0[i] = val; else dst1[i - ns0] = val;
+    }
+    __shared__ int ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            if (dflag0) peer_st_flag(dflag0, seq);
+            if (dflag1) peer_st_flag(dflag1, seq);
+        }
+        bool good = true;
+        if (sflag0) good = peer_wait_flag(sflag0, seq) && good;
+        if (sflag1) good = peer_wait_flag(sflag1, seq) && good;
+        ok = good ? 1 : 0;
+    }
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) S->peerError = 1; return; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (int64_t)gridDim.x * blockDim.x)
+        v[recvIdx[i]] = __ldcg(i < nr0 ? src0 + i : src1 + (i - nr0));
+}
+__global__ void __launch_bounds__(256) halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf, const PcgScalars* S) {    pdl_sync();
+
     if (S && S->done) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] = v[idx[i]];
 }
-__global__ void __launch_bounds__(256) halo_unpack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ v, const PcgScalars* S) {
+__global__ void __launch_bounds__(256) halo_unpack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ v, const PcgScalars* S) {    pdl_sync();
+
     if (S && S->done) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[idx[i]] = buf[i];
 }
@@ -363,7 +427,7 @@ static inline int hot_blocks(K kernel, int64_t n) {
 
 void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
     if (A.rowsK.total() <= 0) return;
-    pass1_kernel<<<hot_blocks(pass1_kernel, A.rowsK.total()), HOT_THREADS, 0, st>>>(A, x, w, activeScale, S);
+    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, A.rowsK.total()), HOT_THREADS, st, A, x, w, activeScale, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -372,55 +436,64 @@ void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x,
     // 6 -> 0.132 ms, 7 / 8 spill and fall back to 0.137 ms
     static const int occ = getenv("PS_PASS2_OCC") ? atoi(getenv("PS_PASS2_OCC")) : 6;
     const int64_t rows = A.rowsP.total() + A.rowsE.total();
-    if (occ >= 6) pass2_kernel<6><<<hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
-    else if (occ == 5) pass2_kernel<5><<<hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
-    else pass2_kernel<4><<<hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, 0, st>>>(A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    if (occ >= 6) launch_chain(pass2_kernel<6>, hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    else if (occ == 5) launch_chain(pass2_kernel<5>, hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    else launch_chain(pass2_kernel<4>, hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_update_xr(cudaStream_t st, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P) {
-    cg_update_xr_kernel<<<hot_blocks(cg_update_xr_kernel, own.total()), HOT_THREADS, 0, st>>>(own, x, r, p, Ap, dotPartial, scal, P);
+    launch_chain(cg_update_xr_kernel, hot_blocks(cg_update_xr_kernel, own.total()), HOT_THREADS, st, own, x, r, p, Ap, dotPartial, scal, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_update_p(cudaStream_t st, const RangeSet& own, double* p, const double* r, PcgScalars* scal, const PeerCtx& P) {
-    cg_update_p_kernel<<<hot_blocks(cg_update_p_kernel, own.total()), HOT_THREADS, 0, st>>>(own, p, r, scal, P);
+    launch_chain(cg_update_p_kernel, hot_blocks(cg_update_p_kernel, own.total()), HOT_THREADS, st, own, p, r, scal, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_init(cudaStream_t st, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P) {
-    cg_init_kernel<<<hot_blocks(cg_init_kernel, own.total()), HOT_THREADS, 0, st>>>(own, b, x, r, p, dotPartial, scal, tol, maxIter, P);
+    launch_chain(cg_init_kernel, hot_blocks(cg_init_kernel, own.total()), HOT_THREADS, st, own, b, x, r, p, dotPartial, scal, tol, maxIter, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_cg_begin(cudaStream_t st, PcgScalars* scal, const PeerCtx& P) {
-    cg_begin_kernel<<<1, 32, 0, st>>>(scal, P);
+    launch_chain(cg_begin_kernel, 1, 32, st, scal, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_pack(cudaStream_t st, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) {
     if (n <= 0) return;
-    halo_pack_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, 0, st>>>(n, idx, v, buf, S);
+    launch_chain(halo_pack_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, st, n, idx, v, buf, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_push_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
                       unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket) {
     const int64_t n = n0 + n1;
-    halo_push_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, 0, st>>>(n0, n1, idx, v, dst0, dst1, flag0, flag1, seq, S, respectDone ? 1 : 0, ticket);
+    launch_chain(halo_push_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, n0, n1, idx, v, dst0, dst1, flag0, flag1, seq, S, respectDone ? 1 : 0, ticket);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_halo_exchange_peer(cudaStream_t st, int64_t ns0, int64_t ns1, const int32_t* sendIdx, double* dst0, double* dst1, unsigned long long* dflag0, unsigned long long* dflag1,
+                          int64_t nr0, int64_t nr1, const int32_t* recvIdx, const double* src0, const double* src1, const unsigned long long* sflag0, const unsigned long long* sflag1,
+                          unsigned long long seq, double* v, PcgScalars* S, bool respectDone, unsigned int* ticket) {
+    const int64_t n = std::max(ns0 + ns1, nr0 + nr1);
+    launch_chain(halo_exchange_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, ns0, ns1, sendIdx, dst0, dst1, dflag0, dflag1,
+                 nr0, nr1, recvIdx, src0, src1, sflag0, sflag1, seq, v, S, respectDone ? 1 : 0, ticket);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_unpack_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* src0, const double* src1, const unsigned long long* flag0, const unsigned long long* flag1,
                         unsigned long long seq, double* v, PcgScalars* S, bool respectDone) {
     const int64_t n = n0 + n1;
-    halo_wait_unpack_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 2)), 256, 0, st>>>(n0, n1, idx, src0, src1, flag0, flag1, seq, v, S, respectDone ? 1 : 0);
+    launch_chain(halo_wait_unpack_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 2)), 256, st, n0, n1, idx, src0, src1, flag0, flag1, seq, v, S, respectDone ? 1 : 0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) {
     if (n <= 0) return;
-    halo_unpack_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, 0, st>>>(n, idx, buf, v, S);
+    launch_chain(halo_unpack_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, st, n, idx, buf, v, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -659,7 +732,8 @@ __device__ __forceinline__ void region_solve(int r, int lane, const int32_t* __r
 // the sums are taken in chunk order whoever comes last, so the result does not depend on the schedule.
 __global__ void __launch_bounds__(MOM_THREADS) reduced_moments_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ chunk, const int32_t* __restrict__ chunkStart,
                                                                      const double* __restrict__ com, const double* __restrict__ wRows, double* partial, const double* __restrict__ Binv,
-                                                                     double* __restrict__ sigma, unsigned int* regionTicket, const PcgScalars* S, int chunk0) {
+                                                                     double* __restrict__ sigma, unsigned int* regionTicket, const PcgScalars* S, int chunk0) {    pdl_sync();
+
     if (S && S->done) return;
     __shared__ double red[MOM_THREADS / 32][10];
     __shared__ double M[30], t[RDOF], sv[RDOF];
@@ -705,7 +779,8 @@ __global__ void __launch_bounds__(MOM_THREADS) reduced_moments_kernel(double dx,
 // one warp per region: ordered sum of the chunk partials -> t -> s = B^-1 t -> sigma
 __global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __restrict__ chunkStart, const int32_t* __restrict__ chunk, const double* __restrict__ partial,
                                                            const double* __restrict__ Binv, const double* __restrict__ extra, double extraScale, double tScale,
-                                                           double* __restrict__ tOut, double* __restrict__ sOut, double* __restrict__ sigma, const PcgScalars* S, int region0) {
+                                                           double* __restrict__ tOut, double* __restrict__ sOut, double* __restrict__ sigma, const PcgScalars* S, int region0) {    pdl_sync();
+
     if (S && S->done) return;
     __shared__ double M[30], t[RDOF], sv[RDOF];
     region_solve(region0 + blockIdx.x, threadIdx.x, chunkStart, chunk, partial, Binv, extra, extraScale, tScale, tOut, sOut, sigma, M, t, sv);
@@ -713,7 +788,8 @@ __global__ void __launch_bounds__(32) reduced_finish_kernel(const int32_t* __res
 // w_f = scale * sigma[region][axis] . monomials(f): one thread per coupled reduced row (sigma / com of a region are shared by
 // neighbouring rows and come through L1)
 __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ rowRegion, const double* __restrict__ com,
-                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S, int rowLo, int rowHi) {
+                                                                    const double* __restrict__ sigma, double* __restrict__ wRows, double scale, const PcgScalars* S, int rowLo, int rowHi) {    pdl_sync();
+
     if (S && S->done) return;
     for (int row = rowLo + blockIdx.x * RED_THREADS + threadIdx.x; row < rowHi; row += gridDim.x * RED_THREADS) {
         const uint32_t xyz = __ldcs(rowXYZ + row);
@@ -728,23 +804,145 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, 
         wRows[row] = scale * v;
     }
 }
+// The whole reduced term of one apply for tiled regions, ONE CTA per region: w_f <- scale * c_f . B_r^-1 (sum_f c_f w_f).
+// Three groups of REG_GROUP threads take the region's x / y / z rows (rowAxisStart), so every load of the region is in flight
+// at once; the 3 x 10 moments are reduced in a fixed order (warp shuffles, then the group's warps in order), B^-1 (staged in
+// shared memory while the rows stream in) is applied by 26 threads, and the same threads that read a row overwrite it with the
+// expanded value.  No inter-CTA hand-off: this replaces moments + last-chunk solve + expand (3 dependent stages, 2 launches)
+// by one launch whose critical path is one row round trip + one 26x26 product.  Regions too large for one CTA (doTile off)
+// keep the chunked kernels above.
+// GROUP threads per axis, ROWS rows per thread kept in registers between the two phases (0: re-read rowXYZ through L1/L2)
+template <int GROUP, int ROWS, int MINB>
+__global__ void __launch_bounds__(3 * GROUP, MINB) reduced_region_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ rowAxisStart, const double* __restrict__ com,
+                                                                       const double* __restrict__ Binv, double* __restrict__ wRows, double scale, const PcgScalars* S, int region0) {
+    constexpr int NW = GROUP / 32, KEEP = ROWS > 0 ? ROWS : 1;
+    __shared__ double Bs[RDOF * RDOF];
+    __shared__ double red[3][NW][10];
+    __shared__ double M[30], t[RDOF], sv[RDOF], sg[30];
+    const int r = region0 + blockIdx.x;
+    // B^-1, the row table and the centres of mass are setup data: they may be fetched before the previous kernel has finished
+    for (int i = threadIdx.x; i < RDOF * RDOF; i += 3 * GROUP) Bs[i] = __ldg(Binv + (size_t)r * RDOF * RDOF + i);
+    const int axis = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+    const int begin = __ldg(rowAxisStart + 3 * r + axis), end = __ldg(rowAxisStart + 3 * r + axis + 1);
+    const double cm[3] = {__ldg(com + 3 * r), __ldg(com + 3 * r + 1), __ldg(com + 3 * r + 2)};
+    pdl_sync();
+    if (S && S->done) return;
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.;
+    uint32_t xyz[KEEP];
+    if (ROWS > 0) {
+        double gk[KEEP];
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int row = begin + lane + i * GROUP;
+            xyz[i] = row < end ? __ldcs(rowXYZ + row) : 0u;
+            gk[i] = row < end ? __ldcs(wRows + row) : 0.;
+        }
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            double m[10];
+            row_monomials(dx, xyz[i], cm, m);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc[k] += m[k] * gk[i];
+        }
+    }
+#pragma unroll 4
+    for (int row = begin + lane + ROWS * GROUP; row < end; row += GROUP) {
+        double m[10];
+        row_monomials(dx, __ldg(rowXYZ + row), cm, m);
+        const double g1 = __ldcs(wRows + row);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] += m[k] * g1;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        const double v = warp_sum(acc[k]);
+        if ((lane & 31) == 0) red[axis][lane >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 30) {
+        const int a = threadIdx.x / 10, k = threadIdx.x % 10;
+        double s = 0.;
+#pragma unroll
+        for (int wI = 0; wI < NW; ++wI) s += red[a][wI][k];
+        M[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) moments_to_t(M, t);
+    __syncthreads();
+    if (threadIdx.x < RDOF) {
+        const double* B = Bs + threadIdx.x * RDOF;
+        double s = 0.;
+#pragma unroll
+        for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
+        sv[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_to_sigma(sv, sg);
+    __syncthreads();
+    double sgl[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sgl[k] = sg[axis * 10 + k];
+    if (ROWS > 0) {
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int row = begin + lane + i * GROUP;
+            if (row < end) {
+                double m[10];
+                row_monomials(dx, xyz[i], cm, m);
+                double v = 0.;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
+                wRows[row] = scale * v;
+            }
+        }
+    }
+#pragma unroll 4
+    for (int row = begin + lane + ROWS * GROUP; row < end; row += GROUP) {
+        double m[10];
+        row_monomials(dx, __ldg(rowXYZ + row), cm, m);
+        double v = 0.;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
+        wRows[row] = scale * v;
+    }
+}
+template <int GROUP, int ROWS, int MINB>
+static void launch_region(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    launch_chain(reduced_region_kernel<GROUP, ROWS, MINB>, (unsigned)(RG.regHi - RG.regLo), 3 * GROUP, st, g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, wRows, scale, S, RG.regLo);
+}
+// w_f <- scale * c_f . B^-1 J w on the coupled reduced rows (the reduced term of one operator apply)
+void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
+    if (RG.regHi <= RG.regLo) return;
+    if (RG.maxRegionRows > fuseLimit) { reduced_moments(st, g, RG, wRows, S, true); reduced_expand(st, g, RG, wRows, scale, S); return; }
+    static const int variant = getenv("PS_REGION_VARIANT") ? atoi(getenv("PS_REGION_VARIANT")) : 0;      // A/B knob (profiles/r01_sweep_region.log)
+    if (variant == 1) launch_region<128, 8, 2>(st, g, RG, wRows, scale, S);
+    else if (variant == 2) launch_region<64, 8, 4>(st, g, RG, wRows, scale, S);
+    else if (variant == 3) launch_region<32, 0, 10>(st, g, RG, wRows, scale, S);
+    else if (variant == 4) launch_region<128, 0, 3>(st, g, RG, wRows, scale, S);
+    else launch_region<64, 0, 6>(st, g, RG, wRows, scale, S);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
 void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S, bool solve) {
     if (RG.rowChunkHi <= RG.rowChunkLo) return;
-    reduced_moments_kernel<<<RG.rowChunkHi - RG.rowChunkLo, MOM_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.rowChunkStart.p, RG.com.p, wRows, RG.partial.p, RG.Binv.p, RG.sigma.p,
+    launch_chain(reduced_moments_kernel, (unsigned)(RG.rowChunkHi - RG.rowChunkLo), MOM_THREADS, st, g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.rowChunkStart.p, RG.com.p, wRows, RG.partial.p, RG.Binv.p, RG.sigma.p,
                                                                                  solve ? RG.regionTicket.p : nullptr, S, RG.rowChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void reduced_finish(cudaStream_t st, const Geom&, const RegionData& RG, const double* extra, double extraScale, double tScale, const PcgScalars* S) {
     if (RG.regHi <= RG.regLo) return;
-    reduced_finish_kernel<<<RG.regHi - RG.regLo, 32, 0, st>>>(RG.rowChunkStart.p, RG.rowChunk.p, RG.partial.p, RG.Binv.p, extra, extraScale, tScale, RG.t.p, RG.s.p, RG.sigma.p, S, RG.regLo);
+    launch_chain(reduced_finish_kernel, (unsigned)(RG.regHi - RG.regLo), 32, st, RG.rowChunkStart.p, RG.rowChunk.p, RG.partial.p, RG.Binv.p, extra, extraScale, tScale, RG.t.p, RG.s.p, RG.sigma.p, S, RG.regLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void reduced_expand(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
     if (RG.ownRowHi <= RG.ownRowLo) return;
     const int n = RG.ownRowHi - RG.ownRowLo;
-    reduced_expand_kernel<<<std::min((n + RED_THREADS - 1) / RED_THREADS, 148 * 8), RED_THREADS, 0, st>>>(g.dx, RG.rowXYZ.p, RG.rowRegion.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.ownRowLo, RG.ownRowHi);
+    launch_chain(reduced_expand_kernel, (unsigned)std::min((n + RED_THREADS - 1) / RED_THREADS, 148 * 8), RED_THREADS, st, g.dx, RG.rowXYZ.p, RG.rowRegion.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.ownRowLo, RG.ownRowHi);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -777,6 +975,9 @@ void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const doubl
         s_to_sigma(sv, sg);
         for (int k = 0; k < 30; ++k) RG.sigma.p[(size_t)r * 30 + k] = sg[k];
     }
+}
+void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    reduced_moments(st, g, RG, wRows, S, true); reduced_expand(st, g, RG, wRows, scale, S);
 }
 void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
     if (S && S->done) return;

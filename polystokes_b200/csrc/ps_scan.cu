@@ -4,7 +4,7 @@
 // a running counter over the voxels for which a predicate holds, visited in UT_VoxelArray order
 // (16^3 tiles, x->y->z, x fastest inside).  The reference does this serially; here one CTA owns one
 // 16^3 tile: (1) per-tile counts, (2) one-CTA exclusive scan of the tile counts, (3) per-tile local
-// scan + write.  A thread owns one 16-voxel x-row of its tile, so its reads are 16 contiguous bytes.
+// scan + write.  A thread owns one z-column of its tile, so every slice is read and written as 16 rows of 16 contiguous voxels.
 #include "ps_solver.hpp"
 #ifndef PS_EMULATE
 #include <cub/device/device_radix_sort.cuh>
@@ -19,16 +19,20 @@ namespace ps {
 
 struct TileGeom { int rx, ry, rz, tx, ty, tz; };
 
-__device__ __forceinline__ int row_count(const uint8_t* flag, const TileGeom& t, int tile, int tid, int64_t& rowBase, int& tw) {
+// Thread t of a tile's CTA owns the voxel column (x0 + (t & 15), y0 + (t >> 4), z0 + 0..15): in every z-slice the 256 threads
+// read 16 x 16 contiguous bytes and their thread order IS the voxel order of the slice (voxels beyond a ragged tile's
+// width / height count as unset).  Returns the 16 slice flags of the column as a bit mask; base = voxel of slice 0.
+__device__ __forceinline__ unsigned column_mask(const uint8_t* __restrict__ flag, const TileGeom& t, int tile, int tid, int64_t& base, int64_t& zStride, int& depth) {
     const int ti = tile % t.tx, tj = (tile / t.tx) % t.ty, tk = tile / (t.tx * t.ty);
-    const int lj = tid & 15, lk = tid >> 4;
-    const int y = (tj << 4) + lj, z = (tk << 4) + lk, x0 = ti << 4;
-    tw = min(16, t.rx - x0);
-    if (y >= t.ry || z >= t.rz) { tw = 0; rowBase = 0; return 0; }
-    rowBase = (int64_t)x0 + (int64_t)t.rx * ((int64_t)y + (int64_t)t.ry * z);
-    int c = 0;
-    for (int i = 0; i < tw; ++i) c += flag[rowBase + i] ? 1 : 0;
-    return c;
+    const int x = (ti << 4) + (tid & 15), y = (tj << 4) + (tid >> 4), z0 = tk << 4;
+    zStride = (int64_t)t.rx * t.ry;
+    depth = min(16, t.rz - z0);
+    base = (int64_t)x + (int64_t)t.rx * ((int64_t)y + (int64_t)t.ry * z0);
+    if (x >= t.rx || y >= t.ry) { depth = 0; return 0u; }
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (k < depth && flag[base + k * zStride]) m |= 1u << k;
+    return m;
 }
 
 // block-wide exclusive scan of one int per thread (256 threads), returns total in `total`
@@ -53,9 +57,9 @@ __device__ __forceinline__ int block_exclusive_scan_256(int v, int& total) {
     return warpBase + inc - v;
 }
 
-__global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* flag, TileGeom t, int32_t* tileCounts) {
-    int64_t rowBase; int tw;
-    const int c = row_count(flag, t, blockIdx.x, threadIdx.x, rowBase, tw);
+__global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* __restrict__ flag, TileGeom t, int32_t* tileCounts) {
+    int64_t base, zStride; int depth;
+    const int c = __popc(column_mask(flag, t, blockIdx.x, threadIdx.x, base, zStride, depth));
     int total;
     block_exclusive_scan_256(c, total);
     if (threadIdx.x == 0) tileCounts[blockIdx.x] = total;
@@ -80,15 +84,35 @@ __global__ void __launch_bounds__(256) tile_offsets_kernel(int32_t* tileCounts, 
     if (threadIdx.x == 0) tileCounts[nTiles] = carry;
 }
 
-__global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* flag, TileGeom t, const int32_t* tileOffsets, int32_t* out) {
-    int64_t rowBase; int tw;
-    const int c = row_count(flag, t, blockIdx.x, threadIdx.x, rowBase, tw);
-    int total;
-    int rank = tileOffsets[blockIdx.x] + block_exclusive_scan_256(c, total);
-    for (int i = 0; i < tw; ++i) {
-        const bool f = flag[rowBase + i] != 0;
-        out[rowBase + i] = f ? rank : -1;
-        rank += f ? 1 : 0;
+__global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* __restrict__ flag, TileGeom t, const int32_t* tileOffsets, int32_t* __restrict__ out) {
+    __shared__ int part[16 * 8 + 1];      // set voxels per (slice, warp), then their exclusive prefix in slice-major order
+    int64_t base, zStride; int depth;
+    const unsigned m = column_mask(flag, t, blockIdx.x, threadIdx.x, base, zStride, depth);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if (lane == 0) part[k * 8 + wid] = __popc(b);
+    }
+    __syncthreads();
+    if (wid == 0) {        // 128 entries: lane owns 4 consecutive ones
+        int v[4], s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = part[4 * lane + i]; s += v[i]; }
+        int inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+        int run = inc - s;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { part[4 * lane + i] = run; run += v[i]; }
+    }
+    __syncthreads();
+    const int tileBase = tileOffsets[blockIdx.x];
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+        if (k < depth) out[base + k * zStride] = ((m >> k) & 1u) ? tileBase + part[k * 8 + wid] + __popc(b & below) : -1;
     }
 }
 

@@ -249,7 +249,7 @@ void Solver::sendValidEarly(const ps_fields_out& out) {
 
 void Solver::buildIntegrationWeightsAlt() {
     StageTimer T(st, &stageMs[PS_STAGE_WEIGHTS]);
-    k_build_weights(st, g, F);
+    k_build_weights(st, g, F, scratch8[0].p, scratch8[1].p);
 }
 
 void Solver::classifyCells() {
@@ -474,11 +474,14 @@ void Solver::constructMatrixBlocks() {
         k_rows_finalize(st, g, nRows, RG.rowRegion.p, RG.rowFace.p, rc.p, RG.rowXYZ.p);
         std::vector<int> perRA = rc.to_host(st, (size_t)3 * R);
         // chunk table: rows are sorted by (region, axis, voxel order); a chunk holds <= 2048 rows of one (region, axis)
-        std::vector<int32_t> start((size_t)R + 1, 0), chunkStart((size_t)R + 1, 0), table;
+        std::vector<int32_t> start((size_t)R + 1, 0), chunkStart((size_t)R + 1, 0), table, axisStart((size_t)3 * R + 1, 0);
         int32_t pos = 0;
+        RG.maxRegionRows = 0;
         for (int r = 0; r < R; ++r) {
             start[r] = pos; chunkStart[r] = (int32_t)(table.size() / 4);
+            RG.maxRegionRows = std::max(RG.maxRegionRows, (int32_t)(perRA[3 * r] + perRA[3 * r + 1] + perRA[3 * r + 2]));
             for (int a = 0; a < 3; ++a) {
+                axisStart[3 * r + a] = pos;
                 const int32_t e = pos + perRA[3 * r + a];
                 for (int32_t b = pos; b < e; b += 2048) { table.push_back(r); table.push_back(b); table.push_back(std::min(b + 2048, e)); table.push_back(a); }
                 pos = e;
@@ -490,6 +493,8 @@ void Solver::constructMatrixBlocks() {
         RG.ownRowLo = start[RG.regLo]; RG.ownRowHi = start[RG.regHi];
         RG.regionTicket.alloc((size_t)R + 1); RG.regionTicket.zero(st, (size_t)R + 1);
         for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
+        axisStart[(size_t)3 * R] = pos;
+        RG.rowAxisStart.from_host(st, axisStart.data(), axisStart.size());
         RG.rowStart.from_host(st, start.data(), start.size());
         RG.rowChunk.from_host(st, table.data(), table.size());
         RG.rowChunkStart.from_host(st, chunkStart.data(), chunkStart.size());
@@ -626,8 +631,13 @@ void Solver::exchange(Halo& H, double* v, const PcgScalars* S) {
             dst[i] = peer.recv(pr, kind, par, 1 - i); dflag[i] = &peer.sync(pr)->haloFlag[kind][par][1 - i];
             src[i] = peer.recv(part.rank, kind, par, i); sflag[i] = &peer.sync(part.rank)->haloFlag[kind][par][i];
         }
-        k_halo_push_peer(st, H.nSend[0], H.nSend[1], H.sendIdx.p, v, dst[0], dst[1], dflag[0], dflag[1], seq, scal.p, S != nullptr, &scal.p->ticket[4 + kind]);
-        k_halo_unpack_peer(st, H.nRecv[0], H.nRecv[1], H.recvIdx.p, src[0], src[1], sflag[0], sflag[1], seq, v, scal.p, S != nullptr);
+        static const bool split = getenv("PS_HALO_SPLIT") && atoi(getenv("PS_HALO_SPLIT"));      // the two-launch form, kept for A/B timing
+        if (split) {
+            k_halo_push_peer(st, H.nSend[0], H.nSend[1], H.sendIdx.p, v, dst[0], dst[1], dflag[0], dflag[1], seq, scal.p, S != nullptr, &scal.p->ticket[4 + kind]);
+            k_halo_unpack_peer(st, H.nRecv[0], H.nRecv[1], H.recvIdx.p, src[0], src[1], sflag[0], sflag[1], seq, v, scal.p, S != nullptr);
+        } else
+            k_halo_exchange_peer(st, H.nSend[0], H.nSend[1], H.sendIdx.p, dst[0], dst[1], dflag[0], dflag[1], H.nRecv[0], H.nRecv[1], H.recvIdx.p, src[0], src[1], sflag[0], sflag[1],
+                                 seq, v, scal.p, S != nullptr, &scal.p->ticket[4 + kind]);
         return;
     }
 #endif
@@ -674,10 +684,7 @@ void Solver::assemble() {
 void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
     const OpArgs A = make_op(*this);
     k_pass1(st, A, xin, w.p, g.dt, nullptr);
-    if (RG.count > 0) {
-        reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr, true);
-        reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
-    }
+    if (RG.count > 0) reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     exchange(haloW, w.p, nullptr);
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, PeerCtx(), nullptr, 0);
 }
@@ -686,7 +693,7 @@ void Solver::timedOperator(int which) {
     const OpArgs A = make_op(*this);
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
     if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
-    else if (which == 3 && RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, nullptr, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
+    else if (which == 3 && RG.count > 0) { reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
     else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, PeerCtx(), nullptr, 0);
 }
 
@@ -725,8 +732,7 @@ int Solver::solve() {
             exchange(haloX, p.p, scal.p);                       mark(tr, "halo p");
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);             mark(tr, "pass1");
             if (RG.count > 0) {
-                reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p, true);      // + B^-1 per region by its last chunk
-                reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);
+                reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);          // moments -> B^-1 -> expand, one CTA per region
             }
             mark(tr, "reduced x3");
             exchange(haloW, w.p, scal.p);                       mark(tr, "halo w");
@@ -818,7 +824,7 @@ int Solver::solveEigenCG() {
         const int batch = std::min(every, maxIt - it);
         for (int k = 0; k < batch; ++k) {
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);
-            if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+            if (RG.count > 0) { reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
             k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, PeerCtx(), scal.p, 1);          // tmp = A p, p.tmp -> red[0]
             k_eig_update_xr(st, ownSys, diagA.p, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p);
             k_eig_stage(st, scal.p, 2);
@@ -851,7 +857,7 @@ int Solver::solveBiCGStab() {
     auto applyTo = [&](double* xin, double* y) {
         exchange(haloX, xin, scal.p);
         k_pass1(st, A, xin, w.p, g.dt, scal.p);
-        if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, scal.p, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+        if (RG.count > 0) { reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
         exchange(haloW, w.p, scal.p);
         k_pass2(st, A, w.p, xin, y, 0.5, nullptr, nullptr, PeerCtx(), scal.p, 0);
     };

@@ -76,6 +76,8 @@ struct RegionData {
     DBuf<int32_t> cellChunk;   // [nChunks][3] = region, begin, end
     DBuf<int32_t> rowChunk;    // [nChunks][4] = region, begin, end, face axis (a chunk never mixes axes)
     DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
+    DBuf<int32_t> rowAxisStart;  // [3R+1] first coupled reduced row of (region, face axis): the row ranges of reduced_region_kernel
+    int32_t maxRegionRows = 0;   // largest number of coupled reduced rows of one region (decides fused vs chunked reduced kernels)
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
     DBuf<unsigned int> regionTicket;   // [R] chunks of the region that have delivered their moments (self-resetting)
@@ -233,7 +235,7 @@ public:
 };
 
 // ---- kernels (free functions; see the .cu files for the reference citations) ----
-void k_build_weights(cudaStream_t, const Geom&, const Fields&);
+void k_build_weights(cudaStream_t, const Geom&, const Fields&, uint8_t* signX, uint8_t* signBox);
 void k_classify_cells(cudaStream_t, const Geom&, const Fields&, bool genericToActive);
 void k_air_layer_seed(cudaStream_t, const Geom&, const Fields&, uint8_t* stamp);
 void k_layer_commit(cudaStream_t, const Geom&, const Fields&, const uint8_t* stamp, int layerStamp);
@@ -297,6 +299,8 @@ void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, doub
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal, bool solve = false);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
+// the reduced term of one apply: w_f <- scale * c_f . B^-1 (sum_f c_f w_f); one fused launch for tiled regions, moments + expand otherwise
+void reduced_apply(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
 void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
 void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* scal, const PeerCtx& P);
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
@@ -323,6 +327,9 @@ void k_eig_update_p(cudaStream_t, const RangeSet& own, const double* diag, doubl
 #ifndef PS_EMULATE
 void k_halo_push_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
                       unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket);
+void k_halo_exchange_peer(cudaStream_t, int64_t ns0, int64_t ns1, const int32_t* sendIdx, double* dst0, double* dst1, unsigned long long* dflag0, unsigned long long* dflag1,
+                          int64_t nr0, int64_t nr1, const int32_t* recvIdx, const double* src0, const double* src1, const unsigned long long* sflag0, const unsigned long long* sflag1,
+                          unsigned long long seq, double* v, PcgScalars* S, bool respectDone, unsigned int* ticket);
 void k_halo_unpack_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* src0, const double* src1, const unsigned long long* flag0, const unsigned long long* flag1,
                         unsigned long long seq, double* v, PcgScalars* S, bool respectDone);
 #endif
