@@ -167,6 +167,11 @@ int ps_apply(ps_handle h, const double* x, double* y);
  * run on the current system.  Both need a prior ps_setup / ps_step. */
 double ps_time_kernel(ps_handle h, const char* name, int reps);
 double ps_kernel_bytes(ps_handle h, const char* name);
+/* Stopwatch on the solver's own stream (all of a step's device work runs there; copies of host-memory callers are joined
+ * to it by events): ps_timer(h, 0) records the start event, ps_timer(h, 1) records the stop event, waits for it and
+ * returns the elapsed milliseconds between the two (< 0 on error).  No reference counterpart (the reference times
+ * with UT_StopWatch around solveGasSubclass stages, S.cpp:578-602). */
+double ps_timer(ps_handle h, int stop);
 
 #ifdef __cplusplus
 }

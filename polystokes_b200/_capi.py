@@ -55,7 +55,7 @@ class ps_stats(C.Structure):
 
 # every symbol include/polystokes_b200.h declares
 SYMBOLS = ["ps_create", "ps_destroy", "ps_step", "ps_setup", "ps_solve", "ps_export", "ps_last_error", "ps_get_count", "ps_get_real",
-           "ps_get_index_field", "ps_get_weight_field", "ps_get_csr", "ps_get_vector", "ps_apply", "ps_time_kernel", "ps_kernel_bytes",
+           "ps_get_index_field", "ps_get_weight_field", "ps_get_csr", "ps_get_vector", "ps_apply", "ps_time_kernel", "ps_kernel_bytes", "ps_timer",
            "ps_comm_unique_id", "ps_comm_init", "ps_get_partition"]
 
 _cache = {}
@@ -87,6 +87,7 @@ def load(path=None):
     L.ps_apply.argtypes = [H, C.c_void_p, C.c_void_p]; L.ps_apply.restype = C.c_int
     L.ps_time_kernel.argtypes = [H, C.c_char_p, C.c_int]; L.ps_time_kernel.restype = C.c_double
     L.ps_kernel_bytes.argtypes = [H, C.c_char_p]; L.ps_kernel_bytes.restype = C.c_double
+    L.ps_timer.argtypes = [H, C.c_int]; L.ps_timer.restype = C.c_double
     L.ps_comm_unique_id.argtypes = [C.c_void_p]; L.ps_comm_unique_id.restype = C.c_int
     L.ps_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]; L.ps_comm_init.restype = C.c_int
     L.ps_get_partition.argtypes = [H] + [C.POINTER(C.c_int32)] * 4; L.ps_get_partition.restype = C.c_int

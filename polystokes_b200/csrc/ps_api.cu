@@ -9,7 +9,7 @@
 
 using namespace ps;
 
-struct ps_solver { Solver* S; };
+struct ps_solver { Solver* S; void* tm[2] = {nullptr, nullptr}; };   // tm: the CUDA events of ps_timer
 
 namespace {
 
@@ -201,7 +201,13 @@ int ps_create(const ps_params* params, ps_handle* out) {
     *out = nullptr;
     return guarded([&] { ps_solver* h = new ps_solver; h->S = new Solver(*params); *out = h; return (int)PS_SUCCESS; });
 }
-void ps_destroy(ps_handle h) { if (h) { delete h->S; delete h; } }
+void ps_destroy(ps_handle h) {
+    if (!h) return;
+#ifndef PS_EMULATE
+    for (void* e : h->tm) if (e) cudaEventDestroy((cudaEvent_t)e);
+#endif
+    delete h->S; delete h;
+}
 
 #ifndef PS_EMULATE
 int ps_comm_unique_id(void* id128) {
@@ -371,7 +377,7 @@ double ps_kernel_bytes(ps_handle h, const char* name) {
     if (nm == "pass2") return pass2;
     if (nm == "reduced") return reduced;
     if (nm == "apply") return pass1 + pass2 + reduced;
-    if (nm == "cg_iteration") return pass1 + pass2 + reduced + 48.0 * n /*x,r update*/ + 24.0 * n /*p update*/;
+    if (nm == "cg_iteration") return pass1 + pass2 + reduced + 24.0 * n /*r update: Ap, r in, r out*/ + 40.0 * n /*x,p update: x, p, r in, x, p out*/;
     return 0;
 }
 
@@ -404,6 +410,26 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
         cudaEventDestroy(a); cudaEventDestroy(b);
 #else
         S.timedOperator(which); ms = 0;
+#endif
+        return 0;
+    });
+    return ms;
+}
+
+// Device-side stopwatch for callers that time whole steps: the solver works on its own stream, which an outside event
+// (e.g. torch.cuda.Event on torch's current stream) does not see.
+double ps_timer(ps_handle h, int stop) {
+    if (!h) return -1;
+    double ms = -1;
+    guarded([&] {
+#ifndef PS_EMULATE
+        Solver& S = *h->S;
+        for (void*& e : h->tm) if (!e) { cudaEvent_t ev; PS_CUDA(cudaEventCreate(&ev)); e = ev; }
+        if (!stop) { PS_CUDA(cudaEventRecord((cudaEvent_t)h->tm[0], S.st)); ms = 0; return 0; }
+        PS_CUDA(cudaEventRecord((cudaEvent_t)h->tm[1], S.st)); PS_CUDA(cudaEventSynchronize((cudaEvent_t)h->tm[1]));
+        float t = 0; PS_CUDA(cudaEventElapsedTime(&t, (cudaEvent_t)h->tm[0], (cudaEvent_t)h->tm[1])); ms = t;
+#else
+        ms = 0;
 #endif
         return 0;
     });

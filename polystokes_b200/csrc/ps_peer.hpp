@@ -20,7 +20,7 @@
 namespace ps {
 
 constexpr int PEER_MAX_RANKS = 8;
-constexpr int PEER_SLOTS = 4;      // reduction slots: 0 p.Ap, 1 (r.r, x.x), 2 b.b
+constexpr int PEER_SLOTS = 4;      // reduction slots: 0 p.Ap, 1 r.r, 2 b.b, 3 (x.p, p.p)
 
 struct PeerSync {                  // head of every rank's symmetric block
     unsigned long long haloFlag[2][2][2];                      // [kind x|w][parity][side: from below | from above]
@@ -32,6 +32,7 @@ struct PeerSync {                  // head of every rank's symmetric block
 struct PeerCtx {                   // passed by value to the CG kernels; nranks <= 1 means "no peers"
     int nranks = 1, rank = 0;
     unsigned long long seqIn = 0, seqOut = 0;   // sequence numbers of the reduction this kernel consumes / produces
+    unsigned long long seqIn2 = 0;              // update xp also consumes slot 3 of the previous iteration (0: first iteration, nothing to wait for)
     PeerSync* sync[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -88,14 +89,14 @@ __device__ __forceinline__ void peer_reduce_push(const PeerCtx& P, int slot, con
 }
 // called by every thread of a CTA: waits for the N partials of reduction (slot, seq) and returns their rank-ordered
 // sums in out[0..nvals); returns false (in every thread) on time-out
-__device__ __forceinline__ bool peer_reduce_wait(const PeerCtx& P, int slot, double* out, int nvals) {
+__device__ __forceinline__ bool peer_reduce_wait(const PeerCtx& P, int slot, unsigned long long seq, double* out, int nvals) {
     __shared__ double sh[2];
     __shared__ int ok;
     if (threadIdx.x < 32) {
         const PeerSync* m = P.sync[P.rank];
-        const int par = (int)(P.seqIn & 1ull);
+        const int par = (int)(seq & 1ull);
         bool good = true;
-        if ((int)threadIdx.x < P.nranks) good = peer_wait_flag(&m->redFlag[par][slot][threadIdx.x], P.seqIn);
+        if ((int)threadIdx.x < P.nranks) good = peer_wait_flag(&m->redFlag[par][slot][threadIdx.x], seq);
         good = __all_sync(0xffffffffu, good);
         if (threadIdx.x == 0) {
             ok = good ? 1 : 0;

@@ -157,10 +157,11 @@ void Solver::setupPeer() {
 #endif
 }
 
-PeerCtx Solver::reduceCtx(int slotIn, int slotOut) {
+PeerCtx Solver::reduceCtx(int slotIn, int slotOut, int slotIn2) {
     PeerCtx c = peer.ctx();
     if (peer.on) {
         if (slotIn >= 0) c.seqIn = peer.seqRed[slotIn];           // produced by the previous kernel of the chain
+        if (slotIn2 >= 0) c.seqIn2 = peer.seqRed[slotIn2];        // read before slotOut advances: update xp consumes and produces slot 3
         if (slotOut >= 0) c.seqOut = ++peer.seqRed[slotOut];
     }
     return c;
@@ -712,7 +713,7 @@ int Solver::solve() {
     PcgScalars h; memset(&h, 0, sizeof h);
     if (n == 0) { solveIterations = 0; solveError = 0; result = R_SUCCESS; return result; }
     k_cg_init(st, ownSys, b.p, x.p, r.p, p.p, dotPartial.p, scal.p, P.tolerance, maxIt, reduceCtx(-1, 2));
-    allreduce(scal.p->red + 3, 1);
+    allreduce(scal.p->red + 4, 1);
     k_cg_begin(st, scal.p, reduceCtx(2, -1));
     bool cancelled = false;
     // PS_TRACE=<iteration>: CUDA-event timeline of that CG iteration on stderr (diagnostic; events cost a few us each)
@@ -738,10 +739,10 @@ int Solver::solve() {
             exchange(haloW, w.p, scal.p);                       mark(tr, "halo w");
             k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, reduceCtx(-1, 0), scal.p, 1);   // + this rank's p.Ap to every rank
             allreduce(scal.p->red, 1);                          mark(tr, "pass2 (+allreduce)");
-            k_cg_update_xr(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, reduceCtx(0, 1));    // global p.Ap in, r.r / x.x out
-            allreduce(scal.p->red + 1, 2);                      mark(tr, "update x,r (+allreduce)");
-            k_cg_update_p(st, ownSys, p.p, r.p, scal.p, reduceCtx(1, -1));
-            mark(tr, "update p");
+            k_cg_update_r(st, ownSys, r.p, Ap.p, dotPartial.p, scal.p, reduceCtx(0, 1));               // global p.Ap in, r.r out
+            allreduce(scal.p->red + 1, 3);                      mark(tr, "update r (+allreduce)");     // r.r with the x.p / p.p of the previous update xp
+            k_cg_update_xp(st, ownSys, x.p, p.p, r.p, dotPartial.p, scal.p, reduceCtx(1, 3, it + k == 0 ? -1 : 3));   // global r.r, x.p, p.p in; new x.p / p.p out
+            mark(tr, "update x,p");
         }
         it += batch;
         copy_d2h(&h, scal.p, sizeof h, st);

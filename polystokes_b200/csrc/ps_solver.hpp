@@ -110,9 +110,10 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     double rsold, pAp, alpha, beta, rsnew, xmag, rre;
     int iter, done, maxIter, pad;
     double tol2;
-    unsigned int ticket[8];   // last-CTA-done tickets: 0 pass 2, 1 x/r update, 2 init, 3 p update, 4/5 halo push of p / w
+    unsigned int ticket[8];   // last-CTA-done tickets: 0 pass 2, 1 r update, 2 init, 3 x/p update, 4/5 halo push of p / w
     int peerError, pad2;      // sticky: a peer-memory wait timed out (ps_peer.hpp)
-    double red[4];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.x, [3] b.b
+    double red[5];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.p, [3] p.p (1..3 travel together), [4] b.b
+    double xx;                // global x.x of the current iterate, advanced by |x + alpha p|^2 = x.x + 2 alpha x.p + alpha^2 p.p (ps_pcg.cu)
     // BiCGSTAB fallback (pcg.h:134-200): its own scalars; bred[] = rank-local dot products of the current stage
     double rhoCurr, rhoOld, omega, tol, bred[2];
     // solverType EIGEN (Eigen::ConjugateGradient, ConjugateGradient.h:28-93): |b|^2, max(tol^2 |b|^2, DBL_MIN), r.z
@@ -191,7 +192,7 @@ public:
     PeerLink peer;                      // NVLink peer-memory transport (ps_peer.hpp); off => NCCL for everything
     void setupPeer();                   // collective: allocate + exchange + map the symmetric blocks
     void closePeer();
-    PeerCtx reduceCtx(int slotIn, int slotOut);   // sequence numbers of the reductions one kernel consumes / produces
+    PeerCtx reduceCtx(int slotIn, int slotOut, int slotIn2 = -1);   // sequence numbers of the reductions one kernel consumes / produces
     RowSet rowsK(int rank) const, rowsP(int rank) const, rowsC(int rank) const, rowsE(int rank) const;
     RangeSet rowsSys(int rank) const;
     RowSet ownK, ownP, ownC, ownE;
@@ -301,8 +302,8 @@ void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* 
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
 // the reduced term of one apply: w_f <- scale * c_f . B^-1 (sum_f c_f w_f); one fused launch for tiled regions, moments + expand otherwise
 void reduced_apply(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-void k_cg_update_xr(cudaStream_t, const RangeSet& own, double* x, double* r, const double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
-void k_cg_update_p(cudaStream_t, const RangeSet& own, double* p, const double* r, PcgScalars* scal, const PeerCtx& P);
+void k_cg_update_r(cudaStream_t, const RangeSet& own, double* r, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
+void k_cg_update_xp(cudaStream_t, const RangeSet& own, double* x, double* p, const double* r, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
 void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);
 // BiCGSTAB fallback (pcg.h:134-200).  Dot products land rank-local in scal->bred[], the host enqueues the all-reduce

@@ -263,6 +263,18 @@ class PolyStokesSolver:
             raise PolyStokesError(f"ps_time_kernel({name}) failed: {self.last_error()}")
         return t
 
+    def timer_start(self):
+        """Record the start event of the device stopwatch on the solver's stream (ps_timer)."""
+        if float(self.lib.ps_timer(self.h, 0)) < 0:
+            raise PolyStokesError(f"ps_timer failed: {self.last_error()}")
+
+    def timer_stop(self):
+        """Record the stop event, wait for it, return the device milliseconds since timer_start()."""
+        t = float(self.lib.ps_timer(self.h, 1))
+        if t < 0:
+            raise PolyStokesError(f"ps_timer failed: {self.last_error()}")
+        return t
+
     def kernel_bytes(self, name):
         return float(self.lib.ps_kernel_bytes(self.h, name.encode()))
 
