@@ -119,7 +119,21 @@ def run_cpu_sample(n, full_counts=None, threads=0):
                 full_seconds=t_full, cores=lib().orc_num_threads())
 
 
+def emit(obj):
+    """The ONE JSON line of the contract, on the real stdout (see main: fd 1 is pointed at stderr while the bench runs)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # Libraries chat on stdout (NCCL prints its version banner there when the first communicator is created): keep the
+    # real stdout for the result line only and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -151,7 +165,7 @@ def main():
         sample = (f"oracle (CPU restatement of the reference path, OpenMP) ran the full step on S3 at {n}^3 in {samp:.2f} s "
                   f"({res[0]['iterations']} CG iterations, n={res[0]['nSystemSize']}); scaled to 256^3: setup x{(SCENE_N / n) ** 3:.1f} voxels, "
                   "CG time x system-size ratio x iteration ratio")
-        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        emit(dict({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config, "impl": "reference",
                           "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[0]["cores"], "kind": "port", "sample": sample},
@@ -294,7 +308,7 @@ def main():
                "wall_ms_per_step": wall / a.steps * 1e3, "device_ms_per_step": dev_ms / a.steps, "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                "cg_iterations": counts["iterations"], "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -716,6 +716,12 @@ int Solver::solve() {
     allreduce(scal.p->red + 4, 1);
     k_cg_begin(st, scal.p, reduceCtx(2, -1));
     bool cancelled = false;
+    // PS_DBG_SKIP (timing experiments only, the iterates are WRONG with it): bit 0 drops the halo exchanges, bit 1 the
+    // cross-rank reductions of the CG loop -- what is left is each rank iterating on its own slab (profiles/r01_dist_probe*.log)
+    const int dbgSkip = getenv("PS_DBG_SKIP") ? atoi(getenv("PS_DBG_SKIP")) : 0;
+    auto rctx = [&](int slotIn, int slotOut, int slotIn2 = -1) { return (dbgSkip & 2) ? PeerCtx() : reduceCtx(slotIn, slotOut, slotIn2); };
+    auto xchg = [&](Halo& H, double* v) { if (!(dbgSkip & 1)) exchange(H, v, scal.p); };
+    auto ared = [&](double* buf, int cnt) { if (!(dbgSkip & 2)) allreduce(buf, cnt); };
     // PS_TRACE=<iteration>: CUDA-event timeline of that CG iteration on stderr (diagnostic; events cost a few us each)
     static const int traceIter = getenv("PS_TRACE") ? atoi(getenv("PS_TRACE")) : -1;
     std::vector<std::pair<const char*, double>> trace;
@@ -730,18 +736,18 @@ int Solver::solve() {
         for (int k = 0; k < batch; ++k) {
             const bool tr = (it + k == traceIter);
             mark(tr, "start");
-            exchange(haloX, p.p, scal.p);                       mark(tr, "halo p");
+            xchg(haloX, p.p);                                   mark(tr, "halo p");
             k_pass1(st, A, p.p, w.p, g.dt, scal.p);             mark(tr, "pass1");
             if (RG.count > 0) {
                 reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);          // moments -> B^-1 -> expand, one CTA per region
             }
             mark(tr, "reduced x3");
-            exchange(haloW, w.p, scal.p);                       mark(tr, "halo w");
-            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, reduceCtx(-1, 0), scal.p, 1);   // + this rank's p.Ap to every rank
-            allreduce(scal.p->red, 1);                          mark(tr, "pass2 (+allreduce)");
-            k_cg_update_r(st, ownSys, r.p, Ap.p, dotPartial.p, scal.p, reduceCtx(0, 1));               // global p.Ap in, r.r out
-            allreduce(scal.p->red + 1, 3);                      mark(tr, "update r (+allreduce)");     // r.r with the x.p / p.p of the previous update xp
-            k_cg_update_xp(st, ownSys, x.p, p.p, r.p, dotPartial.p, scal.p, reduceCtx(1, 3, it + k == 0 ? -1 : 3));   // global r.r, x.p, p.p in; new x.p / p.p out
+            xchg(haloW, w.p);                                   mark(tr, "halo w");
+            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, rctx(-1, 0), scal.p, 1);        // + this rank's p.Ap to every rank
+            ared(scal.p->red, 1);                               mark(tr, "pass2 (+allreduce)");
+            k_cg_update_r(st, ownSys, r.p, Ap.p, dotPartial.p, scal.p, rctx(0, 1));                    // global p.Ap in, r.r out
+            ared(scal.p->red + 1, 3);                           mark(tr, "update r (+allreduce)");     // r.r with the x.p / p.p of the previous update xp
+            k_cg_update_xp(st, ownSys, x.p, p.p, r.p, dotPartial.p, scal.p, rctx(1, 3, it + k == 0 ? -1 : 3));        // global r.r, x.p, p.p in; new x.p / p.p out
             mark(tr, "update x,p");
         }
         it += batch;
