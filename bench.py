@@ -115,8 +115,26 @@ def run_cpu_sample(n, full_counts=None, threads=0):
     else:
         it_full, n_full = iters * SCENE_N / n, nsys * vox_ratio
     t_full = t_setup * vox_ratio + (t_solve / iters) * (n_full / nsys) * it_full
-    return dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, iterations=iters - 1, nSystemSize=nsys,
-                full_seconds=t_full, cores=lib().orc_num_threads())
+    out = dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, iterations=iters - 1, nSystemSize=nsys,
+               full_seconds=t_full, cores=lib().orc_num_threads(), refcode=None)
+    # The reference's OWN solve stage (pcg.h + ApplyPressureStressMatrix.h compiled from its sources, oracle/_ref) on the same
+    # matrices: a few CG iterations, to put the paper-era CPU code next to the oracle's lean OpenMP restatement of it.
+    try:
+        from oracle import ref_solve
+        if ref_solve.available():
+            R = ref_solve.RefSolve(o.csr, sc.dt)
+            k = 6
+            t0 = time.perf_counter()
+            R.pcg(o.vector("b"), 0.0, k)                   # tol 0: exactly k iterations (+ the initial apply)
+            t_it = (time.perf_counter() - t0) / (k + 1)
+            R.close()
+            out["refcode"] = {"ms_per_iteration_sample": t_it * 1e3, "iterations_timed": k, "threads": 3,
+                              "full_seconds": t_setup * vox_ratio + t_it * (n_full / nsys) * it_full,
+                              "what": "pcg_external_matrix_A + ApplyPressureStressMatrix::applyMatrixVectorProducts compiled unmodified from the "
+                                      "reference's lib/include (its three `omp sections`), setup stages from the oracle"}
+    except Exception as e:      # the baseline must not take the bench down
+        out["refcode"] = {"error": str(e)}
+    return out
 
 
 def emit(obj):
@@ -168,7 +186,8 @@ def main():
         emit(dict({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config, "impl": "reference",
-                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[0]["cores"], "kind": "port", "sample": sample},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[0]["cores"], "kind": "port", "sample": sample,
+                                           "reference_code_solve_stage": res[0]["refcode"]},
                           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -290,7 +309,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r = run_cpu_sample(128 if a.n >= 128 else a.n, full_counts=counts if a.n == SCENE_N else None)
-        cpu = {"value": 1.0 / r["full_seconds"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        cpu = {"value": 1.0 / r["full_seconds"], "unit": UNIT, "cores": r["cores"], "kind": "port", "reference_code_solve_stage": r["refcode"],
                "sample": (f"oracle full step on S3 at {r['n']}^3: {r['seconds']:.2f} s (setup {r['setup_s']:.2f} s, {r['iterations']} CG its, n={r['nSystemSize']}); "
                           f"scaled to 256^3 (setup x{(SCENE_N / r['n']) ** 3:.0f} voxels, per-iteration time x system-size ratio, GPU-measured iteration count) "
                           f"= {r['full_seconds']:.1f} s/step")}

@@ -139,7 +139,7 @@ int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int
 /* counters by name: nCenter nFaceX nFaceY nFaceZ nEdgeYZ nEdgeXZ nEdgeXY nActiveVs nReducedVs nPressures
  * nStresses nTotalDOFs nSystemSize regionCount iterations result usedBiCGStab nRowsExt */
 int64_t ps_get_count(ps_handle h, const char* name);
-double ps_get_real(ps_handle h, const char* name);     /* solveError */
+double ps_get_real(ps_handle h, const char* name);     /* solveError, xmag (x.x of the CG stop test at the last iteration) */
 /* kind: 0 labels (int8 widened), 1 active indices, 2 reduced indices; slot: 0 centre, 1-3 face x/y/z,
  * 4-6 edge YZ/XZ/XY.  `out` receives int32 values; returns the element count. */
 int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out);

@@ -6,11 +6,17 @@
 // reference file:line it follows (paths relative to the reference checkout:
 // exec/HDK_PolyStokesSolver*.cpp = S*.cpp, lib/include/*.h).
 //
-// PARITY UNPINNED: the reference ships no tests / golden vectors and cannot be
-// compiled here (no HDK, no TBB, vendored Eigen lacks Eigen/Core), so this
-// restatement is pinned only by its own analytic known-answer tests
-// (tests/test_oracle_*.py).  Nothing in the product path (polystokes_b200/)
-// may include, link or call this code.
+// PINNING.  The reference ships no tests / golden vectors.  Its SOLVE STAGE (operator
+// apply Apply.h:102-179, CG pcg.h:268-340, BiCGSTAB fallback pcg.h:134-200) is header-only
+// code and IS compiled here from the reference's own files (oracle/ref_solve.cpp,
+// `make ref` -> oracle/_ref/libps_ref_solve.so, on the Eigen facade of oracle/eigen_facade
+// because the checkout's Eigen lacks Eigen/Core): ps_oracle_solve.cpp is checked against it
+// (tests/test_ref_solve.py, tests/golden `refcode_*`): same iteration counts, apply to 1e-16.
+// PARITY UNPINNED for everything before the solve -- weights, classifier, region algebra,
+// matrix blocks, assembly (exec/HDK_PolyStokesSolver*.cpp): those files need the HDK and
+// cannot be compiled, so that part of this restatement is pinned only by its analytic
+// known-answer tests (tests/test_oracle_kat.py).  Nothing in the product path
+// (polystokes_b200/) may include, link or call this code.
 #pragma once
 #include <cstdint>
 #include <cstddef>

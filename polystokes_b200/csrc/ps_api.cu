@@ -294,6 +294,7 @@ double ps_get_real(ps_handle h, const char* name) {
     if (!h || !name) return NAN;
     const std::string n(name);
     if (n == "solveError") return h->S->solveError;
+    if (n == "xmag") return h->S->solveXmag;
     return NAN;
 }
 

@@ -770,6 +770,7 @@ int Solver::solve() {
     // b == 0: the reference would divide 0/0 (pcg.h:313); we return x = 0 after 0 iterations instead
     solveIterations = (h.done == 1) ? h.iter : maxIt;
     solveError = std::sqrt(h.rre);
+    solveXmag = h.xmag;
     // "have minres as a backup" (S.cpp:784-799): CG used up its iterations -> restart from x = 0 with BiCGSTAB
     if (solveIterations == maxIt && !cgOnly) return solveBiCGStab();
     result = (solveIterations == maxIt) ? R_NOCONVERGE : R_SUCCESS;

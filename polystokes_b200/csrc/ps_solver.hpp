@@ -149,6 +149,7 @@ public:
     int result = R_INCOMPLETE;
     int solveIterations = -1;
     double solveError = -1;
+    double solveXmag = 0;      // x.x as the CG stop test saw it at the last iteration (advanced by the recurrence of ps_pcg.cu)
     int usedBiCGStab = 0;
     bool cgOnly = false;                // ps_time_kernel("cg_iteration"): run exactly maxSolverIterations CG iterations, no fallback
     int fixLoops = 0;

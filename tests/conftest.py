@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # oracle/_ref (the reference's own solve stage, compiled from its sources) exists only where /root/reference does; build it
+    # before collection so tests/test_ref_solve.py is not skipped here.  On the GPU box the prebuilt file travels with the snapshot.
+    if os.path.isdir("/root/reference/lib/include"):
+        import subprocess
+        try:
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
+        except Exception as e:      # the tests that need it will say so
+            print(f"conftest: could not build oracle/_ref: {e}", file=sys.stderr)
 
 
 @pytest.fixture(scope="session")

@@ -1,7 +1,10 @@
 """Regenerates tests/golden/*.npz from the oracle (run from the repo root: python tests/golden/make_golden.py).
 
-The reference has no fixtures of its own and cannot be run here, so these vectors pin the *oracle's* behaviour at the
-time they were generated; the KATs in tests/test_oracle_kat.py pin it analytically.
+The reference has no fixtures of its own and its classifier / assembly cannot be run here (HDK), so the
+label / index / matrix vectors pin the *oracle's* behaviour at the time they were generated; the KATs in tests/test_oracle_kat.py
+pin it analytically.  The `refcode_*` entries are different: they are OUTPUTS OF THE REFERENCE'S OWN CODE -- pcg.h and
+ApplyPressureStressMatrix.h compiled from /root/reference (oracle/_ref/libps_ref_solve.so, `make -C oracle ref`) and run on the
+matrices above: the operator applied to a fixed vector, and the iteration count / error / solution of pcg_external_matrix_A.
 """
 import hashlib
 import os
@@ -13,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from polystokes_b200 import scenes  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
+from oracle import ref_solve  # noqa: E402
 
 CASES = {
     "blob20_tile8_pad1": lambda: scenes.blob_scene(20, seed=21, tile=8, pad=1),
@@ -22,6 +26,10 @@ CASES = {
 
 def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def probe_vector(n):
+    return np.random.default_rng(20261017).standard_normal(n)
 
 
 def collect(sc):
@@ -37,7 +45,16 @@ def collect(sc):
         out[f"{m}_pattern_sha256"] = np.frombuffer(bytes.fromhex(digest(ptr) + digest(idx)), dtype=np.uint8)
         out[f"{m}_values"] = val
     out["b"] = o.vector("b")
+    if ref_solve.available():
+        R = ref_solve.RefSolve(o.csr, sc.dt)
+        out["refcode_probe"] = probe_vector(R.n)
+        out["refcode_apply"] = R.apply(out["refcode_probe"])
+        res, it, x, err, used = R.solve_spd(out["b"], sc.params["tolerance"], sc.params["maxIterations"])
+        out["refcode_result"] = np.array([res, it, used])
+        out["refcode_error"] = np.array([err])
+        out["refcode_solution"] = x
     o.solve()
+    out["oracle_solution"] = o.vector("solution")
     vel, valid = o.writeback()
     out["iterations"] = np.array([o.count("iterations")])
     for a in range(3):

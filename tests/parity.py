@@ -104,6 +104,11 @@ def check_solve(sc, o, s, ov):
         assert np.array_equal(ovalid[a], valid[a]), f"valid field axis {a}"
         scale = max(float(np.abs(ovel[a]).max()), 1e-30)
         assert float(np.abs(ovel[a] - vel[a]).max()) <= tol * scale, f"velocity axis {a}"
+    # the stop test's x.x is advanced by |x + a p|^2 = x.x + 2a x.p + a^2 p.p instead of being summed (ps_pcg.cu): no drift allowed
+    if s.count("usedBiCGStab") == 0 and dict(sc.params, **ov).get("solverType", 0) == 0 and s.count("nSystemSize") > 0:
+        x = s.vector("solution")
+        xx = float(x @ x)
+        assert abs(s.real("xmag") - xx) <= 1e-11 * max(xx, 1e-300), f"x.x recurrence drift {abs(s.real('xmag') - xx) / max(xx, 1e-300):.2e} after {is_} iterations"
     return io, is_
 
 

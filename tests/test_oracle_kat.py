@@ -1,5 +1,5 @@
-"""Known-answer tests that pin the CPU oracle (the reference ships no tests / golden vectors: parity unpinned,
-SURVEY.md section 8c).  Each test checks an analytic property of the restated algorithm."""
+"""Known-answer tests that pin the CPU oracle (the reference ships no tests / golden vectors; only its solve stage can be
+compiled here -- tests/test_ref_solve.py -- so for classification / assembly parity is unpinned).  Each test checks an analytic property of the restated algorithm."""
 import os
 
 import numpy as np

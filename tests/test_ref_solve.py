@@ -1,0 +1,91 @@
+"""The reference's OWN solve stage -- lib/include/pcg.h (pcg_external_matrix_A, bicgstab_external_matrix_A) and
+lib/include/ApplyPressureStressMatrix.h (applyMatrixVectorProducts), compiled unmodified from /root/reference into
+oracle/_ref/libps_ref_solve.so (oracle/Makefile `ref`, on the Eigen facade of oracle/eigen_facade) -- against
+(a) the oracle's restatement of the same stage and (b) the product's kernels, on the same matrices.
+This is what pins SURVEY.md section 8a rows O1 / O2 / P1 and the fallback to reference CODE rather than to a reading of it.
+Skipped when the library has not been built (no /root/reference at build time)."""
+import numpy as np
+import pytest
+
+import parity
+from oracle import ref_solve
+from oracle.oracle import Oracle
+from polystokes_b200 import PolyStokesSolver, scenes
+
+pytestmark = pytest.mark.skipif(not ref_solve.available(), reason="oracle/_ref/libps_ref_solve.so not built (needs /root/reference)")
+
+CASES = {
+    "uniform_box20": lambda: scenes.box_scene(20, doReduced=0, tolerance=1e-6),
+    "blob40_tile8": lambda: scenes.blob_scene(40, seed=3),
+    "blob32_notile": lambda: scenes.blob_scene(32, seed=5, doTile=0),
+    "ragged_36x28x44": lambda: scenes.blob_scene((36, 28, 44), seed=9),
+}
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max()) / max(float(np.abs(np.asarray(a)).max()), 1e-300)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_solve_stage_matches_reference_code(built, case):
+    """Oracle restatement vs the compiled reference headers: operator apply to rounding, CG with the SAME iteration
+    count and error, solution to 1e-7 (the only freedom left is the summation order of the oracle's OpenMP dots)."""
+    sc = CASES[case]()
+    o = Oracle(sc).setup()
+    n = o.count("nSystemSize")
+    R = ref_solve.RefSolve(o.csr, sc.dt)
+    assert R.n == n
+    rng = np.random.default_rng(7)
+    for _ in range(2):
+        x = rng.standard_normal(n)
+        assert rel(R.apply(x), o.apply(x)) <= 1e-13
+    ro = o.solve()
+    res, it, xr, err, used = R.solve_spd(o.vector("b"), sc.params["tolerance"], sc.params["maxIterations"])
+    assert (res, used) == (ro, o.count("usedBiCGStab"))
+    assert it == o.count("iterations"), f"iterations: reference code {it}, oracle {o.count('iterations')}"
+    assert abs(err - o.real("solveError")) <= 1e-9 * err
+    assert rel(xr, o.vector("solution")) <= 1e-7       # dot-product order, amplified by the conditioning
+
+
+def test_oracle_bicgstab_fallback_matches_reference_code(built):
+    """CG cut after 8 iterations -> the reference restarts with bicgstab_external_matrix_A (S.cpp:784-799): same switch,
+    same 8 iterations, iterates equal to rounding."""
+    sc = scenes.blob_scene(32, seed=4, maxIterations=8, tolerance=1e-12, keepNonConvergedResults=1)
+    o = Oracle(sc).setup()
+    ro = o.solve()
+    R = ref_solve.RefSolve(o.csr, sc.dt)
+    res, it, xr, err, used = R.solve_spd(o.vector("b"), sc.params["tolerance"], sc.params["maxIterations"])
+    assert used == 1 == o.count("usedBiCGStab") and res == ro == 0 and it == o.count("iterations") == 8
+    assert rel(xr, o.vector("solution")) <= 1e-9
+    assert abs(err - o.real("solveError")) <= 1e-6 * abs(err)
+
+
+def _product_vs_reference(lib_path, sc):
+    """The product assembles its own matrices; the reference's code then solves on THOSE matrices (exported through
+    ps_get_csr) and must land where the product's own CG did."""
+    s = PolyStokesSolver.from_scene(sc, lib_path=lib_path)
+    rc, vel, valid = s.step_scene(sc)
+    n = s.count("nSystemSize")
+    R = ref_solve.RefSolve(s.csr, sc.dt)
+    assert R.n == n
+    x = np.random.default_rng(11).standard_normal(n)
+    assert rel(R.apply(x), s.apply(x)) <= 1e-12, f"operator apply vs reference code: {rel(R.apply(x), s.apply(x)):.2e}"
+    res, it, xr, err, used = R.solve_spd(s.vector("b"), sc.params["tolerance"], sc.params["maxIterations"])
+    assert res == rc and used == s.count("usedBiCGStab")
+    assert abs(it - s.count("iterations")) <= max(2, int(0.01 * it)), f"iterations: reference code {it}, product {s.count('iterations')}"
+    assert rel(xr, s.vector("solution")) <= 10 * sc.params["tolerance"]
+    assert abs(err - s.real("solveError")) <= 1e-6 * err
+    s.close()
+    return it
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_emulated_kernels_match_reference_code(built, case):
+    _product_vs_reference(parity.EMUL_LIB, CASES[case]())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(CASES) + ["S2_beam_96"])
+def test_gpu_solve_matches_reference_code(built, case):
+    sc = scenes.scene_s2(96) if case == "S2_beam_96" else CASES[case]()
+    _product_vs_reference(None, sc)
