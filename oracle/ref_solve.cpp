@@ -2,6 +2,7 @@
 //   lib/include/ApplyPressureStressMatrix.h  (setupMatrixVectorProducts :24-68, applyMatrixVectorProducts :102-179)
 //   lib/include/pcg.h                         (pcg_external_matrix_A :268-340, bicgstab_external_matrix_A :134-200)
 //   lib/include/util.h, lib/include/units.h   (concatenate_*, manualMatrixTransposeVectorDistribute2, the typedefs)
+//   extern/eigen/unsupported/Eigen/src/SparseExtra/MarketIO.h   (saveMarket / saveMarketVector, the export format)
 // compiled UNMODIFIED from /root/reference by `make -C oracle ref` into oracle/_ref/libps_ref_solve.so.  No reference
 // source is copied into this repository: the four headers are found through -I/root/reference/lib/include.  Eigen, TBB
 // and the HDK are absent offline; oracle/eigen_facade/ supplies the slice of the Eigen API these headers use
@@ -75,5 +76,10 @@ int refsolve_solve(void* hv, int which, const double* b, double tol, unsigned in
     if (rre) *rre = err;
     return it;
 }
+
+// The checkout's own MatrixMarket writer (extern/eigen/unsupported/Eigen/src/SparseExtra/MarketIO.h), called the way
+// S.cpp:533-606 calls it: Eigen::saveMarket(matrix, path) and Eigen::saveMarketVector(vector, path).  Returns 1 on success.
+int refsolve_save_market(const ref_csr* m, const char* path) { return Eigen::saveMarket(load(m->rows, m->cols, m->ptr, m->idx, m->val), std::string(path)) ? 1 : 0; }
+int refsolve_save_market_vector(const double* v, int64_t n, const char* path) { return Eigen::saveMarketVector(to_vec(v, (Index)n), std::string(path)) ? 1 : 0; }
 
 }  // extern "C"

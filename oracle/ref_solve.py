@@ -33,8 +33,26 @@ def lib():
         L.refsolve_size.argtypes = [C.c_void_p]; L.refsolve_size.restype = C.c_int64
         L.refsolve_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refsolve_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_uint, C.c_void_p, C.POINTER(C.c_double)]; L.refsolve_solve.restype = C.c_int
+        L.refsolve_save_market.argtypes = [C.POINTER(_Csr), C.c_char_p]; L.refsolve_save_market.restype = C.c_int
+        L.refsolve_save_market_vector.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]; L.refsolve_save_market_vector.restype = C.c_int
         _lib = L
     return _lib
+
+
+def save_market(csr, path):
+    """Eigen::saveMarket (the checkout's unsupported/Eigen/src/SparseExtra/MarketIO.h:311-335) on ((rows, cols), ptr, idx, val)."""
+    (r, c), ptr, idx, val = csr
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64); idx = np.ascontiguousarray(idx, dtype=np.int32); val = np.ascontiguousarray(val, dtype=np.float64)
+    m = _Csr(int(r), int(c), ptr.ctypes.data, idx.ctypes.data, val.ctypes.data)
+    if lib().refsolve_save_market(C.byref(m), str(path).encode()) != 1:
+        raise IOError(f"saveMarket could not write {path}")
+
+
+def save_market_vector(v, path):
+    """Eigen::saveMarketVector (MarketIO.h:347-382)."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    if lib().refsolve_save_market_vector(v.ctypes.data, v.size, str(path).encode()) != 1:
+        raise IOError(f"saveMarketVector could not write {path}")
 
 
 class RefSolve:

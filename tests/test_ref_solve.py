@@ -84,6 +84,50 @@ def test_emulated_kernels_match_reference_code(built, case):
     _product_vs_reference(parity.EMUL_LIB, CASES[case]())
 
 
+def _export_vs_eigen_writer(lib_path, sc, tmp_path):
+    """exportMatrices / exportComponentMatrices / exportStats (S.cpp:533-606): every file ps_export writes must be byte-identical
+    to what Eigen's own writer (the checkout's MarketIO.h, compiled into oracle/_ref) produces from the same matrix / vector."""
+    s = PolyStokesSolver.from_scene(sc, lib_path=lib_path)
+    s.step_scene(sc)
+    pre = str(tmp_path / "out_")
+    s.export(pre, 7)
+    mats = {"Mat_Mc.mtx": "Mc", "Mat_McInv.mtx": "McInv", "Mat_Mr.mtx": "Mr", "Mat_Mr_plus_2JDtuDJ.mtx": "B", "Mat_Inv_Mr_plus_2JDtuDJ.mtx": "BInv",
+            "Mat_u.mtx": "u", "Mat_uInv.mtx": "uInv", "Mat_G.mtx": "G", "Mat_Dt.mtx": "Dt", "Mat_JG.mtx": "JG", "Mat_JDt.mtx": "JDt"}
+    vecs = {"Vec_b.mtx": "b", "solutionVector.mtx": "solution", "Vec_activeRHS.mtx": "activeRHS", "Vec_reducedRHS.mtx": "reducedRHS",
+            "Vec_pressureRHS.mtx": "pressureRHS", "Vec_stressRHS.mtx": "stressRHS"}
+    for f, name in mats.items():
+        ref_solve.save_market(s.csr(name), pre + "eigen_" + f)
+        assert open(pre + f, "rb").read() == open(pre + "eigen_" + f, "rb").read(), f"{f} differs from Eigen::saveMarket's output"
+    for f, name in vecs.items():
+        ref_solve.save_market_vector(s.vector(name), pre + "eigen_" + f)
+        assert open(pre + f, "rb").read() == open(pre + "eigen_" + f, "rb").read(), f"{f} differs from Eigen::saveMarketVector's output"
+    for f, data in (("dimData.mtx", list(s.stats.dimData)), ("solveData.mtx", list(s.stats.solveData))):
+        ref_solve.save_market_vector(np.array(data), pre + "eigen_" + f)
+        assert open(pre + f, "rb").read() == open(pre + "eigen_" + f, "rb").read(), f
+    s.close()
+
+
+def test_oracle_market_writer_matches_eigen_writer(built, tmp_path):
+    sc = scenes.blob_scene(24, seed=2)
+    o = Oracle(sc).setup()
+    for name in ("G", "JDt", "BInv"):
+        a, b = str(tmp_path / f"o_{name}.mtx"), str(tmp_path / f"e_{name}.mtx")
+        o.save_csr(name, a); ref_solve.save_market(o.csr(name), b)
+        assert open(a, "rb").read() == open(b, "rb").read(), name
+    a, b = str(tmp_path / "o_b.mtx"), str(tmp_path / "e_b.mtx")
+    o.save_vector("b", a); ref_solve.save_market_vector(o.vector("b"), b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_emulated_export_matches_eigen_writer(built, tmp_path):
+    _export_vs_eigen_writer(parity.EMUL_LIB, scenes.blob_scene(24, seed=2), tmp_path)
+
+
+@pytest.mark.gpu
+def test_gpu_export_matches_eigen_writer(built, tmp_path):
+    _export_vs_eigen_writer(None, scenes.blob_scene(24, seed=2), tmp_path)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", list(CASES) + ["S2_beam_96"])
 def test_gpu_solve_matches_reference_code(built, case):
