@@ -139,9 +139,19 @@ def check_bicgstab_fallback(lib_path=None):
     assert ro == rs == 1 and o.count("usedBiCGStab") == s.count("usedBiCGStab") == 1
     io, is_ = o.count("iterations"), s.count("iterations")
     assert abs(io - is_) <= 2 + io // 10, f"BiCGSTAB iterations oracle {io} vs {is_}"
+    # BiCGSTAB's trajectory is chaotic at rounding level (the oracle's OpenMP dot products are not even reproducible from run to run)
+    # and its stop rule min(|e|^2, |e| / |x|) < tol (pcg.h:186-193) is loose: two correct runs may stop a few iterations apart with
+    # velocities that differ by per cents.  What must hold exactly is the rule itself on the returned iterate, checked independently:
+    x, b = s.vector("solution"), o.vector("b")
+    e = b - o.apply(x)
+    rsnew, xmag = float(e @ e), float(np.sqrt(x @ x))
+    rre = min(rsnew, np.sqrt(rsnew) / xmag)
+    tol = dict(sc.params)["tolerance"]
+    assert rre < tol, f"returned BiCGSTAB iterate does not satisfy the reference's stop rule: {rre:.3e} >= {tol:.1e}"
+    assert abs(rre - s.real("solveError")) <= 1e-6 * rre + 1e-14, f"reported error {s.real('solveError'):.6e} vs recomputed {rre:.6e}"
     ovel, _ = o.writeback()
     for a in range(3):
-        assert float(np.abs(ovel[a] - vel[a]).max()) <= 2e-2 * max(float(np.abs(ovel[a]).max()), 1e-30)
+        assert float(np.abs(ovel[a] - vel[a]).max()) <= 1e-1 * max(float(np.abs(ovel[a]).max()), 1e-30)
     s.close()
 
 

@@ -56,6 +56,27 @@ def test_gpu_repeated_steps_are_deterministic(built):
         assert np.array_equal(v1[a], v2[a])
 
 
+def test_gpu_bicgstab_fallback_is_deterministic(built):
+    """BiCGSTAB amplifies every rounding difference, so any race or read of stale memory in the fallback path shows up as a
+    different iterate: three fresh handles (allocations land on different recycled memory) and a repeated step must agree bit for bit."""
+    from polystokes_b200 import PolyStokesSolver, scenes
+    sc = scenes.blob_scene(32, seed=4, maxIterations=60)
+    runs = []
+    for k in range(3):
+        s = PolyStokesSolver.from_scene(sc)
+        for rep in range(2 if k == 0 else 1):
+            rc, v, _ = s.step_scene(sc)
+            assert rc == 1 and s.count("usedBiCGStab") == 1
+            runs.append((s.count("iterations"), s.vector("solution"), v))
+        junk = [PolyStokesSolver.from_scene(scenes.blob_scene(24 + 4 * k)).step_scene(scenes.blob_scene(24 + 4 * k))]    # churn the allocator
+        s.close()
+    it0, x0, v0 = runs[0]
+    for it, x, v in runs[1:]:
+        assert it == it0 and np.array_equal(x, x0), "BiCGSTAB fallback is not reproducible"
+        for a in range(3):
+            assert np.array_equal(v[a], v0[a])
+
+
 def test_gpu_bicgstab_fallback(built):
     """CG out of iterations -> BiCGSTAB (S.cpp:784-799), against the oracle's restatement of pcg.h:134-200."""
     parity.check_bicgstab_fallback()
