@@ -1,0 +1,3 @@
+// hdk_shim: stands in for <UT/UT_DSOVersion.h> of the Houdini Development Kit (absent offline); everything lives in hdk_shim.h
+#pragma once
+#include "../hdk_shim.h"

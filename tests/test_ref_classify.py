@@ -1,0 +1,74 @@
+"""The reference's OWN classifier -- exec/HDK_PolyStokesSolver_Classifier.cpp compiled unmodified from /root/reference into
+oracle/_ref/libps_ref_classify.so (oracle/Makefile `ref`; HDK stand-in oracle/hdk_shim, harness oracle/ref_classify.cpp) -- against
+(a) the oracle's restatement and (b) the product, on the same integration weights.  Labels, the active (DOF) indices, the reduced
+region indices of all 7 sample slots, the counts and the valid-face fields must be BIT-EXACT: this is what pins SURVEY.md section 8a
+rows C1-C12 to reference CODE (on the HDK semantics of BASELINE.md section 3) instead of to a reading of it.
+Skipped when the library has not been built (no /root/reference at build time)."""
+import numpy as np
+import pytest
+
+import parity
+from oracle import ref_classify
+from oracle.oracle import Oracle
+from polystokes_b200 import PolyStokesSolver, scenes
+
+pytestmark = pytest.mark.skipif(not ref_classify.available(), reason="oracle/_ref/libps_ref_classify.so not built (needs /root/reference)")
+
+KINDS = ("labels", "active indices", "reduced indices")
+CASES = dict(parity.SCENE_CASES)
+CASES.update({
+    "S1_uniform_64": lambda: (scenes.scene_s1(), {}),
+    "S2_beam_64_tile8_pad1": lambda: (scenes.scene_s2(64), {}),
+    "S3_jet_64_tile16_pad2": lambda: (scenes.scene_s3(64), {}),
+    "S4_pool_96_tile32_pad3_layers33": lambda: (scenes.scene_s4(96), {}),
+    "S5_blob_quarter_tile8_pad3": lambda: (scenes.scene_s5(0.25, tileSize=8), {}),
+    "blob48_pad0": lambda: (scenes.blob_scene(48, seed=13, tile=8, pad=0), {}),
+    "blob40_layers14": lambda: (scenes.blob_scene(40, seed=17, tile=8, pad=1, liquidLayers=1, solidLayers=4), {}),
+})
+
+
+def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None):
+    prm = dict(sc.params, **ov)
+    fields, counts, valid = ref_classify.classify(sc.nx, sc.ny, sc.nz, sc.dx, sc.dt, prm, weight_field)
+    for kind in range(3):
+        for slot in range(7):
+            mine = np.asarray(fields_of(kind, slot)).astype(np.int64)
+            assert np.array_equal(fields[kind][slot], mine), f"{KINDS[kind]} slot {slot}: {np.count_nonzero(fields[kind][slot] != mine)} of {mine.size} entries differ from the reference classifier"
+    for k, v in counts.items():
+        if k == "regionCount" and not prm["doReduced"]:
+            continue
+        assert v == counts_of(k), f"{k}: reference classifier {v}, here {counts_of(k)}"
+    if valid_of is not None:
+        for a in range(3):
+            assert np.array_equal(valid[a], np.asarray(valid_of(a), dtype=np.float32)), f"valid faces axis {a}"
+    return counts
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_classification_matches_reference_code(built, case):
+    sc, ov = CASES[case]()
+    o = Oracle(sc, **ov).setup()
+    _, ovalid = (o.solve(), o.writeback())[1]
+    counts = _check(sc, ov, o.index_field, o.weight_field, o.count, lambda a: ovalid[a])
+    if case not in ("empty_air",):
+        assert counts["nCenter"] > 0
+
+
+@pytest.mark.parametrize("case", ["tiles8pad1_box40", "blob40_layers31", "blob_ragged_36x44x52", "blob40_notile", "blob33_uniform", "S2_beam_64_tile8_pad1"])
+def test_emulated_classification_matches_reference_code(built, case):
+    sc, ov = CASES[case]()
+    s = PolyStokesSolver.from_scene(sc, lib_path=parity.EMUL_LIB, **ov)
+    rc, vel, valid = s.step_scene(sc)
+    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a])
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(CASES) + ["S3_jet_128_tile16_pad2"])
+def test_gpu_classification_matches_reference_code(built, case):
+    """The CUDA classifier on ITS OWN weights against the reference classifier run on those weights."""
+    sc, ov = (scenes.scene_s3(128), {}) if case == "S3_jet_128_tile16_pad2" else CASES[case]()
+    s = PolyStokesSolver.from_scene(sc, **ov)
+    rc, vel, valid = s.step_scene(sc)
+    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a])
+    s.close()
