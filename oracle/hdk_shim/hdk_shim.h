@@ -341,6 +341,31 @@ public:
         for (int a = 0; a < 3; ++a) pos[a] = myOrig[a] + ((float)idx[a] + off[a]) * (mySize[a] / (float)cells[a]);
         return true;
     }
+    // SIM_RawField::getValue(pos) (closed source): trilinear sample; every position the reference asks for is
+    // a sample position of the same grid, so the index-space coordinates are snapped to multiples of 1/2 (fractions exactly 0 or
+    // 1/2); lerp along x, then y, then z as a + t (b - a) in the field's precision; reads outside follow the border mode.
+    T getValue(const UT_Vector3& pos) const {
+        const float off[3] = {(mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEY || mySample == SIM_SAMPLE_FACEZ || mySample == SIM_SAMPLE_EDGEYZ) ? 0.5f : 0.f,
+                              (mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEX || mySample == SIM_SAMPLE_FACEZ || mySample == SIM_SAMPLE_EDGEXZ) ? 0.5f : 0.f,
+                              (mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEX || mySample == SIM_SAMPLE_FACEY || mySample == SIM_SAMPLE_EDGEXY) ? 0.5f : 0.f};
+        int base[3]; T t[3];
+        for (int a = 0; a < 3; ++a) {
+            const double u = ((double)pos[a] - (double)myOrig[a]) / ((double)mySize[a] / (double)cells[a]) - (double)off[a];
+            const long long twice = std::llround(2. * u);
+            base[a] = (int)std::floor((double)twice / 2.);
+            t[a] = (T)(0.5 * (double)(twice - 2ll * base[a]));
+        }
+        T cz[2];
+        for (int dz = 0; dz < 2; ++dz) {
+            T cy[2];
+            for (int dy = 0; dy < 2; ++dy) {
+                const T c0 = arr.getValue(base[0], base[1] + dy, base[2] + dz), c1 = arr.getValue(base[0] + 1, base[1] + dy, base[2] + dz);
+                cy[dy] = c0 + t[0] * (c1 - c0);
+            }
+            cz[dz] = cy[0] + t[1] * (cy[1] - cy[0]);
+        }
+        return cz[0] + t[2] * (cz[1] - cz[0]);
+    }
     Array arr;
     SIM_FieldSample mySample = SIM_SAMPLE_CENTER;
     UT_Vector3 myOrig, mySize;

@@ -6,17 +6,18 @@
 // reference file:line it follows (paths relative to the reference checkout:
 // exec/HDK_PolyStokesSolver*.cpp = S*.cpp, lib/include/*.h).
 //
-// PINNING.  The reference ships no tests / golden vectors.  Its SOLVE STAGE (operator
-// apply Apply.h:102-179, CG pcg.h:268-340, BiCGSTAB fallback pcg.h:134-200) is header-only
-// code and IS compiled here from the reference's own files (oracle/ref_solve.cpp,
-// `make ref` -> oracle/_ref/libps_ref_solve.so, on the Eigen facade of oracle/eigen_facade
-// because the checkout's Eigen lacks Eigen/Core): ps_oracle_solve.cpp is checked against it
-// (tests/test_ref_solve.py, tests/golden `refcode_*`): same iteration counts, apply to 1e-16.
-// PARITY UNPINNED for everything before the solve -- weights, classifier, region algebra,
-// matrix blocks, assembly (exec/HDK_PolyStokesSolver*.cpp): those files need the HDK and
-// cannot be compiled, so that part of this restatement is pinned only by its analytic
-// known-answer tests (tests/test_oracle_kat.py).  Nothing in the product path
-// (polystokes_b200/) may include, link or call this code.
+// PINNING.  The reference ships no tests / golden vectors, but large parts of it ARE compiled here from its own files
+// (oracle/_ref, `make ref`; stand-ins oracle/eigen_facade for the incomplete Eigen checkout and oracle/hdk_shim for the HDK):
+//   * exec/HDK_PolyStokesSolver_Classifier.cpp           -> ps_oracle_classify.cpp is BIT-EXACT against it (labels, DOF indices,
+//     reduced indices, counts, valid faces; tests/test_ref_classify.py, 15 scenes)
+//   * exec/HDK_PolyStokesSolver_ConstructMatrixBlocks.cpp -> the matrix blocks / right-hand sides of ps_oracle_assemble.cpp are
+//     BIT-EQUAL (patterns incl. explicit zeros and values)
+//   * lib/include/pcg.h, ApplyPressureStressMatrix.h       -> ps_oracle_solve.cpp: same iteration counts, apply to 2e-16
+//     (tests/test_ref_solve.py, tests/golden `refcode_*`)
+// PARITY UNPINNED for what lives only in exec/HDK_PolyStokesSolver.cpp / _AssembleBlocks.cpp / _AssembleSystem.cpp: weights
+// (HDK-defined), centres of mass, least-squares fits, reduced mass / viscosity matrices, B^-1, assembly of b and of the explicit A,
+// velocity recovery.  Those are pinned only by the analytic known-answer tests (tests/test_oracle_kat.py).
+// Nothing in the product path (polystokes_b200/) may include, link or call this code.
 #pragma once
 #include <cstdint>
 #include <cstddef>

@@ -10,7 +10,10 @@
 // destructor, overwriteIndices / copyMaterialLabel (replace / copy one label value, S.cpp:1925-2005), setActiveLayerCells
 // (GENERICFLUID -> ACTIVEFLUID on a cell list, S.cpp:2022-2059) and findOccupiedIndexTiles (mark the tiles a cell list touches,
 // S.cpp:2061-2103).  The integration weights (HDK computeSDFWeightsSampled, closed source) are INPUTS here.
-// The call sequence of refcls_run is HDK_PolyStokes::solveGasSubclass, exec/HDK_PolyStokes.C:344-395.
+// Also compiled unmodified: exec/HDK_PolyStokesSolver_ConstructMatrixBlocks.cpp (constructMatrixBlocks / buildMatrixBlocksByTriplets:
+// M_c, M_c^-1, mu, mu^-1, G, D^T, JG, JD^T and the right-hand sides).  Its inputs from exec/HDK_PolyStokesSolver.cpp are passed in by
+// the caller: the region centres of mass (computeCenterOfMasses) and the basis evaluation buildConversionCoefficients (see below).
+// The call sequence is HDK_PolyStokes::solveGasSubclass, exec/HDK_PolyStokes.C:344-440.
 #include <cstring>
 #include "hdk_shim.h"
 #include <Eigen/Sparse>
@@ -90,6 +93,21 @@ void Solver::findOccupiedIndexTiles(UT_Array<bool>& isTileOccupiedList, const UT
     }
 }
 
+// getLocalDensity / getLocalViscosity (S.cpp:1914-1924) are one-line accessors: the constant density and the trilinear viscosity sample.
+fpreal Solver::getLocalDensity(UT_Vector3I) { return myConstantDensity; }
+fpreal Solver::getLocalViscosity(UT_Vector3 point) { return myViscosityFieldData->getValue(point); }
+// buildConversionCoefficients (S.cpp:2107-2149, the 26 basis functions evaluated at a face offset) is NOT retyped here: the caller
+// passes a function (tests: the oracle's orc_conversion_coefficients, which has its own analytic known-answer tests).
+typedef void (*refcls_coeff_fn)(const double* offset3, int axis, double* out26);
+static refcls_coeff_fn g_coeff = nullptr;
+ColumnVector Solver::buildConversionCoefficients(UT_Vector3T<SolveReal> offset, int axis) {
+    ColumnVector v;
+    double o[3] = {offset[0], offset[1], offset[2]}, c[REDUCED_DOF];
+    g_coeff(o, axis, c);
+    for (int i = 0; i < REDUCED_DOF; ++i) v(i) = c[i];
+    return v;
+}
+
 // ---- the node class: declared by the reference's HDK_PolyStokes.h, its bodies live in HDK_PolyStokes.C (HDK node plumbing) ----
 HDK_PolyStokes::HDK_PolyStokes(const SIM_DataFactory* factory) : GAS_SubSolver(factory) {}
 HDK_PolyStokes::~HDK_PolyStokes() {}
@@ -103,13 +121,28 @@ struct refcls_params {
     int32_t nx, ny, nz;
     double dx, dt;
     int32_t liquidLayers, solidLayers, doReducedRegions, doTile, tileSize, tilePadding;
+    double density;
 };
 
+struct RefCls {
+    SIM_VectorField velocity, collisionVelocity, validFaces;
+    SIM_ScalarField surface, collision, density, viscosity;
+    Node node;
+    Solver* S = nullptr;
+    ~RefCls() { delete S; }
+};
+
+static SIM_RawIndexField* index_field(Solver& S, int kind, int slot) {
+    SIM_RawIndexField* fields[3][7] = {
+        {&S.centerLabels, &S.faceXLabels, &S.faceYLabels, &S.faceZLabels, &S.edgeYZLabels, &S.edgeXZLabels, &S.edgeXYLabels},
+        {&S.centerActiveIndices, &S.faceXActiveIndices, &S.faceYActiveIndices, &S.faceZActiveIndices, &S.edgeYZActiveIndices, &S.edgeXZActiveIndices, &S.edgeXYActiveIndices},
+        {&S.centerReducedIndices, &S.faceXReducedIndices, &S.faceYReducedIndices, &S.faceZReducedIndices, &S.edgeYZReducedIndices, &S.edgeXZReducedIndices, &S.edgeXYReducedIndices}};
+    return fields[kind][slot];
+}
+
 // weights: 14 float arrays in the repository's slot order (0 centre, 1..3 faces x / y / z, 4..6 edges of axis 0 (YZ) / 1 (XZ) / 2 (XY)),
-// liquid first then fluid, each x-fastest with the slot's resolution.  out: 21 int64 arrays, [kind][slot] with kind 0 labels,
-// 1 active indices, 2 reduced indices.  counts[8]: nCenter, nFaceX, nFaceY, nFaceZ, nEdgeYZ, nEdgeXZ, nEdgeXY, regionCount.
-// valid (may be NULL): 3 float arrays (face x / y / z) written by buildValidFaces.
-int refcls_run(const refcls_params* P, const float* const* weights, int64_t* const* out, int64_t* counts, float* const* valid) {
+// liquid first then fluid, each x-fastest with the slot's resolution.  Runs the classification; returns a handle.
+void* refcls_create(const refcls_params* P, const float* const* weights) {
     std::map<std::string, double>& prm = hdk_shim::params();
     prm.clear();
     prm["matrixSetup"] = 0; prm["solverType"] = 0; prm["useInputSurfaceWeights"] = 0; prm["useInputCollisionWeights"] = 0;
@@ -118,16 +151,15 @@ int refcls_run(const refcls_params* P, const float* const* weights, int64_t* con
     prm[SIM_NAME_TOLERANCE] = 1e-3; prm["maxSolverIterations"] = 1; prm["useWarmStart"] = 0; prm["exportMatrices"] = 0; prm["exportComponentMatrices"] = 0;
     prm["exportStats"] = 0; prm["doSolve"] = 0; prm["keepNonConvergedResults"] = 0;
 
+    RefCls* H = new RefCls;
     const UT_Vector3 orig(0.f, 0.f, 0.f), size((float)(P->nx * P->dx), (float)(P->ny * P->dx), (float)(P->nz * P->dx));
-    SIM_VectorField velocity, collisionVelocity, validFaces;
-    SIM_ScalarField surface, collision, density, viscosity;
     const SIM_FieldSample faceSample[3] = {SIM_SAMPLE_FACEX, SIM_SAMPLE_FACEY, SIM_SAMPLE_FACEZ};
     for (int a = 0; a < 3; ++a)
-        for (SIM_VectorField* v : {&velocity, &collisionVelocity, &validFaces}) v->getField(a)->init(faceSample[a], orig, size, P->nx, P->ny, P->nz);
-    for (SIM_ScalarField* s : {&surface, &collision, &density, &viscosity}) s->getField()->init(SIM_SAMPLE_CENTER, orig, size, P->nx, P->ny, P->nz);
+        for (SIM_VectorField* v : {&H->velocity, &H->collisionVelocity, &H->validFaces}) v->getField(a)->init(faceSample[a], orig, size, P->nx, P->ny, P->nz);
+    for (SIM_ScalarField* s : {&H->surface, &H->collision, &H->density, &H->viscosity}) s->getField()->init(SIM_SAMPLE_CENTER, orig, size, P->nx, P->ny, P->nz);
 
-    Node node;
-    Solver S(node, P->dx, P->dt, &velocity, &collisionVelocity, &surface, nullptr, &collision, nullptr, &density, 1000., &viscosity);
+    H->S = new Solver(H->node, P->dx, P->dt, &H->velocity, &H->collisionVelocity, &H->surface, nullptr, &H->collision, nullptr, &H->density, P->density, &H->viscosity);
+    Solver& S = *H->S;
 
     // buildIntegrationWeightsAlt (S.cpp:238-287) with the weights supplied by the caller
     SIM_RawField* liquid[7] = {&S.centerLiquidWeights, &S.faceXLiquidWeights, &S.faceYLiquidWeights, &S.faceZLiquidWeights, &S.edgeYZLiquidWeights, &S.edgeXZLiquidWeights, &S.edgeXYLiquidWeights};
@@ -154,23 +186,69 @@ int refcls_run(const refcls_params* P, const float* const* weights, int64_t* con
     S.constructCenterActiveIndices();
     S.constructFacesActiveIndices();
     S.constructEdgesActiveIndices();
+    return H;
+}
+void refcls_destroy(void* hv) { delete (RefCls*)hv; }
 
-    SIM_RawIndexField* fields[3][7] = {
-        {&S.centerLabels, &S.faceXLabels, &S.faceYLabels, &S.faceZLabels, &S.edgeYZLabels, &S.edgeXZLabels, &S.edgeXYLabels},
-        {&S.centerActiveIndices, &S.faceXActiveIndices, &S.faceYActiveIndices, &S.faceZActiveIndices, &S.edgeYZActiveIndices, &S.edgeXZActiveIndices, &S.edgeXYActiveIndices},
-        {&S.centerReducedIndices, &S.faceXReducedIndices, &S.faceYReducedIndices, &S.faceZReducedIndices, &S.edgeYZReducedIndices, &S.edgeXZReducedIndices, &S.edgeXYReducedIndices}};
+// out: 21 int64 arrays, [kind][slot] with kind 0 labels, 1 active indices, 2 reduced indices.  counts[8]: nCenter, nFaceX, nFaceY, nFaceZ,
+// nEdgeYZ, nEdgeXZ, nEdgeXY, regionCount.  valid (may be NULL): 3 float arrays (face x / y / z) written by buildValidFaces.
+void refcls_results(void* hv, int64_t* const* out, int64_t* counts, float* const* valid) {
+    RefCls* H = (RefCls*)hv; Solver& S = *H->S;
     for (int kind = 0; kind < 3; ++kind)
         for (int slot = 0; slot < 7; ++slot) {
-            const UT_VoxelArrayI& a = *fields[kind][slot]->field();
+            const UT_VoxelArrayI& a = *index_field(S, kind, slot)->field();
             for (size_t i = 0; i < a.d.size(); ++i) out[kind * 7 + slot][i] = (int64_t)a.d[i];
         }
     counts[0] = S.nCenter; counts[1] = S.nFaceX; counts[2] = S.nFaceY; counts[3] = S.nFaceZ; counts[4] = S.nEdgeYZ; counts[5] = S.nEdgeXZ; counts[6] = S.nEdgeXY;
     counts[7] = S.myInteriorRegionCount;
     if (valid) {
-        S.buildValidFaces(validFaces);      // exec/HDK_PolyStokes.C:562-570
-        for (int a = 0; a < 3; ++a) { const UT_VoxelArrayF& v = *validFaces.getField(a)->field(); memcpy(valid[a], v.d.data(), v.d.size() * sizeof(float)); }
+        S.buildValidFaces(H->validFaces);      // exec/HDK_PolyStokes.C:562-570
+        for (int a = 0; a < 3; ++a) { const UT_VoxelArrayF& v = *H->validFaces.getField(a)->field(); memcpy(valid[a], v.d.data(), v.d.size() * sizeof(float)); }
     }
+}
+
+// constructMatrixBlocks (exec/HDK_PolyStokes.C:432-435) on the classified grid.  vel / colvel: 3 face-sampled float arrays each,
+// viscosity: centre-sampled float array, com: regionCount x 3 doubles (computeCenterOfMasses), coeff: see buildConversionCoefficients above.
+int refcls_construct_blocks(void* hv, const float* const* vel, const float* const* colvel, const float* viscosity, const double* com, refcls_coeff_fn coeff) {
+    RefCls* H = (RefCls*)hv; Solver& S = *H->S;
+    for (int a = 0; a < 3; ++a) {
+        UT_VoxelArrayF& v = *H->velocity.getField(a)->fieldNC(); memcpy(v.d.data(), vel[a], v.d.size() * sizeof(float)); v.expandAllTiles();
+        UT_VoxelArrayF& c = *H->collisionVelocity.getField(a)->fieldNC(); memcpy(c.d.data(), colvel[a], c.d.size() * sizeof(float)); c.expandAllTiles();
+    }
+    UT_VoxelArrayF& mu = *H->viscosity.getField()->fieldNC(); memcpy(mu.d.data(), viscosity, mu.d.size() * sizeof(float)); mu.expandAllTiles();
+    S.reducedRegionCOM.setSize(S.myInteriorRegionCount);
+    for (exint r = 0; r < S.myInteriorRegionCount; ++r) S.reducedRegionCOM[r] = UT_Vector3T<SolveReal>(com[3 * r], com[3 * r + 1], com[3 * r + 2]);
+    g_coeff = coeff;
+    S.constructMatrixBlocks();
     return 0;
+}
+
+static const SparseMatrix* block(Solver& S, const char* name) {
+    const std::string n(name);
+    if (n == "Mc") return &S.Mc_Matrix; if (n == "McInv") return &S.McInv_Matrix; if (n == "u") return &S.u_Matrix; if (n == "uInv") return &S.uInv_Matrix;
+    if (n == "G") return &S.G_Matrix; if (n == "Dt") return &S.Dt_Matrix; if (n == "JG") return &S.JG_Matrix; if (n == "JDt") return &S.JDt_Matrix;
+    if (n == "oldActiveVs") return &S.oldActiveVs;
+    return nullptr;
+}
+int refcls_csr_dims(void* hv, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz) {
+    const SparseMatrix* m = block(*((RefCls*)hv)->S, name);
+    if (!m) return -1;
+    *rows = m->rows(); *cols = m->cols(); *nnz = m->nonZeros();
+    return 0;
+}
+int refcls_csr_copy(void* hv, const char* name, int64_t* ptr, int32_t* idx, double* val) {
+    const SparseMatrix* m = block(*((RefCls*)hv)->S, name);
+    if (!m) return -1;
+    for (Eigen::Index r = 0; r <= m->outerSize(); ++r) ptr[r] = m->outerIndexPtr()[r];
+    for (Eigen::Index k = 0; k < m->nonZeros(); ++k) { idx[k] = m->innerIndexPtr()[k]; val[k] = m->valuePtr()[k]; }
+    return 0;
+}
+int64_t refcls_vector(void* hv, const char* name, double* out) {
+    Solver& S = *((RefCls*)hv)->S; const std::string n(name);
+    const Vector* v = n == "activeRHS" ? &S.activeRHSVector : n == "pressureRHS" ? &S.pressureRHSVector : n == "stressRHS" ? &S.stressRHSVector : nullptr;
+    if (!v) return -1;
+    if (out) for (Eigen::Index i = 0; i < v->size(); ++i) out[i] = (*v)(i);
+    return (int64_t)v->size();
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from polystokes_b200 import scenes  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
-from oracle import ref_solve  # noqa: E402
+from oracle import ref_solve, ref_classify  # noqa: E402
 
 CASES = {
     "blob20_tile8_pad1": lambda: scenes.blob_scene(20, seed=21, tile=8, pad=1),
@@ -26,6 +26,9 @@ CASES = {
 
 def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+REF_BLOCKS = ("Mc", "McInv", "u", "uInv", "G", "Dt", "JG", "JDt")
 
 
 def probe_vector(n):
@@ -45,6 +48,19 @@ def collect(sc):
         out[f"{m}_pattern_sha256"] = np.frombuffer(bytes.fromhex(digest(ptr) + digest(idx)), dtype=np.uint8)
         out[f"{m}_values"] = val
     out["b"] = o.vector("b")
+    if ref_classify.available():
+        # outputs of the reference's own classifier + constructMatrixBlocks (oracle/_ref/libps_ref_classify.so) on the oracle's weights
+        R = ref_classify.RefClassifier(sc.nx, sc.ny, sc.nz, sc.dx, sc.dt, sc.params, o.weight_field, density=sc.density)
+        fields, counts, valid = R.results()
+        out["refcode_counts"] = np.array([counts[k] for k in ref_classify.COUNT_NAMES])
+        out["refcode_fields_sha256"] = np.array([digest(np.ascontiguousarray(fields[kind][slot], dtype=np.int64)) for kind in range(3) for slot in range(7)])
+        out["refcode_valid_sha256"] = np.array([digest(np.ascontiguousarray(v, dtype=np.float32)) for v in valid])
+        R.construct_blocks(sc.vel, sc.colvel, sc.viscosity, o.vector("com").reshape(-1, 3), ref_classify.oracle_coeff_fn())
+        for m in REF_BLOCKS:
+            shape, ptr, idx, val = R.csr(m)
+            out[f"refcode_{m}_pattern_sha256"] = np.array([digest(ptr.astype(np.int64)) + digest(idx.astype(np.int32))])
+            out[f"refcode_{m}_values_sha256"] = np.array([digest(val.astype(np.float64))])
+        R.close()
     if ref_solve.available():
         R = ref_solve.RefSolve(o.csr, sc.dt)
         out["refcode_probe"] = probe_vector(R.n)

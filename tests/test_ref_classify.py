@@ -1,13 +1,17 @@
-"""The reference's OWN classifier -- exec/HDK_PolyStokesSolver_Classifier.cpp compiled unmodified from /root/reference into
-oracle/_ref/libps_ref_classify.so (oracle/Makefile `ref`; HDK stand-in oracle/hdk_shim, harness oracle/ref_classify.cpp) -- against
+"""The reference's OWN classifier and matrix-block construction -- exec/HDK_PolyStokesSolver_Classifier.cpp and
+exec/HDK_PolyStokesSolver_ConstructMatrixBlocks.cpp compiled unmodified from /root/reference into oracle/_ref/libps_ref_classify.so
+(oracle/Makefile `ref`; HDK stand-in oracle/hdk_shim, Eigen facade oracle/eigen_facade, harness oracle/ref_classify.cpp) -- against
 (a) the oracle's restatement and (b) the product, on the same integration weights.  Labels, the active (DOF) indices, the reduced
-region indices of all 7 sample slots, the counts and the valid-face fields must be BIT-EXACT: this is what pins SURVEY.md section 8a
-rows C1-C12 to reference CODE (on the HDK semantics of BASELINE.md section 3) instead of to a reading of it.
+region indices of all 7 sample slots, the counts and the valid-face fields must be BIT-EXACT, and so must the sparsity patterns
+(explicit zeros included) of M_c, M_c^-1, mu, mu^-1, G, D^T, JG, JD^T and the three right-hand sides; values bit-equal for the oracle.
+This is what pins SURVEY.md section 8a rows C1-C12 and M1-M9 to reference CODE (on the HDK semantics of BASELINE.md section 3) instead
+of to a reading of it.
 Skipped when the library has not been built (no /root/reference at build time)."""
 import numpy as np
 import pytest
 
 import parity
+from oracle import oracle as orc
 from oracle import ref_classify
 from oracle.oracle import Oracle
 from polystokes_b200 import PolyStokesSolver, scenes
@@ -27,9 +31,27 @@ CASES.update({
 })
 
 
-def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None):
+BLOCKS = ("Mc", "McInv", "u", "uInv", "G", "Dt", "JG", "JDt")
+RHS = ("activeRHS", "pressureRHS", "stressRHS")
+
+
+def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None, csr_of=None, vector_of=None, exact_values=BLOCKS):
     prm = dict(sc.params, **ov)
-    fields, counts, valid = ref_classify.classify(sc.nx, sc.ny, sc.nz, sc.dx, sc.dt, prm, weight_field)
+    R = ref_classify.RefClassifier(sc.nx, sc.ny, sc.nz, sc.dx, sc.dt, prm, weight_field, density=sc.density)
+    fields, counts, valid = R.results()
+    if csr_of is not None and counts["nCenter"] > 0:
+        # constructMatrixBlocks of the reference on its own classification; centres of mass and basis evaluation supplied (ref_classify.cpp)
+        R.construct_blocks(sc.vel, sc.colvel, sc.viscosity, vector_of("com").reshape(-1, 3), ref_classify.oracle_coeff_fn())
+        for m in BLOCKS:
+            (sr, pr, ir, vr), (sm, pm, im, vm) = R.csr(m), csr_of(m)
+            assert tuple(sr) == tuple(sm), f"{m}: shape {sm} vs the reference code's {sr}"
+            assert np.array_equal(pr, pm) and np.array_equal(ir, im), f"{m}: sparsity pattern differs from the reference code's"
+            if m in exact_values:
+                assert np.array_equal(vr, vm), f"{m}: values not bit-equal to the reference code's (rel {parity.rel(vr, vm):.2e})"
+            else:
+                assert parity.rel(vr, vm) <= 1e-8, f"{m}: values rel {parity.rel(vr, vm):.2e}"
+        for v in RHS:
+            assert np.array_equal(R.vector(v), vector_of(v)), f"{v} not bit-equal to the reference code's"
     for kind in range(3):
         for slot in range(7):
             mine = np.asarray(fields_of(kind, slot)).astype(np.int64)
@@ -48,8 +70,8 @@ def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None):
 def test_oracle_classification_matches_reference_code(built, case):
     sc, ov = CASES[case]()
     o = Oracle(sc, **ov).setup()
-    _, ovalid = (o.solve(), o.writeback())[1]
-    counts = _check(sc, ov, o.index_field, o.weight_field, o.count, lambda a: ovalid[a])
+    _, ovalid = o.writeback()        # buildValidFaces only needs the labels: no solve
+    counts = _check(sc, ov, o.index_field, o.weight_field, o.count, lambda a: ovalid[a], o.csr, o.vector)
     if case not in ("empty_air",):
         assert counts["nCenter"] > 0
 
@@ -59,7 +81,7 @@ def test_emulated_classification_matches_reference_code(built, case):
     sc, ov = CASES[case]()
     s = PolyStokesSolver.from_scene(sc, lib_path=parity.EMUL_LIB, **ov)
     rc, vel, valid = s.step_scene(sc)
-    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a])
+    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS)
     s.close()
 
 
@@ -70,5 +92,5 @@ def test_gpu_classification_matches_reference_code(built, case):
     sc, ov = (scenes.scene_s3(128), {}) if case == "S3_jet_128_tile16_pad2" else CASES[case]()
     s = PolyStokesSolver.from_scene(sc, **ov)
     rc, vel, valid = s.step_scene(sc)
-    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a])
+    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS)
     s.close()
