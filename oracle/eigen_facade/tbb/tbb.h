@@ -19,3 +19,16 @@ private:
 };
 template <class R, class F> inline void parallel_for(const R& r, const F& f) { if (!r.empty()) f(r); }
 }
+#include <vector>
+namespace tbb {
+// one "thread": local() is the single instance, combine_each visits it once
+template <class T>
+class enumerable_thread_specific {
+public:
+    T& local() { return v; }
+    template <class F> void combine_each(F f) const { f(v); }
+    void clear() { v = T(); }
+private:
+    T v;
+};
+}

@@ -12,11 +12,13 @@
 //     reduced indices, counts, valid faces; tests/test_ref_classify.py, 15 scenes)
 //   * exec/HDK_PolyStokesSolver_ConstructMatrixBlocks.cpp -> the matrix blocks / right-hand sides of ps_oracle_assemble.cpp are
 //     BIT-EQUAL (patterns incl. explicit zeros and values)
+//   * exec/HDK_PolyStokesSolver_AssembleBlocks.cpp + _AssembleSystem.cpp -> M_r, B, B^-1, reduced rhs BIT-EQUAL, b to 2e-15, explicit A
+//     pattern bit-exact / values 4e-16 (on the oracle's region matrices)
 //   * lib/include/pcg.h, ApplyPressureStressMatrix.h       -> ps_oracle_solve.cpp: same iteration counts, apply to 2e-16
 //     (tests/test_ref_solve.py, tests/golden `refcode_*`)
-// PARITY UNPINNED for what lives only in exec/HDK_PolyStokesSolver.cpp / _AssembleBlocks.cpp / _AssembleSystem.cpp: weights
-// (HDK-defined), centres of mass, least-squares fits, reduced mass / viscosity matrices, B^-1, assembly of b and of the explicit A,
-// velocity recovery.  Those are pinned only by the analytic known-answer tests (tests/test_oracle_kat.py).
+// PARITY UNPINNED for what lives only in exec/HDK_PolyStokesSolver.cpp: weights (HDK-defined), centres of mass, least-squares fits,
+// reduced mass / viscosity matrices, the basis evaluation, velocity recovery / write-back.  Those are pinned only by the analytic
+// known-answer tests (tests/test_oracle_kat.py).
 // Nothing in the product path (polystokes_b200/) may include, link or call this code.
 #pragma once
 #include <cstdint>

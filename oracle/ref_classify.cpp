@@ -13,7 +13,10 @@
 // Also compiled unmodified: exec/HDK_PolyStokesSolver_ConstructMatrixBlocks.cpp (constructMatrixBlocks / buildMatrixBlocksByTriplets:
 // M_c, M_c^-1, mu, mu^-1, G, D^T, JG, JD^T and the right-hand sides).  Its inputs from exec/HDK_PolyStokesSolver.cpp are passed in by
 // the caller: the region centres of mass (computeCenterOfMasses) and the basis evaluation buildConversionCoefficients (see below).
-// The call sequence is HDK_PolyStokes::solveGasSubclass, exec/HDK_PolyStokes.C:344-440.
+// And exec/HDK_PolyStokesSolver_AssembleBlocks.cpp + _AssembleSystem.cpp (assemble(): M_r, B, B^-1, reduced right-hand side, b, and the
+// explicit A of assembleSystemPressureStress); their inputs from the region algebra of exec/HDK_PolyStokesSolver.cpp (per-region mass /
+// viscosity matrices, best-fit vectors) are passed in by the caller.
+// The call sequence is HDK_PolyStokes::solveGasSubclass, exec/HDK_PolyStokes.C:344-446.
 #include <cstring>
 #include "hdk_shim.h"
 #include <Eigen/Sparse>
@@ -122,6 +125,7 @@ struct refcls_params {
     double dx, dt;
     int32_t liquidLayers, solidLayers, doReducedRegions, doTile, tileSize, tilePadding;
     double density;
+    int32_t solverType;        // units.h:76-94: 0 PCG_MATRIX_VECTOR_PRODUCTS (factored), 1 EIGEN (explicit A)
 };
 
 struct RefCls {
@@ -145,7 +149,7 @@ static SIM_RawIndexField* index_field(Solver& S, int kind, int slot) {
 void* refcls_create(const refcls_params* P, const float* const* weights) {
     std::map<std::string, double>& prm = hdk_shim::params();
     prm.clear();
-    prm["matrixSetup"] = 0; prm["solverType"] = 0; prm["useInputSurfaceWeights"] = 0; prm["useInputCollisionWeights"] = 0;
+    prm["matrixSetup"] = 0; prm["solverType"] = P->solverType; prm["useInputSurfaceWeights"] = 0; prm["useInputCollisionWeights"] = 0;
     prm["minDensity"] = 0; prm["maxDensity"] = 1e30; prm["activeLiquidBoundaryLayerSize"] = P->liquidLayers; prm["activeSolidBoundaryLayerSize"] = P->solidLayers;
     prm["doReducedRegions"] = P->doReducedRegions; prm["doTile"] = P->doTile; prm["tileSize"] = P->tileSize; prm["tilePadding"] = P->tilePadding;
     prm[SIM_NAME_TOLERANCE] = 1e-3; prm["maxSolverIterations"] = 1; prm["useWarmStart"] = 0; prm["exportMatrices"] = 0; prm["exportComponentMatrices"] = 0;
@@ -223,8 +227,32 @@ int refcls_construct_blocks(void* hv, const float* const* vel, const float* cons
     return 0;
 }
 
+// assemble() (exec/HDK_PolyStokes.C:436-446 with initializeGuessVectors, S.cpp:512-519) from exec/HDK_PolyStokesSolver_AssembleSystem.cpp and
+// _AssembleBlocks.cpp: M_r, B = M_r / dt + 2 JD^T mu D J^T, B^-1, the reduced right-hand side, b, and for solverType EIGEN the explicit A.
+// Inputs that exec/HDK_PolyStokesSolver.cpp would have computed (region algebra D3-D5, not compiled): per region the 26 x 26 mass and
+// viscosity matrices (row-major) and the 26 best-fit coefficients.
+int refcls_assemble(void* hv, const double* massDense, const double* viscDense, const double* bestFit) {
+    RefCls* H = (RefCls*)hv; Solver& S = *H->S;
+    const exint R = S.myInteriorRegionCount;
+    S.reducedMassMatrices.setSize(R); S.reducedViscosityMatrices.setSize(R); S.reducedRegionBestFitVectors.setSize(R);
+    for (exint r = 0; r < R; ++r) {
+        for (int i = 0; i < REDUCED_DOF; ++i) {
+            for (int j = 0; j < REDUCED_DOF; ++j) {
+                S.reducedMassMatrices[r](i, j) = massDense[(r * REDUCED_DOF + i) * REDUCED_DOF + j];
+                S.reducedViscosityMatrices[r](i, j) = viscDense[(r * REDUCED_DOF + i) * REDUCED_DOF + j];
+            }
+            S.reducedRegionBestFitVectors[r](i) = bestFit[r * REDUCED_DOF + i];
+        }
+    }
+    S.activeGuessVector = Vector::Zero(S.nActiveVs); S.reducedGuessVector = Vector::Zero(S.nReducedVs);
+    S.pressureGuessVector = Vector::Zero(S.nPressures); S.stressGuessVector = Vector::Zero(S.nStresses);
+    S.assemble();
+    return 0;
+}
+
 static const SparseMatrix* block(Solver& S, const char* name) {
     const std::string n(name);
+    if (n == "Mr") return &S.Mr_Matrix; if (n == "B") return &S.Mr_plus_2JDtuDJ_Matrix; if (n == "BInv") return &S.Inv_Mr_plus_2JDtuDJ_Matrix; if (n == "A") return &S.A;
     if (n == "Mc") return &S.Mc_Matrix; if (n == "McInv") return &S.McInv_Matrix; if (n == "u") return &S.u_Matrix; if (n == "uInv") return &S.uInv_Matrix;
     if (n == "G") return &S.G_Matrix; if (n == "Dt") return &S.Dt_Matrix; if (n == "JG") return &S.JG_Matrix; if (n == "JDt") return &S.JDt_Matrix;
     if (n == "oldActiveVs") return &S.oldActiveVs;
@@ -245,7 +273,8 @@ int refcls_csr_copy(void* hv, const char* name, int64_t* ptr, int32_t* idx, doub
 }
 int64_t refcls_vector(void* hv, const char* name, double* out) {
     Solver& S = *((RefCls*)hv)->S; const std::string n(name);
-    const Vector* v = n == "activeRHS" ? &S.activeRHSVector : n == "pressureRHS" ? &S.pressureRHSVector : n == "stressRHS" ? &S.stressRHSVector : nullptr;
+    const Vector* v = n == "activeRHS" ? &S.activeRHSVector : n == "pressureRHS" ? &S.pressureRHSVector : n == "stressRHS" ? &S.stressRHSVector :
+                      n == "reducedRHS" ? &S.reducedRHSVector : n == "b" ? &S.b : nullptr;
     if (!v) return -1;
     if (out) for (Eigen::Index i = 0; i < v->size(); ++i) out[i] = (*v)(i);
     return (int64_t)v->size();

@@ -16,7 +16,7 @@ COEFF_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_doubl
 class _Params(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("dx", C.c_double), ("dt", C.c_double), ("liquidLayers", C.c_int32),
                 ("solidLayers", C.c_int32), ("doReducedRegions", C.c_int32), ("doTile", C.c_int32), ("tileSize", C.c_int32), ("tilePadding", C.c_int32),
-                ("density", C.c_double)]
+                ("density", C.c_double), ("solverType", C.c_int32)]
 
 
 def available():
@@ -40,6 +40,7 @@ def lib():
         L.refcls_destroy.argtypes = [C.c_void_p]
         L.refcls_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refcls_construct_blocks.restype = C.c_int; L.refcls_construct_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, COEFF_FN]
+        L.refcls_assemble.restype = C.c_int; L.refcls_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refcls_csr_dims.restype = C.c_int; L.refcls_csr_dims.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.refcls_csr_copy.restype = C.c_int; L.refcls_csr_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refcls_vector.restype = C.c_int64; L.refcls_vector.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
@@ -53,13 +54,13 @@ class RefClassifier:
     `weight_field(liquid, slot)` returns the float32 weight array of a slot (liquid = 1: liquid weights, 0: fluid = non-solid
     weights), e.g. Oracle.weight_field or PolyStokesSolver.weight_field.  `params`: the scene's parameter dict."""
 
-    def __init__(self, nx, ny, nz, dx, dt, params, weight_field, density=1000.0):
+    def __init__(self, nx, ny, nz, dx, dt, params, weight_field, density=1000.0, solver_type=0):
         self.nx, self.ny, self.nz = nx, ny, nz
         W = [np.ascontiguousarray(weight_field(liq, slot), dtype=np.float32) for liq in (1, 0) for slot in range(7)]
         for i, w in enumerate(W):
             assert w.shape == slot_shape(i % 7, nx, ny, nz), (i, w.shape)
         p = _Params(nx, ny, nz, float(dx), float(dt), int(params["liquidLayers"]), int(params["solidLayers"]), int(params["doReduced"]), int(params["doTile"]),
-                    int(params["tileSize"]), int(params["tilePadding"]), float(density))
+                    int(params["tileSize"]), int(params["tilePadding"]), float(density), int(solver_type))
         wp = (C.c_void_p * 14)(*[w.ctypes.data for w in W])
         self.h = lib().refcls_create(C.byref(p), wp)
         if not self.h:
@@ -102,6 +103,15 @@ class RefClassifier:
         rc = lib().refcls_construct_blocks(self.h, vp, cp, keep[6].ctypes.data, com.ctypes.data if com.size else None, self._cb)
         if rc != 0:
             raise RuntimeError(f"refcls_construct_blocks returned {rc}")
+
+    def assemble(self, mass_dense, visc_dense, best_fit):
+        """assemble() (AssembleSystem.cpp / AssembleBlocks.cpp) after construct_blocks.  mass_dense / visc_dense: (R, 26, 26) row-major,
+        best_fit: (R, 26) -- the region algebra of exec/HDK_PolyStokesSolver.cpp, supplied by the caller."""
+        m = np.ascontiguousarray(mass_dense, dtype=np.float64).reshape(-1); v = np.ascontiguousarray(visc_dense, dtype=np.float64).reshape(-1)
+        f = np.ascontiguousarray(best_fit, dtype=np.float64).reshape(-1)
+        rc = lib().refcls_assemble(self.h, m.ctypes.data if m.size else None, v.ctypes.data if v.size else None, f.ctypes.data if f.size else None)
+        if rc != 0:
+            raise RuntimeError(f"refcls_assemble returned {rc}")
 
     def csr(self, name):
         r, c, n = C.c_int64(), C.c_int64(), C.c_int64()

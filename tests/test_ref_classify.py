@@ -35,7 +35,7 @@ BLOCKS = ("Mc", "McInv", "u", "uInv", "G", "Dt", "JG", "JDt")
 RHS = ("activeRHS", "pressureRHS", "stressRHS")
 
 
-def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None, csr_of=None, vector_of=None, exact_values=BLOCKS):
+def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None, csr_of=None, vector_of=None, exact_values=BLOCKS, asm_tol=1e-13):
     prm = dict(sc.params, **ov)
     R = ref_classify.RefClassifier(sc.nx, sc.ny, sc.nz, sc.dx, sc.dt, prm, weight_field, density=sc.density)
     fields, counts, valid = R.results()
@@ -52,6 +52,14 @@ def _check(sc, ov, fields_of, weight_field, counts_of, valid_of=None, csr_of=Non
                 assert parity.rel(vr, vm) <= 1e-8, f"{m}: values rel {parity.rel(vr, vm):.2e}"
         for v in RHS:
             assert np.array_equal(R.vector(v), vector_of(v)), f"{v} not bit-equal to the reference code's"
+        # assemble() of the reference (AssembleBlocks.cpp + AssembleSystem.cpp) on the caller's region matrices (D3-D5 are not compiled)
+        R.assemble(vector_of("MrDense"), vector_of("ViscDense"), vector_of("bestFit"))
+        for m in ("Mr", "B", "BInv"):
+            (sr, pr, ir, vr), (sm, pm, im, vm) = R.csr(m), csr_of(m)
+            assert tuple(sr) == tuple(sm) and np.array_equal(pr, pm) and np.array_equal(ir, im), f"{m}: pattern differs from the reference code's"
+            assert parity.rel(vr, vm) <= asm_tol, f"{m}: values rel {parity.rel(vr, vm):.2e} vs the reference code's"
+        assert parity.rel(R.vector("reducedRHS"), vector_of("reducedRHS")) <= asm_tol
+        assert parity.rel(R.vector("b"), vector_of("b")) <= max(asm_tol, 1e-12), f"b rel {parity.rel(R.vector('b'), vector_of('b')):.2e} vs the reference code's"
     for kind in range(3):
         for slot in range(7):
             mine = np.asarray(fields_of(kind, slot)).astype(np.int64)
@@ -76,12 +84,54 @@ def test_oracle_classification_matches_reference_code(built, case):
         assert counts["nCenter"] > 0
 
 
+EXPLICIT = {"blob32_tile8": lambda: scenes.blob_scene(32, seed=6, tile=8, pad=1, solverType=1), "box20_uniform": lambda: scenes.box_scene(20, doReduced=0, solverType=1),
+            "blob24_notile": lambda: scenes.blob_scene(24, seed=8, doTile=0, solverType=1)}
+
+
+def _explicit_A(sc, weight_field, csr_of, vector_of, tol):
+    """assembleSystemPressureStress (S_AS:351-430, solverType EIGEN): the explicit A from the reference's own sparse triple products."""
+    R = ref_classify.RefClassifier(sc.nx, sc.ny, sc.nz, sc.dx, sc.dt, sc.params, weight_field, density=sc.density, solver_type=1)
+    R.construct_blocks(sc.vel, sc.colvel, sc.viscosity, vector_of("com").reshape(-1, 3), ref_classify.oracle_coeff_fn())
+    R.assemble(vector_of("MrDense"), vector_of("ViscDense"), vector_of("bestFit"))
+    (sr, pr, ir, vr), (sm, pm, im, vm) = R.csr("A"), csr_of("A")
+    assert tuple(sr) == tuple(sm) and np.array_equal(pr, pm) and np.array_equal(ir, im), "explicit A: sparsity pattern (explicit zeros included) differs from the reference code's"
+    assert parity.rel(vr, vm) <= tol, f"explicit A values rel {parity.rel(vr, vm):.2e}"
+    assert parity.rel(R.vector("b"), vector_of("b")) <= max(tol, 1e-12)
+
+
+@pytest.mark.parametrize("case", list(EXPLICIT))
+def test_oracle_explicit_A_matches_reference_code(built, case):
+    sc = EXPLICIT[case]()
+    o = Oracle(sc).setup()
+    o.assemble_explicit_A()
+    _explicit_A(sc, o.weight_field, o.csr, o.vector, 1e-13)
+
+
+@pytest.mark.parametrize("case", list(EXPLICIT))
+def test_emulated_explicit_A_matches_reference_code(built, case):
+    sc = EXPLICIT[case]()
+    s = PolyStokesSolver.from_scene(sc, lib_path=parity.EMUL_LIB)
+    s.setup_scene(sc)
+    _explicit_A(sc, s.weight_field, s.csr, s.vector, 1e-9)
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(EXPLICIT))
+def test_gpu_explicit_A_matches_reference_code(built, case):
+    sc = EXPLICIT[case]()
+    s = PolyStokesSolver.from_scene(sc)
+    s.setup_scene(sc)
+    _explicit_A(sc, s.weight_field, s.csr, s.vector, 1e-9)
+    s.close()
+
+
 @pytest.mark.parametrize("case", ["tiles8pad1_box40", "blob40_layers31", "blob_ragged_36x44x52", "blob40_notile", "blob33_uniform", "S2_beam_64_tile8_pad1"])
 def test_emulated_classification_matches_reference_code(built, case):
     sc, ov = CASES[case]()
     s = PolyStokesSolver.from_scene(sc, lib_path=parity.EMUL_LIB, **ov)
     rc, vel, valid = s.step_scene(sc)
-    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS)
+    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS, asm_tol=1e-9)
     s.close()
 
 
@@ -92,5 +142,5 @@ def test_gpu_classification_matches_reference_code(built, case):
     sc, ov = (scenes.scene_s3(128), {}) if case == "S3_jet_128_tile16_pad2" else CASES[case]()
     s = PolyStokesSolver.from_scene(sc, **ov)
     rc, vel, valid = s.step_scene(sc)
-    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS)
+    _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS, asm_tol=1e-9)
     s.close()
