@@ -371,7 +371,44 @@ public:
     UT_Vector3 myOrig, mySize;
     int cells[3] = {0, 0, 0};
 };
-class SIM_RawField : public SIM_RawFieldT<fpreal32> {};
+class SIM_RawField : public SIM_RawFieldT<fpreal32> {
+public:
+    // SIM_RawField::computeSDFWeightsSampled (closed source; semantics DEFINED in BASELINE.md section 3): weight of a sample =
+    // (1/8) * #{2 x 2 x 2 sub-sample points at +-1/4 voxel around the sample position where the trilinearly interpolated SDF is < 0}.
+    // The five-argument form is the reference's "fluid" (non-solid) weight, S.cpp:322-323: 1 in fluid, 0 in solid (S_Cls:106-107),
+    // i.e. the test is "outside the collision SDF" (>= 0).  Interpolation fractions are exactly 1/4 or 3/4; the trilinear sum is
+    // evaluated in double, where every product is exact.  SDF reads outside the grid clamp to the edge.
+    void computeSDFWeightsSampled(const SIM_RawField* sdf, int samplesperaxis, bool invert, fpreal minweight) { sampleWeights(*sdf, invert); (void)samplesperaxis; (void)minweight; }
+    void computeSDFWeightsSampled(const SIM_RawField* sdf, int samplesperaxis, bool invert, fpreal minweight, fpreal dilate) { sampleWeights(*sdf, !invert); (void)samplesperaxis; (void)minweight; (void)dilate; }
+    void setScaleDivideThreshold(fpreal, const SIM_RawField*, const SIM_RawField*, fpreal) {}
+private:
+    void sampleWeights(const SIM_RawField& sdf, bool countNonNegative) {
+        const int off2[3] = {(mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEY || mySample == SIM_SAMPLE_FACEZ || mySample == SIM_SAMPLE_EDGEYZ) ? 1 : 0,
+                             (mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEX || mySample == SIM_SAMPLE_FACEZ || mySample == SIM_SAMPLE_EDGEXZ) ? 1 : 0,
+                             (mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEX || mySample == SIM_SAMPLE_FACEY || mySample == SIM_SAMPLE_EDGEXY) ? 1 : 0};   // sample offset in half voxels
+        const UT_VoxelArrayF& S = *sdf.field();
+        for (int k = 0; k < arr.r[2]; ++k) for (int j = 0; j < arr.r[1]; ++j) for (int i = 0; i < arr.r[0]; ++i) {
+            const int idx[3] = {i, j, k};
+            int count = 0;
+            for (int sub = 0; sub < 8; ++sub) {
+                int base[3]; double fr[3];
+                for (int a = 0; a < 3; ++a) {
+                    const int q = 4 * idx[a] + 2 * off2[a] - 2 + (((sub >> a) & 1) ? 1 : -1);      // quarter-voxel coordinate relative to the cell centres
+                    const int fl = (q >= 0) ? q / 4 : -((-q + 3) / 4);
+                    base[a] = fl; fr[a] = (q - 4 * fl) * 0.25;
+                }
+                double acc = 0.;
+                for (int dz = 0; dz < 2; ++dz) for (int dy = 0; dy < 2; ++dy) for (int dxx = 0; dxx < 2; ++dxx) {
+                    const double w = (dxx ? fr[0] : 1. - fr[0]) * (dy ? fr[1] : 1. - fr[1]) * (dz ? fr[2] : 1. - fr[2]);
+                    acc += w * (double)S.getValue(base[0] + dxx, base[1] + dy, base[2] + dz);
+                }
+                if (countNonNegative ? (acc >= 0.) : (acc < 0.)) ++count;
+            }
+            arr.d[arr.lin(i, j, k)] = (float)count * 0.125f;
+        }
+        arr.expandAllTiles();
+    }
+};
 class SIM_RawIndexField : public SIM_RawFieldT<exint> {};
 
 class SIM_ScalarField { public: SIM_RawField* getField() const { return const_cast<SIM_RawField*>(&f); } SIM_RawField f; };
@@ -448,12 +485,37 @@ class SIM_DataFactory {};
 class SIM_DopDescription {};
 class SIM_Geometry {};
 class SIM_GeometryCopy {};
-class GU_Detail {};
+// viewport dumps (printAllData, S.cpp:1030-1270): accepted and dropped
+typedef exint GA_Offset;
+enum GA_AttributeOwner { GA_ATTRIB_VERTEX, GA_ATTRIB_POINT, GA_ATTRIB_PRIMITIVE, GA_ATTRIB_GLOBAL };
+class GA_Defaults { public: GA_Defaults(double) {} };
+class GA_AttributeSet { public: void bumpAllDataIds(GA_AttributeOwner) {} };
+class GU_Detail {
+public:
+    void clear() { n = 0; }
+    void addFloatTuple(GA_AttributeOwner, const char*, int, const GA_Defaults&) {}
+    GA_Offset appendPoint() { return n++; }
+    GA_Offset appendPointBlock(exint k) { const GA_Offset o = n; n += k; return o; }
+    void setPos3(GA_Offset, const UT_Vector3&) {}
+    GA_AttributeSet& getAttributes() { return attrs; }
+private:
+    exint n = 0; GA_AttributeSet attrs;
+};
+class GA_RWHandleF {
+public:
+    GA_RWHandleF() {}
+    GA_RWHandleF(GU_Detail*, GA_AttributeOwner, const char*) {}
+    bool isValid() const { return true; }
+    void bumpDataId() {}
+    void set(GA_Offset, fpreal) {}
+};
+class SIM_GeometryAutoWriteLock { public: SIM_GeometryAutoWriteLock(SIM_GeometryCopy*, int) {} GU_Detail& getGdp() { return gdp; } private: GU_Detail gdp; };
 class PRM_Template {};
 class GAS_SubSolver {
 public:
     explicit GAS_SubSolver(const SIM_DataFactory*) {}
     virtual ~GAS_SubSolver() {}
+    SIM_GeometryCopy* getOrCreateGeometry(SIM_Object*, const char*) { static SIM_GeometryCopy g; return &g; }
 protected:
     virtual bool solveGasSubclass(SIM_Engine&, SIM_Object*, SIM_Time, SIM_Time) = 0;
 };
