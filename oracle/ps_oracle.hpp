@@ -6,19 +6,15 @@
 // reference file:line it follows (paths relative to the reference checkout:
 // exec/HDK_PolyStokesSolver*.cpp = S*.cpp, lib/include/*.h).
 //
-// PINNING.  The reference ships no tests / golden vectors, but large parts of it ARE compiled here from its own files
-// (oracle/_ref, `make ref`; stand-ins oracle/eigen_facade for the incomplete Eigen checkout and oracle/hdk_shim for the HDK):
-//   * exec/HDK_PolyStokesSolver_Classifier.cpp           -> ps_oracle_classify.cpp is BIT-EXACT against it (labels, DOF indices,
-//     reduced indices, counts, valid faces; tests/test_ref_classify.py, 15 scenes)
-//   * exec/HDK_PolyStokesSolver_ConstructMatrixBlocks.cpp -> the matrix blocks / right-hand sides of ps_oracle_assemble.cpp are
-//     BIT-EQUAL (patterns incl. explicit zeros and values)
-//   * exec/HDK_PolyStokesSolver_AssembleBlocks.cpp + _AssembleSystem.cpp -> M_r, B, B^-1, reduced rhs BIT-EQUAL, b to 2e-15, explicit A
-//     pattern bit-exact / values 4e-16 (on the oracle's region matrices)
-//   * lib/include/pcg.h, ApplyPressureStressMatrix.h       -> ps_oracle_solve.cpp: same iteration counts, apply to 2e-16
-//     (tests/test_ref_solve.py, tests/golden `refcode_*`)
-// PARITY UNPINNED for what lives only in exec/HDK_PolyStokesSolver.cpp: weights (HDK-defined), centres of mass, least-squares fits,
-// reduced mass / viscosity matrices, the basis evaluation, velocity recovery / write-back.  Those are pinned only by the analytic
-// known-answer tests (tests/test_oracle_kat.py).
+// PINNING.  The reference ships no tests / golden vectors, but its WHOLE solver is compiled here from its own files
+// (oracle/_ref/libps_ref_full.so, `make ref`: all six exec/HDK_PolyStokesSolver*.cpp + lib/, unmodified, on the stand-ins
+// oracle/hdk_shim for the closed-source HDK and oracle/eigen_facade for the incomplete Eigen checkout), and this restatement is
+// checked against it stage by stage (tests/test_ref_full.py, test_ref_classify.py, test_ref_solve.py): weights, classification,
+// centres of mass, least-squares fits, region matrices, matrix blocks, B / B^-1, right-hand sides BIT-EQUAL; b 2e-15; same CG /
+// BiCGSTAB / Eigen-CG iteration counts; velocity within the solver tolerance.
+// Pinned MODULO the stand-ins: the HDK primitives (tile iteration order, connected components, computeSDFWeightsSampled,
+// trilinear getValue, border modes -- defined in BASELINE.md section 3, implemented once in hdk_shim.h and once here) and the
+// per-operation rounding of the Eigen calls.  Against a real Houdini build only those could differ.
 // Nothing in the product path (polystokes_b200/) may include, link or call this code.
 #pragma once
 #include <cstdint>

@@ -1,5 +1,6 @@
-"""Known-answer tests that pin the CPU oracle (the reference ships no tests / golden vectors; only its solve stage can be
-compiled here -- tests/test_ref_solve.py -- so for classification / assembly parity is unpinned).  Each test checks an analytic property of the restated algorithm."""
+"""Analytic known-answer tests of the CPU oracle.  (The reference ships no tests / golden vectors; its whole solver is compiled here from its
+own sources -- tests/test_ref_full.py -- and the oracle is bit-equal to it, modulo the stand-ins' definitions of the HDK primitives.  These
+tests check the properties that do not depend on any reference build.)  Each test checks an analytic property of the restated algorithm."""
 import os
 
 import numpy as np

@@ -99,9 +99,9 @@ def test_emulated_step_matches_compiled_reference(built, case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", list(CASES) + ["S3_jet_96"])
+@pytest.mark.parametrize("case", list(CASES))
 def test_gpu_step_matches_compiled_reference(built, case):
-    _product_vs_reference(scenes.scene_s3(96) if case == "S3_jet_96" else CASES[case](), None)
+    _product_vs_reference(CASES[case](), None)
 
 
 def test_compiled_reference_bicgstab_fallback_and_eigen_cg(built):
