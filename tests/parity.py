@@ -132,13 +132,14 @@ def check_bicgstab_fallback(lib_path=None):
         assert float(np.abs(ovel[a] - vel[a]).max()) <= 4e-7 * max(float(np.abs(ovel[a]).max()), 1e-30)
     s.close()
     sc = scenes.blob_scene(32, seed=4, maxIterations=60)
-    o = Oracle(sc).setup()
+    o = Oracle(sc, threads=1).setup()        # one thread: the oracle's count moves between 37 and 44 from run to run with OpenMP reductions
     ro = o.solve()
     s = PolyStokesSolver.from_scene(sc, lib_path=lib_path)
     rs, vel, valid = s.step_scene(sc)
     assert ro == rs == 1 and o.count("usedBiCGStab") == s.count("usedBiCGStab") == 1
     io, is_ = o.count("iterations"), s.count("iterations")
-    assert abs(io - is_) <= 2 + io // 10, f"BiCGSTAB iterations oracle {io} vs {is_}"
+    # a chaotic iteration: two correct implementations that round differently land in the same ballpark, not on the same count
+    assert abs(io - is_) <= 2 + io // 2, f"BiCGSTAB iterations oracle {io} vs {is_}"
     # BiCGSTAB's trajectory is chaotic at rounding level (the oracle's OpenMP dot products are not even reproducible from run to run)
     # and its stop rule min(|e|^2, |e| / |x|) < tol (pcg.h:186-193) is loose: two correct runs may stop a few iterations apart with
     # velocities that differ by per cents.  What must hold exactly is the rule itself on the returned iterate, checked independently:
