@@ -7,8 +7,9 @@ runs it once here and commits a small JSON digest per scene (tests/golden/fullsi
   * a SHA-256 of every label / active-index / reduced-index field (int8 / int32, x fastest) and of every weight field (eighths as uint8),
   * a SHA-256 of the CSR patterns of G and D^T (rowptr int64 + colidx int32) and of their values (bit-equal on the GPU),
   * |b|, the CG iteration count, the reference stop-test error, and a strided sample of the solved velocity fields.
-tests/test_gpu_fullsize.py recomputes the same digests from the CUDA path.  Like every fixture here they pin the ORACLE
-(the reference has no golden vectors of its own).
+tests/test_gpu_fullsize.py recomputes the same digests from the CUDA path.  The digests come from the oracle (fast, OpenMP);
+tests/golden/verify_fullsize_with_reference.py re-derives the setup part (counts, field hashes, G / D^T, |b|) with the COMPILED
+REFERENCE SOLVER (oracle/_ref/libps_ref_full.so) and finds them equal -- log in profiles/r01_fullsize_digests_vs_compiled_reference.log.
 """
 import hashlib
 import json
