@@ -136,10 +136,10 @@ def test_emulated_classification_matches_reference_code(built, case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", list(CASES) + ["S3_jet_128_tile16_pad2"])
+@pytest.mark.parametrize("case", list(CASES) + ["S3_jet_112_tile16_pad2"])
 def test_gpu_classification_matches_reference_code(built, case):
     """The CUDA classifier on ITS OWN weights against the reference classifier run on those weights."""
-    sc, ov = (scenes.scene_s3(128), {}) if case == "S3_jet_128_tile16_pad2" else CASES[case]()
+    sc, ov = (scenes.scene_s3(112), {}) if case == "S3_jet_112_tile16_pad2" else CASES[case]()
     s = PolyStokesSolver.from_scene(sc, **ov)
     rc, vel, valid = s.step_scene(sc)
     _check(sc, ov, s.index_field, s.weight_field, s.count, lambda a: valid[a], s.csr, s.vector, exact_values=parity.BITEXACT_MATS, asm_tol=1e-9)

@@ -132,7 +132,7 @@ def test_gpu_export_matches_eigen_writer(built, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", list(CASES) + ["S2_beam_96"])
+@pytest.mark.parametrize("case", list(CASES) + ["S2_beam_64"])
 def test_gpu_solve_matches_reference_code(built, case):
-    sc = scenes.scene_s2(96) if case == "S2_beam_96" else CASES[case]()
+    sc = scenes.scene_s2(64) if case == "S2_beam_64" else CASES[case]()
     _product_vs_reference(None, sc)
