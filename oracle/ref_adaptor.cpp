@@ -1,0 +1,66 @@
+// ref_adaptor.cpp -- TEST INFRASTRUCTURE.  Compiles the node-side binding integration/hdk_polystokes_b200_adaptor.cpp against the HDK
+// stand-in (oracle/hdk_shim) and the reference's OWN node class declaration (exec/HDK_PolyStokes.h), and exposes one C call that builds
+// the SIM fields of a scene, runs the adaptor and returns the fields it wrote back -- the drop-in boundary of INTEGRATION.md exercised
+// with the reference's types.  The ps_* symbols stay undefined here: the caller loads libpolystokes_b200.so (or its emulation twin in
+// the CPU tests) with RTLD_GLOBAL first.
+#include <cstring>
+#include "hdk_shim.h"
+#include <Eigen/Sparse>
+#include <tbb/tbb.h>
+#define private public
+#define protected public
+#include "HDK_PolyStokes.h"
+#undef private
+#undef protected
+#include "../integration/hdk_polystokes_b200_adaptor.cpp"
+
+HDK_PolyStokes::HDK_PolyStokes(const SIM_DataFactory* factory) : GAS_SubSolver(factory) {}
+HDK_PolyStokes::~HDK_PolyStokes() {}
+bool HDK_PolyStokes::solveGasSubclass(SIM_Engine&, SIM_Object*, SIM_Time, SIM_Time) { return false; }
+const SIM_DopDescription* HDK_PolyStokes::getDopDescription() { return nullptr; }
+namespace { struct Node : HDK_PolyStokes { Node() : HDK_PolyStokes(nullptr) {} }; }
+
+extern "C" {
+struct refadp_params {
+    int32_t nx, ny, nz;
+    double dx, dt, density, tolerance;
+    int32_t maxIterations, liquidLayers, solidLayers, doReducedRegions, doTile, tileSize, tilePadding, solverType, useWarmStart, keepNonConvergedResults;
+};
+static void fill(SIM_RawField* f, const float* src) { UT_VoxelArrayF& a = *f->fieldNC(); memcpy(a.d.data(), src, a.d.size() * sizeof(float)); a.expandAllTiles(); }
+
+// velOut / validOut: 3 face-sampled float arrays each; steps: how many times the node is cooked on the same handle
+int refadp_run(const refadp_params* P, const float* surface, const float* collision, const float* viscosity, const float* const* vel, const float* const* colvel,
+               int steps, float* const* velOut, float* const* validOut, char* errorOut, int errorLen) {
+    std::map<std::string, double>& prm = hdk_shim::params();
+    prm.clear();
+    prm["matrixSetup"] = 0; prm["solverType"] = P->solverType; prm["useInputSurfaceWeights"] = 0; prm["useInputCollisionWeights"] = 0;
+    prm["minDensity"] = 0; prm["maxDensity"] = 1e30; prm["activeLiquidBoundaryLayerSize"] = P->liquidLayers; prm["activeSolidBoundaryLayerSize"] = P->solidLayers;
+    prm["doReducedRegions"] = P->doReducedRegions; prm["doTile"] = P->doTile; prm["tileSize"] = P->tileSize; prm["tilePadding"] = P->tilePadding;
+    prm[SIM_NAME_TOLERANCE] = P->tolerance; prm["maxSolverIterations"] = P->maxIterations; prm["useWarmStart"] = P->useWarmStart;
+    prm["exportMatrices"] = 0; prm["exportComponentMatrices"] = 0; prm["exportStats"] = 0; prm["doSolve"] = 1; prm["keepNonConvergedResults"] = P->keepNonConvergedResults;
+    SIM_VectorField velocity, collisionVelocity, validFaces;
+    SIM_ScalarField surf, coll, visc;
+    const UT_Vector3 orig(0.f, 0.f, 0.f), size((float)(P->nx * P->dx), (float)(P->ny * P->dx), (float)(P->nz * P->dx));
+    const SIM_FieldSample faceSample[3] = {SIM_SAMPLE_FACEX, SIM_SAMPLE_FACEY, SIM_SAMPLE_FACEZ};
+    for (int a = 0; a < 3; ++a)
+        for (SIM_VectorField* v : {&velocity, &collisionVelocity, &validFaces}) v->getField(a)->init(faceSample[a], orig, size, P->nx, P->ny, P->nz);
+    for (SIM_ScalarField* s : {&surf, &coll, &visc}) s->getField()->init(SIM_SAMPLE_CENTER, orig, size, P->nx, P->ny, P->nz);
+    fill(surf.getField(), surface); fill(coll.getField(), collision); fill(visc.getField(), viscosity);
+    for (int a = 0; a < 3; ++a) fill(collisionVelocity.getField(a), colvel[a]);
+    Node node;
+    polystokes_b200_node_state state;
+    std::string error;
+    int result = PS_INCOMPLETE;
+    for (int s = 0; s < steps; ++s) {
+        for (int a = 0; a < 3; ++a) fill(velocity.getField(a), vel[a]);      // every cook starts from the same input velocity
+        result = polystokes_b200_step(node, state, P->dx, P->dt, P->density, &velocity, &collisionVelocity, &surf, &coll, &visc, &validFaces, &error);
+    }
+    polystokes_b200_release(state);
+    for (int a = 0; a < 3; ++a) {
+        const UT_VoxelArrayF& v = *velocity.getField(a)->field(); memcpy(velOut[a], v.d.data(), v.d.size() * sizeof(float));
+        const UT_VoxelArrayF& w = *validFaces.getField(a)->field(); memcpy(validOut[a], w.d.data(), w.d.size() * sizeof(float));
+    }
+    if (errorOut && errorLen > 0) { strncpy(errorOut, error.c_str(), (size_t)errorLen - 1); errorOut[errorLen - 1] = 0; }
+    return result;
+}
+}
