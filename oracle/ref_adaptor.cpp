@@ -1,9 +1,17 @@
 // ref_adaptor.cpp -- TEST INFRASTRUCTURE.  Compiles the node-side binding integration/hdk_polystokes_b200_adaptor.cpp against the HDK
 // stand-in (oracle/hdk_shim) and the reference's OWN node class declaration (exec/HDK_PolyStokes.h), and exposes one C call that builds
 // the SIM fields of a scene, runs the adaptor and returns the fields it wrote back -- the drop-in boundary of INTEGRATION.md exercised
-// with the reference's types.  The ps_* symbols stay undefined here: the caller loads libpolystokes_b200.so (or its emulation twin in
-// the CPU tests) with RTLD_GLOBAL first.
+// with the reference's types.  In the plugin the adaptor links against libpolystokes_b200.so directly; here its four ps_* calls are routed
+// (by renaming them for this translation unit only -- the adaptor source is compiled as it stands) through pointers that refadp_bind()
+// resolves with dlopen(RTLD_LOCAL) from the library the test names: the product, or its emulation twin in the CPU tests.  Nothing is loaded
+// RTLD_GLOBAL, so the two libraries never see each other's symbols.
 #include <cstring>
+#include <dlfcn.h>
+#define ps_create refadp_ps_create
+#define ps_destroy refadp_ps_destroy
+#define ps_step refadp_ps_step
+#define ps_last_error refadp_ps_last_error
+#include "polystokes_b200.h"
 #include "hdk_shim.h"
 #include <Eigen/Sparse>
 #include <tbb/tbb.h>
@@ -13,6 +21,37 @@
 #undef private
 #undef protected
 #include "../integration/hdk_polystokes_b200_adaptor.cpp"
+#undef ps_create
+#undef ps_destroy
+#undef ps_step
+#undef ps_last_error
+
+namespace {
+struct Backend {
+    void* lib = nullptr;
+    int (*create)(const ps_params*, ps_handle*) = nullptr;
+    void (*destroy)(ps_handle) = nullptr;
+    int (*step)(ps_handle, const ps_fields_in*, ps_fields_out*, ps_stats*) = nullptr;
+    const char* (*last_error)(void) = nullptr;
+} g_backend;
+}
+extern "C" {
+int refadp_ps_create(const ps_params* p, ps_handle* out) { return g_backend.create ? g_backend.create(p, out) : PS_FAILED; }
+void refadp_ps_destroy(ps_handle h) { if (g_backend.destroy) g_backend.destroy(h); }
+int refadp_ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* st) { return g_backend.step ? g_backend.step(h, in, out, st) : PS_FAILED; }
+const char* refadp_ps_last_error(void) { return g_backend.last_error ? g_backend.last_error() : "refadp_bind was not called"; }
+// which library stands behind the C ABI (0 on success)
+int refadp_bind(const char* path) {
+    void* lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return -1;
+    g_backend.lib = lib;
+    g_backend.create = (int (*)(const ps_params*, ps_handle*))dlsym(lib, "ps_create");
+    g_backend.destroy = (void (*)(ps_handle))dlsym(lib, "ps_destroy");
+    g_backend.step = (int (*)(ps_handle, const ps_fields_in*, ps_fields_out*, ps_stats*))dlsym(lib, "ps_step");
+    g_backend.last_error = (const char* (*)(void))dlsym(lib, "ps_last_error");
+    return (g_backend.create && g_backend.destroy && g_backend.step && g_backend.last_error) ? 0 : -2;
+}
+}
 
 HDK_PolyStokes::HDK_PolyStokes(const SIM_DataFactory* factory) : GAS_SubSolver(factory) {}
 HDK_PolyStokes::~HDK_PolyStokes() {}

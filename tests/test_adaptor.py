@@ -26,9 +26,9 @@ class _P(C.Structure):
 
 
 def cook(sc, backend, steps=1):
-    C.CDLL(backend, mode=C.RTLD_GLOBAL)              # the ps_* entry points the adaptor links against
     L = C.CDLL(ADAPTOR)
     L.refadp_run.restype = C.c_int
+    assert L.refadp_bind(backend.encode()) == 0, f"could not bind the C ABI of {backend}"      # dlopen(RTLD_LOCAL): no symbol leaks between libraries
     p = sc.params
     P = _P(sc.nx, sc.ny, sc.nz, float(sc.dx), float(sc.dt), float(sc.density), float(p["tolerance"]), int(p["maxIterations"]), int(p["liquidLayers"]), int(p["solidLayers"]),
            int(p["doReduced"]), int(p["doTile"]), int(p["tileSize"]), int(p["tilePadding"]), int(p.get("solverType", 0)), int(p.get("useWarmStart", 0)),
