@@ -24,7 +24,7 @@ CASES.update({
     "S1_uniform_64": lambda: (scenes.scene_s1(), {}),
     "S2_beam_64_tile8_pad1": lambda: (scenes.scene_s2(64), {}),
     "S3_jet_64_tile16_pad2": lambda: (scenes.scene_s3(64), {}),
-    "S4_pool_96_tile32_pad3_layers33": lambda: (scenes.scene_s4(96), {}),
+    "S4_pool_80_tile32_pad3_layers33": lambda: (scenes.scene_s4(80), {}),
     "S5_blob_quarter_tile8_pad3": lambda: (scenes.scene_s5(0.25, tileSize=8), {}),
     "blob48_pad0": lambda: (scenes.blob_scene(48, seed=13, tile=8, pad=0), {}),
     "blob40_layers14": lambda: (scenes.blob_scene(40, seed=17, tile=8, pad=1, liquidLayers=1, solidLayers=4), {}),
