@@ -36,7 +36,7 @@ def probe_vector(n):
 
 
 def collect(sc):
-    o = Oracle(sc).setup()
+    o = Oracle(sc, threads=1).setup()        # one thread: reproducible reductions
     out = {}
     for slot in range(7):
         out[f"labels{slot}"] = o.index_field(0, slot).astype(np.int8)

@@ -31,7 +31,7 @@ def test_oracle_solve_stage_matches_reference_code(built, case):
     """Oracle restatement vs the compiled reference headers: operator apply to rounding, CG with the SAME iteration
     count and error, solution to 1e-7 (the only freedom left is the summation order of the oracle's OpenMP dots)."""
     sc = CASES[case]()
-    o = Oracle(sc).setup()
+    o = Oracle(sc, threads=1).setup()        # one thread: reproducible dot products
     n = o.count("nSystemSize")
     R = ref_solve.RefSolve(o.csr, sc.dt)
     assert R.n == n
@@ -51,7 +51,7 @@ def test_oracle_bicgstab_fallback_matches_reference_code(built):
     """CG cut after 8 iterations -> the reference restarts with bicgstab_external_matrix_A (S.cpp:784-799): same switch,
     same 8 iterations, iterates equal to rounding."""
     sc = scenes.blob_scene(32, seed=4, maxIterations=8, tolerance=1e-12, keepNonConvergedResults=1)
-    o = Oracle(sc).setup()
+    o = Oracle(sc, threads=1).setup()
     ro = o.solve()
     R = ref_solve.RefSolve(o.csr, sc.dt)
     res, it, xr, err, used = R.solve_spd(o.vector("b"), sc.params["tolerance"], sc.params["maxIterations"])
