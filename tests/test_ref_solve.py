@@ -47,6 +47,32 @@ def test_oracle_solve_stage_matches_reference_code(built, case):
     assert rel(xr, o.vector("solution")) <= 1e-7       # dot-product order, amplified by the conditioning
 
 
+def test_reference_code_apply_matches_scipy(built):
+    """Second opinion that does not involve the oracle's arithmetic or the Eigen facade's: the compiled reference operator
+    (ApplyPressureStressMatrix::applyMatrixVectorProducts on the facade) against y = -dt K^T Mc^-1 K x - J^T B^-1 J x - 1/2 [0; mu^-1 x_tau]
+    evaluated by scipy.sparse from the same component matrices, and the reference's explicit A (assembleSystemPressureStress) against the same
+    formula as sparse triple products."""
+    import scipy.sparse as sp
+    from oracle import ref_full
+    sc = scenes.blob_scene(28, seed=6, tile=8, pad=1, solverType=1)
+    R = ref_full.RefFull(sc).setup()
+    M = {}
+    for name in ("McInv", "BInv", "uInv", "G", "JG", "Dt", "JDt", "A"):
+        shape, ptr, idx, val = R.csr(name)
+        M[name] = sp.csr_matrix((val, idx, ptr), shape=shape)
+    K = sp.hstack([M["G"], M["Dt"]]).tocsr(); J = sp.hstack([M["JG"], M["JDt"]]).tocsr()
+    nP, nT = M["G"].shape[1], M["Dt"].shape[1]
+    C22 = sp.block_diag([sp.csr_matrix((nP, nP)), M["uInv"]]).tocsr()
+    A = -sc.dt * (K.T @ M["McInv"] @ K) - J.T @ M["BInv"] @ J - 0.5 * C22
+    assert abs(A - M["A"]).max() <= 1e-12 * abs(A).max(), "explicit A of the compiled reference vs scipy triple products"
+    shape, ptr, idx, val = R.csr("B")
+    B = sp.csr_matrix((val, idx, ptr), shape=shape)
+    assert abs(M["BInv"] @ B - sp.identity(shape[0])).max() <= 1e-9, "B^-1 of the compiled reference (26 x 26 partial-pivot inverses) times B"
+    x = np.random.default_rng(3).standard_normal(nP + nT)
+    S = ref_solve.RefSolve(R.csr, sc.dt)
+    assert rel(S.apply(x), A @ x) <= 1e-12, "factored apply of the compiled reference vs scipy"
+
+
 def test_oracle_bicgstab_fallback_matches_reference_code(built):
     """CG cut after 8 iterations -> the reference restarts with bicgstab_external_matrix_A (S.cpp:784-799): same switch,
     same 8 iterations, iterates equal to rounding."""
