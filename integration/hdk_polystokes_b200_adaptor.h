@@ -6,7 +6,7 @@
 // arrays, makes ONE C call (ps_step, include/polystokes_b200.h) and writes the velocity and `valid` fields back (PS.C:562-584).
 // It uses HDK types only through the members the reference itself uses (SIM_VectorField::getField, SIM_RawField::field / fieldNC /
 // getVoxelRes, UT_VoxelArray::getValue / setValue), so the same source compiles against the real HDK in the plugin and against
-// oracle/hdk_shim here, where tests/test_adaptor.py runs it next to the compiled reference solver.
+// oracle/hdk_shim here, where tests/test_zz_adaptor.py runs it next to the compiled reference solver.
 #pragma once
 #include <string>
 #include "polystokes_b200.h"

@@ -1,4 +1,4 @@
-"""The drop-in boundary with the reference's own types: integration/hdk_polystokes_b200_adaptor.cpp -- the body a maintainer puts in
+"""(Named test_zz_* so that it runs last.)  The drop-in boundary with the reference's own types: integration/hdk_polystokes_b200_adaptor.cpp -- the body a maintainer puts in
 HDK_PolyStokes::solveGasSubclass instead of PS.C:329-584 -- compiled against the HDK stand-in and the reference's exec/HDK_PolyStokes.h
 (oracle/_ref/libps_ref_adaptor.so), cooked on the SIM fields of a scene, next to the compiled reference solver (libps_ref_full.so) cooked
 on the same fields: same `valid` field, same velocity within the parity gate, same result code.  CPU: the emulation twin stands behind the
