@@ -7,7 +7,7 @@
 // oracle/_ref/libps_ref_classify.so.  What is the reference's: every flood, stencil rule, sweep order, remap and numbering
 // loop of the classifier.  What is this shim's (and therefore the same definition the oracle restates): the 16^3 tile
 // iteration order of UT_VoxelArray, the connected-component labelling of SIM_VolumetricConnectedComponentBuilder, the
-// SIM::FieldUtils index maps, border modes, and "threading" (one job, serial).
+// SIM::FieldUtils index maps, border modes, and threading (HDK_SHIM_THREADS jobs on std::thread; default one job, serial).
 #pragma once
 #include <algorithm>
 #include <cassert>
@@ -21,6 +21,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 typedef int64_t exint;
@@ -107,39 +108,51 @@ private:
     std::deque<T> d;
 };
 
-// ---- "threading": one job, everything serial and in order ----
+// ---- threading: HDK_SHIM_THREADS jobs (default 1: everything serial and in order, which is what the bit-exact parity tests use) ----
+// The reference splits its voxel sweeps by tile over UT_ThreadedAlgorithm jobs (per-job accumulators indexed by info.job(), merged in job
+// order, e.g. S_CMB:324-341, S.cpp:1285-1324), its per-region work over tbb::parallel_for and a few loops over UTparallelFor*.  The stand-in
+// runs job j of n on its own std::thread with the SAME contiguous split the single job would walk in order, so list-building stages give
+// identical results for any n; floating-point sums that are accumulated per job (centres of mass, Gram matrices) differ in the last bits
+// between different n, exactly as they do between machines with different core counts in Houdini.  bench.py sets the job count to the
+// number of host cores (reffull_set_threads); tests leave it at 1.
+#include "shim_threads.h"
 class UT_JobInfo {
 public:
-    int job() const { return 0; }
-    int numJobs() const { return 1; }
-    void divideWork(exint units, exint& start, exint& end) const { start = 0; end = units; }
-    void divideWork(int units, int& start, int& end) const { start = 0; end = units; }
+    UT_JobInfo() {}
+    UT_JobInfo(int j, int n) : myJob(j), myNum(n) {}
+    int job() const { return myJob; }
+    int numJobs() const { return myNum; }
+    void divideWork(exint units, exint& start, exint& end) const { start = units * myJob / myNum; end = units * (myJob + 1) / myNum; }
+    void divideWork(int units, int& start, int& end) const { start = (int)((int64_t)units * myJob / myNum); end = (int)((int64_t)units * (myJob + 1) / myNum); }
+private:
+    int myJob = 0, myNum = 1;
 };
 class UT_ThreadedAlgorithm {
 public:
-    template <class F> void run(F f) { UT_JobInfo info; f(info); }
+    template <class F> void run(F f) { const int n = hdk_shim::threads(); hdk_shim::runJobs(n, [&](int j) { UT_JobInfo info(j, n); f(info); }); }
 };
-class UT_Thread { public: static int getNumProcessors() { return 1; } };
+class UT_Thread { public: static int getNumProcessors() { return hdk_shim::threads(); } };
 class UT_Interrupt { public: bool opInterrupt(int = -1) { return false; } bool opStart(const char* = nullptr) { return true; } void opEnd() {} };
 inline UT_Interrupt* UTgetInterrupt() { static UT_Interrupt boss; return &boss; }
 class UT_AutoInterrupt { public: explicit UT_AutoInterrupt(const char*) {} bool wasInterrupted() { return false; } };
 template <class T>
 class UT_BlockedRange { public: UT_BlockedRange(T b, T e, size_t = 1) : b(b), e(e) {} T begin() const { return b; } T end() const { return e; } private: T b, e; };
-template <class I, class F> inline void UTparallelForEachNumber(I n, const F& f) { if (n > 0) f(UT_BlockedRange<I>(I(0), n)); }
-template <class R, class F> inline void UTparallelFor(const R& r, const F& f, int = 0, int = 0) { f(r); }
-template <class R, class F> inline void UTparallelForLightItems(const R& r, const F& f) { f(r); }
-template <class R, class F> inline void UTparallelForHeavyItems(const R& r, const F& f) { f(r); }
+template <class I, class F> inline void UTparallelForEachNumber(I n, const F& f) { hdk_shim::forRange(I(0), n, [&](I lo, I hi) { f(UT_BlockedRange<I>(lo, hi)); }); }
+template <class R, class F> inline void UTparallelFor(const R& r, const F& f, int = 0, int = 0) { hdk_shim::forRange(r.begin(), r.end(), [&](decltype(r.begin()) lo, decltype(r.begin()) hi) { f(R(lo, hi)); }); }
+template <class R, class F> inline void UTparallelForLightItems(const R& r, const F& f) { UTparallelFor(r, f); }
+template <class R, class F> inline void UTparallelForHeavyItems(const R& r, const F& f) { UTparallelFor(r, f); }
 template <class R, class F> inline void UTserialFor(const R& r, const F& f) { f(r); }
 template <class It, class C> inline void UTparallelSort(It b, It e, C c) { std::sort(b, e, c); }
 template <class It> inline void UTparallelSort(It b, It e) { std::sort(b, e); }
 template <class It, class C> inline void UTparallelStableSort(It b, It e, C c) { std::stable_sort(b, e, c); }
 
-// THREADED_METHODn(CLASS, DOMULTI, METHOD, types/names...): METHOD(args) runs METHODPartial(args, info) once
-#define THREADED_METHOD(C, DOMULTI, M) void M() { M##Partial(UT_JobInfo()); }
-#define THREADED_METHOD1(C, DOMULTI, M, T1, P1) void M(T1 P1) { M##Partial(P1, UT_JobInfo()); }
-#define THREADED_METHOD2(C, DOMULTI, M, T1, P1, T2, P2) void M(T1 P1, T2 P2) { M##Partial(P1, P2, UT_JobInfo()); }
-#define THREADED_METHOD3(C, DOMULTI, M, T1, P1, T2, P2, T3, P3) void M(T1 P1, T2 P2, T3 P3) { M##Partial(P1, P2, P3, UT_JobInfo()); }
-#define THREADED_METHOD4(C, DOMULTI, M, T1, P1, T2, P2, T3, P3, T4, P4) void M(T1 P1, T2 P2, T3 P3, T4 P4) { M##Partial(P1, P2, P3, P4, UT_JobInfo()); }
+// THREADED_METHODn(CLASS, DOMULTI, METHOD, types/names...): METHOD(args) runs METHODPartial(args, info) once per job
+#define HDK_SHIM_JOBS(CALL) do { const int n_ = hdk_shim::threads(); hdk_shim::runJobs(n_, [&](int j_) { const UT_JobInfo info(j_, n_); CALL; }); } while (0)
+#define THREADED_METHOD(C, DOMULTI, M) void M() { HDK_SHIM_JOBS(M##Partial(info)); }
+#define THREADED_METHOD1(C, DOMULTI, M, T1, P1) void M(T1 P1) { HDK_SHIM_JOBS(M##Partial(P1, info)); }
+#define THREADED_METHOD2(C, DOMULTI, M, T1, P1, T2, P2) void M(T1 P1, T2 P2) { HDK_SHIM_JOBS(M##Partial(P1, P2, info)); }
+#define THREADED_METHOD3(C, DOMULTI, M, T1, P1, T2, P2, T3, P3) void M(T1 P1, T2 P2, T3 P3) { HDK_SHIM_JOBS(M##Partial(P1, P2, P3, info)); }
+#define THREADED_METHOD4(C, DOMULTI, M, T1, P1, T2, P2, T3, P3, T4, P4) void M(T1 P1, T2 P2, T3 P3, T4 P4) { HDK_SHIM_JOBS(M##Partial(P1, P2, P3, P4, info)); }
 
 // ---- UT_VoxelArray: dense storage, logical 16^3 tiles (partial at the high edges), tile-linear index tx fastest ----
 enum UT_VoxelBorderType { UT_VOXELBORDER_CONSTANT, UT_VOXELBORDER_REPEAT, UT_VOXELBORDER_STREAK, UT_VOXELBORDER_EXTRAP };
@@ -330,7 +343,7 @@ public:
     UT_Vector3I getVoxelRes() const { return arr.getVoxelRes(); }
     T getCellValue(int x, int y, int z) const { return arr.getValue(x, y, z); }
     T operator()(int x, int y, int z) const { return arr.getValue(x, y, z); }       // reads follow the border mode
-    bool shouldMultiThread() const { return false; }
+    bool shouldMultiThread() const { return hdk_shim::threads() > 1; }
     bool isMatching(const SIM_RawFieldT&) const { return true; }
     // position of sample (x, y, z): cell corner + sample offset, in the float precision of the HDK
     bool indexToPos(int x, int y, int z, UT_Vector3& pos) const {
@@ -387,7 +400,9 @@ private:
                              (mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEX || mySample == SIM_SAMPLE_FACEZ || mySample == SIM_SAMPLE_EDGEXZ) ? 1 : 0,
                              (mySample == SIM_SAMPLE_CENTER || mySample == SIM_SAMPLE_FACEX || mySample == SIM_SAMPLE_FACEY || mySample == SIM_SAMPLE_EDGEXY) ? 1 : 0};   // sample offset in half voxels
         const UT_VoxelArrayF& S = *sdf.field();
-        for (int k = 0; k < arr.r[2]; ++k) for (int j = 0; j < arr.r[1]; ++j) for (int i = 0; i < arr.r[0]; ++i) {
+        // z-planes split over the jobs (the HDK's own routine is threaded by tile); every voxel is independent
+        hdk_shim::forRange(0, arr.r[2], [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) for (int j = 0; j < arr.r[1]; ++j) for (int i = 0; i < arr.r[0]; ++i) {
             const int idx[3] = {i, j, k};
             int count = 0;
             for (int sub = 0; sub < 8; ++sub) {
@@ -398,6 +413,15 @@ private:
                     base[a] = fl; fr[a] = (q - 4 * fl) * 0.25;
                 }
                 double acc = 0.;
+                if (base[0] >= 0 && base[1] >= 0 && base[2] >= 0 && base[0] + 1 < S.r[0] && base[1] + 1 < S.r[1] && base[2] + 1 < S.r[2]) {
+                    // all eight corners inside the grid: same sum, same order, without the border handling of getValue
+                    const float* c = S.d.data() + S.lin(base[0], base[1], base[2]);
+                    const size_t sy = (size_t)S.r[0], sz = (size_t)S.r[0] * (size_t)S.r[1];
+                    for (int dz = 0; dz < 2; ++dz) for (int dy = 0; dy < 2; ++dy) for (int dxx = 0; dxx < 2; ++dxx) {
+                        const double w = (dxx ? fr[0] : 1. - fr[0]) * (dy ? fr[1] : 1. - fr[1]) * (dz ? fr[2] : 1. - fr[2]);
+                        acc += w * (double)c[(size_t)dxx + sy * (size_t)dy + sz * (size_t)dz];
+                    }
+                } else
                 for (int dz = 0; dz < 2; ++dz) for (int dy = 0; dy < 2; ++dy) for (int dxx = 0; dxx < 2; ++dxx) {
                     const double w = (dxx ? fr[0] : 1. - fr[0]) * (dy ? fr[1] : 1. - fr[1]) * (dz ? fr[2] : 1. - fr[2]);
                     acc += w * (double)S.getValue(base[0] + dxx, base[1] + dy, base[2] + dz);
@@ -406,6 +430,7 @@ private:
             }
             arr.d[arr.lin(i, j, k)] = (float)count * 0.125f;
         }
+        });
         arr.expandAllTiles();
     }
 };

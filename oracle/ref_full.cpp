@@ -8,8 +8,11 @@
 // Houdini node (parameter templates, field fetching, addError): its stage sequence, exec/HDK_PolyStokes.C:329-608, is what reffull_step
 // below calls, and the four out-of-line members of the node class are defined here as stubs.
 // What remains the stand-ins' (not the reference's): tile iteration order, connected components, computeSDFWeightsSampled, trilinear
-// getValue, border modes, one-job threading (hdk_shim.h), and the per-operation arithmetic of the Eigen calls (eigen_facade/Eigen/Core).
+// getValue, border modes, the job pool behind UT_ThreadedAlgorithm / tbb::parallel_for (hdk_shim.h; one job unless reffull_set_threads), and the per-operation arithmetic of the Eigen calls (eigen_facade/Eigen/Core).
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "hdk_shim.h"
 #include <Eigen/Sparse>
 #include <tbb/tbb.h>
@@ -70,29 +73,41 @@ void* reffull_create(const reffull_params* P, const float* surface, const float*
     return H;
 }
 void reffull_destroy(void* hv) { delete (RefFull*)hv; }
+// jobs of the HDK stand-in's thread pool (UT_ThreadedAlgorithm / UTparallelFor* / tbb::parallel_for); 0 = all hardware threads.  Set BEFORE
+// reffull_create (the solver reads UT_Thread::getNumProcessors() in its constructor, S.cpp:154).  Returns the job count in effect.
+int reffull_set_threads(int n) { hdk_shim::setThreads(n); return hdk_shim::threads(); }
+int reffull_get_threads() { return hdk_shim::threads(); }
 
 // exec/HDK_PolyStokes.C:344-476: everything up to and including assemble() (the reference's "setup" clock)
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// PS_REF_TIMING=1: per-stage wall clock of the reference's setup on stderr (diagnostic)
+#define STAGE(name, stmt) do { const double t0_ = now_s(); stmt; if (timing) fprintf(stderr, "[ref stage] %-40s %8.3f s\n", name, now_s() - t0_); } while (0)
 int reffull_setup(void* hv) {
     RefFull* H = (RefFull*)hv; Solver& S = *H->S; HDK_PolyStokes& node = H->node;
+    const bool timing = getenv("PS_REF_TIMING") && atoi(getenv("PS_REF_TIMING"));
     S.setupClockStart();
-    S.buildIntegrationWeightsAlt();
-    S.classifyCells();
-    if (S.doReducedRegions()) S.constructReducedRegions(); else S.constructOnlyActiveRegions();
-    S.classifyFaces();
-    S.classifyEdges();
-    if (S.doReducedRegions()) { S.constructCenterReducedIndices(); S.constructFacesReducedIndices(); S.constructEdgesReducedIndices(); }
-    S.constructCenterActiveIndices(); S.constructFacesActiveIndices(); S.constructEdgesActiveIndices();
+    STAGE("buildIntegrationWeightsAlt", S.buildIntegrationWeightsAlt());
+    STAGE("classifyCells", S.classifyCells());
+    STAGE("constructReducedRegions", if (S.doReducedRegions()) S.constructReducedRegions(); else S.constructOnlyActiveRegions());
+    STAGE("classifyFaces", S.classifyFaces());
+    STAGE("classifyEdges", S.classifyEdges());
     if (S.doReducedRegions()) {
-        S.computeCenterOfMasses();
-        S.computeLeastSquaresFits();
-        S.computeReducedMassMatrices();
-        if (node.getMatrixScheme() == HDK_PolyStokes_Options::MatrixScheme::ALL_DOFS_EXPLICIT_INTERIOR_STRESS) S.computeReducedViscosityMatrices();
-        else S.computeReducedViscosityMatricesInteriorOnly();
+        STAGE("constructCenterReducedIndices", S.constructCenterReducedIndices());
+        STAGE("constructFacesReducedIndices", S.constructFacesReducedIndices());
+        STAGE("constructEdgesReducedIndices", S.constructEdgesReducedIndices());
     }
-    S.constructMatrixBlocks();
+    STAGE("construct*ActiveIndices", S.constructCenterActiveIndices(); S.constructFacesActiveIndices(); S.constructEdgesActiveIndices());
+    if (S.doReducedRegions()) {
+        STAGE("computeCenterOfMasses", S.computeCenterOfMasses());
+        STAGE("computeLeastSquaresFits", S.computeLeastSquaresFits());
+        STAGE("computeReducedMassMatrices", S.computeReducedMassMatrices());
+        if (node.getMatrixScheme() == HDK_PolyStokes_Options::MatrixScheme::ALL_DOFS_EXPLICIT_INTERIOR_STRESS) S.computeReducedViscosityMatrices();
+        else STAGE("computeReducedViscosityMatricesInteriorOnly", S.computeReducedViscosityMatricesInteriorOnly());
+    }
+    STAGE("constructMatrixBlocks", S.constructMatrixBlocks());
     S.initializeGuessVectors();
     if (node.getUseWarmStart()) S.constructGuessVectors();
-    S.assemble();
+    STAGE("assemble", S.assemble());
     S.setupClockEnd();
     return 0;
 }

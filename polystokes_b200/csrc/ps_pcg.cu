@@ -5,12 +5,13 @@
 //     y = -dt K^T Mc^-1 K x  -  J^T B^-1 J x  -  1/2 [0; mu^-1 x_tau],   K = [G D^T], J = [JG JD^T]
 // and the CG loop lib/include/pcg.h:268-340.  Here J is never stored: J = C K_red (see ps_assemble.cu), so
 //   pass 1 : w = K_ext x, one thread per face row (8-wide slot-major ELL, coalesced 8B/4B streams, x gathered
-//            through L1/L2); active rows are scaled by dt Mc^-1, coupled reduced rows keep the raw product
-//   reduced: one CTA per (region, axis) chunk of coupled reduced rows accumulates the 10 monomial moments of w_f;
-//            one warp per region sums the chunk partials in order, t_r -> s_r = B_r^-1 t_r -> sigma_r;
-//            expand overwrites w_f = sigma . monomials(f)
+//            through L1/L2); active rows are scaled by dt Mc^-1.  The coupled reduced rows come in chunks of <= 256 rows of
+//            one (region, face axis): a chunk does not store its products but their 10 monomial moments; the LAST chunk of
+//            a region to finish sums the moments in chunk order, t_r -> s_r = B_r^-1 t_r -> sigma_r, and writes the region's
+//            rows w_f = sigma . monomials(f) -- the whole reduced term of the operator inside the same launch
+//            (regions too large for that -- doTile off -- use the chunked kernels moments -> solve -> expand instead)
 //   pass 2 : y = -K_ext^T w - 1/2 mu^-1 x_tau         (one thread per DOF row, ELL widths 6/2/4), fused with
-//            the p.Ap dot product (warp shuffle -> CTA partial -> last CTA finishes in fixed order)
+//            the dot products p.Ap, r.Ap, Ap.Ap (warp shuffle -> CTA partial -> last CTA finishes in fixed order)
 // All CG scalars live in device memory; the host only polls a convergence flag every few iterations.
 #include "ps_solver.hpp"
 #include "ps_peer.hpp"
@@ -54,23 +55,28 @@ PS_D double sum_partials(const double* p, int n) { double s = 0.; for (int i = 0
 // with more than one rank -- all-reduced in place by the host-enqueued collective (or inside the kernels over peer
 // memory); the consumers below read the global value.  alpha = rsold / p.Ap (pcg.h:313).
 //
-// Vector traffic of one iteration (pcg.h:313-336 does x += a p, r -= a Ap, r.r, x.x, p = r + b p as five sweeps):
-//   update r : r -= alpha Ap, fused r.r                                   reads Ap, r      writes r       (24 B / row)
-//   update xp: x += alpha p, p = r + beta p, fused x.p and p.p            reads x, p, r    writes x, p    (40 B / row)
-// x is only touched while p is in registers anyway, so it is never streamed on its own.  The stop test needs x.x
-// one kernel before the new x exists; it follows from the dots of the PREVIOUS update xp by
+// pcg.h:313-336 sweeps the vectors five times per iteration (x += a p, r -= a Ap, r.r, x.x, p = r + b p) with two
+// reductions (p.Ap before, r.r between).  Here ONE kernel does all three updates:
+//   update : x += alpha p, r -= alpha Ap, p = r + beta p, fused r.r, x.p, p.p      reads x, r, p, Ap   writes x, r, p   (56 B / row)
+// beta = r_new.r_new / r.r is needed before r_new exists; it follows from the dots pass 2 takes while Ap is in registers:
+//   |r - alpha Ap|^2 = r.r - 2 alpha r.Ap + alpha^2 Ap.Ap
+// an identity of the computed vectors (no conjugacy assumed), exact up to a few ulp of r.r.  r.r itself is re-summed directly
+// by the update every iteration (it is the next alpha's numerator and the base of the next recurrence step), so nothing drifts.
+// The stop test needs x.x of the new x as well; it follows from the dots of the PREVIOUS update by
 //   |x + alpha p|^2 = x.x + 2 alpha x.p + alpha^2 p.p
 // (x_0 = 0; in CG every term is >= 0 -- |x_k| grows monotonically -- so the recurrence does not cancel).
-PS_D double cg_alpha(const PcgScalars* S) { return S->rsold / S->red[0]; }
+// One reduction is consumed right after it is produced (pass 2 -> update); the update's own sums are consumed one
+// whole operator apply later.
 // stop test of pcg.h:316-325: min(rr, rr/xx) < tol^2
 PS_D double cg_rre2(double rr, double xx) { double rre = rr; if (rr / xx < rre) rre = rr / xx; return rre; }
 PS_D double cg_next_xx(double xx, double alpha, double xp, double pp) { return xx + (2. * alpha) * xp + (alpha * alpha) * pp; }
-// once per iteration, after every reader of rsold / xx is done (last CTA of update xp): pcg.h:326-336
-PS_D void cg_advance(PcgScalars* S, double rr, double xx) {
+PS_D double cg_next_rr(double rr, double alpha, double rAp, double ApAp) { return (rr - (2. * alpha) * rAp) + (alpha * alpha) * ApAp; }
+// once per iteration, after every reader of the scalars is done (last CTA of the update): pcg.h:326-336
+PS_D void cg_advance(PcgScalars* S, double rsold, double rr, double xx, double alpha, double pAp) {
     const double rre = cg_rre2(rr, xx);
-    S->rsnew = rr; S->xmag = xx; S->xx = xx; S->rre = rre; S->pAp = S->red[0];
+    S->rsnew = rr; S->xmag = xx; S->xx = xx; S->rre = rre; S->pAp = pAp; S->alpha = alpha;
     if (rre < S->tol2) { S->done = 1; return; }
-    S->beta = rr / S->rsold;
+    S->beta = rr / rsold;
     S->rsold = rr;
     S->iter += 1;
     if (S->iter >= S->maxIter) S->done = 2;
@@ -135,37 +141,170 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
     return last;
 }
 
-// pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
-// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.
-// (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
-__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S) {    pdl_sync();
+// sums of v[0..9] over the 32 lanes of a warp by recursive halving (12 double shuffles instead of 50): after the call lane
+// L with (L & 1) == 0 holds the total of value warp_reduce10_index(L) (or -1: padding).  Fixed association: deterministic.
+__device__ __forceinline__ double warp_reduce10(const double* v) {
+    const unsigned lane = threadIdx.x & 31u;
+    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u, b1 = lane & 2u;
+    double u[5], t[3], q[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { const double send = b4 ? v[i] : v[i + 5], keep = b4 ? v[i + 5] : v[i]; u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+    const double u5 = 0.;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const double hi = i + 3 < 5 ? u[i + 3 < 5 ? i + 3 : 4] : u5; const double send = b3 ? u[i] : hi, keep = b3 ? hi : u[i]; t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const double hi = i + 2 < 3 ? t[2] : 0.; const double send = b2 ? t[i] : hi, keep = b2 ? hi : t[i]; q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+    const double send = b1 ? q[0] : q[1], keep = b1 ? q[1] : q[0];
+    double z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    return z;
+}
+__device__ __forceinline__ int warp_reduce10_index(unsigned lane) {
+    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u, b1 = lane & 2u;
+    int k;
+    if (!b3) k = !b2 ? (b1 ? 1 : 0) : (b1 ? -1 : 2);
+    else k = !b2 ? (b1 ? 4 : 3) : -1;
+    return k < 0 ? -1 : k + (b4 ? 5 : 0);
+}
+// the small solve of one region by one whole CTA (pass 1's region epilogue): ordered sum of the chunk moments -> t ->
+// s = B^-1 (tScale t + extraScale extra) -> sigma (shared memory sg[30], and RegionOp::sigma)
+__device__ __forceinline__ void region_epilogue_solve(const RegionOp& R, const int32_t* __restrict__ rowChunk, int region, double* M, double* tv, double* sv, double* sg) {
+    const int tid = threadIdx.x;
+    if (tid < 30) {
+        const int axis = tid / 10, k = tid % 10;
+        double s = 0.;
+        for (int ch = __ldg(R.rowChunkStart + region), e = __ldg(R.rowChunkStart + region + 1); ch < e; ++ch)
+            if (__ldg(rowChunk + 4 * ch + 3) == axis) s += __ldcg(R.partial + (size_t)ch * 10 + k);
+        M[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) moments_to_t(M, tv);
+    __syncthreads();
+    if (tid < RDOF) { double v = R.tScale * tv[tid]; if (R.extra) v += R.extraScale * R.extra[(size_t)region * RDOF + tid]; tv[tid] = v; }
+    __syncthreads();
+    // s_i = sum_j B_ij t_j: 8 lanes per row (coalesced 64 B pieces of B^-1), lane partials combined in a fixed order
+    {
+        const int i = tid >> 3, jp = tid & 7;
+        double acc = 0.;
+        if (i < RDOF) {
+            const double* B = R.Binv + (size_t)region * RDOF * RDOF + i * RDOF;
+#pragma unroll
+            for (int j = jp; j < RDOF; j += 8) acc += __ldg(B + j) * tv[j];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (i < RDOF && jp == 0) sv[i] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) s_to_sigma(sv, sg);
+    __syncthreads();
+    if (tid < 30 && R.sigma) R.sigma[(size_t)region * 30 + tid] = sg[tid];
+}
 
+// pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
+// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.  Work items (256-row blocks of the x / y / z face rows and row chunks of
+// the coupled reduced rows, merged by position in tile order) are handed out dynamically -- the region epilogue makes their
+// cost uneven -- with the next item fetched while the current one is processed.
+// (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
+__device__ __forceinline__ double pass1_row(const OpArgs& A, int64_t r, const double* __restrict__ x, double sc) {
+    const uint64_t word = __ldcs(A.kcode + r);
+    int32_t c[6];
+#pragma unroll
+    for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
+    const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
+    const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
+    const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
+    double xv[8];
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
+    double s = 0.;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
+    return s;
+}
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const __grid_constant__ RegionOp R, const double* __restrict__ x, double* __restrict__ w,
+                                                              double activeScale, const PcgScalars* S, int dynamic) {
+    pdl_sync();
     __shared__ double lut[65];
+    __shared__ int sNext[2];
+    __shared__ int sLast;
+    __shared__ double red[HOT_THREADS / 32][10];
+    __shared__ double M[30], tv[RDOF], sv[RDOF], sg[30];
     if (S && S->done) return;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
+    if (threadIdx.x == 0) sNext[0] = dynamic ? (int)atomicAdd(A.sched1Ctl, 1u) : (int)blockIdx.x;
     __syncthreads();
     const double sc = A.valScale;
-    // owned rows in the merged block order of the four ranges (SchedRanges, ps_solver.hpp)
-#pragma unroll 2
-    for (int g = blockIdx.x; g < A.nSched1; g += gridDim.x) {
-        const int32_t e = __ldg(A.sched1 + g);
+    int cur = sNext[0], buf = 0;
+    while (cur < A.nSched1) {
+        if (threadIdx.x == 0) sNext[buf ^ 1] = dynamic ? (int)atomicAdd(A.sched1Ctl, 1u) : cur + (int)gridDim.x;     // arrives while this item is processed
+        const int32_t e = __ldg(A.sched1 + cur);
         const int k = (int)((uint32_t)e >> 28);
-        const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
-        if (r >= A.s1.hi[k]) continue;
-        const uint64_t word = __ldcs(A.kcode + r);
-        int32_t c[6];
+        if (k < 3) {
+            const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
+            if (r < A.s1.hi[k]) w[r] = activeScale * lut[__ldcs(A.kmc + r)] * pass1_row(A, r, x, sc);
+        } else {
+            // row chunk of the coupled reduced rows: (K_red x)_f, raw
+            const int ch = (int)A.s1.lo[3] + (int)(e & 0x0fffffff);
+            const int region = __ldg(A.rowChunk + 4 * ch), begin = __ldg(A.rowChunk + 4 * ch + 1), end = __ldg(A.rowChunk + 4 * ch + 2);
+            if (R.mode == 0) {
+                for (int row = begin + threadIdx.x; row < end; row += HOT_THREADS) w[A.nActiveVs + row] = pass1_row(A, A.nActiveVs + row, x, sc);
+            } else {
+                const double cm[3] = {__ldg(R.com + 3 * region), __ldg(R.com + 3 * region + 1), __ldg(R.com + 3 * region + 2)};
+                double acc[10];
 #pragma unroll
-        for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
-        const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
-        const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
-        const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
-        double xv[8];
+                for (int q = 0; q < 10; ++q) acc[q] = 0.;
+                for (int row = begin + threadIdx.x; row < end; row += HOT_THREADS) {
+                    const double gk = pass1_row(A, A.nActiveVs + row, x, sc);
+                    double m[10];
+                    row_monomials(R.dx, __ldcs(R.rowXYZ + row), cm, m);
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
-        double s = 0.;
+                    for (int q = 0; q < 10; ++q) acc[q] += m[q] * gk;
+                }
+                const double tot = warp_reduce10(acc);
+                const int ki = warp_reduce10_index(threadIdx.x & 31u);
+                if (!(threadIdx.x & 1) && ki >= 0) red[threadIdx.x >> 5][ki] = tot;
+                __syncthreads();
+                if (threadIdx.x < 10) {
+                    double s2 = 0.;
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
-        w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
+                    for (int wI = 0; wI < HOT_THREADS / 32; ++wI) s2 += red[wI][threadIdx.x];
+                    R.partial[(size_t)ch * 10 + threadIdx.x] = s2;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __threadfence();
+                    const unsigned nch = (unsigned)(__ldg(R.rowChunkStart + region + 1) - __ldg(R.rowChunkStart + region));
+                    const unsigned tk = atomicInc(R.regionTicket + region, nch - 1);
+                    sLast = (tk == nch - 1);
+                    if (sLast) __threadfence();
+                }
+                __syncthreads();
+                if (sLast) {
+                    region_epilogue_solve(R, A.rowChunk, region, M, tv, sv, sg);
+                    // expand: the region's rows (all three axes) <- outScale * sigma[axis] . monomials(f)
+                    for (int row = __ldg(R.rowStart + region) + threadIdx.x, rend = __ldg(R.rowStart + region + 1); row < rend; row += HOT_THREADS) {
+                        const uint32_t xyz = __ldg(R.rowXYZ + row);
+                        const double* sgl = sg + 10 * (int)(xyz >> 30);
+                        double m[10];
+                        row_monomials(R.dx, xyz, cm, m);
+                        double v = 0.;
+#pragma unroll
+                        for (int q = 0; q < 10; ++q) v += sgl[q] * m[q];
+                        w[A.nActiveVs + row] = R.outScale * v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        buf ^= 1;
+        cur = sNext[buf];
+    }
+    // the last CTA to run out of items re-arms the schedule for the next launch
+    if (dynamic && threadIdx.x == 0) {
+        const unsigned t = atomicInc(A.sched1Ctl + 1, gridDim.x - 1);
+        if (t == gridDim.x - 1) { A.sched1Ctl[0] = 0u; __threadfence(); }
     }
 }
 // last CTA of a producer: a, b are valid in thread 0; every rank's block receives this rank's partial sums

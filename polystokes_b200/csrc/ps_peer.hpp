@@ -20,19 +20,20 @@
 namespace ps {
 
 constexpr int PEER_MAX_RANKS = 8;
-constexpr int PEER_SLOTS = 4;      // reduction slots: 0 p.Ap, 1 r.r, 2 b.b, 3 (x.p, p.p)
+constexpr int PEER_SLOTS = 2;      // reduction slots: 0 (p.Ap, r.Ap, Ap.Ap) of pass 2, 1 (r.r, x.p, p.p) of the x/r/p update (or b.b, 0, b.b from init)
+constexpr int PEER_VALS = 3;       // values per reduction
 
 struct PeerSync {                  // head of every rank's symmetric block
     unsigned long long haloFlag[2][2][2];                      // [kind x|w][parity][side: from below | from above]
     unsigned long long redFlag[2][PEER_SLOTS][PEER_MAX_RANKS]; // [parity][slot][source rank]
-    double redVal[2][PEER_SLOTS][2][PEER_MAX_RANKS];           // [parity][slot][value][source rank]
+    double redVal[2][PEER_SLOTS][PEER_VALS][PEER_MAX_RANKS];   // [parity][slot][value][source rank]
     unsigned long long pad[16];
 };
 
 struct PeerCtx {                   // passed by value to the CG kernels; nranks <= 1 means "no peers"
     int nranks = 1, rank = 0;
     unsigned long long seqIn = 0, seqOut = 0;   // sequence numbers of the reduction this kernel consumes / produces
-    unsigned long long seqIn2 = 0;              // update xp also consumes slot 3 of the previous iteration (0: first iteration, nothing to wait for)
+    unsigned long long seqIn2 = 0;              // the x/r/p update also consumes slot 1 of the previous update (or of init)
     PeerSync* sync[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -42,7 +43,7 @@ struct PeerLink {
     int rank = 0, nranks = 1;
     void* block[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // block[rank] = mine, others IPC-mapped
     size_t cap = 0;                               // doubles per halo receive buffer
-    unsigned long long seqHalo[2] = {0, 0}, seqRed[PEER_SLOTS] = {0, 0, 0, 0};
+    unsigned long long seqHalo[2] = {0, 0}, seqRed[PEER_SLOTS] = {0, 0};
     PeerSync* sync(int r) const { return (PeerSync*)block[r]; }
     double* recv(int r, int kind, int par, int side) const { return (double*)((char*)block[r] + sizeof(PeerSync)) + ((size_t)((kind * 2 + par) * 2 + side)) * cap; }
     size_t bytes() const { return sizeof(PeerSync) + 8 * cap * sizeof(double); }
@@ -90,7 +91,7 @@ __device__ __forceinline__ void peer_reduce_push(const PeerCtx& P, int slot, con
 // called by every thread of a CTA: waits for the N partials of reduction (slot, seq) and returns their rank-ordered
 // sums in out[0..nvals); returns false (in every thread) on time-out
 __device__ __forceinline__ bool peer_reduce_wait(const PeerCtx& P, int slot, unsigned long long seq, double* out, int nvals) {
-    __shared__ double sh[2];
+    __shared__ double sh[PEER_VALS];
     __shared__ int ok;
     if (threadIdx.x < 32) {
         const PeerSync* m = P.sync[P.rank];

@@ -50,8 +50,10 @@ constexpr int SCHED_BLOCK = 256;
 struct SchedRanges {
     int n = 0;
     int64_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    int64_t items[4] = {-1, -1, -1, -1};     // >= 0: the range is a list of that many work items (lo = first item), not 256-row blocks
     void add(int64_t a, int64_t b) { lo[n] = a; hi[n] = b > a ? b : a; ++n; }
-    int64_t blocks(int k) const { return (hi[k] - lo[k] + SCHED_BLOCK - 1) / SCHED_BLOCK; }
+    void addItems(int64_t first, int64_t count) { lo[n] = first; hi[n] = first + (count > 0 ? count : 0); items[n] = count > 0 ? count : 0; ++n; }
+    int64_t blocks(int k) const { return items[k] >= 0 ? items[k] : (hi[k] - lo[k] + SCHED_BLOCK - 1) / SCHED_BLOCK; }
 };
 std::vector<int32_t> merge_schedule(const SchedRanges& R);
 
@@ -78,6 +80,7 @@ struct RegionData {
     DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
     DBuf<int32_t> rowAxisStart;  // [3R+1] first coupled reduced row of (region, face axis): the row ranges of reduced_region_kernel
     int32_t maxRegionRows = 0;   // largest number of coupled reduced rows of one region (decides fused vs chunked reduced kernels)
+    bool fusedRegions = false;   // regions small enough for the fused epilogue of pass 1 (row chunks of <= 256 rows)
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
     DBuf<unsigned int> regionTicket;   // [R] chunks of the region that have delivered their moments (self-resetting)
@@ -110,9 +113,10 @@ struct PcgScalars {   // device-resident CG state: no host round trip inside an 
     double rsold, pAp, alpha, beta, rsnew, xmag, rre;
     int iter, done, maxIter, pad;
     double tol2;
-    unsigned int ticket[8];   // last-CTA-done tickets: 0 pass 2, 1 r update, 2 init, 3 x/p update, 4/5 halo push of p / w
-    int peerError, pad2;      // sticky: a peer-memory wait timed out (ps_peer.hpp)
-    double red[5];            // rank-local sums handed to the all-reduce: [0] p.Ap, [1] r.r, [2] x.p, [3] p.p (1..3 travel together), [4] b.b
+    unsigned int ticket[8];   // last-CTA-done tickets: 0 pass 2, 2 init, 3 x/r/p update, 4/5 halo push of p / w, 6 BiCGSTAB / Eigen sweeps
+    int peerError, pad2;      // a peer-memory wait timed out (ps_peer.hpp); cleared when the host has reported it
+    // rank-local sums handed to the all-reduces: [0..2] p.Ap, r.Ap, Ap.Ap (pass 2), [3..5] r.r, x.p, p.p (x/r/p update, or b.b, 0, b.b from init), [6] b.b
+    double red[7];
     double xx;                // global x.x of the current iterate, advanced by |x + alpha p|^2 = x.x + 2 alpha x.p + alpha^2 p.p (ps_pcg.cu)
     // BiCGSTAB fallback (pcg.h:134-200): its own scalars; bred[] = rank-local dot products of the current stage
     double rhoCurr, rhoOld, omega, tol, bred[2];
@@ -219,6 +223,8 @@ public:
     CompactOp Op;                 // K_ext and K_ext^T
     SchedRanges sr1, sr2;         // block schedules of pass 1 / pass 2 over the owned rows (merge_schedule)
     DBuf<int32_t> sched1, sched2;
+    DBuf<unsigned int> sched1Ctl; // dynamic-schedule counters of pass 1 (OpArgs::sched1Ctl)
+    RegionOp regionOp(int mode, const double* extra = nullptr, double extraScale = 0., double tScale = 1., double outScale = 1.) const;
     int nSched1 = 0, nSched2 = 0;
     void buildSchedules();
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
@@ -287,24 +293,39 @@ void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, Comp
 // ps_pcg.cu
 struct OpArgs {   // everything one operator apply touches
     int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
-    SchedRanges s1, s2;           // pass 1: face rows x, y, z, coupled reduced rows; pass 2: cells, edges yz, xz, xy (edge numbering)
+    SchedRanges s1, s2;           // pass 1: face rows x, y, z, row chunks of the coupled reduced rows; pass 2: cells, edges yz, xz, xy (edge numbering)
     const int32_t* sched1; const int32_t* sched2; int nSched1, nSched2;
+    unsigned int* sched1Ctl;      // [0] next item of pass 1's dynamic schedule, [1] CTAs that have run out of items (the last one resets both)
+    const int32_t* rowChunk;      // [nChunks][4] = region, begin, end, axis of the row chunks (RegionData)
     RowSet rowsK, rowsP, rowsE;   // rows this rank computes (all rows on one GPU); the centre-stress rows follow rowsP
     const uint64_t* kcode; const int32_t* kcol; const uint8_t* kmc; const double* mcInvLut;
     const uint64_t* ccode; const int32_t* ccol; const uint32_t* ecode; const int32_t* ecol;
     const double* uInv;
     double valScale;              // invDx / 64
 };
-void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal);
-void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode);
+// What pass 1 does with the coupled reduced rows of the owned regions.  mode 0: store the raw products (K_red x)_f in w.
+// mode 1 (regions of <= a few thousand rows, RegionData::fusedRegions): the reduced term of the operator in the same launch --
+// every row chunk leaves its 10 monomial moments, the last chunk of a region to finish sums them in chunk order,
+// s = B^-1 (tScale t + extraScale extra), sigma, and overwrites the region's rows with w_f = outScale * c_f . s.
+struct RegionOp {
+    int mode = 0;
+    double dx = 0;
+    const uint32_t* rowXYZ = nullptr; const int32_t* rowChunkStart = nullptr; const int32_t* rowStart = nullptr;
+    const double* com = nullptr; const double* Binv = nullptr; double* partial = nullptr; unsigned int* regionTicket = nullptr;
+    const double* extra = nullptr; double extraScale = 0, tScale = 1, outScale = 1;
+    double* sigma = nullptr;
+};
+void k_pass1(cudaStream_t, const OpArgs&, const RegionOp&, const double* x, double* w, double activeScale, const PcgScalars* scal);
+// mode bit 0: dot(x, y) (p.Ap) -> red[0]; bit 1: also dot(r2, y), dot(y, y) (r.Ap, Ap.Ap) -> red[1], red[2]
+void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode,
+             const double* r2 = nullptr);
 // moments of w_f per chunk; with `solve` the last chunk of every region also runs reduced_finish(nullptr, 0, 1) for it (one launch less)
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal, bool solve = false);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
 // the reduced term of one apply: w_f <- scale * c_f . B^-1 (sum_f c_f w_f); one fused launch for tiled regions, moments + expand otherwise
 void reduced_apply(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-void k_cg_update_r(cudaStream_t, const RangeSet& own, double* r, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
-void k_cg_update_xp(cudaStream_t, const RangeSet& own, double* x, double* p, const double* r, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
+void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
 void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);
 // BiCGSTAB fallback (pcg.h:134-200).  Dot products land rank-local in scal->bred[], the host enqueues the all-reduce
