@@ -82,22 +82,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample_size(steps_total):
-    """S3 at reduced resolution, sized so steps_total oracle steps finish within a few minutes."""
-    budget = 150.0 / max(1, steps_total)
-    for n, est in ((128, 22.0), (96, 9.0), (64, 3.5)):
-        if est <= budget:
-            return n
-    return 48
-
-
-def ref_sample_size(steps_total):
-    """Same for the compiled reference (oracle/_ref/libps_ref_full.so: one job + the three omp sections of its operator apply)."""
-    budget = 150.0 / max(1, steps_total)
-    for n, est in ((96, 50.0), (80, 28.0), (64, 13.0), (48, 6.0)):
-        if est <= budget:
-            return n
-    return 32
+REF_CACHE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "polystokes_b200_reference_run.json")
 
 
 def reference_available():
@@ -108,43 +93,88 @@ def reference_available():
         return False
 
 
-def run_ref_sample(n, full_counts=None):
-    """One full step of the REFERENCE'S OWN solver (all of exec/HDK_PolyStokesSolver*.cpp + lib/, compiled unmodified into
-    oracle/_ref/libps_ref_full.so on the HDK stand-in / Eigen facade) on S3 at n^3, timed by the reference's own setup / solve clocks
-    (S.cpp setupClockStart..End, S.cpp:760-805) plus the write-back; extrapolated to 256^3 like run_cpu_sample."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return float(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def _ref_worker(n, threads, q):
+    """One COMPLETE step of the REFERENCE'S OWN solver on S3 at n^3 (child process, so its memory goes back to the OS).
+
+    The solver is all of exec/HDK_PolyStokesSolver*.cpp + lib/, compiled unmodified into oracle/_ref/libps_ref_full.so on the HDK stand-in /
+    Eigen facade, driven in the stage order of exec/HDK_PolyStokes.C:344-584.  Threads: `threads` jobs behind UT_ThreadedAlgorithm /
+    UTparallelFor / tbb::parallel_for (setup sweeps), OpenMP for Eigen's row-parallel SpMV and the 3 `omp sections` of the operator apply
+    (lib/include/ApplyPressureStressMatrix.h:122-164; nested regions are serial, as in the real plugin)."""
+    import resource
     from polystokes_b200 import scenes
-    from oracle.ref_full import RefFull
+    from oracle import ref_full
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    L = ref_full.lib()
+    jobs = L.reffull_set_threads(int(threads))
     sc = scenes.scene_s3(n)
     devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)      # the reference chats on stdout
     try:
         t0 = time.perf_counter()
-        R = RefFull(sc).setup()
+        R = ref_full.RefFull(sc).setup()
         t_setup = time.perf_counter() - t0
         t0 = time.perf_counter()
         rc = R.solve()
         t_solve = time.perf_counter() - t0
     finally:
         os.dup2(saved, 1); os.close(saved); os.close(devnull)
-    iters = max(1, R.count("iterations") + 1)
-    nsys = max(1, R.count("nSystemSize"))
-    cg_s = R.real("solveWallclockMs") * 1e-3
+    out = dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, cg_s=R.real("solveWallclockMs") * 1e-3, iterations=int(R.count("iterations")),
+               nSystemSize=int(R.count("nSystemSize")), result=int(rc), jobs=int(jobs), cores=int(threads),
+               maxrss_gb=resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6)
     R.close()
-    vox_ratio = (SCENE_N / n) ** 3
-    if full_counts:
-        it_full, n_full = full_counts["iterations"] + 1, full_counts["nSystemSize"]
-    else:
-        it_full, n_full = iters * SCENE_N / n, nsys * vox_ratio
-    t_full = (t_setup + (t_solve - cg_s)) * vox_ratio + (cg_s / iters) * (n_full / nsys) * it_full
-    return dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, cg_s=cg_s, iterations=iters - 1, nSystemSize=nsys, full_seconds=t_full,
-                cores=3, result=rc)
+    q.put(out)
 
 
-def run_cpu_sample(n, full_counts=None, threads=0):
-    """One full oracle step on S3 at n^3; returns measured seconds and the extrapolation to 256^3.
+def run_ref_full(n, threads=None):
+    """Measured, unscaled: one full step of the compiled reference at n^3 with all host cores."""
+    import multiprocessing as mp
+    threads = threads or host_cores()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    pr = ctx.Process(target=_ref_worker, args=(n, threads, q))
+    pr.start()
+    res = None
+    while res is None:
+        try:
+            res = q.get(timeout=1.0)
+        except Exception:
+            if not pr.is_alive():
+                raise RuntimeError(f"reference run at {n}^3 died (exit code {pr.exitcode}; out of memory?)")
+    pr.join()
+    return res
 
-    Extrapolation: setup scales with the voxel count; a CG iteration scales with the
-    system size; the iteration count at 256^3 is the one the GPU arm measured (else scaled ~ linearly in n).
-    """
+
+def choose_ref_grid(budget_s, cal):
+    """Largest S3 grid whose predicted reference time fits `budget_s` and whose predicted memory fits the host.  `cal` is a measured run at a small
+    grid; setup scales with the voxel count, CG with rows x iterations (iterations ~ n on S3: 63 / 97 / 129 / 258 at 64 / 96 / 128 / 256)."""
+    avail = mem_available_gb()
+    for n in (256, 192, 128, 96):
+        f3 = (n / cal["n"]) ** 3
+        pred_s = (cal["seconds"] - cal["cg_s"]) * f3 + cal["cg_s"] * f3 * (n / cal["n"])
+        pred_gb = cal["maxrss_gb"] * f3 * 1.15
+        if pred_s <= budget_s and pred_gb <= 0.7 * avail:
+            return n, pred_s, pred_gb
+    return cal["n"], cal["seconds"], cal["maxrss_gb"]
+
+
+def run_cpu_sample(n, threads=0):
+    """One full step of the oracle (CPU restatement, OpenMP) on S3 at n^3; measured seconds, no scaling."""
     from polystokes_b200 import scenes
     from oracle.oracle import Oracle, lib
     sc = scenes.scene_s3(n)
@@ -155,17 +185,8 @@ def run_cpu_sample(n, full_counts=None, threads=0):
     o.solve()
     o.writeback()
     t_solve = time.perf_counter() - t0
-    iters = max(1, o.count("iterations") + 1)
-    nsys = max(1, o.count("nSystemSize"))
-    vox_ratio = (SCENE_N / n) ** 3
-    if full_counts:
-        it_full, n_full = full_counts["iterations"] + 1, full_counts["nSystemSize"]
-    else:
-        it_full, n_full = iters * SCENE_N / n, nsys * vox_ratio
-    t_full = t_setup * vox_ratio + (t_solve / iters) * (n_full / nsys) * it_full
-    out = dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, iterations=iters - 1, nSystemSize=nsys,
-               full_seconds=t_full, cores=lib().orc_num_threads())
-    return out
+    return dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, iterations=int(o.count("iterations")), nSystemSize=int(o.count("nSystemSize")),
+                cores=lib().orc_num_threads())
 
 
 def emit(obj):
@@ -201,38 +222,58 @@ def main():
               "l2": "inputs (9 fp32 grids, 0.6 GB at 256^3) and matrices (>2 GB) exceed the 126 MB L2; no flush needed"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
+    # ONE measured, unscaled step of the reference's own solver with every host core, at the largest S3 grid that fits the time / memory budget
+    # (256^3 = the metric's configuration if it fits); `config.grid` is what actually ran.  --steps / --warmup do not apply to a run of this
+    # length: the line reports steps 1, warmup 0.  Under torchrun only rank 0 works; at N > 1 the N = 1 measurement of this box is reused (the CPU
+    # path does not depend on N) and marked "cached".
     if a.impl == "reference":
         if rank != 0:
             return
-        use_ref = reference_available()
-        if use_ref:
-            n = ref_sample_size(a.steps + a.warmup) if a.n == SCENE_N else a.n
-            run = run_ref_sample
-        else:
-            n = cpu_sample_size(a.steps + a.warmup) if a.n == SCENE_N else a.n
-            run = run_cpu_sample
-        for _ in range(a.warmup):
-            run(n)
-        res = [run(n) for _ in range(a.steps)]
-        full = sum(r["full_seconds"] for r in res) / len(res)
-        samp = sum(r["seconds"] for r in res) / len(res)
-        value = 1.0 / full
-        if use_ref:
-            kind = "reference"
-            sample = (f"the reference's own solver (exec/HDK_PolyStokesSolver*.cpp + lib/, compiled unmodified into oracle/_ref/libps_ref_full.so on the HDK "
-                      f"stand-in / Eigen facade; one job + the 3 omp sections of its operator apply) ran the full step on S3 at {n}^3 in {samp:.2f} s "
-                      f"(setup {res[0]['setup_s']:.2f} s, {res[0]['iterations']} CG iterations in {res[0]['cg_s']:.2f} s, n={res[0]['nSystemSize']}); scaled to 256^3: "
-                      f"setup + write-back x{(SCENE_N / n) ** 3:.1f} voxels, CG time x system-size ratio x iteration ratio")
-        else:
-            kind = "port"
-            sample = (f"oracle (CPU restatement of the reference path, OpenMP) ran the full step on S3 at {n}^3 in {samp:.2f} s "
-                      f"({res[0]['iterations']} CG iterations, n={res[0]['nSystemSize']}); scaled to 256^3: setup x{(SCENE_N / n) ** 3:.1f} voxels, "
-                      "CG time x system-size ratio x iteration ratio")
-        emit(dict({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                          "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic", "config": config, "impl": "reference",
-                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[0]["cores"], "kind": kind, "sample": sample},
-                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        cores = host_cores()
+        budget = float(os.environ.get("PS_REF_BUDGET_S", "1300"))
+        res = None
+        cached = False
+        if a.gpus > 1 and os.path.exists(REF_CACHE):
+            try:
+                with open(REF_CACHE) as f:
+                    res = json.load(f)
+                cached = res.get("scene") == "S3" and res.get("kind") is not None
+                if not cached:
+                    res = None
+            except Exception:
+                res = None
+        if res is None:
+            if reference_available():
+                if a.n != SCENE_N:
+                    n, note = a.n, "grid forced by --n"
+                else:
+                    cal = run_ref_full(64, cores)
+                    n, pred_s, pred_gb = choose_ref_grid(budget, cal)
+                    note = (f"grid chosen from a 64^3 calibration run ({cal['seconds']:.1f} s, {cal['maxrss_gb']:.1f} GB): predicted {pred_s:.0f} s / {pred_gb:.0f} GB at {n}^3 "
+                            f"against a budget of {budget:.0f} s and {mem_available_gb():.0f} GB available")
+                res = run_ref_full(n, cores) if n != 64 or a.n == 64 else cal
+                res.update(kind="reference", scene="S3", note=note)
+            else:
+                n = a.n if a.n != SCENE_N else 128
+                res = run_cpu_sample(n)
+                res.update(kind="port", scene="S3", note="oracle/_ref absent: the oracle (CPU restatement, OpenMP, all cores) ran instead", cg_s=res["solve_s"], maxrss_gb=0.0, jobs=res["cores"])
+            try:
+                with open(REF_CACHE, "w") as f:
+                    json.dump(res, f)
+            except Exception:
+                pass
+        n = res["n"]
+        value = 1.0 / res["seconds"]
+        config = dict(config, grid=[n] * 3, workload=config["workload"].replace(f"{a.n}^3", f"{n}^3"),
+                      same_grid_as_metric=(n == SCENE_N))
+        sample = (f"{'the reference solver (exec/HDK_PolyStokesSolver*.cpp + lib/, compiled unmodified into oracle/_ref/libps_ref_full.so)' if res['kind'] == 'reference' else 'the oracle port'}"
+                  f" ran ONE complete step on S3 at {n}^3 in {res['seconds']:.1f} s: setup {res['setup_s']:.1f} s ({res['jobs']} jobs), solve + write-back {res['solve_s']:.1f} s "
+                  f"({res['iterations']} CG iterations in {res['cg_s']:.1f} s: 3 omp sections, lib/include/ApplyPressureStressMatrix.h:122), n = {res['nSystemSize']} rows, "
+                  f"peak RSS {res['maxrss_gb']:.1f} GB; measured, not scaled; {res['note']}" + ("; reused from this box's N = 1 run" if cached else ""))
+        emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": 1, "warmup": 0, "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference", "cached": cached,
+              "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": sample},
+              "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ------------------------------------------------------------------ our arm (CUDA)
@@ -335,37 +376,80 @@ def main():
     peak, peak_src = measured_peak()
     solver.setup(d_in[0], d_in[1], d_in[2], d_vel, d_cvel)
     kern = {}
-    for k in ("pass1", "pass2", "apply", "cg_iteration"):
+    for k in ("pass1", "pass1_sweep", "pass2", "pass2_dots", "apply", "cg_update", "cg_iteration"):
         ms = solver.time_kernel(k, a.kernel_reps)
         by = solver.kernel_bytes(k) / world          # per-GPU share of the algorithmic bytes (rows are split ~evenly over the slabs)
         kern[k] = {"ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+    # the dominant kernel = the longest of the three kernels of a CG iteration, as timed above
+    names = {"pass1": "pass1_kernel (w = K_ext p with dt Mc^-1, fused region term: moments -> B^-1 -> expand)",
+             "pass2_dots": "pass2_kernel (Ap = -K_ext^T w - 1/2 mu^-1 p, fused p.Ap, r.Ap, Ap.Ap)",
+             "cg_update": "cg_update_kernel (x += a p, r -= a Ap, p = r + b p, fused r.r, x.p, p.p)"}
+    dom = max(names, key=lambda k: kern[k]["ms"])
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture of this build (profiles/ncu_traffic.json, single GPU, full grid): only
+    # meaningful next to the N = 1 launch; at N > 1 the per-rank kernel was not captured -> null
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            tj = json.load(f)
-            traffic = next((v for k, v in tj.items() if "pass2_kernel" in k), None)
-    except Exception:
-        pass
-    roofline = {"kernel": "pass2_kernel (y = -K_ext^T w - 1/2 mu^-1 x, fused p.Ap)", "bound": "hbm", "achieved": kern["pass2"]["gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kern["pass2"]["frac"], "traffic": traffic, "peak_source": peak_src, "kernels": kern}
+    if world == 1 and a.n == SCENE_N:
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            key = names[dom].split(" ")[0]
+            traffic = next((v for k, v in tj.items() if key in k), None)
+        except Exception:
+            traffic = None
+    working_set = kern[dom]["algorithmic_bytes"]
+    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic,
+                "peak_source": peak_src, "l2_resident": bool(working_set < 126e6),
+                "note": ("per-rank working set below the 126 MB L2: frac is not HBM evidence" if working_set < 126e6 else
+                         "achieved = algorithmic bytes of one launch (DESIGN.md section 5, ps_kernel_bytes) / CUDA-event time on the solver's stream"),
+                "spmv": {"pass1_frac": kern["pass1"]["frac"], "pass2_frac": kern["pass2_dots"]["frac"]}, "kernels": kern}
 
-    # ---- CPU baseline: the oracle on the box's host cores, bounded sample (rank 0, N=1 only)
+    # ---- the same step at the grids the CPU arms ran (N = 1): same-configuration ratios without any scaling
+    def gpu_step_rates(n, steps=3):
+        sc2 = scenes.scene_s3(n)
+        s2 = PolyStokesSolver.from_scene(sc2, device=local)
+        hin = [pin(sc2.surface), pin(sc2.collision), pin(sc2.viscosity)]; hv = [pin(v) for v in sc2.vel]; hc = [pin(v) for v in sc2.colvel]
+        ho = [torch.empty_like(v).pin_memory() for v in hv]; hval = [torch.empty_like(v).pin_memory() for v in hv]
+        def one():
+            rc = s2.step(hin[0].numpy(), hin[1].numpy(), hin[2].numpy(), npv(hv), npv(hc), npv(ho), npv(hval))
+            if rc != PS_SUCCESS:
+                raise SystemExit(f"bench.py: solver returned {rc} at {n}^3")
+        one(); one()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        its = s2.count("iterations"); nsys = s2.count("nSystemSize")
+        s2.close()
+        return {"grid": n, "e2e_steps_per_s": 1.0 / dt, "e2e_ms_per_step": dt * 1e3, "cg_iterations": its, "nSystemSize": nsys}
+
+    # ---- CPU baseline: the reference's own solver on the box's host cores, BOUNDED sample (rank 0, N = 1 only): one measured step at 96^3
     cpu = None
+    same_grid = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = run_cpu_sample(128 if a.n >= 128 else a.n, full_counts=counts if a.n == SCENE_N else None)
-        port = {"value": 1.0 / r["full_seconds"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                "sample": (f"oracle (OpenMP restatement, all host cores) full step on S3 at {r['n']}^3: {r['seconds']:.2f} s (setup {r['setup_s']:.2f} s, {r['iterations']} CG its, "
-                           f"n={r['nSystemSize']}); scaled to 256^3 (setup x{(SCENE_N / r['n']) ** 3:.0f} voxels, per-iteration time x system-size ratio, GPU-measured "
-                           f"iteration count) = {r['full_seconds']:.1f} s/step")}
-        cpu = port
+        ncal = 96 if a.n >= 96 else a.n
         if reference_available():
-            q = run_ref_sample(64 if a.n >= 64 else a.n, full_counts=counts if a.n == SCENE_N else None)
-            cpu = {"value": 1.0 / q["full_seconds"], "unit": UNIT, "cores": q["cores"], "kind": "reference",
-                   "sample": (f"the reference's own solver (oracle/_ref/libps_ref_full.so: exec/HDK_PolyStokesSolver*.cpp + lib/ compiled unmodified on the HDK stand-in / "
-                              f"Eigen facade; one job + the 3 omp sections of its operator apply) full step on S3 at {q['n']}^3: {q['seconds']:.2f} s (setup {q['setup_s']:.2f} s, "
-                              f"{q['iterations']} CG its in {q['cg_s']:.2f} s, n={q['nSystemSize']}); scaled to 256^3 (setup + write-back x{(SCENE_N / q['n']) ** 3:.0f} voxels, "
-                              f"per-iteration time x system-size ratio, GPU-measured iteration count) = {q['full_seconds']:.1f} s/step"),
-                   "port_all_cores": port}
+            q = run_ref_full(ncal)
+            g96 = gpu_step_rates(ncal)
+            cpu = {"value": 1.0 / q["seconds"], "unit": UNIT, "cores": q["cores"], "kind": "reference", "grid": [ncal] * 3,
+                   "sample": (f"the reference's own solver (oracle/_ref/libps_ref_full.so: exec/HDK_PolyStokesSolver*.cpp + lib/ compiled unmodified on the HDK stand-in / Eigen "
+                              f"facade, {q['jobs']} setup jobs + OpenMP) ran ONE full step of the same scene S3 at {ncal}^3 (bounded sample; value = measured steps/s AT THAT GRID, "
+                              f"not scaled): {q['seconds']:.2f} s (setup {q['setup_s']:.2f} s, {q['iterations']} CG its in {q['cg_s']:.2f} s, n={q['nSystemSize']})"),
+                   "gpu_same_grid": g96, "same_grid_ratio_e2e": g96["e2e_steps_per_s"] * q["seconds"]}
+        else:
+            q = run_cpu_sample(ncal)
+            cpu = {"value": 1.0 / q["seconds"], "unit": UNIT, "cores": q["cores"], "kind": "port", "grid": [ncal] * 3,
+                   "sample": f"oracle (OpenMP restatement, all host cores) ran ONE full step of S3 at {ncal}^3 (bounded sample, not scaled): {q['seconds']:.2f} s ({q['iterations']} CG its)"}
+        # the full-size run of the reference arm on this box, if it ran before us (bench.py --impl reference writes it)
+        try:
+            with open(REF_CACHE) as f:
+                full = json.load(f)
+            gfull = {"grid": a.n, "e2e_steps_per_s": e2e["value"], "e2e_ms_per_step": e2e["ms_per_step"]} if full["n"] == a.n else gpu_step_rates(full["n"])
+            same_grid = {"grid": [full["n"]] * 3, "reference_seconds_per_step": full["seconds"], "reference_cores": full["cores"], "reference_kind": full["kind"],
+                         "ours_e2e_steps_per_s": gfull["e2e_steps_per_s"], "same_config_ratio": gfull["e2e_steps_per_s"] * full["seconds"],
+                         "source": "this box's `bench.py --impl reference` run (measured, unscaled)"}
+        except Exception:
+            same_grid = None
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -379,7 +463,7 @@ def main():
                                                    "device_ms_per_step = sum of per-stage CUDA-event times"),
                "wall_ms_per_step": wall / a.steps * 1e3, "device_ms_per_step": dev_ms / a.steps, "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                "cg_iterations": counts["iterations"], "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-               "roofline": roofline, "cpu_baseline": cpu}
+               "roofline": roofline, "cpu_baseline": cpu, "vs_reference_same_grid": same_grid}
         emit(out)
     if dist is not None:
         dist.destroy_process_group()

@@ -9,13 +9,36 @@
 
 using namespace ps;
 
-struct ps_solver { Solver* S; void* tm[2] = {nullptr, nullptr}; };   // tm: the CUDA events of ps_timer
+struct ps_solver { Solver* S; void* tm[2] = {nullptr, nullptr}; Scratch scratch; };   // tm: the CUDA events of ps_timer
 
 namespace {
 
 template <class Fn>
 int guarded(Fn&& fn) {
     try { return fn(); }
+    catch (const std::exception& e) { g_lastError = e.what(); return PS_FAILED; }
+    catch (...) { g_lastError = "unknown error"; return PS_FAILED; }
+}
+// Every entry point that takes a handle runs on the handle's device with the handle's scratch buffers, whatever thread calls it
+// (Houdini cooks a DOP on arbitrary worker threads whose current device is 0), and leaves the caller's current device untouched.
+struct Enter {
+    int prev = -1; Scratch* prevScratch;
+    explicit Enter(ps_solver* h) : prevScratch(g_scratch) {
+        g_scratch = &h->scratch;
+#ifndef PS_EMULATE
+        if (h->S) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != h->S->P.device) PS_CUDA(cudaSetDevice(h->S->P.device)); else prev = -1; }
+#endif
+    }
+    ~Enter() {
+        g_scratch = prevScratch;
+#ifndef PS_EMULATE
+        if (prev >= 0) cudaSetDevice(prev);
+#endif
+    }
+};
+template <class Fn>
+int guarded(ps_solver* h, Fn&& fn) {
+    try { Enter e(h); return fn(); }
     catch (const std::exception& e) { g_lastError = e.what(); return PS_FAILED; }
     catch (...) { g_lastError = "unknown error"; return PS_FAILED; }
 }
@@ -199,25 +222,35 @@ const char* ps_last_error(void) { return g_lastError.c_str(); }
 int ps_create(const ps_params* params, ps_handle* out) {
     if (!params || !out) { g_lastError = "ps_create: null argument"; return PS_INVALID; }
     *out = nullptr;
-    return guarded([&] { ps_solver* h = new ps_solver; h->S = new Solver(*params); *out = h; return (int)PS_SUCCESS; });
+    return guarded([&] {
+        ps_solver* h = new ps_solver; h->S = nullptr;
+        int prev = -1;
+#ifndef PS_EMULATE
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+#endif
+        try { h->S = new Solver(*params); } catch (...) { delete h; throw; }
+#ifndef PS_EMULATE
+        if (prev >= 0 && prev != params->device) cudaSetDevice(prev);      // the constructor selected the handle's device
+#endif
+        *out = h; return (int)PS_SUCCESS; });
 }
 void ps_destroy(ps_handle h) {
     if (!h) return;
 #ifndef PS_EMULATE
     for (void* e : h->tm) if (e) cudaEventDestroy((cudaEvent_t)e);
 #endif
-    delete h->S; delete h;
+    try { Enter e(h); delete h->S; h->S = nullptr; } catch (...) {}
+    delete h;      // the scratch buffers go with it (cudaFree finds the owning device from the pointer)
 }
 
 #ifndef PS_EMULATE
 int ps_comm_unique_id(void* id128) {
     if (!id128) { g_lastError = "ps_comm_unique_id: null argument"; return PS_INVALID; }
-    return guarded([&] { nccl_unique_id(id128); return (int)PS_SUCCESS; });
+    return guarded([&] { nccl_unique_id(id128); return (int)PS_SUCCESS; });  // no handle
 }
 int ps_comm_init(ps_handle h, int rank, int nranks, const void* id128) {
     if (!h || !id128) { g_lastError = "ps_comm_init: null argument"; return PS_INVALID; }
-    return guarded([&] {
-        PS_CUDA(cudaSetDevice(h->S->P.device));
+    return guarded(h, [&] {
         h->S->initComm(make_nccl_comm(rank, nranks, id128));
         h->S->setupPeer();
         return (int)PS_SUCCESS;
@@ -229,7 +262,7 @@ int ps_comm_unique_id(void* id128) { if (id128) memset(id128, 0, 128); return PS
 int ps_comm_init(ps_handle, int, int, const void*) { g_lastError = "ps_comm_init: the emulation twin takes ps_comm_init_callbacks"; return PS_FAILED; }
 int ps_comm_init_callbacks(ps_handle h, int rank, int nranks, ps_allreduce_cb ar, ps_sendrecv_cb sr, void* ctx) {
     if (!h || !ar || !sr) return PS_INVALID;
-    return guarded([&] { h->S->initComm(make_callback_comm(rank, nranks, ar, sr, ctx)); return (int)PS_SUCCESS; });
+    return guarded(h, [&] { h->S->initComm(make_callback_comm(rank, nranks, ar, sr, ctx)); return (int)PS_SUCCESS; });
 }
 #endif
 int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int32_t* zCut) {
@@ -244,7 +277,7 @@ int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int
 
 int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* stats) {
     if (!h || !in) { g_lastError = "ps_step: null argument"; return PS_INVALID; }
-    return guarded([&] {
+    return guarded(h, [&] {
         Solver& S = *h->S;
         const int res = S.step(*in, out, stats);
         if (S.P.exportMatrices || S.P.exportComponentMatrices || S.P.exportStats)
@@ -254,14 +287,14 @@ int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* s
 }
 int ps_setup(ps_handle h, const ps_fields_in* in) {
     if (!h || !in) { g_lastError = "ps_setup: null argument"; return PS_INVALID; }
-    return guarded([&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; 
+    return guarded(h, [&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; 
         try { S.setInputs(*in); S.setup(); }
         catch (...) { stream_sync(S.stIn); S.lateInputsPending = false; throw; }   // no copy may outlive the error return
         return (int)PS_SUCCESS; });
 }
 int ps_solve(ps_handle h, ps_fields_out* out, ps_stats* stats) {
     if (!h) { g_lastError = "ps_solve: null handle"; return PS_INVALID; }
-    return guarded([&] {
+    return guarded(h, [&] {
         Solver& S = *h->S;
         if (!S.haveSetup) throw Error("ps_solve: call ps_setup first");
         S.stageMs[PS_STAGE_SOLVE] = 0; S.stageMs[PS_STAGE_WRITEBACK] = 0;
@@ -286,6 +319,7 @@ int64_t ps_get_count(ps_handle h, const char* name) {
     if (n == "nTotalDOFs") return C.nTotalDOFs; if (n == "nSystemSize") return C.nSystemSize;
     if (n == "regionCount") return S.RG.count; if (n == "iterations") return S.solveIterations;
     if (n == "peerTransport") return S.peer.on ? 1 : 0;
+    if (n == "slabLocal") return S.part.local ? 1 : 0;
     if (n == "result") return S.result; if (n == "usedBiCGStab") return S.usedBiCGStab;
     if (n == "nRowsExt") return C.nRowsExt; if (n == "fixLoops") return S.fixLoops;
     return INT64_MIN;
@@ -303,7 +337,7 @@ int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out) {
     Solver& S = *h->S;
     const size_t n = (size_t)S.g.n[slot];
     if (!out) return (int64_t)n;
-    int rc = guarded([&] {
+    int rc = guarded(h, [&] {
         if (kind == 0) { std::vector<int8_t> v = S.dLabel[slot].to_host(S.st, n); for (size_t i = 0; i < n; ++i) out[i] = v[i]; }
         else { std::vector<int32_t> v = (kind == 1 ? S.dAidx[slot] : S.dRidx[slot]).to_host(S.st, n); std::copy(v.begin(), v.end(), out); }
         return 0;
@@ -315,13 +349,13 @@ int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out) {
     Solver& S = *h->S;
     const size_t n = (size_t)S.g.n[slot];
     if (!out) return (int64_t)n;
-    int rc = guarded([&] { std::vector<uint8_t> v = (liquid ? S.dLiqW[slot] : S.dFluW[slot]).to_host(S.st, n); for (size_t i = 0; i < n; ++i) out[i] = (float)v[i] * 0.125f; return 0; });
+    int rc = guarded(h, [&] { std::vector<uint8_t> v = (liquid ? S.dLiqW[slot] : S.dFluW[slot]).to_host(S.st, n); for (size_t i = 0; i < n; ++i) out[i] = (float)v[i] * 0.125f; return 0; });
     return rc == 0 ? (int64_t)n : -1;
 }
 
 int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz, int64_t* rowptr, int32_t* colidx, double* vals) {
     if (!h || !name) return PS_INVALID;
-    return guarded([&] {
+    return guarded(h, [&] {
         HostCsr m;
         if (!get_matrix(*h->S, name, m)) { g_lastError = std::string("ps_get_csr: unknown matrix ") + name; return (int)PS_INVALID; }
         mask_region_blocks(*h->S, name, m);
@@ -335,17 +369,17 @@ int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int6
 int64_t ps_get_vector(ps_handle h, const char* name, double* out) {
     if (!h || !name) return -1;
     int64_t n = -1;
-    guarded([&] { std::vector<double> v; if (get_vector(*h->S, name, v)) { n = (int64_t)v.size(); if (out) std::copy(v.begin(), v.end(), out); } return 0; });
+    guarded(h, [&] { std::vector<double> v; if (get_vector(*h->S, name, v)) { n = (int64_t)v.size(); if (out) std::copy(v.begin(), v.end(), out); } return 0; });
     return n;
 }
 
 int ps_apply(ps_handle h, const double* x, double* y) {
     if (!h || !x || !y) return PS_INVALID;
-    return guarded([&] {
+    return guarded(h, [&] {
         Solver& S = *h->S;
         if (!S.haveSetup) throw Error("ps_apply: call ps_setup first");
         const size_t n = (size_t)S.C.nSystemSize;
-        static thread_local DBuf<double> dx, dy;
+        DBuf<double>& dx = scratch().applyX; DBuf<double>& dy = scratch().applyY;
         dx.alloc(n); dy.alloc(n);
         copy_h2d(dx.p, x, n * sizeof(double), S.st);
         dy.zero(S.st, n);                       // several ranks: rows of other ranks stay 0 (sum over ranks = A x)
@@ -364,28 +398,38 @@ double ps_kernel_bytes(ps_handle h, const char* name) {
     const double nE = (double)(C.nEdge[0] + C.nEdge[1] + C.nEdge[2]);
     const double n = (double)C.nSystemSize;
     const double nRed = (double)S.RG.nRows;
-    const double pass1 = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs /*matrix*/ + 8.0 * n /*x*/ + 8.0 * C.nRowsExt /*w write*/;
+    // pass 1 with the fused region term: the compact rows of K_ext, x once, w written once (active rows by their threads, coupled reduced
+    // rows by the region epilogue), the packed coordinates of the coupled rows twice (moments, expand), B^-1 + sigma per region
+    const double regionTerm = nRed * (4.0 + 4.0) + (double)S.RG.count * (RDOF * RDOF + 30) * 8.0;
+    const double pass1 = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs /*matrix*/ + 8.0 * n /*x*/ + 8.0 * C.nRowsExt /*w write*/ + (S.RG.fusedRegions ? regionTerm : 0.0);
+    // the sweep alone (raw products on the coupled rows): the figure "pass1_sweep" is timed on
+    const double pass1Sweep = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs + 8.0 * n + 8.0 * C.nRowsExt;
     const double pass2 = 32.0 * C.nCenter + 20.0 * nE /*matrix*/ + 8.0 * C.nRowsExt /*w read*/ + 8.0 * (C.nCenter + nE) /*mu^-1: once per cell / edge*/
                        + 8.0 * n /*x (stress part: the mu term; pressure part: the fused dot)*/ + 8.0 * n /*y*/;
+    const double pass2Dots = pass2 + 8.0 * n /*r for the fused r.Ap*/;
     const double csrPass1 = 12.0 * 8.0 * C.nRowsExt + 8.0 * n + 8.0 * C.nActiveVs + 8.0 * C.nRowsExt;
     const double csrPass2 = 12.0 * (6.0 * C.nPressures + 2.0 * 3 * C.nCenter + 4.0 * nE) + 8.0 * C.nRowsExt + 8.0 * C.nStresses + 8.0 * C.nStresses + 8.0 * n;
     if (nm == "csr_pass1") return csrPass1;
     if (nm == "csr_pass2") return csrPass2;
     if (nm == "csr_apply") return csrPass1 + csrPass2 + nRed * 24.0 + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
-    // reduced rows: w read + packed coordinates (moments), packed coordinates + w write (expand), B^-1 + t,s,sigma per region
-    const double reduced = nRed * (8.0 + 4.0) + nRed * (4.0 + 8.0) + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
+    // chunked region kernels (regions too large for the fused epilogue): w read + packed coordinates (moments), packed coordinates + w write (expand)
+    const double reducedChunked = nRed * (8.0 + 4.0) + nRed * (4.0 + 8.0) + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
+    const double reduced = S.RG.fusedRegions ? 0.0 : reducedChunked;
     if (nm == "pass1") return pass1;
+    if (nm == "pass1_sweep") return pass1Sweep;
     if (nm == "pass2") return pass2;
-    if (nm == "reduced") return reduced;
+    if (nm == "pass2_dots") return pass2Dots;
+    if (nm == "reduced") return S.RG.fusedRegions ? regionTerm : reducedChunked;
     if (nm == "apply") return pass1 + pass2 + reduced;
-    if (nm == "cg_iteration") return pass1 + pass2 + reduced + 24.0 * n /*r update: Ap, r in, r out*/ + 40.0 * n /*x,p update: x, p, r in, x, p out*/;
+    if (nm == "cg_update") return 56.0 * n;
+    if (nm == "cg_iteration") return pass1 + pass2Dots + reduced + 56.0 * n /*x, r, p update: x, r, p, Ap in; x, r, p out*/;
     return 0;
 }
 
 double ps_time_kernel(ps_handle h, const char* name, int reps) {
     if (!h || !name || reps <= 0) return -1;
     double ms = -1;
-    guarded([&] {
+    guarded(h, [&] {
         Solver& S = *h->S; const std::string nm(name);
         if (!S.haveSetup) throw Error("ps_time_kernel: call ps_setup first");
         if (nm == "cg_iteration") {
@@ -399,8 +443,11 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
             S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
             return 0;
         }
-        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : nm == "reduced" ? 3 : -1;
+        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : nm == "pass1_sweep" ? 3 : nm == "pass2_dots" ? 4 : nm == "cg_update" ? 5 : -1;
         if (which < 0) throw Error("ps_time_kernel: unknown kernel name");
+        // the CG kernels look at the device scalars: a fresh state that cannot converge or run out of iterations while timed (the iterates are
+        // garbage -- only the memory traffic matters here)
+        k_cg_init(S.st, S.ownSys, S.b.p, S.x.p, S.r.p, S.p.p, S.dotPartial.p, S.scal.p, 0.0, reps + 8, PeerCtx());
 #ifndef PS_EMULATE
         cudaEvent_t a, b; PS_CUDA(cudaEventCreate(&a)); PS_CUDA(cudaEventCreate(&b));
         S.timedOperator(which);
@@ -422,7 +469,7 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
 double ps_timer(ps_handle h, int stop) {
     if (!h) return -1;
     double ms = -1;
-    guarded([&] {
+    guarded(h, [&] {
 #ifndef PS_EMULATE
         Solver& S = *h->S;
         for (void*& e : h->tm) if (!e) { cudaEvent_t ev; PS_CUDA(cudaEventCreate(&ev)); e = ev; }
@@ -439,7 +486,7 @@ double ps_timer(ps_handle h, int stop) {
 
 int ps_export(ps_handle h, const char* prefix, int what) {
     if (!h || !prefix) return PS_INVALID;
-    return guarded([&] {
+    return guarded(h, [&] {
         Solver& S = *h->S; const std::string pre(prefix);
         bool ok = true;
         std::vector<double> v;

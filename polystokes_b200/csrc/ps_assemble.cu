@@ -40,7 +40,10 @@ PS_D uint64_t pack_code(uint64_t word, int k, int code) { return word | ((uint64
 
 // K_ext rows: one thread per face of each axis.  Slots: 0,1 pressure of cell(-),cell(+); 2,3 centre stress;
 // 4..7 the two edge axes (ascending) x (dir 0, dir 1).  Empty slots carry value 0 and repeat a valid column.
-void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, CompactOp& Op, double* mcInv, double* mc, double* rhsU, double* oldVs) {
+// Only the rows in `own` are written (all rows on one GPU / with replicated setup): the faces of the rank's window are visited, a
+// face whose row belongs to another rank is skipped.
+void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, CompactOp& Op, double* mcInv, double* mc, double* rhsU, double* oldVs, const RowSet& ownRows) {
+    const RowSet own = ownRows;
     const int64_t nRows = C.nRowsExt, nAct = C.nActiveVs, nP = C.nPressures;
     uint64_t* kcode = Op.kcode.p; int32_t* kcol = Op.kcol.p; uint8_t* kmc = Op.kmc.p;
     {   // M_c^-1 by weight product (S_CMB:361-380): 1 / (rho * clamp(k / 64, MINWEIGHT^2, 1))
@@ -58,9 +61,11 @@ void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts&
         const int64_t eOff1 = nP + C.stressOff[3 + e1], eOff2 = nP + C.stressOff[3 + e2];
         const float* vel = F.vel[axis];
         const double density = g.density;
-        ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) {
+        int64_t lo, hi;
+        z_range(g, SL_FACE + axis, g.wzLo, g.wzHi, lo, hi);
+        ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
             const int64_t row = krow[q];
-            if (row < 0) return;
+            if (row < 0 || !own.has(row)) return;
             const I3 f = delin(g, SL_FACE + axis, q);
             const int fw = ffw[q];
             uint64_t word = 0; int32_t c[6] = {0, 0, 0, 0, 0, 0};
@@ -110,7 +115,9 @@ void k_assemble_K(cudaStream_t st, const Geom& g, const Fields& F, const Counts&
 }
 
 // K_ext^T rows + the stress diagonal + the moving-solid right-hand sides, one thread per cell / edge.
-void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, CompactOp& Op, double* uInv, double* uDiag, double* rhsPT) {
+// Rows of the rank's own cells / edges only (voxels of its slab; everything on one GPU / with replicated setup).
+void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, CompactOp& Op, double* uInv, double* uDiag, double* rhsPT, bool ownOnly) {
+    const int zA = ownOnly ? g.zLo : 0, zB = ownOnly ? g.zHi : g.nz;
     const int64_t nP = C.nPressures, nC = C.nCenter;
     const double invDx = g.invDx;
     const double MINWEIGHT = 0.1;
@@ -123,7 +130,9 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
         const float* cv0 = F.colvel[0]; const float* cv1 = F.colvel[1]; const float* cv2 = F.colvel[2];
         const float* visc = F.viscosity;
         const int64_t nAct = C.nActiveVs;
-        ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+        int64_t lo, hi;
+        z_range(g, SL_CENTER, zA, zB, lo, hi);
+        ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
             const int ci = CA[q];
             if (ci < 0) return;
             const I3 c = delin(g, SL_CENTER, q);
@@ -184,7 +193,9 @@ void k_assemble_Kt(cudaStream_t st, const Geom& g, const Fields& F, const Counts
         const int64_t eRowOff = C.stressOff[3 + e] - 3 * nC;     // row inside the edge block
         const int64_t tOff = C.stressOff[3 + e];                 // row inside the stress block
         const int64_t nAct = C.nActiveVs;
-        ps_for(st, g.n[SL_EDGE + e], PS_LAMBDA(int64_t q) {
+        int64_t lo, hi;
+        z_range(g, SL_EDGE + e, zA, zB, lo, hi);
+        ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
             if (!is_active(EL[q])) return;
             const int ei = EA[q];
             const I3 ed = delin(g, SL_EDGE + e, q);

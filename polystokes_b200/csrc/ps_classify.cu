@@ -8,6 +8,14 @@
 
 namespace ps {
 
+// every sweep visits the rank's window of the grid only (Geom::wzLo / wzHi; the whole grid on one GPU): voxel indices stay global
+template <class F>
+static inline void for_window(cudaStream_t st, const Geom& g, int slot, F f, int margin = 0) {
+    int64_t lo, hi;
+    z_range(g, slot, g.wzLo - margin, g.wzHi + margin, lo, hi);
+    ps_for_range(st, lo, hi, f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Integration weights.  HDK computeSDFWeightsSampled(sdf, 2, false, 0) (call sites
 // exec/HDK_PolyStokesSolver.cpp:304, 322-323) -- shim: 2x2x2 sub-samples at +-dx/4, trilinear SDF
@@ -23,7 +31,7 @@ void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* s
     // runs near the interfaces.
     {
         const float* surf = F.surface; const float* coll = F.collision;
-        ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+        for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
             const I3 c = delin(g, SL_CENTER, q);
             int code = 0;
             for (int d = -1; d <= 1; ++d) {
@@ -32,8 +40,8 @@ void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* s
                 code |= (sv < 0.f ? 1 : 0) | (sv >= 0.f ? 2 : 0) | (cv < 0.f ? 4 : 0) | (cv >= 0.f ? 8 : 0);
             }
             signX[q] = (uint8_t)code;
-        });
-        ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+        }, 1);
+        for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
             const I3 c = delin(g, SL_CENTER, q);
             int code = 0;
             for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy)
@@ -48,7 +56,7 @@ void k_build_weights(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* s
         const int o0 = off2[0], o1 = off2[1], o2 = off2[2];
         const float* surf = F.surface; const float* coll = F.collision;
         uint8_t* lw = F.liqW[slot]; uint8_t* fw = F.fluW[slot];
-        ps_for(st, g.n[slot], PS_LAMBDA(int64_t q) {
+        for_window(st, g, slot, PS_LAMBDA(int64_t q) {
             const I3 c = delin(g, slot, q);
             {
                 const int box = signBox[lin(g, SL_CENTER, clamped(g, SL_CENTER, c))];
@@ -109,7 +117,7 @@ void k_classify_cells(cudaStream_t st, const Geom& g, const Fields& F, bool gene
     int8_t* L = F.label[SL_CENTER];
     const uint8_t* clw = F.liqW[SL_CENTER]; const uint8_t* cfw = F.fluW[SL_CENTER];
     const uint8_t* fx = F.liqW[SL_FACE + 0]; const uint8_t* fy = F.liqW[SL_FACE + 1]; const uint8_t* fz = F.liqW[SL_FACE + 2];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         const I3 c = delin(g, SL_CENTER, q);
         bool inSolve = clw[q] > 0;
         if (!inSolve) {
@@ -130,7 +138,7 @@ void k_classify_cells(cudaStream_t st, const Geom& g, const Fields& F, bool gene
 void k_air_layer_seed(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* stamp) {
     int8_t* L = F.label[SL_CENTER];
     const uint8_t* fw0 = F.liqW[SL_FACE + 0]; const uint8_t* fw1 = F.liqW[SL_FACE + 1]; const uint8_t* fw2 = F.liqW[SL_FACE + 2];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         stamp[q] = 0;
         if (L[q] != L_GENERICFLUID) return;
         const I3 c = delin(g, SL_CENTER, q);
@@ -151,14 +159,14 @@ void k_air_layer_seed(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* 
 // marks stamped cells of `layer` ACTIVE (setActiveLayerCells, S.cpp:2022-2060)
 void k_layer_commit(cudaStream_t st, const Geom& g, const Fields& F, const uint8_t* stamp, int layerStamp) {
     int8_t* L = F.label[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) { if (stamp[q] == layerStamp) L[q] = L_ACTIVEFLUID; });
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) { if (stamp[q] == layerStamp) L[q] = L_ACTIVEFLUID; });
 }
 // buildNextLiquidBoundaryLayer (S_Cls:432-508): GENERICFLUID neighbours of the previous layer through
 // faces with liquid weight > 0
 void k_air_layer_grow(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* stamp, int prevStamp) {
     const int8_t* L = F.label[SL_CENTER];
     const uint8_t* fw0 = F.liqW[SL_FACE + 0]; const uint8_t* fw1 = F.liqW[SL_FACE + 1]; const uint8_t* fw2 = F.liqW[SL_FACE + 2];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         if (L[q] != L_GENERICFLUID || stamp[q] != 0) return;
         const I3 c = delin(g, SL_CENTER, q);
         bool hit = false;
@@ -179,7 +187,7 @@ void k_air_layer_grow(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* 
 // or to the domain wall; then S-1 growth sweeps through liquid faces into unvisited GENERIC/ACTIVE cells.
 void k_solid_layer_seed(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* stamp) {
     const int8_t* L = F.label[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         stamp[q] = 0;
         const int lab = L[q];
         if (lab != L_GENERICFLUID && lab != L_ACTIVEFLUID) return;
@@ -197,7 +205,7 @@ void k_solid_layer_seed(cudaStream_t st, const Geom& g, const Fields& F, uint8_t
 void k_solid_layer_grow(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* stamp, int prevStamp) {
     const int8_t* L = F.label[SL_CENTER];
     const uint8_t* fw0 = F.liqW[SL_FACE + 0]; const uint8_t* fw1 = F.liqW[SL_FACE + 1]; const uint8_t* fw2 = F.liqW[SL_FACE + 2];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         const int lab = L[q];
         if ((lab != L_GENERICFLUID && lab != L_ACTIVEFLUID) || stamp[q] != 0) return;   // stamp != 0 <=> VISITED
         const I3 c = delin(g, SL_CENTER, q);
@@ -218,7 +226,7 @@ void k_solid_layer_grow(cudaStream_t st, const Geom& g, const Fields& F, uint8_t
 // C4 constructTiles (S_Cls:705-746) fused with the final GENERICFLUID -> REDUCED overwrite (S_Cls:189)
 void k_tiles_and_reduce(cudaStream_t st, const Geom& g, const Fields& F, bool doTile, int tileSize, int tilePadding) {
     int8_t* L = F.label[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         if (L[q] != L_GENERICFLUID) return;
         const I3 c = delin(g, SL_CENTER, q);
         bool pad = false;
@@ -235,7 +243,7 @@ void k_classify_faces(cudaStream_t st, const Geom& g, const Fields& F) {
         const uint8_t* ffw = F.fluW[SL_FACE + axis];
         const int e1 = (axis + 1) % 3, e2 = (axis + 2) % 3;
         const uint8_t* ew1 = F.liqW[SL_EDGE + e1]; const uint8_t* ew2 = F.liqW[SL_EDGE + e2];
-        ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) {
+        for_window(st, g, SL_FACE + axis, PS_LAMBDA(int64_t q) {
             const I3 f = delin(g, SL_FACE + axis, q);
             bool activeVel = false;
             const I3 c0 = shifted(f, axis, -1);
@@ -261,7 +269,7 @@ void k_classify_edges(cudaStream_t st, const Geom& g, const Fields& F) {
         const uint8_t* elw = F.liqW[SL_EDGE + e]; const uint8_t* efw = F.fluW[SL_EDGE + e];
         const int fa0 = (e == 0) ? 1 : 0, fa1 = (e == 2) ? 1 : 2;   // XY->(X,Y)  XZ->(X,Z)  YZ->(Y,Z)
         const uint8_t* w0 = F.liqW[SL_FACE + fa0]; const uint8_t* w1 = F.liqW[SL_FACE + fa1];
-        ps_for(st, g.n[SL_EDGE + e], PS_LAMBDA(int64_t q) {
+        for_window(st, g, SL_EDGE + e, PS_LAMBDA(int64_t q) {
             const I3 ed = delin(g, SL_EDGE + e, q);
             bool in = elw[q] != 0 && efw[q] != 0;
             if (in) {
@@ -282,11 +290,14 @@ void k_classify_edges(cudaStream_t st, const Geom& g, const Fields& F) {
 // ---------------------------------------------------------------------------------------------
 void k_cc_init(cudaStream_t st, const Geom& g, const Fields& F, int32_t* parent) {
     const int8_t* L = F.label[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) { parent[q] = (L[q] == L_REDUCED) ? (int32_t)q : -1; });
+    // Only the rank's own cells take part: with slab-local setup a region never crosses a z cut (tiles are aligned to the cuts), so
+    // the components of the own cells ARE the own regions; REDUCED cells of the halo keep region -1 until the neighbour's ids arrive.
+    const int64_t plane = (int64_t)g.r[SL_CENTER][0] * g.r[SL_CENTER][1];
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) { const int z = (int)(q / plane); parent[q] = (L[q] == L_REDUCED && (!g.slabLocal || (z >= g.zLo && z < g.zHi))) ? (int32_t)q : -1; });
 }
 void k_cc_sweep(cudaStream_t st, const Geom& g, const Fields& F, int32_t* parent, int* changed) {
     const uint8_t* fw0 = F.liqW[SL_FACE + 0]; const uint8_t* fw1 = F.liqW[SL_FACE + 1]; const uint8_t* fw2 = F.liqW[SL_FACE + 2];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         int32_t mine = parent[q];
         if (mine < 0) return;
         const I3 c = delin(g, SL_CENTER, q);
@@ -310,7 +321,7 @@ void k_cc_sweep(cudaStream_t st, const Geom& g, const Fields& F, int32_t* parent
 }
 // every member posts its tile-order key to its representative
 void k_cc_minkey(cudaStream_t st, const Geom& g, const int32_t* parent, int32_t* minKey) {
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         const int32_t root = parent[q];
         if (root < 0) return;
         atomic_min(&minKey[root], (int32_t)tile_key(g, SL_CENTER, delin(g, SL_CENTER, q)));
@@ -318,7 +329,7 @@ void k_cc_minkey(cudaStream_t st, const Geom& g, const int32_t* parent, int32_t*
 }
 // flag = 1 on the first cell (in tile order) of every component
 void k_cc_first_flags(cudaStream_t st, const Geom& g, const int32_t* parent, const int32_t* minKey, uint8_t* flag) {
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         const int32_t root = parent[q];
         flag[q] = (root >= 0 && minKey[root] == (int32_t)tile_key(g, SL_CENTER, delin(g, SL_CENTER, q))) ? 1 : 0;
     });
@@ -326,11 +337,11 @@ void k_cc_first_flags(cudaStream_t st, const Geom& g, const int32_t* parent, con
 // firstRank[q] (from the tile-order scan of the flags) is valid on first cells; publish it on the root,
 // then every member reads its root's id
 void k_cc_publish(cudaStream_t st, const Geom& g, const int32_t* parent, const uint8_t* flag, const int32_t* firstRank, int32_t* rootId) {
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) { if (flag[q]) rootId[parent[q]] = firstRank[q]; });
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) { if (flag[q]) rootId[parent[q]] = firstRank[q]; });
 }
 void k_cc_assign(cudaStream_t st, const Geom& g, const Fields& F, const int32_t* parent, const int32_t* rootId) {
     int32_t* R = F.ridx[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) { const int32_t root = parent[q]; R[q] = root >= 0 ? rootId[root] : -1; });
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) { const int32_t root = parent[q]; R[q] = root >= 0 ? rootId[root] : -1; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -375,7 +386,7 @@ PS_D bool fix_fires(const Geom& g, const int8_t* L, const int32_t* R, const uint
 // candidates: fluid cells whose initial 6-neighbourhood touches >= 2 different regions
 void k_fix_candidates(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* cand, uint8_t* firedA, uint8_t* firedB, int* anyCand) {
     const int8_t* L = F.label[SL_CENTER]; const int32_t* R = F.ridx[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         firedA[q] = 0; firedB[q] = 0;
         uint8_t isCand = 0;
         const int lab = L[q];
@@ -398,7 +409,7 @@ void k_fix_candidates(cudaStream_t st, const Geom& g, const Fields& F, uint8_t* 
 }
 void k_fix_iterate(cudaStream_t st, const Geom& g, const Fields& F, const uint8_t* cand, const uint8_t* firedIn, uint8_t* firedOut, int* changed) {
     const int8_t* L = F.label[SL_CENTER]; const int32_t* R = F.ridx[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         uint8_t f = 0;
         if (cand[q]) f = fix_fires(g, L, R, firedIn, delin(g, SL_CENTER, q), q) ? 1 : 0;
         firedOut[q] = f;
@@ -408,7 +419,7 @@ void k_fix_iterate(cudaStream_t st, const Geom& g, const Fields& F, const uint8_
 // end of sweep: every REDUCED cell adjacent to a fired cell becomes ACTIVEFLUID / UNASSIGNED
 void k_fix_apply(cudaStream_t st, const Geom& g, const Fields& F, const uint8_t* fired, int* anyFired) {
     int8_t* L = F.label[SL_CENTER]; int32_t* R = F.ridx[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         if (fired[q]) *anyFired = 1;
         if (L[q] != L_REDUCED) return;
         const I3 c = delin(g, SL_CENTER, q);
@@ -426,9 +437,10 @@ void k_fix_apply(cudaStream_t st, const Geom& g, const Fields& F, const uint8_t*
 // C7 fixSmallReducedRegions (S_Cls:1174-1313, 1418-1467): bounding boxes by atomics
 void k_region_bbox(cudaStream_t st, const Geom& g, const Fields& F, int* bbMin, int* bbMax) {
     const int8_t* L = F.label[SL_CENTER]; const int32_t* R = F.ridx[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
         if (L[q] != L_REDUCED) return;
         const int r = R[q];
+        if (r < 0) return;                    // REDUCED cell of a neighbour's region (halo)
         const I3 c = delin(g, SL_CENTER, q);
         atomic_min(&bbMin[3 * r + 0], c.x); atomic_min(&bbMin[3 * r + 1], c.y); atomic_min(&bbMin[3 * r + 2], c.z);
         atomic_max(&bbMax[3 * r + 0], c.x); atomic_max(&bbMax[3 * r + 1], c.y); atomic_max(&bbMax[3 * r + 2], c.z);
@@ -436,8 +448,8 @@ void k_region_bbox(cudaStream_t st, const Geom& g, const Fields& F, int* bbMin, 
 }
 void k_region_remap(cudaStream_t st, const Geom& g, const Fields& F, const int32_t* remap) {
     int8_t* L = F.label[SL_CENTER]; int32_t* R = F.ridx[SL_CENTER];
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
-        if (L[q] != L_REDUCED) return;
+    for_window(st, g, SL_CENTER, PS_LAMBDA(int64_t q) {
+        if (L[q] != L_REDUCED || R[q] < 0) return;
         const int nr = remap[R[q]];
         if (nr < 0) { L[q] = L_ACTIVEFLUID; R[q] = -1; } else R[q] = nr;
     });
@@ -448,7 +460,7 @@ void k_faces_reduced(cudaStream_t st, const Geom& g, const Fields& F) {
     const int8_t* CL = F.label[SL_CENTER]; const int32_t* CR = F.ridx[SL_CENTER];
     for (int axis = 0; axis < 3; ++axis) {
         int8_t* FL = F.label[SL_FACE + axis]; int32_t* FR = F.ridx[SL_FACE + axis];
-        ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) {
+        for_window(st, g, SL_FACE + axis, PS_LAMBDA(int64_t q) {
             const I3 f = delin(g, SL_FACE + axis, q);
             int idx = -1;
             const I3 c0 = shifted(f, axis, -1);
@@ -469,7 +481,7 @@ void k_edges_reduced(cudaStream_t st, const Geom& g, const Fields& F) {
         const int8_t* L0 = F.label[SL_FACE + fa0]; const int8_t* L1 = F.label[SL_FACE + fa1];
         const int32_t* R0 = F.ridx[SL_FACE + fa0]; const int32_t* R1 = F.ridx[SL_FACE + fa1];
         const int32_t* RX = F.ridx[SL_FACE + 0]; const int32_t* RY = F.ridx[SL_FACE + 1];
-        ps_for(st, g.n[SL_EDGE + e], PS_LAMBDA(int64_t q) {
+        for_window(st, g, SL_EDGE + e, PS_LAMBDA(int64_t q) {
             const I3 ed = delin(g, SL_EDGE + e, q);
             const I3 f[4] = {ed, shifted(ed, 3 - fa0 - e, -1), ed, shifted(ed, 3 - fa1 - e, -1)};
             bool red[4];
@@ -493,7 +505,7 @@ void k_edges_reduced(cudaStream_t st, const Geom& g, const Fields& F) {
 
 // GENERICFLUID -> ACTIVEFLUID (S_Cls:260-280) and the isActive flag the tile-order scan consumes
 void k_generic_to_active_flags(cudaStream_t st, const Geom& g, int slot, int8_t* L, uint8_t* flag) {
-    ps_for(st, g.n[slot], PS_LAMBDA(int64_t q) {
+    for_window(st, g, slot, PS_LAMBDA(int64_t q) {
         int lab = L[q];
         if (lab == L_GENERICFLUID) { lab = L_ACTIVEFLUID; L[q] = L_ACTIVEFLUID; }
         flag[q] = is_active(lab) ? 1 : 0;
@@ -504,7 +516,7 @@ void k_generic_to_active_flags(cudaStream_t st, const Geom& g, int slot, int8_t*
 void k_valid_faces(cudaStream_t st, const Geom& g, const Fields& F, float* const valid[3]) {
     for (int axis = 0; axis < 3; ++axis) {
         const int8_t* FL = F.label[SL_FACE + axis]; float* v = valid[axis];
-        ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) { const int l = FL[q]; v[q] = (l == L_UNSOLVED || l == L_UNASSIGNED) ? 0.f : 1.f; });
+        for_window(st, g, SL_FACE + axis, PS_LAMBDA(int64_t q) { const int l = FL[q]; v[q] = (l == L_UNSOLVED || l == L_UNASSIGNED) ? 0.f : 1.f; });
     }
 }
 

@@ -27,6 +27,11 @@ struct Geom {
     int64_t n[N_SLOTS];
     double dx, invDx, dt, invDt, density;
     int zLo, zHi;          // owned z-slab [zLo, zHi) of this rank (whole grid on one GPU)
+    // Slab-local setup (ps_part.hpp): the grid fields stay addressed by GLOBAL voxel index (so no stencil, position or tile
+    // rule changes), but a rank only fills the cell layers [wzLo, wzHi) -- its slab plus a halo -- and the sweeps only visit
+    // that window.  One GPU / replicated setup: the window is the whole grid.
+    int wzLo, wzHi;
+    int slabLocal;         // 1: slab-local setup (the fields exist on the window only, regions / numbering are per slab)
 };
 
 inline Geom make_geom(int nx, int ny, int nz, double dx, double dt, double density) {
@@ -39,9 +44,20 @@ inline Geom make_geom(int nx, int ny, int nz, double dx, double dt, double densi
         for (int a = 0; a < 3; ++a) g.r[s][a] = r[a];
         g.n[s] = (int64_t)r[0] * r[1] * r[2];
     }
-    g.zLo = 0; g.zHi = nz;
+    g.zLo = 0; g.zHi = nz; g.wzLo = 0; g.wzHi = nz; g.slabLocal = 0;
     return g;
 }
+
+// voxel index range [lo, hi) of the layers z in [zA, zB) of a slot (clipped to the slot's extent; zB >= nz includes the slot's
+// extra top layer); dense x-fastest layout: a z-range is one contiguous index range
+PS_HD void z_range(const Geom& g, int slot, int zA, int zB, int64_t& lo, int64_t& hi) {
+    const int rz = g.r[slot][2];
+    const int a = zA < 0 ? 0 : (zA > rz ? rz : zA), b = zB >= g.nz ? rz : (zB < a ? a : zB);
+    const int64_t plane = (int64_t)g.r[slot][0] * g.r[slot][1];
+    lo = plane * a; hi = plane * b;
+}
+// does this rank own layer z of a slot?  (the extra top layer of a slot belongs to the last slab)
+PS_HD bool owns_z(const Geom& g, int z) { return z >= g.zLo && (z < g.zHi || g.zHi >= g.nz); }
 
 struct I3 { int x, y, z; };
 PS_HD int comp(const I3& c, int a) { return a == 0 ? c.x : a == 1 ? c.y : c.z; }

@@ -71,6 +71,13 @@ struct Partition {
     std::vector<int32_t> regionCut;                     // [nranks+1] region-id cut
     std::vector<int64_t> redRowCut;                     // [nranks+1] coupled-reduced-row cut (relative to nActiveVs)
     bool multi() const { return nranks > 1; }
+    // Slab-local setup: every rank uploads, classifies, numbers and assembles only its slab plus `halo` cell layers; global DOF /
+    // region / row numbers follow from an all-gather of the per-slab counts (the reference numbering is a scan in tile order, tiles
+    // z-slowest, and a slab is a whole number of tile layers), the halo layers of the label / index fields come from the neighbour.
+    // Needs regions that cannot interact across a cut: reduced regions off, or tiles with padding >= 2 (the boundary fix-up
+    // S_Cls:1073-1172 never fires then).  Otherwise the setup is replicated on every rank as in round 1.
+    bool local = false;
+    int halo = 0;
 };
 
 }  // namespace ps

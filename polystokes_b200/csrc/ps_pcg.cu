@@ -48,6 +48,25 @@ PS_D double kt_edge_row(const OpArgs& A, int64_t e, const double* __restrict__ w
     return s;
 }
 
+// t (26) from the per-axis moments M[3][10]
+PS_D void moments_to_t(const double* M, double* t) {
+    for (int n = 0; n < RDOF; ++n) t[n] = 0.;
+    const double* A = M; const double* B = M + 10; const double* Cz = M + 20;
+    t[0] = A[0]; t[3] = A[1]; t[4] = A[2]; t[5] = A[3]; for (int k = 0; k < 6; ++k) t[6 + k] = A[4 + k];
+    t[1] = B[0]; t[12] = B[1]; t[13] = B[2]; t[14] = B[3]; for (int k = 0; k < 6; ++k) t[15 + k] = B[4 + k];
+    t[2] += Cz[0]; t[3] += -Cz[3]; t[6] += -2. * Cz[6]; t[7] += -Cz[8]; t[8] += -0.5 * Cz[9];
+    t[13] += -Cz[3]; t[16] += -Cz[6]; t[18] += -2. * Cz[8]; t[19] += -0.5 * Cz[9];
+    t[21] += Cz[1]; t[22] += Cz[2]; t[23] += Cz[4]; t[24] += Cz[5]; t[25] += Cz[7];
+}
+// sigma[3][10] from s (26): w_f = sum_m sigma[axis][m] * mono_m
+PS_D void s_to_sigma(const double* s, double* sg) {
+    sg[0] = s[0]; sg[1] = s[3]; sg[2] = s[4]; sg[3] = s[5]; for (int k = 0; k < 6; ++k) sg[4 + k] = s[6 + k];
+    sg[10] = s[1]; sg[11] = s[12]; sg[12] = s[13]; sg[13] = s[14]; for (int k = 0; k < 6; ++k) sg[14 + k] = s[15 + k];
+    double* z = sg + 20;
+    z[0] = s[2]; z[1] = s[21]; z[2] = s[22]; z[3] = -s[3] - s[13]; z[4] = s[23]; z[5] = s[24];
+    z[6] = -2. * s[6] - s[16]; z[7] = s[25]; z[8] = -s[7] - 2. * s[18]; z[9] = -0.5 * s[8] - 0.5 * s[19];
+}
+
 // fixed-order finish of a dot product: called by the last CTA (or the emulation) over the CTA partials
 PS_D double sum_partials(const double* p, int n) { double s = 0.; for (int i = 0; i < n; ++i) s += p[i]; return s; }
 
@@ -166,47 +185,19 @@ __device__ __forceinline__ int warp_reduce10_index(unsigned lane) {
     else k = !b2 ? (b1 ? 4 : 3) : -1;
     return k < 0 ? -1 : k + (b4 ? 5 : 0);
 }
-// the small solve of one region by one whole CTA (pass 1's region epilogue): ordered sum of the chunk moments -> t ->
-// s = B^-1 (tScale t + extraScale extra) -> sigma (shared memory sg[30], and RegionOp::sigma)
-__device__ __forceinline__ void region_epilogue_solve(const RegionOp& R, const int32_t* __restrict__ rowChunk, int region, double* M, double* tv, double* sv, double* sg) {
-    const int tid = threadIdx.x;
-    if (tid < 30) {
-        const int axis = tid / 10, k = tid % 10;
-        double s = 0.;
-        for (int ch = __ldg(R.rowChunkStart + region), e = __ldg(R.rowChunkStart + region + 1); ch < e; ++ch)
-            if (__ldg(rowChunk + 4 * ch + 3) == axis) s += __ldcg(R.partial + (size_t)ch * 10 + k);
-        M[tid] = s;
-    }
-    __syncthreads();
-    if (tid == 0) moments_to_t(M, tv);
-    __syncthreads();
-    if (tid < RDOF) { double v = R.tScale * tv[tid]; if (R.extra) v += R.extraScale * R.extra[(size_t)region * RDOF + tid]; tv[tid] = v; }
-    __syncthreads();
-    // s_i = sum_j B_ij t_j: 8 lanes per row (coalesced 64 B pieces of B^-1), lane partials combined in a fixed order
-    {
-        const int i = tid >> 3, jp = tid & 7;
-        double acc = 0.;
-        if (i < RDOF) {
-            const double* B = R.Binv + (size_t)region * RDOF * RDOF + i * RDOF;
-#pragma unroll
-            for (int j = jp; j < RDOF; j += 8) acc += __ldg(B + j) * tv[j];
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (i < RDOF && jp == 0) sv[i] = acc;
-    }
-    __syncthreads();
-    if (tid == 0) s_to_sigma(sv, sg);
-    __syncthreads();
-    if (tid < 30 && R.sigma) R.sigma[(size_t)region * 30 + tid] = sg[tid];
-}
-
 // pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
-// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.  Work items (256-row blocks of the x / y / z face rows and row chunks of
-// the coupled reduced rows, merged by position in tile order) are handed out dynamically -- the region epilogue makes their
-// cost uneven -- with the next item fetched while the current one is processed.
+// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.  Work items = 256-row blocks of the x / y / z face rows and row chunks
+// (<= 256 rows of one (region, face axis)) of the coupled reduced rows, merged by position in tile order and walked grid-stride.
+// There is NO CTA barrier in the sweep: the 8 warps of a CTA run through their items independently (the gathers need every
+// warp's loads in flight), so everything the region term needs is done at warp granularity:
+//   * a warp leaves the 10 monomial moments of its 32 rows (12 shuffles, fixed order);
+//   * the last warp of a chunk (ticket) adds the 8 warp partials in warp order, the last chunk of a region (ticket) makes
+//     that warp solve the region: moments in chunk order -> t -> s = B^-1 t -> sigma, then it raises the region's flag;
+//   * after its share of the sweep every warp expands its share of the row chunks, w_f = sigma[axis] . monomials(f),
+//     waiting on the region's flag -- which by then is almost always up: regions complete in sweep order.
+// The waiting is deadlock free: the sweep never waits, and all CTAs of the persistent grid are resident.
 // (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
+constexpr int P1_MAX_CHUNKS = 32;      // chunks of one region the fused solve can sum (Solver::constructMatrixBlocks keeps larger regions on the chunked kernels)
 __device__ __forceinline__ double pass1_row(const OpArgs& A, int64_t r, const double* __restrict__ x, double sc) {
     const uint64_t word = __ldcs(A.kcode + r);
     int32_t c[6];
@@ -223,114 +214,168 @@ __device__ __forceinline__ double pass1_row(const OpArgs& A, int64_t r, const do
     for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
     return s;
 }
+// ticket with release / acquire semantics in ONE instruction.  (__threadfence() is fence.sc.gpu: sequentially consistent fences are
+// ordered globally, and one per warp and item -- 10^5 per launch -- serialises the whole kernel: 2 ns each, profiles/r02_probe_s3_256_v3.log)
+__device__ __forceinline__ unsigned atom_inc_acq_rel(unsigned* p, unsigned wrap) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(wrap) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// The solve of one region by ONE warp (the warp whose chunk completed the region); buf = 64 doubles of warp-private shared memory.
+__device__ __forceinline__ void region_solve_warp(const OpArgs& A, const RegionOp& R, int region, double* buf) {
+    const int lane = threadIdx.x & 31;
+    const int chS = __ldg(R.rowChunkStart + region), nch = __ldg(R.rowChunkStart + region + 1) - chS;
+    // chunks of a region are ordered by face axis: contiguous chunk ranges per axis from one ballot each
+    const int myAxis = lane < nch ? __ldg(A.rowChunk + 4 * (chS + lane) + 3) : -1;
+    const unsigned m0 = __ballot_sync(0xffffffffu, myAxis == 0), m1 = __ballot_sync(0xffffffffu, myAxis == 1), m2 = __ballot_sync(0xffffffffu, myAxis == 2);
+    double Mv = 0.;
+    if (lane < 30) {
+        const int axis = lane / 10, k = lane % 10;
+        const unsigned mk = axis == 0 ? m0 : axis == 1 ? m1 : m2;
+        const int first = mk ? __ffs(mk) - 1 : 0, cnt = __popc(mk);
+        const double* P0 = R.partial + (size_t)(chS + first) * 10 + k;
+#pragma unroll 4
+        for (int c = 0; c < cnt; ++c) Mv += __ldcg(P0 + (size_t)c * 10);
+        buf[lane] = Mv;
+    }
+    __syncwarp();
+    if (lane == 0) moments_to_t(buf, buf + 32);
+    __syncwarp();
+    if (lane < RDOF) { double v = R.tScale * buf[32 + lane]; if (R.extra) v += R.extraScale * R.extra[(size_t)region * RDOF + lane]; buf[32 + lane] = v; }
+    __syncwarp();
+    double si = 0.;
+    if (lane < RDOF) {      // row `lane` of B^-1, a few independent loads at a time (this path runs once per region and launch)
+        const double* B = R.Binv + (size_t)region * RDOF * RDOF + lane * RDOF;
+#pragma unroll 1
+        for (int j0 = 0; j0 < RDOF; j0 += 13) {
+            double bj[13];
+#pragma unroll
+            for (int j = 0; j < 13; ++j) bj[j] = __ldg(B + j0 + j);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) si += bj[j] * buf[32 + j0 + j];
+        }
+    }
+    __syncwarp();
+    if (lane < RDOF) buf[lane] = si;
+    __syncwarp();
+    if (lane == 0) s_to_sigma(buf, buf + 32);
+    __syncwarp();
+    if (lane < 30) __stcg(R.sigma + (size_t)region * 30 + lane, buf[32 + lane]);
+    __syncwarp();
+    if (lane == 0) st_release_u32(R.solved + region, R.seq);      // releases sigma (ordered before it by __syncwarp)
+}
+// flags: bit 1 = walk the schedule backwards (A/B knob, Solver::solve)
+template <int UNROLL>
 __global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const __grid_constant__ RegionOp R, const double* __restrict__ x, double* __restrict__ w,
-                                                              double activeScale, const PcgScalars* S, int dynamic) {
+                                                              double activeScale, const PcgScalars* S, int flags) {
     pdl_sync();
     __shared__ double lut[65];
-    __shared__ int sNext[2];
-    __shared__ int sLast;
-    __shared__ double red[HOT_THREADS / 32][10];
-    __shared__ double M[30], tv[RDOF], sv[RDOF], sg[30];
+    __shared__ double wbuf[HOT_THREADS / 32][64];
     if (S && S->done) return;
+    const bool reverse = flags & 2;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
-    if (threadIdx.x == 0) sNext[0] = dynamic ? (int)atomicAdd(A.sched1Ctl, 1u) : (int)blockIdx.x;
     __syncthreads();
     const double sc = A.valScale;
-    int cur = sNext[0], buf = 0;
-    while (cur < A.nSched1) {
-        if (threadIdx.x == 0) sNext[buf ^ 1] = dynamic ? (int)atomicAdd(A.sched1Ctl, 1u) : cur + (int)gridDim.x;     // arrives while this item is processed
-        const int32_t e = __ldg(A.sched1 + cur);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // ---- the sweep: owned rows in the merged block order of the four ranges (SchedRanges, ps_solver.hpp)
+#pragma unroll UNROLL
+    for (int g = blockIdx.x; g < A.nSched1; g += gridDim.x) {
+        const int32_t e = __ldg(A.sched1 + (reverse ? A.nSched1 - 1 - g : g));
         const int k = (int)((uint32_t)e >> 28);
         if (k < 3) {
             const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
             if (r < A.s1.hi[k]) w[r] = activeScale * lut[__ldcs(A.kmc + r)] * pass1_row(A, r, x, sc);
-        } else {
-            // row chunk of the coupled reduced rows: (K_red x)_f, raw
-            const int ch = (int)A.s1.lo[3] + (int)(e & 0x0fffffff);
-            const int region = __ldg(A.rowChunk + 4 * ch), begin = __ldg(A.rowChunk + 4 * ch + 1), end = __ldg(A.rowChunk + 4 * ch + 2);
-            if (R.mode == 0) {
-                for (int row = begin + threadIdx.x; row < end; row += HOT_THREADS) w[A.nActiveVs + row] = pass1_row(A, A.nActiveVs + row, x, sc);
-            } else {
-                const double cm[3] = {__ldg(R.com + 3 * region), __ldg(R.com + 3 * region + 1), __ldg(R.com + 3 * region + 2)};
-                double acc[10];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) acc[q] = 0.;
-                for (int row = begin + threadIdx.x; row < end; row += HOT_THREADS) {
-                    const double gk = pass1_row(A, A.nActiveVs + row, x, sc);
-                    double m[10];
-                    row_monomials(R.dx, __ldcs(R.rowXYZ + row), cm, m);
-#pragma unroll
-                    for (int q = 0; q < 10; ++q) acc[q] += m[q] * gk;
-                }
-                const double tot = warp_reduce10(acc);
-                const int ki = warp_reduce10_index(threadIdx.x & 31u);
-                if (!(threadIdx.x & 1) && ki >= 0) red[threadIdx.x >> 5][ki] = tot;
-                __syncthreads();
-                if (threadIdx.x < 10) {
-                    double s2 = 0.;
-#pragma unroll
-                    for (int wI = 0; wI < HOT_THREADS / 32; ++wI) s2 += red[wI][threadIdx.x];
-                    R.partial[(size_t)ch * 10 + threadIdx.x] = s2;
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    __threadfence();
-                    const unsigned nch = (unsigned)(__ldg(R.rowChunkStart + region + 1) - __ldg(R.rowChunkStart + region));
-                    const unsigned tk = atomicInc(R.regionTicket + region, nch - 1);
-                    sLast = (tk == nch - 1);
-                    if (sLast) __threadfence();
-                }
-                __syncthreads();
-                if (sLast) {
-                    region_epilogue_solve(R, A.rowChunk, region, M, tv, sv, sg);
-                    // expand: the region's rows (all three axes) <- outScale * sigma[axis] . monomials(f)
-                    for (int row = __ldg(R.rowStart + region) + threadIdx.x, rend = __ldg(R.rowStart + region + 1); row < rend; row += HOT_THREADS) {
-                        const uint32_t xyz = __ldg(R.rowXYZ + row);
-                        const double* sgl = sg + 10 * (int)(xyz >> 30);
-                        double m[10];
-                        row_monomials(R.dx, xyz, cm, m);
-                        double v = 0.;
-#pragma unroll
-                        for (int q = 0; q < 10; ++q) v += sgl[q] * m[q];
-                        w[A.nActiveVs + row] = R.outScale * v;
-                    }
-                }
-            }
+            continue;
         }
-        __syncthreads();
-        buf ^= 1;
-        cur = sNext[buf];
+        const int ch = (int)A.s1.lo[3] + (int)(e & 0x0fffffff);
+        const int begin = __ldg(A.rowChunk + 4 * ch + 1), end = __ldg(A.rowChunk + 4 * ch + 2);
+        if (R.mode == 0) {      // raw products (K_red x)_f; chunks may be longer than the CTA here (giant regions)
+            for (int row = begin + (int)threadIdx.x; row < end; row += HOT_THREADS) w[A.nActiveVs + row] = pass1_row(A, A.nActiveVs + row, x, sc);
+            continue;
+        }
+        // fused region term; a chunk holds at most one row per thread
+        const int region = __ldg(A.rowChunk + 4 * ch);
+        const int row = begin + (int)threadIdx.x;
+        const double gk = row < end ? pass1_row(A, A.nActiveVs + row, x, sc) : 0.;
+        const double cm[3] = {__ldg(R.com + 3 * region), __ldg(R.com + 3 * region + 1), __ldg(R.com + 3 * region + 2)};
+        double acc[10];
+        row_monomials(R.dx, row < end ? __ldcs(R.rowXYZ + row) : 0u, cm, acc);
+#pragma unroll
+        for (int q = 0; q < 10; ++q) acc[q] *= gk;
+        const double tot = warp_reduce10(acc);
+        const int ki = warp_reduce10_index((unsigned)lane);
+        if (!(lane & 1) && ki >= 0) __stcg(R.wpartial + ((size_t)ch * 8 + wid) * 10 + ki, tot);
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = atom_inc_acq_rel(R.chunkTicket + ch, 7u) == 7u;      // releases the warp's partials (ordered before it by __syncwarp), acquires the others'
+
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        // last warp of the chunk: the 8 warp partials in warp order
+        if (lane < 10) {
+            double s2 = 0.;
+#pragma unroll
+            for (int wI = 0; wI < 8; ++wI) s2 += __ldcg(R.wpartial + ((size_t)ch * 8 + wI) * 10 + lane);
+            __stcg(R.partial + (size_t)ch * 10 + lane, s2);
+        }
+        __syncwarp();
+        unsigned lastR = 0;
+        if (lane == 0) {
+            const unsigned nch = (unsigned)(__ldg(R.rowChunkStart + region + 1) - __ldg(R.rowChunkStart + region));
+            lastR = atom_inc_acq_rel(R.regionTicket + region, nch - 1) == nch - 1;
+        }
+        lastR = __shfl_sync(0xffffffffu, lastR, 0);
+        if (lastR) region_solve_warp(A, R, region, wbuf[wid]);
     }
-    // the last CTA to run out of items re-arms the schedule for the next launch
-    if (dynamic && threadIdx.x == 0) {
-        const unsigned t = atomicInc(A.sched1Ctl + 1, gridDim.x - 1);
-        if (t == gridDim.x - 1) { A.sched1Ctl[0] = 0u; __threadfence(); }
+    if (R.mode == 0) return;
+    // ---- expand: w_f = outScale * sigma[axis] . monomials(f) on this CTA's share of the row chunks
+    const int chLo = (int)A.s1.lo[3], chHi = (int)A.s1.hi[3];
+#pragma unroll 1
+    for (int ch = chLo + (int)blockIdx.x; ch < chHi; ch += (int)gridDim.x) {
+        const int region = __ldg(A.rowChunk + 4 * ch), begin = __ldg(A.rowChunk + 4 * ch + 1), end = __ldg(A.rowChunk + 4 * ch + 2), axis = __ldg(A.rowChunk + 4 * ch + 3);
+        const int row = begin + (int)threadIdx.x;
+        if (begin + wid * 32 >= end) continue;          // this warp has no rows in the chunk
+        const uint32_t xyz = row < end ? __ldcs(R.rowXYZ + row) : 0u;
+        const double cm[3] = {__ldg(R.com + 3 * region), __ldg(R.com + 3 * region + 1), __ldg(R.com + 3 * region + 2)};
+        if (lane == 0) { while ((int)(ld_acquire_u32(R.solved + region) - R.seq) < 0) __nanosleep(40); }
+        __syncwarp();
+        double m[10];
+        row_monomials(R.dx, xyz, cm, m);
+        const double* sg = R.sigma + (size_t)region * 30 + axis * 10;
+        double v = 0.;
+#pragma unroll
+        for (int q = 0; q < 10; ++q) v += __ldcg(sg + q) * m[q];
+        if (row < end) w[A.nActiveVs + row] = R.outScale * v;
     }
 }
-// last CTA of a producer: a, b are valid in thread 0; every rank's block receives this rank's partial sums
-__device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, double a, double b, int nvals) {
-    __shared__ double pv[2];
-    if (threadIdx.x == 0) { pv[0] = a; pv[1] = b; }
+// last CTA of a producer: v0..v2 are valid in thread 0; every rank's block receives this rank's partial sums
+__device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, double v0, double v1, double v2) {
+    __shared__ double pv[PEER_VALS];
+    if (threadIdx.x == 0) { pv[0] = v0; pv[1] = v1; pv[2] = v2; }
     __syncthreads();
-    const double vals[2] = {pv[0], pv[1]};
-    peer_reduce_push(P, slot, vals, nvals);
+    const double vals[PEER_VALS] = {pv[0], pv[1], pv[2]};
+    peer_reduce_push(P, slot, vals, PEER_VALS);
 }
-// y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) (p.Ap) -> S->red[0] / the peers.
+// y = -K_ext^T w - muScale * mu^-1 x_tau + add.  mode bit 0: accumulate dot(x, y) (p.Ap) -> S->red[0] / the peers; bit 1: also
+// dot(r2, y) and dot(y, y) (r.Ap, Ap.Ap) -> red[1], red[2] while y is in registers (the update kernel's beta, see above).
 // Cell sweep: one thread computes the pressure row and the xx / yy / zz stress rows of its cell from ONE set of 6
 // columns, codes and w gathers (32 B of matrix per cell); edge sweep: 4 columns + 4 codes (20 B per edge).
 template <int OCC>
 __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
-                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P) {    pdl_sync();
+                                                              double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P,
+                                                              const double* __restrict__ r2, int reverse) {    pdl_sync();
 
     if (S && S->done) return;
-    const bool dot = mode & 1;
+    const bool dot = mode & 1, dot3 = mode & 2;
     const double sc = A.valScale;
     const int64_t nC = A.nC, nP = A.nP, oE = A.nP + 3 * A.nC;
-    double acc = 0.;
+    double acc = 0., accR = 0., accY = 0.;
     // owned rows in the merged block order: range 0 = cells, 1..3 = yz / xz / xy edges (SchedRanges, ps_solver.hpp)
 #pragma unroll 1
     for (int g = blockIdx.x; g < A.nSched2; g += gridDim.x) {
-        const int32_t se = __ldg(A.sched2 + g);
+        const int32_t se = __ldg(A.sched2 + (reverse ? A.nSched2 - 1 - g : g));
         const int k = (int)((uint32_t)se >> 28);
         const int64_t row = A.s2.lo[k] + (int64_t)(se & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
         if (row >= A.s2.hi[k]) continue;
@@ -351,6 +396,7 @@ __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_co
             if (add) yp += add[ci];
             y[ci] = yp;
             if (dot) acc += x[ci] * yp;
+            if (dot3) { accR += r2[ci] * yp; accY += yp * yp; }
             const double ui = muScale != 0. ? muScale * A.uInv[ci] : 0.;      // mu^-1 is the same for xx, yy, zz of a cell
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -363,6 +409,7 @@ __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_co
                 if (add) yt += add[jj];
                 y[jj] = yt;
                 acc += xj * yt;
+                if (dot3) { accR += r2[jj] * yt; accY += yt * yt; }
             }
         } else {
             const int64_t e = row;
@@ -381,80 +428,77 @@ __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_co
             if (add) yt += add[jj];
             y[jj] = yt;
             acc += xj * yt;
+            if (dot3) { accR += r2[jj] * yt; accY += yt * yt; }
         }
     }
     if (dot) {
         const double bs = block_sum(acc);
         if (threadIdx.x == 0) dotPartial[blockIdx.x] = bs;
+        if (dot3) {
+            const double bR = block_sum(accR), bY = block_sum(accY);
+            if (threadIdx.x == 0) { dotPartial[gridDim.x + blockIdx.x] = bR; dotPartial[2 * gridDim.x + blockIdx.x] = bY; }
+        }
         if (last_block(&S->ticket[0])) {
             const double t = block_sum_partials(dotPartial, gridDim.x);
-            if (threadIdx.x == 0) S->red[0] = t;
-            if (P.nranks > 1) publish_partials(P, 0, t, 0., 1);     // fused all-reduce, producer side (ps_peer.hpp)
+            double tR = 0., tY = 0.;
+            if (dot3) { tR = block_sum_partials(dotPartial + gridDim.x, gridDim.x); tY = block_sum_partials(dotPartial + 2 * gridDim.x, gridDim.x); }
+            if (threadIdx.x == 0) { S->red[0] = t; S->red[1] = tR; S->red[2] = tY; }
+            if (P.nranks > 1) publish_partials(P, 0, t, tR, tY);     // fused all-reduce, producer side (ps_peer.hpp)
         }
     }
 }
-// r -= alpha Ap with the fused r.r (alpha from the global p.Ap of pass 2)
-__global__ void __launch_bounds__(HOT_THREADS) cg_update_r_kernel(RangeSet own, double* __restrict__ r, const double* __restrict__ Ap,
-                                                                 double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P) {    pdl_sync();
+// The three vector updates of one CG iteration in one sweep (see the comment above cg_rre2): alpha from the global p.Ap of
+// pass 2 and the global r.r of the previous update, beta from |r - alpha Ap|^2 = r.r - 2 alpha r.Ap + alpha^2 Ap.Ap.
+// x += alpha p always (pcg.h:314 runs before the stop test); r and p are only advanced if the stop test did not fire.
+// The last CTA then advances the CG state (every CTA has read the scalars by then).
+__global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, const double* __restrict__ Ap,
+                                                               double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P, int reverse) {    pdl_sync();
 
     if (S->done) return;
-    double pAp = S->red[0];
-    if (P.nranks > 1 && !peer_reduce_wait(P, 0, P.seqIn, &pAp, 1)) { if (threadIdx.x == 0) S->peerError = 1; return; }    // fused all-reduce, consumer side
-    const double alpha = S->rsold / pAp;
+    double a[3] = {S->red[0], S->red[1], S->red[2]}, b[3] = {S->red[3], S->red[4], S->red[5]};
+    if (P.nranks > 1) {        // fused all-reduces, consumer side: this iteration's pass 2, and the previous update (or init)
+        if (!peer_reduce_wait(P, 0, P.seqIn, a, 3)) { if (threadIdx.x == 0) S->peerError = 1; return; }
+        if (!peer_reduce_wait(P, 1, P.seqIn2, b, 3)) { if (threadIdx.x == 0) S->peerError = 1; return; }
+    }
+    const double rsold = b[0], alpha = rsold / a[0];
+    const double rrNew = cg_next_rr(rsold, alpha, a[1], a[2]);
+    const double xxNew = cg_next_xx(S->xx, alpha, b[1], b[2]);
+    const bool converged = cg_rre2(rrNew, xxNew) < S->tol2;
+    const double beta = rrNew / rsold;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-    double rr = 0.;
+    double rr = 0., xp = 0., pp = 0.;
+    if (!converged && reverse) {
+        // the same sweep from the far end (local item total - 1 - l): starts on the part of Ap that pass 2 wrote last
+        const int64_t total = own.total();
 #pragma unroll 4
-    for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) {
-        const int64_t i = it.j;
-        const double ri = r[i] - alpha * Ap[i];
-        r[i] = ri;
-        rr += ri * ri;
-    }
-    const double brr = block_sum(rr);
-    if (threadIdx.x == 0) dotPartial[blockIdx.x] = brr;
-    if (last_block(&S->ticket[1])) {
-        const double trr = block_sum_partials(dotPartial, gridDim.x);
-        if (threadIdx.x == 0) { S->red[1] = trr; S->alpha = alpha; if (P.nranks > 1) S->red[0] = pAp; }
-        if (P.nranks > 1) publish_partials(P, 1, trr, 0., 1);
-    }
-}
-// x += alpha p always (pcg.h:314 runs before the stop test); p = r + beta p unless the stop test fired, with the fused x.p / p.p
-// of the NEW x and p for the next iteration's x.x.  The last CTA then advances the CG state (every CTA has read rsold / xx by then).
-__global__ void __launch_bounds__(HOT_THREADS) cg_update_xp_kernel(RangeSet own, double* __restrict__ x, double* __restrict__ p, const double* __restrict__ r,
-                                                                  double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P) {    pdl_sync();
-
-    if (S->done) return;
-    double rr = S->red[1], d[2] = {S->red[2], S->red[3]};
-    const double rsold = S->rsold, alpha = S->alpha;
-    if (P.nranks > 1) {
-        if (!peer_reduce_wait(P, 1, P.seqIn, &rr, 1)) { if (threadIdx.x == 0) S->peerError = 1; return; }
-        if (P.seqIn2 == 0) { d[0] = 0.; d[1] = rsold; }                 // first iteration: x = 0, p = b, p.p = b.b = rsold
-        else if (!peer_reduce_wait(P, 3, P.seqIn2, d, 2)) { if (threadIdx.x == 0) S->peerError = 1; return; }
-    }
-    const double xxNew = cg_next_xx(S->xx, alpha, d[0], d[1]);
-    const bool converged = cg_rre2(rr, xxNew) < S->tol2;
-    const double beta = rr / rsold;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-    double xp = 0., pp = 0.;
-    if (!converged) {
+        for (int64_t l = tid; l < total; l += stride) {
+            const int64_t i = own.at(total - 1 - l);
+            const double pi = p[i];
+            const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
+            const double pn = ri + beta * pi;
+            x[i] = xi; r[i] = ri; p[i] = pn;
+            rr += ri * ri; xp += xi * pn; pp += pn * pn;
+        }
+    } else if (!converged) {
 #pragma unroll 4
         for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) {
             const int64_t i = it.j;
             const double pi = p[i];
-            const double xi = x[i] + alpha * pi, pn = r[i] + beta * pi;
-            x[i] = xi; p[i] = pn;
-            xp += xi * pn; pp += pn * pn;
+            const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
+            const double pn = ri + beta * pi;
+            x[i] = xi; r[i] = ri; p[i] = pn;
+            rr += ri * ri; xp += xi * pn; pp += pn * pn;
         }
     } else {
 #pragma unroll 4
         for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) { const int64_t i = it.j; x[i] += alpha * p[i]; }
     }
-    const double bxp = block_sum(xp), bpp = block_sum(pp);
-    if (threadIdx.x == 0) { dotPartial[blockIdx.x] = bxp; dotPartial[gridDim.x + blockIdx.x] = bpp; }
+    const double brr = block_sum(rr), bxp = block_sum(xp), bpp = block_sum(pp);
+    if (threadIdx.x == 0) { dotPartial[blockIdx.x] = brr; dotPartial[gridDim.x + blockIdx.x] = bxp; dotPartial[2 * gridDim.x + blockIdx.x] = bpp; }
     if (last_block(&S->ticket[3])) {
-        const double txp = block_sum_partials(dotPartial, gridDim.x), tpp = block_sum_partials(dotPartial + gridDim.x, gridDim.x);
-        if (threadIdx.x == 0) { S->red[1] = rr; cg_advance(S, rr, xxNew); S->red[2] = txp; S->red[3] = tpp; }
-        if (P.nranks > 1) publish_partials(P, 3, txp, tpp, 2);
+        const double trr = block_sum_partials(dotPartial, gridDim.x), txp = block_sum_partials(dotPartial + gridDim.x, gridDim.x), tpp = block_sum_partials(dotPartial + 2 * gridDim.x, gridDim.x);
+        if (threadIdx.x == 0) { cg_advance(S, rsold, rrNew, xxNew, alpha, a[0]); S->red[3] = trr; S->red[4] = txp; S->red[5] = tpp; }
+        if (P.nranks > 1) publish_partials(P, 1, trr, txp, tpp);
     }
 }
 __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, const double* __restrict__ b, double* x, double* r, double* p, double* dotPartial, PcgScalars* S, double tol, int maxIter,
@@ -473,19 +517,19 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, cons
         const double rs = block_sum_partials(dotPartial, gridDim.x);
         if (threadIdx.x == 0) {
             S->rsold = 0.; S->pAp = 0.; S->alpha = 0.; S->beta = 0.; S->rsnew = 0.; S->xmag = 0.; S->rre = 0.;
-            S->red[0] = 0.; S->red[1] = 0.; S->red[2] = 0.; S->red[3] = rs; S->red[4] = rs; S->xx = 0.;      // x = 0: x.p = 0; p = b: p.p = b.b
+            S->red[0] = 0.; S->red[1] = 0.; S->red[2] = 0.; S->red[3] = rs; S->red[4] = 0.; S->red[5] = rs; S->red[6] = rs; S->xx = 0.;      // r = p = b: r.r = p.p = b.b; x = 0: x.p = 0
             S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
-            S->ticket[0] = 0; S->ticket[1] = 0; S->ticket[3] = 0;      // nothing else is in flight: heal tickets after an aborted solve
+            S->ticket[0] = 0; S->ticket[3] = 0;      // nothing else is in flight: heal tickets after an aborted solve
         }
-        if (P.nranks > 1) publish_partials(P, 2, rs, 0., 1);
+        if (P.nranks > 1) publish_partials(P, 1, rs, 0., rs);
     }
 }
 // after the all-reduce of b.b: rsold, and the b == 0 early out
 __global__ void cg_begin_kernel(PcgScalars* S, const __grid_constant__ PeerCtx P) {    pdl_sync();
 
-    double bb = S->red[4];
-    if (P.nranks > 1 && !peer_reduce_wait(P, 2, P.seqIn, &bb, 1)) { if (threadIdx.x == 0) { S->peerError = 1; S->done = 1; } return; }
-    if (threadIdx.x == 0) { S->red[4] = bb; S->rsold = bb; S->done = (bb == 0.) ? 1 : 0; }
+    double bb[3] = {S->red[3], S->red[4], S->red[5]};
+    if (P.nranks > 1 && !peer_reduce_wait(P, 1, P.seqIn, bb, 3)) { if (threadIdx.x == 0) { S->peerError = 1; S->done = 1; } return; }
+    if (threadIdx.x == 0) { S->red[6] = bb[0]; S->rsold = bb[0]; S->done = (bb[0] == 0.) ? 1 : 0; }
 }
 // halo exchange over peer memory, sender side: gather the boundary entries and store them straight into the
 // neighbours' receive buffers (NVLink), then raise their sequence flags once every CTA's stores are fenced
@@ -596,30 +640,29 @@ static inline int hot_blocks(K kernel, int64_t n) {
     return (int)b;
 }
 
-void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
-    if (A.rowsK.total() <= 0) return;
-    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, A.rowsK.total()), HOT_THREADS, st, A, x, w, activeScale, S);
+void k_pass1(cudaStream_t st, const OpArgs& A, const RegionOp& R, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse) {
+    if (A.nSched1 <= 0) return;
+    static const int unroll = getenv("PS_PASS1_UNROLL") ? atoi(getenv("PS_PASS1_UNROLL")) : 2;      // A/B knob
+    if (unroll >= 2) launch_chain(pass1_kernel<2>, hot_blocks(pass1_kernel<2>, (int64_t)A.nSched1 * HOT_THREADS), HOT_THREADS, st, A, R, x, w, activeScale, S, reverse ? 2 : 0);
+    else launch_chain(pass1_kernel<1>, hot_blocks(pass1_kernel<1>, (int64_t)A.nSched1 * HOT_THREADS), HOT_THREADS, st, A, R, x, w, activeScale, S, reverse ? 2 : 0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode) {
+void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode, const double* r2, bool reverse) {
     // resident CTAs per SM the kernel is compiled for.  Measured on S3 256^3 (profiles/r01_sweep_occupancy.log): 4 -> 0.148 ms, 5 -> 0.137 ms,
     // 6 -> 0.132 ms, 7 / 8 spill and fall back to 0.137 ms
     static const int occ = getenv("PS_PASS2_OCC") ? atoi(getenv("PS_PASS2_OCC")) : 6;
     const int64_t rows = A.rowsP.total() + A.rowsE.total();
-    if (occ >= 6) launch_chain(pass2_kernel<6>, hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P);
-    else if (occ == 5) launch_chain(pass2_kernel<5>, hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P);
-    else launch_chain(pass2_kernel<4>, hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P);
+    if (rows <= 0 && !(mode & 1)) return;
+    const int rev = reverse ? 1 : 0;
+    if (occ >= 6) launch_chain(pass2_kernel<6>, hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev);
+    else if (occ == 5) launch_chain(pass2_kernel<5>, hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev);
+    else launch_chain(pass2_kernel<4>, hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_update_r(cudaStream_t st, const RangeSet& own, double* r, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P) {
-    launch_chain(cg_update_r_kernel, hot_blocks(cg_update_r_kernel, own.total()), HOT_THREADS, st, own, r, Ap, dotPartial, scal, P);
-    PS_COUNT_LAUNCH(1);
-    PS_CUDA(cudaGetLastError());
-}
-void k_cg_update_xp(cudaStream_t st, const RangeSet& own, double* x, double* p, const double* r, double* dotPartial, PcgScalars* scal, const PeerCtx& P) {
-    launch_chain(cg_update_xp_kernel, hot_blocks(cg_update_xp_kernel, own.total()), HOT_THREADS, st, own, x, p, r, dotPartial, scal, P);
+void k_cg_update(cudaStream_t st, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse) {
+    launch_chain(cg_update_kernel, hot_blocks(cg_update_kernel, own.total()), HOT_THREADS, st, own, x, r, p, Ap, dotPartial, scal, P, reverse ? 1 : 0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -669,19 +712,52 @@ void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double*
     PS_CUDA(cudaGetLastError());
 }
 #else  // ---- serial twins ----
-void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S) {
+void k_pass1(cudaStream_t, const OpArgs& A, const RegionOp& R, const double* x, double* w, double activeScale, const PcgScalars* S, bool) {
     if (S && S->done) return;
-    for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInvLut[A.kmc[r]] * s : s; }
+    for (int k = 0; k < 3; ++k)
+        for (int64_t r = A.s1.lo[k]; r < A.s1.hi[k]; ++r) w[r] = activeScale * A.mcInvLut[A.kmc[r]] * k_row(A, r, x);
+    // row chunks of the coupled reduced rows of the owned regions
+    const int chLo = (int)A.s1.lo[3], chHi = (int)A.s1.hi[3];
+    for (int ch = chLo; ch < chHi; ++ch) {
+        const int region = A.rowChunk[4 * ch], begin = A.rowChunk[4 * ch + 1], end = A.rowChunk[4 * ch + 2];
+        double acc[10] = {0};
+        for (int row = begin; row < end; ++row) {
+            const double gk = k_row(A, A.nActiveVs + row, x);
+            if (R.mode == 0) { w[A.nActiveVs + row] = gk; continue; }
+            double m[10]; row_monomials(R.dx, R.rowXYZ[row], R.com + 3 * region, m);
+            for (int q = 0; q < 10; ++q) acc[q] += m[q] * gk;
+        }
+        if (R.mode != 0) for (int q = 0; q < 10; ++q) R.partial[(size_t)ch * 10 + q] = acc[q];
+    }
+    if (R.mode == 0 || chHi <= chLo) return;
+    for (int region = A.rowChunk[4 * chLo]; region <= A.rowChunk[4 * (chHi - 1)]; ++region) {
+        double M[30] = {0}, t[RDOF], sv[RDOF], sg[30];
+        for (int ch = R.rowChunkStart[region]; ch < R.rowChunkStart[region + 1]; ++ch)
+            for (int q = 0; q < 10; ++q) M[A.rowChunk[4 * ch + 3] * 10 + q] += R.partial[(size_t)ch * 10 + q];
+        moments_to_t(M, t);
+        for (int n = 0; n < RDOF; ++n) t[n] = R.tScale * t[n] + (R.extra ? R.extraScale * R.extra[(size_t)region * RDOF + n] : 0.);
+        for (int i = 0; i < RDOF; ++i) { double s2 = 0.; for (int j = 0; j < RDOF; ++j) s2 += R.Binv[(size_t)region * RDOF * RDOF + i * RDOF + j] * t[j]; sv[i] = s2; }
+        s_to_sigma(sv, sg);
+        if (R.sigma) for (int q = 0; q < 30; ++q) R.sigma[(size_t)region * 30 + q] = sg[q];
+        for (int row = R.rowStart[region]; row < R.rowStart[region + 1]; ++row) {
+            const uint32_t xyz = R.rowXYZ[row];
+            double m[10]; row_monomials(R.dx, xyz, R.com + 3 * region, m);
+            double v = 0.;
+            for (int q = 0; q < 10; ++q) v += sg[10 * (int)(xyz >> 30) + q] * m[q];
+            w[A.nActiveVs + row] = R.outScale * v;
+        }
+    }
 }
-void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode) {
+void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode, const double* r2, bool) {
     if (S && S->done) return;
-    double acc = 0.;
+    double acc = 0., accR = 0., accY = 0.;
     auto finish = [&](int64_t j, double ktw) {
         double v = -ktw;
         const double xj = (mode & 1) || j >= A.nP ? (x ? x[j] : 0.) : 0.;
         if (j >= A.nP && muScale != 0.) v -= muScale * A.uInv[j - A.nP] * xj;
         if (add) v += add[j];
         y[j] = v; acc += xj * v;
+        if (mode & 2) { accR += r2[j] * v; accY += v * v; }
     };
     for (int64_t l = 0; l < A.rowsP.total(); ++l) {
         const int64_t ci = A.rowsP.at(l);
@@ -691,37 +767,31 @@ void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, do
         for (int a = 0; a < 3; ++a) finish(A.nP + a * A.nC + ci, out[1 + a]);
     }
     for (int64_t l = 0; l < A.rowsE.total(); ++l) { const int64_t e = A.rowsE.at(l); finish(A.nP + 3 * A.nC + e, kt_edge_row(A, e, w)); }
-    if (mode & 1) S->red[0] = acc;
+    if (mode & 1) { S->red[0] = acc; S->red[1] = accR; S->red[2] = accY; }
 }
-void k_cg_update_r(cudaStream_t, const RangeSet& own, double* r, const double* Ap, double*, PcgScalars* S, const PeerCtx&) {
+void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double*, PcgScalars* S, const PeerCtx&, bool) {
     if (S->done) return;
-    const double alpha = cg_alpha(S);
-    double rr = 0.;
-    for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); r[i] -= alpha * Ap[i]; rr += r[i] * r[i]; }
-    S->red[1] = rr; S->alpha = alpha;
-}
-void k_cg_update_xp(cudaStream_t, const RangeSet& own, double* x, double* p, const double* r, double*, PcgScalars* S, const PeerCtx&) {
-    if (S->done) return;
-    const double rr = S->red[1], alpha = S->alpha;
-    const double xxNew = cg_next_xx(S->xx, alpha, S->red[2], S->red[3]);
-    const bool converged = cg_rre2(rr, xxNew) < S->tol2;
-    const double beta = rr / S->rsold;
-    double xp = 0., pp = 0.;
+    const double rsold = S->red[3], alpha = rsold / S->red[0];
+    const double rrNew = cg_next_rr(rsold, alpha, S->red[1], S->red[2]);
+    const double xxNew = cg_next_xx(S->xx, alpha, S->red[4], S->red[5]);
+    const bool converged = cg_rre2(rrNew, xxNew) < S->tol2;
+    const double beta = rrNew / rsold;
+    double rr = 0., xp = 0., pp = 0.;
     for (int64_t l = 0; l < own.total(); ++l) {
         const int64_t i = own.at(l);
         x[i] += alpha * p[i];
-        if (!converged) { p[i] = r[i] + beta * p[i]; xp += x[i] * p[i]; pp += p[i] * p[i]; }
+        if (!converged) { r[i] -= alpha * Ap[i]; p[i] = r[i] + beta * p[i]; rr += r[i] * r[i]; xp += x[i] * p[i]; pp += p[i] * p[i]; }
     }
-    cg_advance(S, rr, xxNew);
-    S->red[2] = xp; S->red[3] = pp;
+    cg_advance(S, rsold, rrNew, xxNew, alpha, S->red[0]);
+    S->red[3] = rr; S->red[4] = xp; S->red[5] = pp;
 }
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double*, PcgScalars* S, double tol, int maxIter, const PeerCtx&) {
     double rr = 0.;
     for (int64_t l = 0; l < own.total(); ++l) { const int64_t i = own.at(l); x[i] = 0.; r[i] = b[i]; p[i] = b[i]; rr += b[i] * b[i]; }
-    S->rsold = S->pAp = S->alpha = S->beta = S->rsnew = S->xmag = S->rre = S->xx = 0.; S->red[0] = S->red[1] = S->red[2] = 0.; S->red[3] = rr; S->red[4] = rr;
+    S->rsold = S->pAp = S->alpha = S->beta = S->rsnew = S->xmag = S->rre = S->xx = 0.; S->red[0] = S->red[1] = S->red[2] = 0.; S->red[3] = rr; S->red[4] = 0.; S->red[5] = rr; S->red[6] = rr;
     S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
 }
-void k_cg_begin(cudaStream_t, PcgScalars* S, const PeerCtx&) { S->rsold = S->red[4]; S->done = (S->red[4] == 0.) ? 1 : 0; }
+void k_cg_begin(cudaStream_t, PcgScalars* S, const PeerCtx&) { S->red[6] = S->red[3]; S->rsold = S->red[3]; S->done = (S->red[3] == 0.) ? 1 : 0; }
 void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) buf[i] = v[idx[i]]; }
 void k_halo_unpack(cudaStream_t, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) { if (S && S->done) return; for (int64_t i = 0; i < n; ++i) v[idx[i]] = buf[i]; }
 #endif
@@ -853,25 +923,6 @@ void k_mark_Kt_columns(cudaStream_t st, const OpArgs& A, const RowSet& cellRows,
 // offset (S.cpp:2107-2149), so a chunk of same-axis rows only accumulates 10 moments per row; the 26-vector
 // t_r is a fixed sparse image of the 3x10 moments, and w_f is a 10-term polynomial with coefficients
 // sigma[axis] = (that image)^T s_r.
-// t (26) from the per-axis moments M[3][10]
-PS_D void moments_to_t(const double* M, double* t) {
-    for (int n = 0; n < RDOF; ++n) t[n] = 0.;
-    const double* A = M; const double* B = M + 10; const double* Cz = M + 20;
-    t[0] = A[0]; t[3] = A[1]; t[4] = A[2]; t[5] = A[3]; for (int k = 0; k < 6; ++k) t[6 + k] = A[4 + k];
-    t[1] = B[0]; t[12] = B[1]; t[13] = B[2]; t[14] = B[3]; for (int k = 0; k < 6; ++k) t[15 + k] = B[4 + k];
-    t[2] += Cz[0]; t[3] += -Cz[3]; t[6] += -2. * Cz[6]; t[7] += -Cz[8]; t[8] += -0.5 * Cz[9];
-    t[13] += -Cz[3]; t[16] += -Cz[6]; t[18] += -2. * Cz[8]; t[19] += -0.5 * Cz[9];
-    t[21] += Cz[1]; t[22] += Cz[2]; t[23] += Cz[4]; t[24] += Cz[5]; t[25] += Cz[7];
-}
-// sigma[3][10] from s (26): w_f = sum_m sigma[axis][m] * mono_m
-PS_D void s_to_sigma(const double* s, double* sg) {
-    sg[0] = s[0]; sg[1] = s[3]; sg[2] = s[4]; sg[3] = s[5]; for (int k = 0; k < 6; ++k) sg[4 + k] = s[6 + k];
-    sg[10] = s[1]; sg[11] = s[12]; sg[12] = s[13]; sg[13] = s[14]; for (int k = 0; k < 6; ++k) sg[14 + k] = s[15 + k];
-    double* z = sg + 20;
-    z[0] = s[2]; z[1] = s[21]; z[2] = s[22]; z[3] = -s[3] - s[13]; z[4] = s[23]; z[5] = s[24];
-    z[6] = -2. * s[6] - s[16]; z[7] = s[25]; z[8] = -s[7] - 2. * s[18]; z[9] = -0.5 * s[8] - 0.5 * s[19];
-}
-
 #ifndef PS_EMULATE
 constexpr int RED_THREADS = 256;
 constexpr int MOM_THREADS = 64;
@@ -983,128 +1034,6 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, 
         wRows[row] = scale * v;
     }
 }
-// The whole reduced term of one apply for tiled regions, ONE CTA per region: w_f <- scale * c_f . B_r^-1 (sum_f c_f w_f).
-// Three groups of REG_GROUP threads take the region's x / y / z rows (rowAxisStart), so every load of the region is in flight
-// at once; the 3 x 10 moments are reduced in a fixed order (warp shuffles, then the group's warps in order), B^-1 (staged in
-// shared memory while the rows stream in) is applied by 26 threads, and the same threads that read a row overwrite it with the
-// expanded value.  No inter-CTA hand-off: this replaces moments + last-chunk solve + expand (3 dependent stages, 2 launches)
-// by one launch whose critical path is one row round trip + one 26x26 product.  Regions too large for one CTA (doTile off)
-// keep the chunked kernels above.
-// GROUP threads per axis, ROWS rows per thread kept in registers between the two phases (0: re-read rowXYZ through L1/L2)
-template <int GROUP, int ROWS, int MINB>
-__global__ void __launch_bounds__(3 * GROUP, MINB) reduced_region_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ rowAxisStart, const double* __restrict__ com,
-                                                                       const double* __restrict__ Binv, double* __restrict__ wRows, double scale, const PcgScalars* S, int region0) {
-    constexpr int NW = GROUP / 32, KEEP = ROWS > 0 ? ROWS : 1;
-    __shared__ double Bs[RDOF * RDOF];
-    __shared__ double red[3][NW][10];
-    __shared__ double M[30], t[RDOF], sv[RDOF], sg[30];
-    const int r = region0 + blockIdx.x;
-    // B^-1, the row table and the centres of mass are setup data: they may be fetched before the previous kernel has finished
-    for (int i = threadIdx.x; i < RDOF * RDOF; i += 3 * GROUP) Bs[i] = __ldg(Binv + (size_t)r * RDOF * RDOF + i);
-    const int axis = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
-    const int begin = __ldg(rowAxisStart + 3 * r + axis), end = __ldg(rowAxisStart + 3 * r + axis + 1);
-    const double cm[3] = {__ldg(com + 3 * r), __ldg(com + 3 * r + 1), __ldg(com + 3 * r + 2)};
-    pdl_sync();
-    if (S && S->done) return;
-    double acc[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] = 0.;
-    uint32_t xyz[KEEP];
-    if (ROWS > 0) {
-        double gk[KEEP];
-#pragma unroll
-        for (int i = 0; i < KEEP; ++i) {
-            const int row = begin + lane + i * GROUP;
-            xyz[i] = row < end ? __ldcs(rowXYZ + row) : 0u;
-            gk[i] = row < end ? __ldcs(wRows + row) : 0.;
-        }
-#pragma unroll
-        for (int i = 0; i < KEEP; ++i) {
-            double m[10];
-            row_monomials(dx, xyz[i], cm, m);
-#pragma unroll
-            for (int k = 0; k < 10; ++k) acc[k] += m[k] * gk[i];
-        }
-    }
-#pragma unroll 4
-    for (int row = begin + lane + ROWS * GROUP; row < end; row += GROUP) {
-        double m[10];
-        row_monomials(dx, __ldg(rowXYZ + row), cm, m);
-        const double g1 = __ldcs(wRows + row);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) acc[k] += m[k] * g1;
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        const double v = warp_sum(acc[k]);
-        if ((lane & 31) == 0) red[axis][lane >> 5][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 30) {
-        const int a = threadIdx.x / 10, k = threadIdx.x % 10;
-        double s = 0.;
-#pragma unroll
-        for (int wI = 0; wI < NW; ++wI) s += red[a][wI][k];
-        M[threadIdx.x] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) moments_to_t(M, t);
-    __syncthreads();
-    if (threadIdx.x < RDOF) {
-        const double* B = Bs + threadIdx.x * RDOF;
-        double s = 0.;
-#pragma unroll
-        for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
-        sv[threadIdx.x] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_to_sigma(sv, sg);
-    __syncthreads();
-    double sgl[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) sgl[k] = sg[axis * 10 + k];
-    if (ROWS > 0) {
-#pragma unroll
-        for (int i = 0; i < KEEP; ++i) {
-            const int row = begin + lane + i * GROUP;
-            if (row < end) {
-                double m[10];
-                row_monomials(dx, xyz[i], cm, m);
-                double v = 0.;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
-                wRows[row] = scale * v;
-            }
-        }
-    }
-#pragma unroll 4
-    for (int row = begin + lane + ROWS * GROUP; row < end; row += GROUP) {
-        double m[10];
-        row_monomials(dx, __ldg(rowXYZ + row), cm, m);
-        double v = 0.;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
-        wRows[row] = scale * v;
-    }
-}
-template <int GROUP, int ROWS, int MINB>
-static void launch_region(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
-    launch_chain(reduced_region_kernel<GROUP, ROWS, MINB>, (unsigned)(RG.regHi - RG.regLo), 3 * GROUP, st, g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, wRows, scale, S, RG.regLo);
-}
-// w_f <- scale * c_f . B^-1 J w on the coupled reduced rows (the reduced term of one operator apply)
-void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
-    static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
-    if (RG.regHi <= RG.regLo) return;
-    if (RG.maxRegionRows > fuseLimit) { reduced_moments(st, g, RG, wRows, S, true); reduced_expand(st, g, RG, wRows, scale, S); return; }
-    static const int variant = getenv("PS_REGION_VARIANT") ? atoi(getenv("PS_REGION_VARIANT")) : 0;      // A/B knob (profiles/r01_sweep_region.log)
-    if (variant == 1) launch_region<128, 8, 2>(st, g, RG, wRows, scale, S);
-    else if (variant == 2) launch_region<64, 8, 4>(st, g, RG, wRows, scale, S);
-    else if (variant == 3) launch_region<32, 0, 10>(st, g, RG, wRows, scale, S);
-    else if (variant == 4) launch_region<128, 0, 3>(st, g, RG, wRows, scale, S);
-    else launch_region<64, 0, 6>(st, g, RG, wRows, scale, S);
-    PS_COUNT_LAUNCH(1);
-    PS_CUDA(cudaGetLastError());
-}
 void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S, bool solve) {
     if (RG.rowChunkHi <= RG.rowChunkLo) return;
     launch_chain(reduced_moments_kernel, (unsigned)(RG.rowChunkHi - RG.rowChunkLo), MOM_THREADS, st, g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.rowChunkStart.p, RG.com.p, wRows, RG.partial.p, RG.Binv.p, RG.sigma.p,
@@ -1154,9 +1083,6 @@ void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const doubl
         s_to_sigma(sv, sg);
         for (int k = 0; k < 30; ++k) RG.sigma.p[(size_t)r * 30 + k] = sg[k];
     }
-}
-void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
-    reduced_moments(st, g, RG, wRows, S, true); reduced_expand(st, g, RG, wRows, scale, S);
 }
 void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
     if (S && S->done) return;
@@ -1299,16 +1225,18 @@ void k_recover_active(cudaStream_t st, const Geom& g, const RowSet& rows, const 
 
 // W2 applySolutionToVelocity (S.cpp:937-1028) fused with buildValidFaces (S_Cls:4-54).  With several ranks a
 // face carrying a DOF is written by the rank that owns the DOF; faces without one are written by everybody.
-void k_writeback_velocity(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, const RegionData& RG, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut, FaceOwner own) {
+// Visits the faces [lo, hi); `valid` is written on [validLo, validHi) only (the part of the field this rank delivers).
+void k_writeback_velocity(cudaStream_t st, const Geom& g, const Fields& F, const Counts& C, const RegionData& RG, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut, FaceOwner own,
+                          int64_t lo, int64_t hi, int64_t validLo, int64_t validHi) {
     const int8_t* FL = F.label[SL_FACE + axis]; const int32_t* FA = F.aidx[SL_FACE + axis]; const int32_t* FR = F.ridx[SL_FACE + axis];
     const float* cvel = F.colvel[axis];
     const double* com = RG.com.p;
     const int64_t faceOff = C.faceOff[axis], nAct = C.nActiveVs;
     const bool haveReduced = RG.count > 0;
-    ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) {
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
         const int lab = FL[q];
         const bool valid = !(lab == L_UNSOLVED || lab == L_UNASSIGNED);
-        if (writeValid) validOut[q] = valid ? 1.f : 0.f;
+        if (writeValid && q >= validLo && q < validHi) validOut[q] = valid ? 1.f : 0.f;
         if (!valid || !velOut) return;
         double v = 0.;
         const int ri = haveReduced ? FR[q] : -1;

@@ -40,6 +40,7 @@ struct PeerCtx {                   // passed by value to the CG kernels; nranks 
 // host-side state of the peer transport of one solver
 struct PeerLink {
     bool on = false;
+    bool needResync = false;                      // a wait timed out / a solve was cancelled: flags and sequence numbers are re-agreed at the next setup
     int rank = 0, nranks = 1;
     void* block[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // block[rank] = mine, others IPC-mapped
     size_t cap = 0;                               // doubles per halo receive buffer

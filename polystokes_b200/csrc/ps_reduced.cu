@@ -18,23 +18,28 @@ namespace ps {
 void k_region_com(cudaStream_t st, const Geom& g, const Fields& F, int32_t R, unsigned long long* sums, double* com) {
     const int8_t* L = F.label[SL_CENTER]; const int32_t* Rg = F.ridx[SL_CENTER];
     dev_memset(sums, 0, (size_t)R * 4 * sizeof(unsigned long long), st);
-    ps_for(st, g.n[SL_CENTER], PS_LAMBDA(int64_t q) {
+    int64_t lo, hi;
+    z_range(g, SL_CENTER, g.zLo, g.zHi, lo, hi);          // the rank's own cells: a region never crosses a z cut
+    if (!g.slabLocal) { lo = 0; hi = g.n[SL_CENTER]; }     // one GPU / replicated setup: every region
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
         if (L[q] != L_REDUCED) return;
         const int r = Rg[q];
+        if (r < 0) return;
         const I3 c = delin(g, SL_CENTER, q);
         atomic_add(&sums[4 * r + 0], (unsigned long long)c.x); atomic_add(&sums[4 * r + 1], (unsigned long long)c.y);
         atomic_add(&sums[4 * r + 2], (unsigned long long)c.z); atomic_add(&sums[4 * r + 3], 1ull);
     });
     const double dx = g.dx;
     ps_for(st, R, PS_LAMBDA(int64_t r) {
+        if (sums[4 * r + 3] == 0ull) return;              // a region of another rank
         const double s = dx / (double)sums[4 * r + 3];
         for (int a = 0; a < 3; ++a) com[3 * r + a] = mul_rn((double)sums[4 * r + a], s);
     });
 }
 
 // scatter (region, voxel) pairs of flagged voxels to their voxel-order rank (input of the stable sort)
-void k_collect_region_keys(cudaStream_t st, const Geom& g, const int32_t* rank, const uint8_t* flag, const int32_t* region, int64_t n, int32_t tag, int32_t rankOffset, int32_t* keys, int32_t* vals) {
-    ps_for(st, n, PS_LAMBDA(int64_t q) {
+void k_collect_region_keys(cudaStream_t st, const Geom& g, const int32_t* rank, const uint8_t* flag, const int32_t* region, int64_t lo, int64_t hi, int32_t tag, int32_t rankOffset, int32_t* keys, int32_t* vals) {
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
         if (!flag[q]) return;
         const int64_t pos = (int64_t)rankOffset + rank[q];
         keys[pos] = region[q]; vals[pos] = (int32_t)q | tag;
@@ -464,15 +469,16 @@ void region_gram_finish(cudaStream_t st, const Geom& g, RegionData& RG, int nChu
 
 // a REDUCED face is a row of K_ext iff it has at least one entry of G / D^T (S_CMB:393-639):
 // an adjacent cell with a pressure index and positive coefficient, or an adjacent isActive edge
-void k_flag_coupled_faces(cudaStream_t st, const Geom& g, const Fields& F, int axis, uint8_t* flag) {
-    const int8_t* FL = F.label[SL_FACE + axis]; const uint8_t* ffw = F.fluW[SL_FACE + axis];
+// (only faces of the regions [regLo, regHi) this rank owns; lo / hi = the voxel range to visit)
+void k_flag_coupled_faces(cudaStream_t st, const Geom& g, const Fields& F, int axis, uint8_t* flag, int32_t regLo, int32_t regHi, int64_t lo, int64_t hi) {
+    const int8_t* FL = F.label[SL_FACE + axis]; const uint8_t* ffw = F.fluW[SL_FACE + axis]; const int32_t* FR = F.ridx[SL_FACE + axis];
     const int32_t* CA = F.aidx[SL_CENTER]; const uint8_t* clw = F.liqW[SL_CENTER];
     const int e1 = axis == 0 ? 1 : 0, e2 = axis == 2 ? 1 : 2;
     const int8_t* EL1 = F.label[SL_EDGE + e1]; const int8_t* EL2 = F.label[SL_EDGE + e2];
     const uint8_t* ew1 = F.liqW[SL_EDGE + e1]; const uint8_t* ew2 = F.liqW[SL_EDGE + e2];
-    ps_for(st, g.n[SL_FACE + axis], PS_LAMBDA(int64_t q) {
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) {
         uint8_t f = 0;
-        if (FL[q] == L_REDUCED && ffw[q] > 0) {
+        if (FL[q] == L_REDUCED && ffw[q] > 0 && FR[q] >= regLo && FR[q] < regHi) {
             const I3 fc = delin(g, SL_FACE + axis, q);
             for (int dir = 0; dir < 2; ++dir) {
                 const I3 cell = dir ? fc : shifted(fc, axis, -1);

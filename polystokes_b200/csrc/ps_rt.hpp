@@ -62,6 +62,22 @@ inline void ps_for(cudaStream_t s, int64_t n, F f) {
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
+// the same over the index range [lo, hi)
+template <class F>
+__global__ void __launch_bounds__(256) ps_for_range_kernel(int64_t lo, int64_t n, F f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(lo + i);
+}
+template <class F>
+inline void ps_for_range(cudaStream_t s, int64_t lo, int64_t hi, F f) {
+    const int64_t n = hi - lo;
+    if (n <= 0) return;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    ps_for_range_kernel<<<(unsigned)blocks, 256, 0, s>>>(lo, n, f);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
 inline void* dev_alloc_bytes(size_t bytes) { void* p = nullptr; if (bytes == 0) bytes = 16; PS_CUDA(cudaMalloc(&p, bytes)); return p; }
 inline void dev_free(void* p) { if (p) cudaFree(p); }
 inline void dev_memset(void* p, int v, size_t bytes, cudaStream_t s) { if (bytes) PS_CUDA(cudaMemsetAsync(p, v, bytes, s)); }
@@ -88,6 +104,8 @@ PS_D int atomic_or(int* a, int v) { return atomicOr(a, v); }
 #else
 template <class F>
 inline void ps_for(cudaStream_t, int64_t n, F f) { for (int64_t i = 0; i < n; ++i) f(i); }
+template <class F>
+inline void ps_for_range(cudaStream_t, int64_t lo, int64_t hi, F f) { for (int64_t i = lo; i < hi; ++i) f(i); }
 inline void* dev_alloc_bytes(size_t bytes) { if (bytes == 0) bytes = 16; void* p = calloc(1, bytes); if (!p) throw Error("calloc failed"); return p; }
 inline void dev_free(void* p) { free(p); }
 inline void dev_memset(void* p, int v, size_t bytes, cudaStream_t) { if (bytes) memset(p, v, bytes); }
@@ -130,5 +148,19 @@ struct DBuf {
     std::vector<T> to_host(cudaStream_t s, size_t count) const { std::vector<T> h(count); copy_d2h(h.data(), p, count * sizeof(T), s); return h; }
     void from_host(cudaStream_t s, const T* h, size_t count) { alloc(count); copy_h2d(p, h, count * sizeof(T), s); }
 };
+
+// Grow-only scratch buffers of the setup stages.  They belong to ONE solver (its device, its stream): every C-ABI entry point
+// points `g_scratch` at the handle's instance for the duration of the call (ps_api.cu), so two handles on different devices
+// driven from one host thread never share device memory, and a handle called from many host threads does not leak a copy per thread.
+struct Scratch {
+    DBuf<uint8_t> selTmp, sortTmp, scanTmp, haloFlag;
+    DBuf<int32_t> selCnt, selStaging, dremap, keys, kt, vt;
+    DBuf<int> bb, rc;
+    DBuf<unsigned long long> sums;
+    DBuf<float> planes;
+    DBuf<double> applyX, applyY;
+};
+extern thread_local Scratch* g_scratch;
+inline Scratch& scratch() { static thread_local Scratch fallback; return g_scratch ? *g_scratch : fallback; }
 
 }  // namespace ps

@@ -57,9 +57,9 @@ __device__ __forceinline__ int block_exclusive_scan_256(int v, int& total) {
     return warpBase + inc - v;
 }
 
-__global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* __restrict__ flag, TileGeom t, int32_t* tileCounts) {
+__global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* __restrict__ flag, TileGeom t, int32_t* tileCounts, int tile0) {
     int64_t base, zStride; int depth;
-    const int c = __popc(column_mask(flag, t, blockIdx.x, threadIdx.x, base, zStride, depth));
+    const int c = __popc(column_mask(flag, t, tile0 + blockIdx.x, threadIdx.x, base, zStride, depth));
     int total;
     block_exclusive_scan_256(c, total);
     if (threadIdx.x == 0) tileCounts[blockIdx.x] = total;
@@ -84,10 +84,10 @@ __global__ void __launch_bounds__(256) tile_offsets_kernel(int32_t* tileCounts, 
     if (threadIdx.x == 0) tileCounts[nTiles] = carry;
 }
 
-__global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* __restrict__ flag, TileGeom t, const int32_t* tileOffsets, int32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* __restrict__ flag, TileGeom t, const int32_t* tileOffsets, int32_t* __restrict__ out, int tile0) {
     __shared__ int part[16 * 8 + 1];      // set voxels per (slice, warp), then their exclusive prefix in slice-major order
     int64_t base, zStride; int depth;
-    const unsigned m = column_mask(flag, t, blockIdx.x, threadIdx.x, base, zStride, depth);
+    const unsigned m = column_mask(flag, t, tile0 + blockIdx.x, threadIdx.x, base, zStride, depth);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -117,17 +117,19 @@ __global__ void __launch_bounds__(256) tile_write_kernel(const uint8_t* __restri
 }
 
 int64_t tile_order_scan(cudaStream_t st, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts,
-                        const std::vector<int>* zCut, std::vector<int64_t>* cuts) {
+                        const std::vector<int>* zCut, std::vector<int64_t>* cuts, const int* tileZ) {
     TileGeom t;
     t.rx = g.r[slot][0]; t.ry = g.r[slot][1]; t.rz = g.r[slot][2];
     t.tx = (t.rx + 15) >> 4; t.ty = (t.ry + 15) >> 4; t.tz = (t.rz + 15) >> 4;
-    const int nTiles = t.tx * t.ty * t.tz;
+    const int tzA = tileZ ? std::max(0, std::min(tileZ[0], t.tz)) : 0, tzB = tileZ ? std::max(tzA, std::min(tileZ[1], t.tz)) : t.tz;
+    const int tile0 = t.tx * t.ty * tzA, nTiles = t.tx * t.ty * (tzB - tzA);
     tileCounts.alloc((size_t)nTiles + 1);
-    tile_count_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p);
+    if (nTiles <= 0) return 0;
+    tile_count_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p, tile0);
     PS_COUNT_LAUNCH(1);
     tile_offsets_kernel<<<1, 256, 0, st>>>(tileCounts.p, nTiles);
     PS_COUNT_LAUNCH(1);
-    tile_write_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p, out);
+    tile_write_kernel<<<nTiles, 256, 0, st>>>(flag, t, tileCounts.p, out, tile0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
     if (zCut && cuts) {
@@ -151,8 +153,8 @@ int64_t tile_order_scan(cudaStream_t st, const Geom& g, int slot, const uint8_t*
 // ascending list of the indices i < n with flag[i] != 0, written to out[outOffset...]; returns the count
 int64_t select_flagged(cudaStream_t st, int64_t n, const uint8_t* flag, DBuf<int32_t>& out, int64_t outOffset) {
     if (n <= 0) return 0;
-    static thread_local DBuf<uint8_t> tmp;
-    static thread_local DBuf<int32_t> cnt, staging;
+    DBuf<uint8_t>& tmp = scratch().selTmp;
+    DBuf<int32_t>& cnt = scratch().selCnt; DBuf<int32_t>& staging = scratch().selStaging;
     cnt.alloc(1); staging.alloc((size_t)n);
     cub::CountingInputIterator<int32_t> idx(0);
     size_t tmpBytes = 0;
@@ -179,7 +181,7 @@ void sort_pairs_by_key(cudaStream_t st, int64_t n, int keyBits, DBuf<int32_t>& k
     keysTmp.alloc((size_t)n); valsTmp.alloc((size_t)n);
     size_t tmpBytes = 0;
     PS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysTmp.p, vals.p, valsTmp.p, (int)n, 0, keyBits, st));
-    static thread_local DBuf<uint8_t> tmp;
+    DBuf<uint8_t>& tmp = scratch().sortTmp;
     tmp.alloc(tmpBytes);
     PS_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysTmp.p, vals.p, valsTmp.p, (int)n, 0, keyBits, st));
     copy_d2d(keys.p, keysTmp.p, (size_t)n * sizeof(int32_t), st);
@@ -190,7 +192,7 @@ int64_t exclusive_scan_i64(cudaStream_t st, int64_t n, const int64_t* in, int64_
     if (n <= 0) return 0;
     size_t tmpBytes = 0;
     PS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, in, out, (int)n, st));
-    static thread_local DBuf<uint8_t> tmp;
+    DBuf<uint8_t>& tmp = scratch().scanTmp;
     tmp.alloc(tmpBytes);
     PS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, in, out, (int)n, st));
     int64_t last[2] = {0, 0};
@@ -208,11 +210,12 @@ int64_t exclusive_scan_i64(cudaStream_t, int64_t n, const int64_t* in, int64_t* 
 }
 
 int64_t tile_order_scan(cudaStream_t, const Geom& g, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>&,
-                        const std::vector<int>* zCut, std::vector<int64_t>* cuts) {
+                        const std::vector<int>* zCut, std::vector<int64_t>* cuts, const int* tileZ) {
     const int rx = g.r[slot][0], ry = g.r[slot][1], rz = g.r[slot][2];
     int32_t n = 0;
     if (zCut && cuts) cuts->assign(zCut->size(), -1);
-    for (int tk = 0; tk < rz; tk += 16) for (int tj = 0; tj < ry; tj += 16) for (int ti = 0; ti < rx; ti += 16) {
+    const int zA = tileZ ? std::max(0, tileZ[0] * 16) : 0, zB = tileZ ? std::min(rz, tileZ[1] * 16) : rz;
+    for (int tk = zA; tk < zB; tk += 16) for (int tj = 0; tj < ry; tj += 16) for (int ti = 0; ti < rx; ti += 16) {
         if (zCut && cuts && tj == 0 && ti == 0) for (size_t k = 0; k < zCut->size(); ++k) if ((*zCut)[k] == tk) (*cuts)[k] = n;
         for (int k = tk; k < std::min(tk + 16, rz); ++k) for (int j = tj; j < std::min(tj + 16, ry); ++j) for (int i = ti; i < std::min(ti + 16, rx); ++i) {
             const int64_t q = (int64_t)i + (int64_t)rx * ((int64_t)j + (int64_t)ry * k);

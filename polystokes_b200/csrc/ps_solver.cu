@@ -9,13 +9,14 @@ namespace ps {
 
 thread_local std::string g_lastError;
 thread_local int64_t g_launches = 0;
+thread_local Scratch* g_scratch = nullptr;
 
 // ---- small helper kernels (free functions: extended lambdas may not live in private members) ----
-static void k_flag_label(cudaStream_t st, int64_t n, const int8_t* L, int value, uint8_t* flag) {
-    ps_for(st, n, PS_LAMBDA(int64_t q) { flag[q] = (L[q] == value) ? 1 : 0; });
+static void k_flag_label(cudaStream_t st, int64_t lo, int64_t hi, const int8_t* L, int value, uint8_t* flag) {
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) { flag[q] = (L[q] == value) ? 1 : 0; });
 }
-static void k_krow_active(cudaStream_t st, int64_t n, const int32_t* aidx, int32_t offset, int32_t* krow) {
-    ps_for(st, n, PS_LAMBDA(int64_t q) { const int a = aidx[q]; krow[q] = a >= 0 ? a + offset : -1; });
+static void k_krow_active(cudaStream_t st, int64_t lo, int64_t hi, const int32_t* aidx, int32_t offset, int32_t* krow) {
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) { const int a = aidx[q]; krow[q] = a >= 0 ? a + offset : -1; });
 }
 static void k_krow_reduced(cudaStream_t st, int64_t nRows, const int32_t* rowFace, int32_t base, int32_t* kr0, int32_t* kr1, int32_t* kr2) {
     ps_for(st, nRows, PS_LAMBDA(int64_t i) {
@@ -95,6 +96,14 @@ void Solver::initComm(Comm* c) {
     part.zCut[0] = 0; part.zCut[c->nranks] = g.nz;
     for (int k = 0; k < c->nranks; ++k) if (part.zCut[k + 1] <= part.zCut[k]) throw Error("ps_comm_init: empty z-slab");
     g.zLo = part.zCut[c->rank]; g.zHi = part.zCut[c->rank + 1];
+    // slab-local setup where regions cannot interact across a cut (ps_part.hpp); PS_SETUP_REPLICATED=1 forces the round-1 behaviour
+    const bool forceRep = getenv("PS_SETUP_REPLICATED") && atoi(getenv("PS_SETUP_REPLICATED"));
+    part.local = c->nranks > 1 && !forceRep && (!P.doReducedRegions || (P.doTile && P.tilePadding >= 2));
+    part.halo = std::min(16, std::max(4, P.activeLiquidBoundaryLayerSize + P.activeSolidBoundaryLayerSize + 3));
+    if (part.local && P.activeLiquidBoundaryLayerSize + P.activeSolidBoundaryLayerSize + 3 > 16) part.local = false;      // the floods reach further than one tile layer
+    g.wzLo = part.local ? std::max(0, g.zLo - part.halo) : 0;
+    g.wzHi = part.local ? std::min(g.nz, g.zHi + part.halo) : g.nz;
+    g.slabLocal = part.local ? 1 : 0;
     delete comm;
     comm = guard.release();
     haveSetup = false;
@@ -157,11 +166,119 @@ void Solver::setupPeer() {
 #endif
 }
 
+// sum over the ranks of one host value (collective; a host sync -- setup / poll paths only)
+double Solver::hostAllreduceSum(double v) {
+    if (!part.multi() || !comm) return v;
+    hostRed.alloc(1);
+    copy_h2d(hostRed.p, &v, sizeof(double), st);
+    comm->allreduce_sum(hostRed.p, 1, st);
+    copy_d2h(&v, hostRed.p, sizeof(double), st);
+    return v;
+}
+std::vector<double> Solver::hostAllgather(const std::vector<double>& mine) {
+    const size_t k = mine.size(), n = k * (size_t)part.nranks;
+    std::vector<double> all(n, 0.);
+    std::copy(mine.begin(), mine.end(), all.begin() + k * (size_t)part.rank);
+    if (!part.multi() || !comm) return all;
+    hostRed.alloc(n);
+    copy_h2d(hostRed.p, all.data(), n * sizeof(double), st);
+    comm->allreduce_sum(hostRed.p, (int)n, st);
+    copy_d2h(all.data(), hostRed.p, n * sizeof(double), st);
+    return all;
+}
+// prefix sums over the ranks of item `item` of an all-gathered table with `stride` entries per rank
+std::vector<int64_t> Solver::cutsFromCounts(const std::vector<double>& all, int stride, int item) const {
+    std::vector<int64_t> cut((size_t)part.nranks + 1, 0);
+    for (int k = 0; k < part.nranks; ++k) cut[k + 1] = cut[k] + (int64_t)std::llround(all[(size_t)k * stride + item]);
+    return cut;
+}
+// tile layers [tz[0], tz[1]) of the own slab (cuts are multiples of 16); the last slab takes the slot's extra top layer, and
+// `extraTop` further tile layers can be added above (faces on the upper cut plane that belong to an own region)
+void Solver::ownTileZ(int slot, int tz[2], int extraTop) const {
+    const int rz = g.r[slot][2];
+    tz[0] = g.zLo >> 4;
+    tz[1] = g.zHi >= g.nz ? (rz + 15) >> 4 : std::min((rz + 15) >> 4, (g.zHi >> 4) + extraTop);
+}
+// Halo layers of grid fields: my lower / upper `halo` layers go to the neighbours, theirs arrive in my halo.  Dense x-fastest
+// arrays addressed by global voxel index: a z-range is one contiguous byte range, the same on both sides.
+void Solver::exchangeLayers(const std::vector<LayerField>& fields) {
+    if (!part.local || !comm) return;
+    const int H = part.halo;
+    std::vector<int> peers; std::vector<const void*> sb; std::vector<size_t> sby; std::vector<void*> rb; std::vector<size_t> rby;
+    for (const LayerField& f : fields) {
+        for (int side = 0; side < 2; ++side) {
+            const int pr = side == 0 ? part.rank - 1 : part.rank + 1;
+            if (pr < 0 || pr >= part.nranks) continue;
+            int64_t slo, shi, rlo, rhi;
+            if (side == 0) { z_range(g, f.slot, g.zLo, std::min(g.zLo + H, g.zHi), slo, shi); z_range(g, f.slot, std::max(g.zLo - H, part.zCut[pr]), g.zLo, rlo, rhi); }
+            else { z_range(g, f.slot, std::max(g.zHi - H, g.zLo), g.zHi, slo, shi); z_range(g, f.slot, g.zHi, std::min(g.zHi + H, part.zCut[pr + 1]), rlo, rhi); }
+            // z_range gives the slot's extra top layer to a range that ends at nz: only the last slab may send / receive it
+            peers.push_back(pr);
+            sb.push_back((const char*)f.base + slo * f.elem); sby.push_back((size_t)(shi - slo) * f.elem);
+            rb.push_back((char*)f.base + rlo * f.elem); rby.push_back((size_t)(rhi - rlo) * f.elem);
+        }
+    }
+    if (!peers.empty()) comm->sendrecv((int)peers.size(), peers.data(), sb.data(), sby.data(), rb.data(), rby.data(), st);
+}
+static void k_merge_max_i32(cudaStream_t st, int64_t n, int32_t* dst, const int32_t* src) {
+    ps_for(st, n, PS_LAMBDA(int64_t i) { const int32_t a = dst[i], b = src[i]; dst[i] = a > b ? a : b; });
+}
+// A z-face plane on a cut carries rows of both ranks: active faces are numbered by the upper slab, coupled reduced faces belong
+// to a region of the lower one.  Both sides exchange their copy of the plane and keep the larger entry (-1 = none).
+void Solver::mergeSharedPlanes(int32_t* f) {
+    if (!part.local || !comm) return;
+    const int slot = SL_FACE + 2;
+    const int64_t plane = (int64_t)g.r[slot][0] * g.r[slot][1];
+    xchgTmp.alloc((size_t)plane * 2 * sizeof(int32_t));
+    int32_t* tmp = (int32_t*)xchgTmp.p;
+    const int peers[2] = {part.rank > 0 ? part.rank - 1 : -1, part.rank + 1 < part.nranks ? part.rank + 1 : -1};
+    const int kz[2] = {g.zLo, g.zHi};
+    const void* sb[2] = {f + plane * kz[0], f + plane * kz[1]};
+    void* rb[2] = {tmp, tmp + plane};
+    const size_t bytes[2] = {peers[0] >= 0 ? (size_t)plane * sizeof(int32_t) : 0, peers[1] >= 0 ? (size_t)plane * sizeof(int32_t) : 0};
+    comm->sendrecv(2, peers, sb, bytes, rb, bytes, st);
+    for (int i = 0; i < 2; ++i) if (peers[i] >= 0) k_merge_max_i32(st, plane, f + plane * kz[i], tmp + plane * i);
+}
+
+// a peer-memory wait that timed out leaves the ranks out of step (sequence numbers, flags): report it once, clear the device flag and
+// ask for a collective resynchronisation at the next setup
+void Solver::checkPeer(const char* where) {
+#ifndef PS_EMULATE
+    if (!peer.on) return;
+    int err = 0;
+    copy_d2h(&err, &scal.p->peerError, sizeof(int), st);
+    if (!err) return;
+    dev_memset(&scal.p->peerError, 0, sizeof(int), st);
+    peer.needResync = true;
+    result = R_FAILED;
+    throw Error(std::string("a peer-memory wait timed out in ") + where + " (another rank died or fell out of step)");
+#else
+    (void)where;
+#endif
+}
+// collective, at the start of every setup: if any rank saw a time-out (or was cancelled mid-solve), every rank zeroes its own
+// block and restarts the sequence numbers, so one failed step does not poison the handle
+void Solver::peerResync() {
+#ifndef PS_EMULATE
+    if (!peer.on || !comm || !part.multi()) return;
+    const double any = hostAllreduceSum(peer.needResync ? 1. : 0.);
+    peer.needResync = false;
+    if (any < 0.5) return;
+    stream_sync(st);
+    PS_CUDA(cudaMemsetAsync(peer.block[peer.rank], 0, sizeof(PeerSync), st));
+    dev_memset(&scal.p->peerError, 0, sizeof(int), st);
+    for (auto& q : peer.seqHalo) q = 0;
+    for (auto& q : peer.seqRed) q = 0;
+    stream_sync(st);
+    hostAllreduceSum(0.);          // barrier: every block is clean before anybody stores into it again
+#endif
+}
+
 PeerCtx Solver::reduceCtx(int slotIn, int slotOut, int slotIn2) {
     PeerCtx c = peer.ctx();
     if (peer.on) {
         if (slotIn >= 0) c.seqIn = peer.seqRed[slotIn];           // produced by the previous kernel of the chain
-        if (slotIn2 >= 0) c.seqIn2 = peer.seqRed[slotIn2];        // read before slotOut advances: update xp consumes and produces slot 3
+        if (slotIn2 >= 0) c.seqIn2 = peer.seqRed[slotIn2];        // read before slotOut advances: the x/r/p update consumes and produces slot 1
         if (slotOut >= 0) c.seqOut = ++peer.seqRed[slotOut];
     }
     return c;
@@ -184,8 +301,15 @@ void Solver::setInputs(const ps_fields_in& in) {
     const bool dev = in.memory == PS_MEM_DEVICE;
     const size_t nc = (size_t)g.n[SL_CENTER];
     dSurface.alloc(nc); dCollision.alloc(nc); dViscosity.alloc(nc);
-    copy_any2d(dSurface.p, in.surface, nc * sizeof(float), dev, st);
-    copy_any2d(dCollision.p, in.collision, nc * sizeof(float), dev, st);
+    // Only the layers of the rank's window (+ the margin the stencils reach) cross PCIe: 1 / nranks of the grid with slab-local
+    // setup, everything on one GPU.  The caller's arrays are full-grid either way (global voxel index = offset).
+    auto upload = [&](float* d, const float* src, int slot, int margin, cudaStream_t s2) {
+        int64_t lo, hi;
+        z_range(g, slot, g.wzLo - margin, g.wzHi + margin, lo, hi);
+        copy_any2d(d + lo, src + lo, (size_t)(hi - lo) * sizeof(float), dev, s2);
+    };
+    upload(dSurface.p, in.surface, SL_CENTER, 2, st);
+    upload(dCollision.p, in.collision, SL_CENTER, 2, st);
     // host inputs: only the two SDFs are needed at once (weights); the other seven fields are first read by the region
     // matrices, so they cross PCIe on the copy stream while weights / classification / numbering run (waitLateInputs)
     cudaStream_t sLate = st;
@@ -197,24 +321,33 @@ void Solver::setInputs(const ps_fields_in& in) {
         lateInputsPending = true;
     }
 #endif
-    copy_any2d(dViscosity.p, in.viscosity, nc * sizeof(float), dev, sLate);
+    upload(dViscosity.p, in.viscosity, SL_CENTER, 2, sLate);
     for (int a = 0; a < 3; ++a) {
         const size_t nf = (size_t)g.n[SL_FACE + a];
         dVel[a].alloc(nf); dColVel[a].alloc(nf);
-        copy_any2d(dVel[a].p, in.velocity[a], nf * sizeof(float), dev, sLate);
-        copy_any2d(dColVel[a].p, in.collisionvel[a], nf * sizeof(float), dev, sLate);
+        upload(dVel[a].p, in.velocity[a], SL_FACE + a, 1, sLate);
+        upload(dColVel[a].p, in.collisionvel[a], SL_FACE + a, 1, sLate);
         F.vel[a] = dVel[a].p; F.colvel[a] = dColVel[a].p;
     }
     validSent = false;
     F.surface = dSurface.p; F.collision = dCollision.p; F.viscosity = dViscosity.p;
-    // labels / indices start UNASSIGNED (S.cpp:94-152); byte 0xFF = -1 for int8 and int32 alike
+    // labels / indices start UNASSIGNED (S.cpp:94-152); byte 0xFF = -1 for int8 and int32 alike (window + the margin stencils reach)
     for (int s = 0; s < N_SLOTS; ++s) {
         const size_t n = (size_t)g.n[s];
         dLiqW[s].alloc(n); dFluW[s].alloc(n); dLabel[s].alloc(n); dAidx[s].alloc(n); dRidx[s].alloc(n);
-        dLabel[s].fill_byte(st, 0xFF, n); dAidx[s].fill_byte(st, 0xFF, n); dRidx[s].fill_byte(st, 0xFF, n);
+        int64_t lo, hi;
+        z_range(g, s, g.wzLo - 2, g.wzHi + 2, lo, hi);
+        dev_memset(dLabel[s].p + lo, 0xFF, (size_t)(hi - lo), st);
+        dev_memset(dAidx[s].p + lo, 0xFF, (size_t)(hi - lo) * sizeof(int32_t), st);
+        dev_memset(dRidx[s].p + lo, 0xFF, (size_t)(hi - lo) * sizeof(int32_t), st);
         F.liqW[s] = dLiqW[s].p; F.fluW[s] = dFluW[s].p; F.label[s] = dLabel[s].p; F.aidx[s] = dAidx[s].p; F.ridx[s] = dRidx[s].p;
     }
-    for (int a = 0; a < 3; ++a) { dKrow[a].alloc((size_t)g.n[SL_FACE + a]); F.krow[a] = dKrow[a].p; }
+    for (int a = 0; a < 3; ++a) {
+        dKrow[a].alloc((size_t)g.n[SL_FACE + a]); F.krow[a] = dKrow[a].p;
+        int64_t lo, hi;
+        z_range(g, SL_FACE + a, g.wzLo - 2, g.wzHi + 2, lo, hi);
+        dev_memset(dKrow[a].p + lo, 0xFF, (size_t)(hi - lo) * sizeof(int32_t), st);
+    }
     size_t nmax = 0;
     for (int s = 0; s < N_SLOTS; ++s) nmax = std::max(nmax, (size_t)g.n[s]);
     for (auto& b : scratch8) b.alloc(nmax);
@@ -243,7 +376,11 @@ void Solver::sendValidEarly(const ps_fields_out& out) {
     k_valid_faces(st, g, F, v);
     cudaEvent_t e; PS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     PS_CUDA(cudaEventRecord(e, st)); PS_CUDA(cudaStreamWaitEvent(stOut, e, 0)); PS_CUDA(cudaEventDestroy(e));
-    for (int a = 0; a < 3; ++a) copy_d2any(out.valid[a], v[a], (size_t)g.n[SL_FACE + a] * sizeof(float), false, stOut);
+    for (int a = 0; a < 3; ++a) {
+        int64_t lo, hi;
+        outRange(SL_FACE + a, lo, hi);
+        copy_d2any(out.valid[a] + lo, v[a] + lo, (size_t)(hi - lo) * sizeof(float), false, stOut);
+    }
     validSent = true;
 #endif
 }
@@ -281,33 +418,50 @@ void Solver::classifyEdges() { k_classify_edges(st, g, F); }
 static int read_flag(cudaStream_t st, const int* dflag) { int v = 0; copy_d2h(&v, dflag, sizeof(int), st); return v; }
 
 // constructCenterReducedIndices (S_Cls:217-239): connected components, stencil-overlap fix, small regions
+static void k_add_offset_i32(cudaStream_t st, int64_t lo, int64_t hi, int32_t* f, int32_t off) {
+    if (off == 0) return;
+    ps_for_range(st, lo, hi, PS_LAMBDA(int64_t q) { const int32_t v = f[q]; if (v >= 0) f[q] = v + off; });
+}
+
 void Solver::constructCenterReducedIndices() {
     const int64_t nc = g.n[SL_CENTER];
     int32_t* parent = scratch32[0].p; int32_t* minKey = scratch32[1].p; int32_t* firstRank = scratch32[2].p; int32_t* rootId = scratch32[3].p;
     int* dflag = flags.p;
+    int64_t wlo, whi;
+    z_range(g, SL_CENTER, g.wzLo, g.wzHi, wlo, whi);
+    int tz[2];
+    ownTileZ(SL_CENTER, tz);
     k_cc_init(st, g, F, parent);
     for (int sweep = 0; sweep < 100000; ++sweep) {
         dev_memset(dflag, 0, sizeof(int), st);
         k_cc_sweep(st, g, F, parent, dflag);
         if (!read_flag(st, dflag)) break;
     }
-    dev_memset(minKey, 0x7f, (size_t)nc * sizeof(int32_t), st);
+    dev_memset(minKey + wlo, 0x7f, (size_t)(whi - wlo) * sizeof(int32_t), st);
     k_cc_minkey(st, g, parent, minKey);
     uint8_t* first = scratch8[0].p;
     k_cc_first_flags(st, g, parent, minKey, first);
-    int64_t R = tile_order_scan(st, g, SL_CENTER, first, firstRank, tileCounts);
+    // slab-local: only the own cells are members (k_cc_init), so the first cells all lie in the own tile layers
+    int64_t R = tile_order_scan(st, g, SL_CENTER, first, firstRank, tileCounts, nullptr, nullptr, part.local ? tz : nullptr);
     k_cc_publish(st, g, parent, first, firstRank, rootId);
     k_cc_assign(st, g, F, parent, rootId);
 
     // fixReducedRegionBoundaries (S_Cls:1073-1172), see ps_classify.cu for the recurrence
     fixLoops = 0;
-    if (R > 0) {
+    if (R > 0 || part.local) {
         uint8_t* cand = scratch8[0].p; uint8_t* fa = scratch8[1].p; uint8_t* fb = scratch8[2].p;
         for (;;) {
             fixLoops++;
             dev_memset(dflag, 0, 2 * sizeof(int), st);
             k_fix_candidates(st, g, F, cand, fa, fb, dflag);
-            if (!read_flag(st, dflag)) break;            // sweep finds nothing to fix -> done
+            const int any = read_flag(st, dflag);
+            if (part.local) {
+                // padding >= 2 keeps two regions at least two cells apart: the sweep has nothing to do; anything else would need the
+                // serial order across the cuts
+                if (hostAllreduceSum(any ? 1. : 0.) > 0.5) throw Error("slab-local setup met a cell between two reduced regions (boundary fix-up across slabs): set PS_SETUP_REPLICATED=1");
+                break;
+            }
+            if (!any) break;            // sweep finds nothing to fix -> done
             uint8_t* in = fa; uint8_t* out = fb;
             for (int it = 0; it < 1000000; ++it) {
                 dev_memset(dflag, 0, sizeof(int), st);
@@ -323,7 +477,7 @@ void Solver::constructCenterReducedIndices() {
 
     // fixSmallReducedRegions (S_Cls:1174-1262)
     if (R > 0) {
-        static thread_local DBuf<int> bb;
+        DBuf<int>& bb = scratch().bb;
         bb.alloc((size_t)6 * R);
         dev_memset(bb.p, 0x7f, (size_t)3 * R * sizeof(int), st);
         dev_memset(bb.p + 3 * R, 0x80, (size_t)3 * R * sizeof(int), st);
@@ -342,12 +496,26 @@ void Solver::constructCenterReducedIndices() {
             if (!remove) remap[r] = next++;
         }
         if (next < R) {
-            static thread_local DBuf<int32_t> dremap;
+            DBuf<int32_t>& dremap = scratch().dremap;
             dremap.from_host(st, remap.data(), (size_t)R);
             k_region_remap(st, g, F, dremap.p);
             R = next;
         }
     }
+    if (part.local) {
+        // global region ids: regions are numbered by their first cell in tile order (tiles z-slowest), a slab is a whole number of
+        // tile layers and holds its regions entirely => ids of slab k follow those of the slabs below it
+        const std::vector<double> all = hostAllgather({(double)R});
+        const std::vector<int64_t> cut = cutsFromCounts(all, 1, 0);
+        part.regionCut.assign(cut.begin(), cut.end());
+        int64_t lo, hi;
+        z_range(g, SL_CENTER, g.zLo, g.zHi, lo, hi);
+        k_add_offset_i32(st, lo, hi, F.ridx[SL_CENTER], (int32_t)cut[part.rank]);
+        R = cut[part.nranks];
+        // labels / region ids of the halo cells from their owners (small-region removal is the owner's decision)
+        exchangeLayers({{F.label[SL_CENTER], SL_CENTER, 1}, {F.ridx[SL_CENTER], SL_CENTER, 4}});
+    }
+    (void)nc;
     RG.count = (int32_t)R;
 }
 
@@ -358,6 +526,25 @@ void Solver::constructEdgesReducedIndices() { k_edges_reduced(st, g, F); }
 void Solver::constructActiveIndices() {
     uint8_t* flag = scratch8[0].p;
     int64_t cnt[N_SLOTS];
+    if (part.local) {
+        // every slab numbers its own voxels from 0 (the scan visits its tile layers only); the global index adds the counts of the
+        // slabs below -- exactly the reference's running counter, because tile order is z-slowest
+        std::vector<double> mine(N_SLOTS);
+        for (int s = 0; s < N_SLOTS; ++s) {
+            int tz[2];
+            ownTileZ(s, tz);
+            k_generic_to_active_flags(st, g, s, F.label[s], flag);
+            mine[s] = (double)tile_order_scan(st, g, s, flag, F.aidx[s], tileCounts, nullptr, nullptr, tz);
+        }
+        const std::vector<double> all = hostAllgather(mine);
+        for (int s = 0; s < N_SLOTS; ++s) {
+            part.slotCut[s] = cutsFromCounts(all, N_SLOTS, s);
+            cnt[s] = part.slotCut[s][part.nranks];
+            int64_t lo, hi;
+            z_range(g, s, g.zLo, g.zHi, lo, hi);
+            k_add_offset_i32(st, lo, hi, F.aidx[s], (int32_t)part.slotCut[s][part.rank]);
+        }
+    } else
     for (int s = 0; s < N_SLOTS; ++s) {
         k_generic_to_active_flags(st, g, s, F.label[s], flag);
         if (part.multi()) cnt[s] = tile_order_scan(st, g, s, flag, F.aidx[s], tileCounts, &part.zCut, &part.slotCut[s]);
@@ -398,28 +585,32 @@ static void build_chunks(const std::vector<int>& perRegion, int chunk, std::vect
 // computeReducedViscosityMatricesInteriorOnly (S.cpp:328-490) + the AssembleBlocks dense part (S_AB)
 void Solver::computeReducedRegionMatrices() {
     const int R = RG.count;
-    part.regionCut.assign((size_t)part.nranks + 1, 0);
+    if (!part.local) part.regionCut.assign((size_t)part.nranks + 1, 0);      // slab-local: known since the regions were numbered
     RG.regLo = RG.regHi = 0; RG.cellChunkLo = RG.cellChunkHi = 0;
     if (R <= 0) return;
     const int64_t nc = g.n[SL_CENTER];
-    static thread_local DBuf<unsigned long long> sums;
+    DBuf<unsigned long long>& sums = scratch().sums;
     sums.alloc((size_t)4 * R);
     RG.com.alloc((size_t)3 * R);
     k_region_com(st, g, F, R, sums.p, RG.com.p);
     // REDUCED cells sorted by (region, voxel order)
     uint8_t* flag = scratch8[0].p; int32_t* rank = scratch32[0].p;
-    k_flag_label(st, nc, F.label[SL_CENTER], L_REDUCED, flag);
-    const int64_t nRed = tile_order_scan(st, g, SL_CENTER, flag, rank, tileCounts);
-    static thread_local DBuf<int32_t> keys, kt, vt;
+    int64_t clo = 0, chi = nc;
+    int tz[2];
+    ownTileZ(SL_CENTER, tz);
+    if (part.local) z_range(g, SL_CENTER, g.zLo, g.zHi, clo, chi);      // the cells of the own regions
+    k_flag_label(st, clo, chi, F.label[SL_CENTER], L_REDUCED, flag);
+    const int64_t nRed = tile_order_scan(st, g, SL_CENTER, flag, rank, tileCounts, nullptr, nullptr, part.local ? tz : nullptr);
+    DBuf<int32_t>& keys = scratch().keys; DBuf<int32_t>& kt = scratch().kt; DBuf<int32_t>& vt = scratch().vt;
     keys.alloc((size_t)nRed); RG.cellList.alloc((size_t)nRed);
-    k_collect_region_keys(st, g, rank, flag, F.ridx[SL_CENTER], nc, 0, 0, keys.p, RG.cellList.p);
+    k_collect_region_keys(st, g, rank, flag, F.ridx[SL_CENTER], clo, chi, 0, 0, keys.p, RG.cellList.p);
     sort_pairs_by_key(st, nRed, key_bits(R), keys, RG.cellList, kt, vt);
     std::vector<unsigned long long> hs = sums.to_host(st, (size_t)4 * R);
     std::vector<int> perRegion((size_t)R);
     for (int r = 0; r < R; ++r) perRegion[r] = (int)hs[4 * r + 3];
     // region -> rank: regions are numbered by their first cell in voxel order (z-slowest tiles) and never span a
-    // z cut, so every rank owns one contiguous id range
-    {
+    // z cut, so every rank owns one contiguous id range (slab-local setup: already known from the all-gathered counts)
+    if (!part.local) {
         int owner = 0;
         for (int r = 0; r < R; ++r) {
             const int zmean = (int)(hs[4 * r + 2] / std::max<unsigned long long>(hs[4 * r + 3], 1ull));
@@ -450,41 +641,87 @@ void Solver::computeReducedRegionMatrices() {
 // constructMatrixBlocks (S_CMB:9-868): row numbering of K_ext, then the ELL fills
 void Solver::constructMatrixBlocks() {
     const int R = RG.count;
-    for (int a = 0; a < 3; ++a) k_krow_active(st, g.n[SL_FACE + a], F.aidx[SL_FACE + a], (int32_t)C.faceOff[a], F.krow[a]);
+    // slab-local: the DOF indices of the halo voxels come from their owners (every kernel below reads its neighbours' indices)
+    if (part.local) {
+        std::vector<LayerField> f;
+        for (int s = 0; s < N_SLOTS; ++s) f.push_back({F.aidx[s], s, 4});
+        exchangeLayers(f);
+    }
+    for (int a = 0; a < 3; ++a) {
+        int64_t lo, hi;
+        z_range(g, SL_FACE + a, g.wzLo, g.wzHi, lo, hi);
+        k_krow_active(st, lo, hi, F.aidx[SL_FACE + a], (int32_t)C.faceOff[a], F.krow[a]);
+    }
     RG.nRows = 0; RG.nRowChunks = 0; RG.rowChunkLo = RG.rowChunkHi = 0; RG.ownRowLo = RG.ownRowHi = 0;
     part.redRowCut.assign((size_t)part.nranks + 1, 0);
     if (R > 0) {
+        // the coupled reduced faces of the regions this rank builds rows for: all regions (one GPU, replicated setup) or its own;
+        // a region's faces reach one plane above the slab (the z-faces on the upper cut)
+        const int32_t fLo = part.local ? RG.regLo : 0, fHi = part.local ? RG.regHi : R;
         int64_t cnt[3], off[3];
         for (int a = 0; a < 3; ++a) {
-            k_flag_coupled_faces(st, g, F, a, scratch8[a].p);
-            cnt[a] = tile_order_scan(st, g, SL_FACE + a, scratch8[a].p, scratch32[a].p, tileCounts);
+            int64_t lo = 0, hi = g.n[SL_FACE + a];
+            int tz[2];
+            ownTileZ(SL_FACE + a, tz, 1);
+            if (part.local) z_range(g, SL_FACE + a, g.zLo, std::min(g.nz, g.zHi + 1), lo, hi);
+            if (part.local) { int64_t tlo, thi; z_range(g, SL_FACE + a, tz[0] * 16, std::min(g.nz, tz[1] * 16), tlo, thi); dev_memset(scratch8[a].p + tlo, 0, (size_t)(thi - tlo), st); }
+            k_flag_coupled_faces(st, g, F, a, scratch8[a].p, fLo, fHi, lo, hi);
+            cnt[a] = tile_order_scan(st, g, SL_FACE + a, scratch8[a].p, scratch32[a].p, tileCounts, nullptr, nullptr, part.local ? tz : nullptr);
         }
         off[0] = 0; off[1] = cnt[0]; off[2] = cnt[0] + cnt[1];
-        const int64_t nRows = cnt[0] + cnt[1] + cnt[2];
+        const int64_t nLocal = cnt[0] + cnt[1] + cnt[2];
+        // global row numbers: the rows are sorted by (region, axis, voxel order) and the regions of a slab are contiguous
+        int64_t rowOff = 0, nRows = nLocal;
+        if (part.local) {
+            const std::vector<double> all = hostAllgather({(double)nLocal});
+            part.redRowCut = cutsFromCounts(all, 1, 0);
+            rowOff = part.redRowCut[part.rank]; nRows = part.redRowCut[part.nranks];
+        }
         RG.nRows = nRows;
-        RG.rowFace.alloc((size_t)nRows); RG.rowRegion.alloc((size_t)nRows);
-        for (int a = 0; a < 3; ++a)
-            k_collect_region_keys(st, g, scratch32[a].p, scratch8[a].p, F.ridx[SL_FACE + a], g.n[SL_FACE + a], (int32_t)(a << 29), (int32_t)off[a], RG.rowRegion.p, RG.rowFace.p);
-        static thread_local DBuf<int32_t> kt, vt;
-        sort_pairs_by_key(st, nRows, key_bits(R), RG.rowRegion, RG.rowFace, kt, vt);
+        RG.rowFace.alloc((size_t)nRows + 1); RG.rowRegion.alloc((size_t)nRows + 1);
+        DBuf<int32_t>& lk = scratch().keys; DBuf<int32_t>& lv = scratch().selStaging;      // local (region, face) pairs
+        lk.alloc((size_t)nLocal + 1); lv.alloc((size_t)nLocal + 1);
+        for (int a = 0; a < 3; ++a) {
+            int64_t lo = 0, hi = g.n[SL_FACE + a];
+            if (part.local) z_range(g, SL_FACE + a, g.zLo, std::min(g.nz, g.zHi + 1), lo, hi);
+            k_collect_region_keys(st, g, scratch32[a].p, scratch8[a].p, F.ridx[SL_FACE + a], lo, hi, (int32_t)(a << 29), (int32_t)off[a], lk.p, lv.p);
+        }
+        DBuf<int32_t>& kt = scratch().kt; DBuf<int32_t>& vt = scratch().vt;
+        sort_pairs_by_key(st, nLocal, key_bits(R), lk, lv, kt, vt);
+        copy_d2d(RG.rowRegion.p + rowOff, lk.p, (size_t)nLocal * sizeof(int32_t), st);
+        copy_d2d(RG.rowFace.p + rowOff, lv.p, (size_t)nLocal * sizeof(int32_t), st);
         if (C.nActiveVs + nRows >= INT32_MAX) throw Error("K_ext has too many rows for int32");
-        k_krow_reduced(st, nRows, RG.rowFace.p, (int32_t)C.nActiveVs, F.krow[0], F.krow[1], F.krow[2]);
-        static thread_local DBuf<int> rc;
+        k_krow_reduced(st, nLocal, RG.rowFace.p + rowOff, (int32_t)(C.nActiveVs + rowOff), F.krow[0], F.krow[1], F.krow[2]);
+        DBuf<int>& rc = scratch().rc;
         rc.alloc((size_t)3 * R); rc.zero(st, (size_t)3 * R);
-        RG.rowXYZ.alloc((size_t)nRows);
-        k_rows_finalize(st, g, nRows, RG.rowRegion.p, RG.rowFace.p, rc.p, RG.rowXYZ.p);
+        RG.rowXYZ.alloc((size_t)nRows + 1);
+        k_rows_finalize(st, g, nLocal, RG.rowRegion.p + rowOff, RG.rowFace.p + rowOff, rc.p, RG.rowXYZ.p + rowOff);
         std::vector<int> perRA = rc.to_host(st, (size_t)3 * R);
-        // chunk table: rows are sorted by (region, axis, voxel order); a chunk holds <= 2048 rows of one (region, axis)
+        // chunk table: rows are sorted by (region, axis, voxel order); a chunk holds rows of one (region, axis).  Regions small
+        // enough for the fused epilogue of pass 1 (ps_pcg.cu) get chunks of <= 256 rows (one row per thread; the rows of a
+        // (region, axis) are split evenly, in multiples of a warp); giant regions (doTile off) keep 2048-row chunks.
+        static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
         std::vector<int32_t> start((size_t)R + 1, 0), chunkStart((size_t)R + 1, 0), table, axisStart((size_t)3 * R + 1, 0);
-        int32_t pos = 0;
         RG.maxRegionRows = 0;
+        for (int r = 0; r < R; ++r) RG.maxRegionRows = std::max(RG.maxRegionRows, (int32_t)(perRA[3 * r] + perRA[3 * r + 1] + perRA[3 * r + 2]));
+        // the fused solve sums at most 32 chunks per region (P1_MAX_CHUNKS, ps_pcg.cu): 3 axes x (rows / 256 + 1) pieces
+        {
+            int maxPieces = 0;
+            for (int r = 0; r < R; ++r) { int pc = 0; for (int a = 0; a < 3; ++a) pc += (perRA[3 * r + a] + SCHED_BLOCK - 1) / SCHED_BLOCK; maxPieces = std::max(maxPieces, pc); }
+            RG.fusedRegions = RG.maxRegionRows <= fuseLimit && maxPieces <= 32;
+            // every rank must take the same path (the row numbering does not depend on it, but keep the ranks alike)
+            if (part.local) RG.fusedRegions = hostAllreduceSum(RG.fusedRegions ? 0. : 1.) < 0.5;
+        }
+        int32_t pos = 0;
         for (int r = 0; r < R; ++r) {
+            if (part.local && r == RG.regLo) pos = (int32_t)rowOff;      // the regions below belong to other ranks (no rows here)
             start[r] = pos; chunkStart[r] = (int32_t)(table.size() / 4);
-            RG.maxRegionRows = std::max(RG.maxRegionRows, (int32_t)(perRA[3 * r] + perRA[3 * r + 1] + perRA[3 * r + 2]));
             for (int a = 0; a < 3; ++a) {
                 axisStart[3 * r + a] = pos;
-                const int32_t e = pos + perRA[3 * r + a];
-                for (int32_t b = pos; b < e; b += 2048) { table.push_back(r); table.push_back(b); table.push_back(std::min(b + 2048, e)); table.push_back(a); }
+                const int32_t cntRA = perRA[3 * r + a], e = pos + cntRA;
+                int32_t len = 2048;
+                if (RG.fusedRegions && cntRA > 0) { const int32_t pieces = (cntRA + SCHED_BLOCK - 1) / SCHED_BLOCK; len = ((cntRA + pieces - 1) / pieces + 31) / 32 * 32; }
+                for (int32_t b = pos; b < e; b += len) { table.push_back(r); table.push_back(b); table.push_back(std::min(b + len, e)); table.push_back(a); }
                 pos = e;
             }
         }
@@ -493,7 +730,10 @@ void Solver::constructMatrixBlocks() {
         RG.rowChunkLo = chunkStart[RG.regLo]; RG.rowChunkHi = chunkStart[RG.regHi];
         RG.ownRowLo = start[RG.regLo]; RG.ownRowHi = start[RG.regHi];
         RG.regionTicket.alloc((size_t)R + 1); RG.regionTicket.zero(st, (size_t)R + 1);
-        for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
+        RG.wpartial.alloc((size_t)RG.nRowChunks * 80 + 1);
+        RG.chunkTicket.alloc((size_t)RG.nRowChunks + 1); RG.chunkTicket.zero(st, (size_t)RG.nRowChunks + 1);
+        RG.solved.alloc((size_t)R + 1); RG.solved.zero(st, (size_t)R + 1); RG.solveSeq = 0;
+        if (!part.local) for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
         axisStart[(size_t)3 * R] = pos;
         RG.rowAxisStart.from_host(st, axisStart.data(), axisStart.size());
         RG.rowStart.from_host(st, start.data(), start.size());
@@ -502,17 +742,28 @@ void Solver::constructMatrixBlocks() {
         RG.partial.alloc(std::max((size_t)RG.nRowChunks * 10, RG.partial.n));
         RG.sigma.alloc((size_t)R * 30);
     }
+    if (part.local) {
+        // row numbers of the halo faces from their owners; the z-face planes on the cuts hold rows of both sides
+        exchangeLayers({{F.krow[0], SL_FACE + 0, 4}, {F.krow[1], SL_FACE + 1, 4}});
+        std::vector<LayerField> fz = {{F.krow[2], SL_FACE + 2, 4}};
+        mergeSharedPlanes(F.krow[2]);
+        exchangeLayers(fz);
+        mergeSharedPlanes(F.krow[2]);
+    }
     C.nRowsExt = C.nActiveVs + RG.nRows;
     const int64_t nE = C.nEdge[0] + C.nEdge[1] + C.nEdge[2];
     Op.alloc(C.nRowsExt, C.nActiveVs, C.nCenter, nE);
     mcInv.alloc((size_t)C.nActiveVs); mc.alloc((size_t)C.nActiveVs); rhsU.alloc((size_t)C.nActiveVs); oldVs.alloc((size_t)C.nActiveVs);
-    k_assemble_K(st, g, F, C, Op, mcInv.p, mc.p, rhsU.p, oldVs.p);
+    computeOwnership();
+    RowSet allRows; allRows.add(0, C.nRowsExt);
+    k_assemble_K(st, g, F, C, Op, mcInv.p, mc.p, rhsU.p, oldVs.p, part.local ? ownK : allRows);
     uInv.alloc((size_t)C.nStresses); uDiag.alloc((size_t)C.nStresses); rhsPT.alloc((size_t)C.nSystemSize);
-    k_assemble_Kt(st, g, F, C, Op, uInv.p, uDiag.p, rhsPT.p);
+    k_assemble_Kt(st, g, F, C, Op, uInv.p, uDiag.p, rhsPT.p, part.local);
     const size_t n = (size_t)C.nSystemSize;
     b.alloc(n); x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); w.alloc((size_t)C.nRowsExt + 1);
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
-    dotPartial.alloc(4096);
+    dotPartial.alloc(8192);
+    sched1Ctl.alloc(2); sched1Ctl.zero(st, 2);
     computeOwnership();
     buildSchedules();
     buildHalos();
@@ -567,7 +818,7 @@ void Solver::buildSchedules() {
     const int k = part.rank;
     sr1 = SchedRanges(); sr2 = SchedRanges();
     for (int a = 0; a < 3; ++a) sr1.add(C.faceOff[a] + part.slotCut[SL_FACE + a][k], C.faceOff[a] + part.slotCut[SL_FACE + a][k + 1]);
-    sr1.add(C.nActiveVs + part.redRowCut[k], C.nActiveVs + part.redRowCut[k + 1]);
+    sr1.addItems(RG.rowChunkLo, RG.rowChunkHi - RG.rowChunkLo);          // the coupled reduced rows of the owned regions: one item per row chunk
     sr2.add(part.slotCut[SL_CENTER][k], part.slotCut[SL_CENTER][k + 1]);
     for (int e = 0; e < 3; ++e) { const int64_t off = C.stressOff[3 + e] - 3 * C.nCenter; sr2.add(off + part.slotCut[SL_EDGE + e][k], off + part.slotCut[SL_EDGE + e][k + 1]); }
     const std::vector<int32_t> a = merge_schedule(sr1), b = merge_schedule(sr2);
@@ -587,7 +838,7 @@ void Solver::buildHalos() {
     haloX.reset(); haloW.reset();
     if (!part.multi()) return;
     const int64_t n = C.nSystemSize, nRows = C.nRowsExt;
-    static thread_local DBuf<uint8_t> flag;
+    DBuf<uint8_t>& flag = scratch().haloFlag;
     flag.alloc((size_t)std::max(n, nRows) + 1);
     const int me = part.rank;
     const int peers[2] = {me > 0 ? me - 1 : -1, me + 1 < part.nranks ? me + 1 : -1};
@@ -606,9 +857,26 @@ void Solver::buildHalos() {
         haloX.peers[i] = haloW.peers[i] = peers[i];
         if (peers[i] < 0) continue;
         haloX.nRecv[i] = listX(me, peers[i], haloX.recvIdx, i ? haloX.nRecv[0] : 0);
-        haloX.nSend[i] = listX(peers[i], me, haloX.sendIdx, i ? haloX.nSend[0] : 0);
         haloW.nRecv[i] = listW(me, peers[i], haloW.recvIdx, i ? haloW.nRecv[0] : 0);
-        haloW.nSend[i] = listW(peers[i], me, haloW.sendIdx, i ? haloW.nSend[0] : 0);
+        if (!part.local) {      // replicated matrices: the peer's rows are here too, derive the send side locally
+            haloX.nSend[i] = listX(peers[i], me, haloX.sendIdx, i ? haloX.nSend[0] : 0);
+            haloW.nSend[i] = listW(peers[i], me, haloW.sendIdx, i ? haloW.nSend[0] : 0);
+        }
+    }
+    if (part.local) {
+        // slab-local matrices: a rank only knows what it needs (columns of ITS rows that a neighbour owns).  The neighbours tell
+        // each other: my send list towards h = h's receive list from me (ascending global indices on both sides).
+        for (Halo* H : {&haloX, &haloW}) {
+            std::vector<double> mine = {(double)H->nRecv[0], (double)H->nRecv[1]};
+            const std::vector<double> all = hostAllgather(mine);
+            for (int i = 0; i < 2; ++i) H->nSend[i] = peers[i] >= 0 ? (int64_t)std::llround(all[(size_t)peers[i] * 2 + (1 - i)]) : 0;     // what my lower peer wants from its upper side, and vice versa
+            H->sendIdx.alloc((size_t)H->sendTotal() + 1);
+            const void* sb[2] = {H->recvIdx.p, H->recvIdx.p + H->nRecv[0]};
+            void* rb[2] = {H->sendIdx.p, H->sendIdx.p + H->nSend[0]};
+            const size_t sby[2] = {(size_t)H->nRecv[0] * sizeof(int32_t), (size_t)H->nRecv[1] * sizeof(int32_t)};
+            const size_t rby[2] = {(size_t)H->nSend[0] * sizeof(int32_t), (size_t)H->nSend[1] * sizeof(int32_t)};
+            comm->sendrecv(2, peers, sb, sby, rb, rby, st);
+        }
     }
     for (Halo* H : {&haloX, &haloW}) { H->sendBuf.alloc((size_t)H->sendTotal() + 1); H->recvBuf.alloc((size_t)H->recvTotal() + 1); H->sendIdx.alloc(1); H->recvIdx.alloc(1); }
 }
@@ -661,7 +929,26 @@ static OpArgs make_op(const Solver& S) {
     A.uInv = S.uInv.p; A.valScale = S.g.invDx / 64.;
     A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsE = S.ownE;
     A.s1 = S.sr1; A.s2 = S.sr2; A.sched1 = S.sched1.p; A.sched2 = S.sched2.p; A.nSched1 = S.nSched1; A.nSched2 = S.nSched2;
+    A.sched1Ctl = S.sched1Ctl.p; A.rowChunk = S.RG.rowChunk.p;
     return A;
+}
+RegionOp Solver::regionOp(int mode, const double* extra, double extraScale, double tScale, double outScale) const {
+    RegionOp R;
+    R.mode = (RG.count > 0 && RG.rowChunkHi > RG.rowChunkLo) ? mode : 0;
+    R.dx = g.dx;
+    R.rowXYZ = RG.rowXYZ.p; R.rowChunkStart = RG.rowChunkStart.p; R.rowStart = RG.rowStart.p;
+    R.com = RG.com.p; R.Binv = RG.Binv.p; R.partial = RG.partial.p; R.regionTicket = RG.regionTicket.p;
+    R.extra = extra; R.extraScale = extraScale; R.tScale = tScale; R.outScale = outScale;
+    R.sigma = RG.sigma.p;
+    R.wpartial = RG.wpartial.p; R.chunkTicket = RG.chunkTicket.p; R.solved = RG.solved.p;
+    if (R.mode == 1) R.seq = ++RG.solveSeq;
+    return R;
+}
+// pass 1 of an operator apply including the reduced term: w = [dt Mc^-1 K x ; c_f . B^-1 J x]
+void Solver::pass1Apply(const OpArgs& A, const double* xin, const PcgScalars* S, bool reverse) {
+    if (RG.count > 0 && RG.fusedRegions) { k_pass1(st, A, regionOp(1), xin, w.p, g.dt, S, reverse); return; }
+    k_pass1(st, A, regionOp(0), xin, w.p, g.dt, S, reverse);
+    if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, S, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, S); }
 }
 
 OpArgs Solver::make_op_args() const { return make_op(*this); }
@@ -672,20 +959,25 @@ OpArgs Solver::make_op_args() const { return make_op(*this); }
 void Solver::assemble() {
     const OpArgs A = make_op(*this);
     w.zero(st, (size_t)C.nRowsExt);
-    k_scale_rows(st, C.nActiveVs, mcInv.p, rhsU.p, w.p);
+    if (part.local) {       // only the own rows of Mc^-1 / rhs_u exist here; the neighbours' arrive with the halo of w
+        for (int a = 0; a < 3; ++a) {
+            const int64_t lo = C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank], hi = C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank + 1];
+            k_scale_rows(st, hi - lo, mcInv.p + lo, rhsU.p + lo, w.p + lo);
+        }
+    } else k_scale_rows(st, C.nActiveVs, mcInv.p, rhsU.p, w.p);
     if (RG.count > 0) {
         reduced_finish(st, g, RG, RG.rhsR.p, 1.0, 0.0, nullptr);                     // s = B^-1 rhs_r
         reduced_expand(st, g, RG, w.p + C.nActiveVs, g.invDt, nullptr);
     }
     exchange(haloW, w.p, nullptr);            // the neighbours' coupled reduced rows (active rows are replicated above)
     k_pass2(st, A, w.p, nullptr, b.p, 0.0, rhsPT.p, nullptr, PeerCtx(), nullptr, 0);
+    checkPeer("assemble");
 }
 
 // y = A x (ApplyPressureStressMatrix::applyMatrixVectorProducts, Apply.h:102-179)
 void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
     const OpArgs A = make_op(*this);
-    k_pass1(st, A, xin, w.p, g.dt, nullptr);
-    if (RG.count > 0) reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
+    pass1Apply(A, xin, nullptr);
     exchange(haloW, w.p, nullptr);
     k_pass2(st, A, w.p, xin, y, 0.5, nullptr, dotPart, PeerCtx(), nullptr, 0);
 }
@@ -693,9 +985,18 @@ void Solver::applyOperator(const double* xin, double* y, double* dotPart) {
 void Solver::timedOperator(int which) {
     const OpArgs A = make_op(*this);
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
-    if (which == 1) k_pass1(st, A, b.p, w.p, g.dt, nullptr);
-    else if (which == 3 && RG.count > 0) { reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr); }
-    else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, nullptr, PeerCtx(), nullptr, 0);
+    if (which == 1) pass1Apply(A, b.p, nullptr);                       // includes the reduced term (fused region epilogue)
+    else if (which == 3) k_pass1(st, A, regionOp(0), b.p, w.p, g.dt, nullptr);   // the same sweep without the reduced term (raw products on the coupled rows)
+    else if (which == 5) k_cg_update(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, PeerCtx());   // rank-local (timing only)
+    else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, dotPartial.p, PeerCtx(), scal.p, which == 4 ? 3 : 0, r.p);      // 4: with the three fused dot products of the CG loop
+}
+
+// the caller's cancel callback, polled between iteration batches; with several ranks the decision is summed over the ranks so
+// that all of them leave the loop at the same poll (a rank cancelled alone would leave the others spinning on its flags)
+bool Solver::pollCancel() {
+    if (!P.cancel_cb && !(part.multi() && comm && anyCancelCb)) return false;
+    const double mine = (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) ? 1. : 0.;
+    return hostAllreduceSum(mine) > 0.5;
 }
 
 // solveSPDwithMatrixVectorPCG (S.cpp:734-812) -> pcg_external_matrix_A (pcg.h:268-340): identity
@@ -712,13 +1013,14 @@ int Solver::solve() {
     usedBiCGStab = 0;
     PcgScalars h; memset(&h, 0, sizeof h);
     if (n == 0) { solveIterations = 0; solveError = 0; result = R_SUCCESS; return result; }
-    k_cg_init(st, ownSys, b.p, x.p, r.p, p.p, dotPartial.p, scal.p, P.tolerance, maxIt, reduceCtx(-1, 2));
-    allreduce(scal.p->red + 4, 1);
-    k_cg_begin(st, scal.p, reduceCtx(2, -1));
+    k_cg_init(st, ownSys, b.p, x.p, r.p, p.p, dotPartial.p, scal.p, P.tolerance, maxIt, reduceCtx(-1, 1));
+    allreduce(scal.p->red + 3, 3);
+    k_cg_begin(st, scal.p, reduceCtx(1, -1));
     bool cancelled = false;
     // PS_DBG_SKIP (timing experiments only, the iterates are WRONG with it): bit 0 drops the halo exchanges, bit 1 the
     // cross-rank reductions of the CG loop -- what is left is each rank iterating on its own slab (profiles/r01_dist_probe*.log)
     const int dbgSkip = getenv("PS_DBG_SKIP") ? atoi(getenv("PS_DBG_SKIP")) : 0;
+    static const bool zigzag = getenv("PS_ZIGZAG") && atoi(getenv("PS_ZIGZAG")) != 0;      // A/B knob; off: measured 2 % slower on B200 (profiles/r02_probe_s3_256_v2*.log)
     auto rctx = [&](int slotIn, int slotOut, int slotIn2 = -1) { return (dbgSkip & 2) ? PeerCtx() : reduceCtx(slotIn, slotOut, slotIn2); };
     auto xchg = [&](Halo& H, double* v) { if (!(dbgSkip & 1)) exchange(H, v, scal.p); };
     auto ared = [&](double* buf, int cnt) { if (!(dbgSkip & 2)) allreduce(buf, cnt); };
@@ -736,19 +1038,18 @@ int Solver::solve() {
         for (int k = 0; k < batch; ++k) {
             const bool tr = (it + k == traceIter);
             mark(tr, "start");
+            // The three sweeps of an iteration alternate direction, and so do consecutive iterations: each kernel starts on the end of
+            // the vector its predecessor wrote last (w, Ap, p: 80 - 130 MB each, the L2 holds 126 MB), instead of on the part that
+            // has been evicted.  Results do not depend on the direction (every row is computed the same way; the dot products are
+            // summed per CTA, then over the CTAs in index order).
+            const bool rev = zigzag && ((it + k) & 1);
             xchg(haloX, p.p);                                   mark(tr, "halo p");
-            k_pass1(st, A, p.p, w.p, g.dt, scal.p);             mark(tr, "pass1");
-            if (RG.count > 0) {
-                reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p);          // moments -> B^-1 -> expand, one CTA per region
-            }
-            mark(tr, "reduced x3");
+            pass1Apply(A, p.p, scal.p, rev);                    mark(tr, "pass1 + regions");          // w = [dt Mc^-1 K p ; c_f . B^-1 J p]
             xchg(haloW, w.p);                                   mark(tr, "halo w");
-            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, rctx(-1, 0), scal.p, 1);        // + this rank's p.Ap to every rank
-            ared(scal.p->red, 1);                               mark(tr, "pass2 (+allreduce)");
-            k_cg_update_r(st, ownSys, r.p, Ap.p, dotPartial.p, scal.p, rctx(0, 1));                    // global p.Ap in, r.r out
-            ared(scal.p->red + 1, 3);                           mark(tr, "update r (+allreduce)");     // r.r with the x.p / p.p of the previous update xp
-            k_cg_update_xp(st, ownSys, x.p, p.p, r.p, dotPartial.p, scal.p, rctx(1, 3, it + k == 0 ? -1 : 3));        // global r.r, x.p, p.p in; new x.p / p.p out
-            mark(tr, "update x,p");
+            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, rctx(-1, 0), scal.p, 3, r.p, zigzag && !rev);   // + this rank's p.Ap, r.Ap, Ap.Ap to every rank
+            ared(scal.p->red, 3);                               mark(tr, "pass2 (+allreduce)");
+            k_cg_update(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, rctx(0, 1, 1), rev);    // global p.Ap.. and the previous r.r, x.p, p.p in; new r.r, x.p, p.p out
+            ared(scal.p->red + 3, 3);                           mark(tr, "update x,r,p (+allreduce)");
         }
         it += batch;
         copy_d2h(&h, scal.p, sizeof h, st);
@@ -761,12 +1062,12 @@ int Solver::solve() {
             tev.clear(); tname.clear();
         }
 #endif
-        if (h.done) break;
-        if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
+        if (h.done || h.peerError) break;
+        if (pollCancel()) { cancelled = true; break; }
     }
     copy_d2h(&h, scal.p, sizeof h, st);
-    if (h.peerError) { result = R_FAILED; throw Error("a peer-memory wait timed out (another rank died or fell out of step)"); }
-    if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
+    checkPeer("the CG loop");
+    if (cancelled) { result = R_FAILED; peer.needResync = peer.on; g_lastError = "cancelled"; return result; }
     // b == 0: the reference would divide 0/0 (pcg.h:313); we return x = 0 after 0 iterations instead
     solveIterations = (h.done == 1) ? h.iter : maxIt;
     solveError = std::sqrt(h.rre);
@@ -831,8 +1132,7 @@ int Solver::solveEigenCG() {
     for (int it = 0; it < maxIt;) {
         const int batch = std::min(every, maxIt - it);
         for (int k = 0; k < batch; ++k) {
-            k_pass1(st, A, p.p, w.p, g.dt, scal.p);
-            if (RG.count > 0) { reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+            pass1Apply(A, p.p, scal.p);
             k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, PeerCtx(), scal.p, 1);          // tmp = A p, p.tmp -> red[0]
             k_eig_update_xr(st, ownSys, diagA.p, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p);
             k_eig_stage(st, scal.p, 2);
@@ -841,7 +1141,7 @@ int Solver::solveEigenCG() {
         it += batch;
         copy_d2h(&h, scal.p, sizeof h, st);
         if (h.done) break;
-        if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
+        if (pollCancel()) { cancelled = true; break; }
     }
     copy_d2h(&h, scal.p, sizeof h, st);
     if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
@@ -864,8 +1164,7 @@ int Solver::solveBiCGStab() {
     bRhat.alloc(n); bV.alloc(n); bS.alloc(n); bT.alloc(n);
     auto applyTo = [&](double* xin, double* y) {
         exchange(haloX, xin, scal.p);
-        k_pass1(st, A, xin, w.p, g.dt, scal.p);
-        if (RG.count > 0) { reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, scal.p); }
+        pass1Apply(A, xin, scal.p);
         exchange(haloW, w.p, scal.p);
         k_pass2(st, A, w.p, xin, y, 0.5, nullptr, nullptr, PeerCtx(), scal.p, 0);
     };
@@ -894,12 +1193,12 @@ int Solver::solveBiCGStab() {
         }
         it += batch;
         copy_d2h(&h, scal.p, sizeof h, st);
-        if (h.done) break;
-        if (P.cancel_cb && P.cancel_cb(P.cancel_ctx)) { cancelled = true; break; }
+        if (h.done || h.peerError) break;
+        if (pollCancel()) { cancelled = true; break; }
     }
     copy_d2h(&h, scal.p, sizeof h, st);
-    if (h.peerError) { result = R_FAILED; throw Error("a peer-memory wait timed out (another rank died or fell out of step)"); }
-    if (cancelled) { result = R_FAILED; g_lastError = "cancelled"; return result; }
+    checkPeer("the BiCGSTAB loop");
+    if (cancelled) { result = R_FAILED; peer.needResync = peer.on; g_lastError = "cancelled"; return result; }
     solveIterations = (h.done == 1) ? h.iter : maxIt;
     solveError = h.rre;                          // pcg.h:188-190: no square root on this path
     result = (solveIterations == maxIt) ? R_NOCONVERGE : R_SUCCESS;
@@ -910,7 +1209,7 @@ int Solver::solveBiCGStab() {
 void Solver::recoverVelocityFromPressureStress() {
     const OpArgs A = make_op(*this);
     exchange(haloX, x.p, nullptr);
-    k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau)
+    k_pass1(st, A, regionOp(0), x.p, w.p, g.dt, nullptr);            // active rows: dt Mc^-1 (G p + D^T tau); coupled reduced rows: raw (K_red x)_f
     RowSet act;                                                      // the owned active face rows
     for (int a = 0; a < 3; ++a) act.add(C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank], C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank + 1]);
     k_recover_active(st, g, act, w.p, mcInv.p, rhsU.p, velSol.p);
@@ -919,9 +1218,16 @@ void Solver::recoverVelocityFromPressureStress() {
         reduced_finish(st, g, RG, RG.rhsR.p, g.invDt, -1.0, nullptr);                            // B^-1 (rhs_r/dt - J x)
         k_copy_reduced_solution(st, (int64_t)(RG.regHi - RG.regLo) * RDOF, RG.s.p + (size_t)RG.regLo * RDOF, velSol.p + C.nActiveVs + (size_t)RG.regLo * RDOF);
     }
+    checkPeer("the velocity recovery");
 }
 
 // buildValidFaces (S_Cls:4-54) + applySolutionToVelocity (S.cpp:937-1028)
+// the voxels of a slot this rank delivers to the caller: its slab with slab-local setup (the caller's arrays are full-grid, every rank
+// fills its part), everything otherwise
+void Solver::outRange(int slot, int64_t& lo, int64_t& hi) const {
+    if (part.local) z_range(g, slot, g.zLo, g.zHi, lo, hi); else { lo = 0; hi = g.n[slot]; }
+}
+
 void Solver::applySolutionToVelocity(const ps_fields_out& out) {
     const bool dev = out.memory == PS_MEM_DEVICE;
     const bool writeVel = (result == R_SUCCESS || P.keepNonConvergedResults);
@@ -930,21 +1236,25 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
 #endif
     for (int a = 0; a < 3; ++a) {
         const size_t nf = (size_t)g.n[SL_FACE + a];
+        int64_t oLo, oHi, kLo, kHi;
+        outRange(SL_FACE + a, oLo, oHi);
+        // the kernel also visits the plane above the slab: z-faces there can belong to a region of this rank (merged below)
+        if (part.local) z_range(g, SL_FACE + a, g.zLo, std::min(g.nz, g.zHi + (a == 2 ? 1 : 0)), kLo, kHi); else { kLo = 0; kHi = (int64_t)nf; }
         float* velDev = nullptr; float* validDev = nullptr;
         // velocity staging starts as the input velocity: invalid faces are left untouched (S.cpp:975-978)
         if (out.velocity[a] && writeVel) {
-            if (dev) { velDev = out.velocity[a]; if (velDev != dVel[a].p) copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
-            else { outStage[a].alloc(nf); velDev = outStage[a].p; copy_d2d(velDev, dVel[a].p, nf * sizeof(float), st); }
+            if (dev) { velDev = out.velocity[a]; if (velDev != dVel[a].p) copy_d2d(velDev + kLo, dVel[a].p + kLo, (size_t)(kHi - kLo) * sizeof(float), st); }
+            else { outStage[a].alloc(nf); velDev = outStage[a].p; copy_d2d(velDev + kLo, dVel[a].p + kLo, (size_t)(kHi - kLo) * sizeof(float), st); }
         }
         if (out.valid[a] && !(validSent && !dev)) {
             if (dev) validDev = out.valid[a]; else { outStage[3 + a].alloc(nf); validDev = outStage[3 + a].p; }
         }
         const FaceOwner own = {(int32_t)part.slotCut[SL_FACE + a][part.rank], (int32_t)part.slotCut[SL_FACE + a][part.rank + 1], RG.regLo, RG.regHi};
-        k_writeback_velocity(st, g, F, C, RG, velSol.p, a, velDev, validDev != nullptr, validDev, own);
+        k_writeback_velocity(st, g, F, C, RG, velSol.p, a, velDev, validDev != nullptr, validDev, own, kLo, kHi, oLo, oHi);
         if (a == 2 && part.multi() && comm && velDev) {
             // the z-face plane on a slab cut carries DOFs of both neighbours (active: upper rank, reduced: lower rank's regions)
             const size_t plane = (size_t)g.nx * g.ny;
-            static thread_local DBuf<float> planes;
+            DBuf<float>& planes = scratch().planes;
             planes.alloc(2 * plane);
             const int peers[2] = {part.rank > 0 ? part.rank - 1 : -1, part.rank + 1 < part.nranks ? part.rank + 1 : -1};
             const int kz[2] = {g.zLo, g.zHi};
@@ -960,11 +1270,11 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
             cudaEvent_t e; PS_CUDA(cudaEventCreate(&e));
             PS_CUDA(cudaEventRecord(e, st)); PS_CUDA(cudaStreamWaitEvent(stOut, e, 0));
             if (a == 2) evLast = e; else PS_CUDA(cudaEventDestroy(e));
-            if (velDev) copy_d2any(out.velocity[a], velDev, nf * sizeof(float), false, stOut);
-            if (validDev) copy_d2any(out.valid[a], validDev, nf * sizeof(float), false, stOut);
+            if (velDev) copy_d2any(out.velocity[a] + oLo, velDev + oLo, (size_t)(oHi - oLo) * sizeof(float), false, stOut);
+            if (validDev) copy_d2any(out.valid[a] + oLo, validDev + oLo, (size_t)(oHi - oLo) * sizeof(float), false, stOut);
 #else
-            if (velDev) copy_d2any(out.velocity[a], velDev, nf * sizeof(float), false, st);
-            if (validDev) copy_d2any(out.valid[a], validDev, nf * sizeof(float), false, st);
+            if (velDev) copy_d2any(out.velocity[a] + oLo, velDev + oLo, (size_t)(oHi - oLo) * sizeof(float), false, st);
+            if (validDev) copy_d2any(out.valid[a] + oLo, validDev + oLo, (size_t)(oHi - oLo) * sizeof(float), false, st);
 #endif
         }
     }
@@ -981,6 +1291,9 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
 }
 
 void Solver::setup() {
+    peerResync();
+    // every rank must take part in the cancel all-reduce if any rank has a callback: agree on that once per setup
+    anyCancelCb = part.multi() && comm ? hostAllreduceSum(P.cancel_cb ? 1. : 0.) > 0.5 : false;
     buildIntegrationWeightsAlt();
     {
         StageTimer T(st, &stageMs[PS_STAGE_CLASSIFY]);
@@ -1014,11 +1327,13 @@ int Solver::step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* sta
         setup();
         if (out) sendValidEarly(*out);
         if (P.doSolve) res = solve();
+        else { x.alloc((size_t)std::max<int64_t>(C.nSystemSize, 1)); x.zero(st, (size_t)C.nSystemSize); result = R_INCOMPLETE; }     // solutionVector = 0 (S_AS:466), PS.C:513
         if (res == R_UNSUPPORTED_SOLVER) { stream_sync(stOut); validSent = false; if (stats) fillStats(stats); return res; }
         if (out) {
             {
                 StageTimer T(st, &stageMs[PS_STAGE_WRITEBACK]);
-                if (P.doSolve && (res == R_SUCCESS || P.keepNonConvergedResults)) recoverVelocityFromPressureStress();
+                // PS.C:565-572: also without doSolve (the zero solution gives u = Mc^-1 rhs_u, v_r = B^-1 rhs_r / dt)
+                if (res == R_SUCCESS || P.keepNonConvergedResults) recoverVelocityFromPressureStress();
                 applySolutionToVelocity(*out);
             }
             stageMs[PS_STAGE_WRITEBACK] = std::max(0., stageMs[PS_STAGE_WRITEBACK] - stageMs[PS_STAGE_DOWNLOAD]);   // the PCIe tail is its own stage

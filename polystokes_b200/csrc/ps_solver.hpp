@@ -84,6 +84,9 @@ struct RegionData {
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
     DBuf<unsigned int> regionTicket;   // [R] chunks of the region that have delivered their moments (self-resetting)
+    DBuf<double> wpartial;             // [nRowChunks][8][10] per-warp moments of the fused region term (ps_pcg.cu, pass 1)
+    DBuf<unsigned int> chunkTicket, solved;   // [nRowChunks] / [R], see RegionOp
+    mutable unsigned int solveSeq = 0; // launches of the fused region term so far
     int32_t ownRowLo = 0, ownRowHi = 0;   // coupled reduced rows of the owned regions
     // owned pieces of this rank (everything on one GPU): regions [regLo, regHi) and their chunk ranges
     int32_t regLo = 0, regHi = 0, cellChunkLo = 0, cellChunkHi = 0, rowChunkLo = 0, rowChunkHi = 0;
@@ -132,6 +135,22 @@ struct ExplicitA {
     DBuf<double> val;
 };
 struct OpArgs;
+// What pass 1 does with the coupled reduced rows of the owned regions.  mode 0: store the raw products (K_red x)_f in w.
+// mode 1 (regions of <= a few thousand rows, RegionData::fusedRegions): the reduced term of the operator in the same launch --
+// every row chunk leaves its 10 monomial moments, the last chunk of a region to finish sums them in chunk order,
+// s = B^-1 (tScale t + extraScale extra), sigma, and overwrites the region's rows with w_f = outScale * c_f . s.
+struct RegionOp {
+    int mode = 0;
+    double dx = 0;
+    const uint32_t* rowXYZ = nullptr; const int32_t* rowChunkStart = nullptr; const int32_t* rowStart = nullptr;
+    const double* com = nullptr; const double* Binv = nullptr; double* partial = nullptr; unsigned int* regionTicket = nullptr;
+    const double* extra = nullptr; double extraScale = 0, tScale = 1, outScale = 1;
+    double* sigma = nullptr;
+    double* wpartial = nullptr;        // [nChunks][8][10] moments of the 8 warps of a chunk
+    unsigned int* chunkTicket = nullptr;   // [nChunks] warps of the chunk that have delivered (self-resetting)
+    unsigned int* solved = nullptr;    // [R] sequence number of the last launch that solved the region
+    unsigned int seq = 0;              // this launch's sequence number
+};
 
 class Solver {
 public:
@@ -181,6 +200,7 @@ public:
     void buildValidFaces(const ps_fields_out& out);
     void recoverVelocityFromPressureStress();
     void applySolutionToVelocity(const ps_fields_out& out);
+    void outRange(int slot, int64_t& lo, int64_t& hi) const;
 
     void setup();                       // weights .. assemble
     int step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* stats);
@@ -190,7 +210,15 @@ public:
     Partition part;
     Comm* comm = nullptr;
     void initComm(Comm* c);             // takes ownership; computes the z cuts
-    void computeOwnership();            // owned row / DOF ranges of every rank from the replicated numbering
+    void computeOwnership();            // owned row / DOF ranges of every rank from the (replicated or all-gathered) numbering
+    // slab-local setup (Partition::local)
+    struct LayerField { void* base; int slot; int elem; };
+    void exchangeLayers(const std::vector<LayerField>& fields);      // halo layers of grid fields <- the neighbours' own layers
+    void mergeSharedPlanes(int32_t* zFaceField);                     // z-face planes on the cuts: max of the two ranks' values
+    std::vector<double> hostAllgather(const std::vector<double>& mine);   // [nranks][mine.size()], collective host sync
+    void ownTileZ(int slot, int tz[2], int extraTop = 0) const;      // tile layers of the own slab for tile_order_scan
+    std::vector<int64_t> cutsFromCounts(const std::vector<double>& all, int stride, int item) const;
+    DBuf<uint8_t> xchgTmp;
     void buildHalos();                  // send / receive index lists of p (system vector) and w (K_ext rows)
     void exchange(Halo& H, double* v, const PcgScalars* S);
     void allreduce(double* devBuf, int n);   // host-enqueued NCCL all-reduce; a no-op when the peer transport fuses it into the kernels
@@ -198,6 +226,12 @@ public:
     void setupPeer();                   // collective: allocate + exchange + map the symmetric blocks
     void closePeer();
     PeerCtx reduceCtx(int slotIn, int slotOut, int slotIn2 = -1);   // sequence numbers of the reductions one kernel consumes / produces
+    void checkPeer(const char* where);  // throws (and schedules a resync) if a peer-memory wait timed out since the last check
+    void peerResync();                  // collective, start of setup
+    double hostAllreduceSum(double v);
+    bool pollCancel();
+    bool anyCancelCb = false;
+    DBuf<double> hostRed;
     RowSet rowsK(int rank) const, rowsP(int rank) const, rowsC(int rank) const, rowsE(int rank) const;
     RangeSet rowsSys(int rank) const;
     RowSet ownK, ownP, ownC, ownE;
@@ -206,6 +240,7 @@ public:
 
     // operator y = A x on device vectors (Apply.h:102-179)
     void applyOperator(const double* x, double* y, double* pApPartial);
+    void pass1Apply(const OpArgs& A, const double* x, const PcgScalars* S, bool reverse = false);   // pass 1 + the reduced term
     void timedOperator(int which);     // 0 = whole apply, 1 = pass 1 only, 2 = pass 2 only (on b -> Ap)
 
     // ---- device state ----
@@ -272,8 +307,9 @@ void k_valid_faces(cudaStream_t, const Geom&, const Fields&, float* const valid[
 // tile-order exclusive scan of a dense 0/1 flag field: out[q] = rank among flagged voxels in the
 // reference's voxel iteration order, -1 where the flag is 0.  Returns the total (host sync).
 // If `zCut` is given, cuts[k] receives the rank of the first flagged voxel with z >= zCut[k] (cuts multiple of 16).
+// With `tileZ` only the tile layers [tileZ[0], tileZ[1]) are scanned (ranks start at 0 on the first of them; `out` is written there only).
 int64_t tile_order_scan(cudaStream_t, const Geom&, int slot, const uint8_t* flag, int32_t* out, DBuf<int32_t>& tileCounts,
-                        const std::vector<int>* zCut = nullptr, std::vector<int64_t>* cuts = nullptr);
+                        const std::vector<int>* zCut = nullptr, std::vector<int64_t>* cuts = nullptr, const int* tileZ = nullptr);
 // out[k] = in[0] + ... + in[k-1] for k < n; returns the total (host sync)
 int64_t exclusive_scan_i64(cudaStream_t, int64_t n, const int64_t* in, int64_t* out);
 // stable sort of (key, value) pairs by key (keys < 2^keyBits)
@@ -281,14 +317,14 @@ void sort_pairs_by_key(cudaStream_t, int64_t n, int keyBits, DBuf<int32_t>& keys
 
 // ps_reduced.cu
 void k_region_com(cudaStream_t, const Geom&, const Fields&, int32_t R, unsigned long long* sums, double* com);
-void k_collect_region_keys(cudaStream_t, const Geom&, const int32_t* rank, const uint8_t* flag, const int32_t* region, int64_t n, int32_t tag, int32_t rankOffset, int32_t* keys, int32_t* vals);
+void k_collect_region_keys(cudaStream_t, const Geom&, const int32_t* rank, const uint8_t* flag, const int32_t* region, int64_t lo, int64_t hi, int32_t tag, int32_t rankOffset, int32_t* keys, int32_t* vals);
 void region_gram_partials(cudaStream_t, const Geom&, const Fields&, const RegionData&, double* partial);
 void region_gram_finish(cudaStream_t, const Geom&, RegionData&, int nChunks);
-void k_flag_coupled_faces(cudaStream_t, const Geom&, const Fields&, int axis, uint8_t* flag);
+void k_flag_coupled_faces(cudaStream_t, const Geom&, const Fields&, int axis, uint8_t* flag, int32_t regLo, int32_t regHi, int64_t lo, int64_t hi);
 
 // ps_assemble.cu
-void k_assemble_K(cudaStream_t, const Geom&, const Fields&, const Counts&, CompactOp& Op, double* mcInv, double* mc, double* rhsU, double* oldVs);
-void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, CompactOp& Op, double* uInv, double* uDiag, double* rhsPT);
+void k_assemble_K(cudaStream_t, const Geom&, const Fields&, const Counts&, CompactOp& Op, double* mcInv, double* mc, double* rhsU, double* oldVs, const RowSet& ownRows);
+void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, CompactOp& Op, double* uInv, double* uDiag, double* rhsPT, bool ownOnly);
 
 // ps_pcg.cu
 struct OpArgs {   // everything one operator apply touches
@@ -303,29 +339,15 @@ struct OpArgs {   // everything one operator apply touches
     const double* uInv;
     double valScale;              // invDx / 64
 };
-// What pass 1 does with the coupled reduced rows of the owned regions.  mode 0: store the raw products (K_red x)_f in w.
-// mode 1 (regions of <= a few thousand rows, RegionData::fusedRegions): the reduced term of the operator in the same launch --
-// every row chunk leaves its 10 monomial moments, the last chunk of a region to finish sums them in chunk order,
-// s = B^-1 (tScale t + extraScale extra), sigma, and overwrites the region's rows with w_f = outScale * c_f . s.
-struct RegionOp {
-    int mode = 0;
-    double dx = 0;
-    const uint32_t* rowXYZ = nullptr; const int32_t* rowChunkStart = nullptr; const int32_t* rowStart = nullptr;
-    const double* com = nullptr; const double* Binv = nullptr; double* partial = nullptr; unsigned int* regionTicket = nullptr;
-    const double* extra = nullptr; double extraScale = 0, tScale = 1, outScale = 1;
-    double* sigma = nullptr;
-};
-void k_pass1(cudaStream_t, const OpArgs&, const RegionOp&, const double* x, double* w, double activeScale, const PcgScalars* scal);
+void k_pass1(cudaStream_t, const OpArgs&, const RegionOp&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false);
 // mode bit 0: dot(x, y) (p.Ap) -> red[0]; bit 1: also dot(r2, y), dot(y, y) (r.Ap, Ap.Ap) -> red[1], red[2]
 void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode,
-             const double* r2 = nullptr);
+             const double* r2 = nullptr, bool reverse = false);
 // moments of w_f per chunk; with `solve` the last chunk of every region also runs reduced_finish(nullptr, 0, 1) for it (one launch less)
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal, bool solve = false);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-// the reduced term of one apply: w_f <- scale * c_f . B^-1 (sum_f c_f w_f); one fused launch for tiled regions, moments + expand otherwise
-void reduced_apply(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P);
+void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse = false);
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
 void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);
 // BiCGSTAB fallback (pcg.h:134-200).  Dot products land rank-local in scal->bred[], the host enqueues the all-reduce
@@ -359,7 +381,8 @@ void k_halo_unpack_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx
 void k_recover_active(cudaStream_t, const Geom&, const RowSet& rows, const double* wAct, const double* mcInv, const double* rhsU, double* velSol);
 // faces this rank writes: active faces with index in [aLo, aHi), reduced faces of regions [regLo, regHi), every face without a DOF
 struct FaceOwner { int32_t aLo, aHi, regLo, regHi; };
-void k_writeback_velocity(cudaStream_t, const Geom&, const Fields&, const Counts&, const RegionData&, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut, FaceOwner own);
+void k_writeback_velocity(cudaStream_t, const Geom&, const Fields&, const Counts&, const RegionData&, const double* velSol, int axis, float* velOut, bool writeValid, float* validOut, FaceOwner own,
+                          int64_t lo, int64_t hi, int64_t validLo, int64_t validHi);
 void k_merge_face_plane(cudaStream_t, const Geom&, const Fields&, int axis, int k, const float* peerPlane, float* velOut, FaceOwner own);
 // halo plumbing
 void k_halo_pack(cudaStream_t, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* scal);

@@ -38,6 +38,7 @@ DIST_CASES = {
     "box48_uniform": lambda: (scenes.box_scene(48, doReduced=0, tolerance=1e-6), {}),
     "blob_36x40x64_tile16": lambda: (scenes.blob_scene((36, 40, 64), seed=8, tile=16, pad=2), {}),
     "blob64_tile16": lambda: (scenes.blob_scene(64, seed=13, tile=16, pad=2), {}),
+    "blob48_tile16_pad3_layers33": lambda: (scenes.blob_scene(48, seed=5, tile=16, pad=3, liquidLayers=3, solidLayers=3), {}),
     # CG runs out of iterations -> BiCGSTAB fallback, itself stopped after 6 iterations (results kept): checks the arithmetic
     "blob48_bicgstab6": lambda: (scenes.blob_scene(48, seed=21, tile=8, pad=1, maxIterations=6, tolerance=1e-12, keepNonConvergedResults=1), {}),
 }
@@ -248,14 +249,18 @@ def check_distributed(case, ranks):
     world = len(ranks)
     cuts = list(ranks[0]["cuts"])
     assert cuts[0] == 0 and cuts[-1] == sc.nz and all(b > a and a % 16 == 0 for a, b in zip(cuts[:-1], cuts[1:]))
+    def own(arr, r):      # the layers of a grid field rank r is responsible for: its slab; the last slab takes a slot's extra top layer
+        lo, hi = int(r["zlo"]), int(r["zhi"])
+        return arr[lo:(hi if hi < sc.nz else arr.shape[0])]
     for r in ranks:
         assert int(r["nranks"]) == world and list(r["cuts"]) == cuts
-        # the classification is replicated and bit-exact on every rank
+        # global counts and the global numbering are bit-exact on every rank: on its own slab with slab-local setup (the fields of the other
+        # slabs are not computed there), everywhere with replicated setup -- the slabs together cover the grid
         for k in COUNTS:
             assert o.count(k) == int(r["count_" + k]), f"rank {int(r['rank'])} count {k}"
         for slot in range(7):
             for kind, name in ((0, "labels"), (1, "active"), (2, "reduced")):
-                assert np.array_equal(o.index_field(kind, slot), r[f"{name}{slot}"].astype(np.int64)), f"{name} slot {slot} on rank {int(r['rank'])}"
+                assert np.array_equal(own(o.index_field(kind, slot), r), own(r[f"{name}{slot}"].astype(np.int64), r)), f"{name} slot {slot} on rank {int(r['rank'])}"
     # every global vector is the sum of the ranks' shares
     tot = lambda key: sum(r[key] for r in ranks)
     assert rel(o.vector("b"), tot("vec_b")) <= 1e-10, f"b rel {rel(o.vector('b'), tot('vec_b')):.2e}"
@@ -276,7 +281,10 @@ def check_distributed(case, ranks):
         merged = np.empty_like(ovel[a])
         for r in ranks:
             lo, hi = int(r["zlo"]), int(r["zhi"])
-            assert np.array_equal(r[f"valid{a}"], ovalid[a]), f"valid axis {a} rank {int(r['rank'])}"
+            assert np.array_equal(own(r[f"valid{a}"], r), own(ovalid[a], r)), f"valid axis {a} rank {int(r['rank'])}"
+            if int(r["local"]):                       # slab-local: a rank delivers its slab (the last one the top plane too)
+                own(merged, r)[...] = own(r[f"vel{a}"], r)
+                continue
             top = hi + 1 if (a == 2) else hi          # z-faces: the closure of the slab
             merged[lo:top] = r[f"vel{a}"][lo:top]
             if a == 2 and lo > 0:                     # the shared plane must agree with the lower rank's copy

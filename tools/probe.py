@@ -36,7 +36,7 @@ print("counts:", {k: s.count(k) for k in ["nCenter","nActiveVs","nSystemSize","r
 peak = 6448.7
 try: peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception: pass
-for k in ["pass1", "reduced", "pass2", "apply", "cg_iteration"]:
+for k in ["pass1", "pass1_sweep", "pass2", "pass2_dots", "apply", "cg_update", "cg_iteration"]:
     ms = s.time_kernel(k, a.reps); by = s.kernel_bytes(k)
     csr = s.kernel_bytes("csr_" + k)
     extra = f"   [as CSR SpMV (12 B/nnz): {csr/1e9:6.3f} GB -> {csr/ms/1e6:8.1f} GB/s]" if csr else ""
