@@ -189,6 +189,47 @@ def run_cpu_sample(n, threads=0):
                 cores=lib().orc_num_threads())
 
 
+def bench_multi(a, sc, config, metric):
+    """ONE process, a.gpus devices behind one ps_create_multi handle (the way a single cook thread would drive several GPUs): e2e only -- the
+    handle takes the caller's full-grid HOST arrays, every rank uploads / downloads its slab."""
+    import numpy as np
+    import torch
+    from polystokes_b200 import PolyStokesSolver, PS_SUCCESS
+    solver = PolyStokesSolver.from_scene(sc, devices=list(range(a.gpus)))
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    h_in = [pin(sc.surface), pin(sc.collision), pin(sc.viscosity)]
+    h_vel = [pin(v) for v in sc.vel]; h_cvel = [pin(v) for v in sc.colvel]
+    h_out = [torch.empty_like(v).pin_memory() for v in h_vel]; h_valid = [torch.empty_like(v).pin_memory() for v in h_vel]
+    npv = lambda ts: [t.numpy() for t in ts]
+
+    def step():
+        rc = solver.step(h_in[0].numpy(), h_in[1].numpy(), h_in[2].numpy(), npv(h_vel), npv(h_cvel), npv(h_out), npv(h_valid))
+        if rc != PS_SUCCESS:
+            raise SystemExit(f"bench.py: solver returned {rc}")
+    for _ in range(max(a.warmup, 1)):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    launches = 0
+    for _ in range(a.steps):
+        step()
+        launches += int(solver.stats.gpu_launches)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    value = a.steps / wall
+    counts = {k: solver.count(k) for k in ["nCenter", "nActiveVs", "nSystemSize", "regionCount", "nRowsExt", "nTotalDOFs", "iterations"]}
+    h2d = sum(t.numel() * 4 for t in h_in + h_vel + h_cvel); d2h = sum(t.numel() * 4 for t in h_out + h_valid)
+    emit({"metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall / a.steps * 1e3, "higher_is_better": True,
+          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": dict(config, parallelism=f"ONE process, one ps_create_multi handle over {a.gpus} GPUs (one host thread per GPU, slab-local upload / download of the caller's host arrays)",
+                         counts=counts, timing="host clock around K calls of ps_step with pinned host arrays"),
+          "stage_ms": {k: round(v, 3) for k, v in solver.stage_ms().items()}, "cg_iterations": counts["iterations"], "clocks": clocks,
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": wall / a.steps * 1e3}, "gpu_launches": launches,
+          "roofline": None, "cpu_baseline": None})
+    solver.close()
+
+
 def emit(obj):
     """The ONE JSON line of the contract, on the real stdout (see main: fd 1 is pointed at stderr while the bench runs)."""
     os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
@@ -210,6 +251,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=SCENE_N, help="grid resolution of S3 (the metric is quoted at 256)")
+    ap.add_argument("--scene", default="S3", choices=["S3", "S4", "S5"], help="S3 = BASELINE.json configs[2] (the metric's), S4 = configs[3] (384^3), S5 = configs[4] (512x256x256)")
+    ap.add_argument("--tile", type=int, default=0, help="tileSize override (configs[4] sweeps 8 / 16 / 32)")
+    ap.add_argument("--multi", action="store_true", help="ONE process, --gpus N devices behind one ps_create_multi handle (host arrays only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-reps", type=int, default=30)
     a = ap.parse_args()
@@ -217,9 +261,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
-    config = {"workload": f"S3 honey-coil style scene {a.n}^3: floor + pool + jet, reduced tiles 16 pad 2, boundary layers 2/2, CG tol 1e-3 "
-                          "(BASELINE.json configs[2])", "grid": [a.n] * 3, "tileSize": 16, "tilePadding": 2,
-              "l2": "inputs (9 fp32 grids, 0.6 GB at 256^3) and matrices (>2 GB) exceed the 126 MB L2; no flush needed"}
+    if a.scene == "S3":
+        config = {"workload": f"S3 honey-coil style scene {a.n}^3: floor + pool + jet, reduced tiles 16 pad 2, boundary layers 2/2, CG tol 1e-3 "
+                              "(BASELINE.json configs[2])", "grid": [a.n] * 3, "tileSize": a.tile or 16, "tilePadding": 2,
+                  "l2": "inputs (9 fp32 grids, 0.6 GB at 256^3) and matrices (>2 GB) exceed the 126 MB L2; no flush needed"}
+    elif a.scene == "S4":
+        config = {"workload": "S4 armadillos-style pool 384^3 with 6 solid spheres in a solid box, reduced tiles 32 pad 3, boundary layers 3/3, mu 2000, CG tol 1e-4 "
+                              "(BASELINE.json configs[3])", "grid": [384] * 3, "tileSize": a.tile or 32, "tilePadding": 3,
+                  "l2": "inputs (9 fp32 grids, 2 GB) and matrices exceed the 126 MB L2; no flush needed"}
+    else:
+        config = {"workload": "S5 jelly-jam style ellipsoidal blob 512x256x256 on a floor, variable viscosity 400 exp(0.7 s(x)), boundary layers 3/3, pad 3, CG tol 1e-3 "
+                              "(BASELINE.json configs[4])", "grid": [512, 256, 256], "tileSize": a.tile or 16, "tilePadding": 3,
+                  "l2": "inputs (9 fp32 grids, 1.2 GB) and matrices exceed the 126 MB L2; no flush needed"}
+    metric = METRIC if (a.scene == "S3" and a.n == SCENE_N) else f"stokes_steps_per_sec_{a.scene}_{'x'.join(str(v) for v in config['grid'])}"
 
     # ------------------------------------------------------------------ reference arm (CPU)
     # ONE measured, unscaled step of the reference's own solver with every host core, at the largest S3 grid that fits the time / memory budget
@@ -295,7 +349,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sc = scenes.scene_s3(a.n)
+    ov = {"tileSize": a.tile} if a.tile else {}
+    sc = scenes.scene_s3(a.n, **ov) if a.scene == "S3" else scenes.scene_s4(384, **ov) if a.scene == "S4" else scenes.scene_s5(1.0, **ov)
+    if a.multi:
+        return bench_multi(a, sc, config, metric)
     solver = PolyStokesSolver.from_scene(sc, device=local)
     part = None
     if world > 1:
@@ -339,6 +396,38 @@ def main():
     stage_ms = solver.stage_ms()
     counts = {k: solver.count(k) for k in ["nCenter", "nActiveVs", "nSystemSize", "regionCount", "nRowsExt", "nTotalDOFs", "iterations"]}
 
+    # ---- parity of what was just timed (every N): counts, iteration count and a strided sample of the solved velocity against the committed
+    #      oracle digest of this configuration (tests/golden/fullsize_*.json; 10 x tol relative, valid masks by SHA-256).  With several ranks every
+    #      rank delivers its slab: the slabs are summed into full fields first.
+    parity_checked, parity_note = False, "no committed digest for this configuration"
+    gold_path = os.path.join(ROOT, "tests", "golden", f"fullsize_{a.scene}.json")
+    if a.scene == "S3" and a.n == SCENE_N and not a.tile and os.path.exists(gold_path):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_fullsize
+        outs, vals = [t.clone() for t in d_out], [t.clone() for t in d_valid]
+        if dist is not None:
+            lo, hi = part[2], part[3]
+            for t in outs + vals:
+                top = hi if hi < sc.nz else t.shape[0]
+                t[:lo] = 0
+                t[top:] = 0
+                dist.all_reduce(t)
+        if rank == 0:
+            with open(gold_path) as f:
+                gold = json.load(f)
+            got = make_fullsize.velocity_sample([t.cpu().numpy() for t in outs], [t.cpu().numpy() for t in vals])
+            bad = [k for k, v in gold["counts"].items() if solver.count(k) != v]
+            tol = 10 * sc.params["tolerance"]
+            worst = max(float(np.abs(np.array(gold[f"vel{ax}_sample"]) - np.array(got[f"vel{ax}_sample"])).max()) / gold[f"vel{ax}_absmax"] for ax in range(3))
+            ok = (not bad and abs(counts["iterations"] - gold["iterations"]) <= max(2, gold["iterations"] // 100) and worst <= tol
+                  and all(got[f"valid{ax}"] == gold[f"valid{ax}"] for ax in range(3)))
+            parity_note = (f"counts {'equal' if not bad else 'DIFFER ' + str(bad)}, iterations {counts['iterations']} vs {gold['iterations']}, velocity sample max rel diff {worst:.2e} "
+                           f"(gate {tol:.0e}), valid masks {'equal' if all(got[f'valid{ax}'] == gold[f'valid{ax}'] for ax in range(3)) else 'DIFFER'}")
+            if not ok:
+                raise SystemExit("bench.py: parity check failed: " + parity_note)
+            parity_checked = True
+        del outs, vals
+
     # ---- end to end through the public API with HOST (pinned) buffers: H2D + D2H inside the timed region
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     h_in = [pin(sc.surface), pin(sc.collision), pin(sc.viscosity)]
@@ -364,8 +453,14 @@ def main():
         t = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_elapsed = float(t.item())
+    # bytes that cross PCIe per step, all ranks together: every rank moves its slab (+ halo layers of the inputs) with slab-local setup
     h2d = sum(t.numel() * 4 for t in h_in + h_vel + h_cvel)
     d2h = sum(t.numel() * 4 for t in h_out + h_valid)
+    if world > 1 and solver.count("slabLocal"):
+        halo = 2 * (sc.params["liquidLayers"] + sc.params["solidLayers"] + 3 + 2)
+        h2d = int(h2d * min(1.0, (sc.nz + world * halo) / sc.nz))
+    elif world > 1:
+        h2d *= world
     e2e = {"value": a.steps / e2e_elapsed, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_elapsed / a.steps * 1e3,
            "stage_ms": {k: round(v, 3) for k, v in solver.stage_ms().items()},
@@ -452,7 +547,7 @@ def main():
             same_grid = None
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": elapsed / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": dict(config, parallelism="single GPU" if world == 1 else
                                                    f"z-slab decomposition over {world} GPUs, cuts {part[4]} (one process per GPU; per CG iteration: halo exchange of p and w + "
@@ -463,7 +558,7 @@ def main():
                                                    "device_ms_per_step = sum of per-stage CUDA-event times"),
                "wall_ms_per_step": wall / a.steps * 1e3, "device_ms_per_step": dev_ms / a.steps, "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                "cg_iterations": counts["iterations"], "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-               "roofline": roofline, "cpu_baseline": cpu, "vs_reference_same_grid": same_grid}
+               "roofline": roofline, "cpu_baseline": cpu, "vs_reference_same_grid": same_grid, "parity_checked": parity_checked, "parity": parity_note}
         emit(out)
     if dist is not None:
         dist.destroy_process_group()

@@ -124,12 +124,21 @@ const char* ps_last_error(void);
  * intra-solver parallelism.  Call order: every rank creates its handle on its own device; rank 0 calls
  * ps_comm_unique_id and ships the 128 bytes to the others with any host transport (torch.distributed, MPI, a file);
  * every rank then calls ps_comm_init (collective).  Afterwards ps_step / ps_setup / ps_solve / ps_apply /
- * ps_time_kernel("cg_iteration") are collective calls: every rank passes the SAME full-grid input fields (the
- * classification is computed redundantly, in the reference's global numbering) and owns the z-slab reported by
- * ps_get_partition.  Output contract: a rank's velocity is final on the closure of its slab (cells z in [zLo, zHi),
- * z-faces zLo..zHi inclusive); elsewhere faces carrying a DOF of another rank keep their input value.  `valid` is
- * complete on every rank.  Reduced regions need doTile with tilePadding >= 1 (untiled regions may span slabs).
+ * ps_time_kernel("cg_iteration") are collective calls: every rank passes pointers to the SAME full-grid input fields and
+ * owns the z-slab reported by ps_get_partition.  With tilePadding >= 2 (or reduced regions off) the setup is slab-local: a rank
+ * reads, classifies, numbers and assembles only its slab plus a halo of a few layers, the global numbering follows from an
+ * all-gather of per-slab counts (ps_part.hpp); with tilePadding 1 every rank classifies the whole grid redundantly.  Output
+ * contract: a rank writes velocity and `valid` on ITS SLAB of the output arrays (cells / faces / edges with z in [zLo, zHi), the
+ * last rank also the top layer); the rest of the arrays is not touched.  Reduced regions need doTile with tilePadding >= 1
+ * (untiled regions may span slabs).
  * cancel_cb must answer identically on all ranks. */
+/* ---- several GPUs behind ONE handle (the caller is one cook thread, exec/HDK_PolyStokes.C:222-345) ----
+ * ps_create_multi builds the same slab decomposition inside one process: one rank per device devs[0..ndev) (NULL: devices
+ * 0..ndev-1), one host thread per rank, NCCL + NVLink peer memory between them.  The handle is used exactly like a single-GPU
+ * one: ps_step / ps_setup / ps_solve take the full-grid HOST fields of the caller, every rank uploads only its slab (+ halo) and
+ * writes only its slab of velocity / valid, so after the call the caller's arrays are complete.  ps_get_count / ps_get_real /
+ * ps_get_partition answer for the whole job; ps_export / ps_apply and the per-voxel introspection need a single-GPU handle. */
+int ps_create_multi(const ps_params* params, int ndev, const int* devs, ps_handle* out);
 int ps_comm_unique_id(void* id128);
 int ps_comm_init(ps_handle h, int rank, int nranks, const void* id128);
 /* z cuts of all ranks: zCut[nranks+1] (may be NULL); returns nranks, this rank's slab in *zLo, *zHi */

@@ -6,10 +6,69 @@
 #include <array>
 #include <fstream>
 #include <limits>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 
 using namespace ps;
 
-struct ps_solver { Solver* S; void* tm[2] = {nullptr, nullptr}; Scratch scratch; };   // tm: the CUDA events of ps_timer
+struct MultiGroup;
+// S: the solver (for the handle of ps_create_multi: rank 0's, not owned); tm: the CUDA events of ps_timer
+struct ps_solver { Solver* S; void* tm[2] = {nullptr, nullptr}; Scratch scratch; MultiGroup* multi = nullptr; };
+
+// ps_create_multi: one process drives several GPUs.  The handle owns one ordinary single-GPU handle ("rank") per device and one
+// persistent host thread per rank; a collective entry point (ps_step, ps_setup, ps_solve, ps_time_kernel, ps_timer) runs on all
+// ranks at once -- the ranks talk to each other exactly as separate processes would (NCCL for the plumbing, peer memory for
+// the halos / reductions; ps_comm.hpp, ps_peer.hpp) -- and returns when the last rank is done.
+struct MultiGroup {
+    struct Worker {
+        std::thread th; std::mutex m; std::condition_variable cv;
+        std::function<int()> task; bool has = false, quit = false, done = true; int rc = 0; std::string err;
+    };
+    std::vector<ps_solver*> kids;
+    std::vector<std::unique_ptr<Worker>> workers;
+    void start(int n) {
+        for (int k = 0; k < n; ++k) {
+            workers.emplace_back(new Worker);
+            Worker* w = workers.back().get();
+            w->th = std::thread([w] {
+                for (;;) {
+                    std::function<int()> job;
+                    { std::unique_lock<std::mutex> lk(w->m); w->cv.wait(lk, [w] { return w->has || w->quit; }); if (w->quit) return; job = w->task; w->has = false; }
+                    int rc; std::string err;
+                    try { rc = job(); if (rc == PS_FAILED || rc == PS_INVALID) err = g_lastError; }
+                    catch (const std::exception& e) { rc = PS_FAILED; err = e.what(); }
+                    catch (...) { rc = PS_FAILED; err = "unknown error"; }
+                    { std::lock_guard<std::mutex> lk(w->m); w->rc = rc; w->err = err; w->done = true; }
+                    w->cv.notify_all();
+                }
+            });
+        }
+    }
+    // f(rank) on every rank's thread; returns rank 0's result, or the first failure (its message goes to the caller's ps_last_error)
+    int run(const std::function<int(int)>& f) {
+        for (size_t k = 0; k < workers.size(); ++k) {
+            Worker* w = workers[k].get();
+            { std::lock_guard<std::mutex> lk(w->m); w->task = [f, k] { return f((int)k); }; w->has = true; w->done = false; }
+            w->cv.notify_all();
+        }
+        int rc0 = PS_SUCCESS; bool failed = false;
+        for (size_t k = 0; k < workers.size(); ++k) {
+            Worker* w = workers[k].get();
+            std::unique_lock<std::mutex> lk(w->m);
+            w->cv.wait(lk, [w] { return w->done; });
+            if (k == 0) rc0 = w->rc;
+            if ((w->rc == PS_FAILED || w->rc == PS_INVALID) && !failed) { failed = true; rc0 = w->rc; g_lastError = "rank " + std::to_string(k) + ": " + w->err; }
+        }
+        return rc0;
+    }
+    void stop() {
+        for (auto& w : workers) { { std::lock_guard<std::mutex> lk(w->m); w->quit = true; } w->cv.notify_all(); if (w->th.joinable()) w->th.join(); }
+        workers.clear();
+    }
+};
 
 namespace {
 
@@ -236,6 +295,15 @@ int ps_create(const ps_params* params, ps_handle* out) {
 }
 void ps_destroy(ps_handle h) {
     if (!h) return;
+    if (h->multi) {
+        MultiGroup* G = h->multi;
+        G->run([G](int k) { ps_destroy(G->kids[(size_t)k]); return (int)PS_SUCCESS; });     // every rank on its own thread: a rank's teardown may wait for its peers' streams
+        G->stop();
+        delete G;
+        h->S = nullptr; h->multi = nullptr;
+        delete h;
+        return;
+    }
 #ifndef PS_EMULATE
     for (void* e : h->tm) if (e) cudaEventDestroy((cudaEvent_t)e);
 #endif
@@ -250,13 +318,44 @@ int ps_comm_unique_id(void* id128) {
 }
 int ps_comm_init(ps_handle h, int rank, int nranks, const void* id128) {
     if (!h || !id128) { g_lastError = "ps_comm_init: null argument"; return PS_INVALID; }
+    if (h->multi) { g_lastError = "ps_comm_init: a ps_create_multi handle is already decomposed"; return PS_INVALID; }
     return guarded(h, [&] {
         h->S->initComm(make_nccl_comm(rank, nranks, id128));
         h->S->setupPeer();
         return (int)PS_SUCCESS;
     });
 }
+// the caller is ONE cook thread (exec/HDK_PolyStokes.C:222); it cannot run one process per GPU.
+int ps_create_multi(const ps_params* params, int ndev, const int* devs, ps_handle* out) {
+    if (!params || !out || ndev < 1 || ndev > PEER_MAX_RANKS) { g_lastError = "ps_create_multi: bad argument (1 <= ndev <= 8)"; return PS_INVALID; }
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<MultiGroup> G(new MultiGroup);
+        auto cleanup = [&] { for (ps_solver* k : G->kids) ps_destroy(k); G->kids.clear(); G->stop(); };
+        for (int r = 0; r < ndev; ++r) {
+            ps_params P = *params;
+            P.device = devs ? devs[r] : r;
+            ps_handle k = nullptr;
+            if (ps_create(&P, &k) != PS_SUCCESS) { const std::string e = g_lastError; cleanup(); throw Error("ps_create_multi: device " + std::to_string(P.device) + ": " + e); }
+            G->kids.push_back(k);
+        }
+        if (ndev > 1) {
+            unsigned char id[128];
+            nccl_unique_id(id);                  // also loads libnccl once, before the rank threads need it
+            G->start(ndev);
+            MultiGroup* g = G.get();
+            const int rc = g->run([g, ndev, &id](int k) { return ps_comm_init(g->kids[(size_t)k], k, ndev, id); });
+            if (rc != PS_SUCCESS) { const std::string e = g_lastError; cleanup(); throw Error("ps_create_multi: " + e); }
+        } else G->start(1);
+        ps_solver* h = new ps_solver;
+        h->S = G->kids[0]->S;
+        h->multi = G.release();
+        *out = h;
+        return (int)PS_SUCCESS;
+    });
+}
 #else
+int ps_create_multi(const ps_params*, int, const int*, ps_handle* out) { if (out) *out = nullptr; g_lastError = "ps_create_multi: needs CUDA devices (the emulation twin is single process per rank)"; return PS_FAILED; }
 // the emulation twin has no NCCL: tests/ hand it host callbacks (torch.distributed / gloo) instead
 int ps_comm_unique_id(void* id128) { if (id128) memset(id128, 0, 128); return PS_SUCCESS; }
 int ps_comm_init(ps_handle, int, int, const void*) { g_lastError = "ps_comm_init: the emulation twin takes ps_comm_init_callbacks"; return PS_FAILED; }
@@ -275,8 +374,23 @@ int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int
     return p.nranks;
 }
 
+// stats of a collective call: rank 0's, with the slowest rank's stage times and the launches of all ranks
+static void merge_stats(ps_stats* dst, const std::vector<ps_stats>& all) {
+    if (!dst || all.empty()) return;
+    *dst = all[0];
+    dst->gpu_launches = 0;
+    for (const ps_stats& s : all) { dst->gpu_launches += s.gpu_launches; for (int i = 0; i < PS_NUM_STAGES; ++i) dst->stage_ms[i] = std::max(dst->stage_ms[i], s.stage_ms[i]); }
+}
+
 int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* stats) {
     if (!h || !in) { g_lastError = "ps_step: null argument"; return PS_INVALID; }
+    if (h->multi) {
+        MultiGroup* G = h->multi;
+        std::vector<ps_stats> st(G->kids.size());
+        const int rc = G->run([&](int k) { return ps_step(G->kids[(size_t)k], in, out, &st[(size_t)k]); });
+        merge_stats(stats, st);
+        return rc;
+    }
     return guarded(h, [&] {
         Solver& S = *h->S;
         const int res = S.step(*in, out, stats);
@@ -287,6 +401,7 @@ int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* s
 }
 int ps_setup(ps_handle h, const ps_fields_in* in) {
     if (!h || !in) { g_lastError = "ps_setup: null argument"; return PS_INVALID; }
+    if (h->multi) { MultiGroup* G = h->multi; return G->run([&](int k) { return ps_setup(G->kids[(size_t)k], in); }); }
     return guarded(h, [&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; 
         try { S.setInputs(*in); S.setup(); }
         catch (...) { stream_sync(S.stIn); S.lateInputsPending = false; throw; }   // no copy may outlive the error return
@@ -294,6 +409,13 @@ int ps_setup(ps_handle h, const ps_fields_in* in) {
 }
 int ps_solve(ps_handle h, ps_fields_out* out, ps_stats* stats) {
     if (!h) { g_lastError = "ps_solve: null handle"; return PS_INVALID; }
+    if (h->multi) {
+        MultiGroup* G = h->multi;
+        std::vector<ps_stats> st(G->kids.size());
+        const int rc = G->run([&](int k) { return ps_solve(G->kids[(size_t)k], out, &st[(size_t)k]); });
+        merge_stats(stats, st);
+        return rc;
+    }
     return guarded(h, [&] {
         Solver& S = *h->S;
         if (!S.haveSetup) throw Error("ps_solve: call ps_setup first");
@@ -375,6 +497,7 @@ int64_t ps_get_vector(ps_handle h, const char* name, double* out) {
 
 int ps_apply(ps_handle h, const double* x, double* y) {
     if (!h || !x || !y) return PS_INVALID;
+    if (h->multi) { g_lastError = "ps_apply: not available on a ps_create_multi handle (use one handle per rank)"; return PS_INVALID; }
     return guarded(h, [&] {
         Solver& S = *h->S;
         if (!S.haveSetup) throw Error("ps_apply: call ps_setup first");
@@ -398,12 +521,8 @@ double ps_kernel_bytes(ps_handle h, const char* name) {
     const double nE = (double)(C.nEdge[0] + C.nEdge[1] + C.nEdge[2]);
     const double n = (double)C.nSystemSize;
     const double nRed = (double)S.RG.nRows;
-    // pass 1 with the fused region term: the compact rows of K_ext, x once, w written once (active rows by their threads, coupled reduced
-    // rows by the region epilogue), the packed coordinates of the coupled rows twice (moments, expand), B^-1 + sigma per region
-    const double regionTerm = nRed * (4.0 + 4.0) + (double)S.RG.count * (RDOF * RDOF + 30) * 8.0;
-    const double pass1 = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs /*matrix*/ + 8.0 * n /*x*/ + 8.0 * C.nRowsExt /*w write*/ + (S.RG.fusedRegions ? regionTerm : 0.0);
-    // the sweep alone (raw products on the coupled rows): the figure "pass1_sweep" is timed on
-    const double pass1Sweep = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs + 8.0 * n + 8.0 * C.nRowsExt;
+    // pass 1 = the sweep over the compact rows of K_ext (x once, w once) + the region kernel (below)
+    const double pass1Sweep = 32.0 * C.nRowsExt + 1.0 * C.nActiveVs /*matrix*/ + 8.0 * n /*x*/ + 8.0 * C.nRowsExt /*w write*/;
     const double pass2 = 32.0 * C.nCenter + 20.0 * nE /*matrix*/ + 8.0 * C.nRowsExt /*w read*/ + 8.0 * (C.nCenter + nE) /*mu^-1: once per cell / edge*/
                        + 8.0 * n /*x (stress part: the mu term; pressure part: the fused dot)*/ + 8.0 * n /*y*/;
     const double pass2Dots = pass2 + 8.0 * n /*r for the fused r.Ap*/;
@@ -412,22 +531,30 @@ double ps_kernel_bytes(ps_handle h, const char* name) {
     if (nm == "csr_pass1") return csrPass1;
     if (nm == "csr_pass2") return csrPass2;
     if (nm == "csr_apply") return csrPass1 + csrPass2 + nRed * 24.0 + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
-    // chunked region kernels (regions too large for the fused epilogue): w read + packed coordinates (moments), packed coordinates + w write (expand)
-    const double reducedChunked = nRed * (8.0 + 4.0) + nRed * (4.0 + 8.0) + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
-    const double reduced = S.RG.fusedRegions ? 0.0 : reducedChunked;
+    // reduced rows: w read + packed coordinates (moments), packed coordinates + w write (expand), B^-1 + t,s,sigma per region
+    const double reduced = nRed * (8.0 + 4.0) + nRed * (4.0 + 8.0) + (double)S.RG.count * (RDOF * RDOF + 2 * RDOF + 30) * 8.0;
+    const double pass1 = pass1Sweep + reduced;
     if (nm == "pass1") return pass1;
     if (nm == "pass1_sweep") return pass1Sweep;
     if (nm == "pass2") return pass2;
     if (nm == "pass2_dots") return pass2Dots;
-    if (nm == "reduced") return S.RG.fusedRegions ? regionTerm : reducedChunked;
-    if (nm == "apply") return pass1 + pass2 + reduced;
+    if (nm == "reduced") return reduced;
+    if (nm == "apply") return pass1 + pass2;
     if (nm == "cg_update") return 56.0 * n;
-    if (nm == "cg_iteration") return pass1 + pass2Dots + reduced + 56.0 * n /*x, r, p update: x, r, p, Ap in; x, r, p out*/;
+    if (nm == "cg_iteration") return pass1 + pass2Dots + 56.0 * n /*x, r, p update: x, r, p, Ap in; x, r, p out*/;
     return 0;
 }
 
 double ps_time_kernel(ps_handle h, const char* name, int reps) {
     if (!h || !name || reps <= 0) return -1;
+    if (h->multi) {     // collective; the slowest rank's time
+        MultiGroup* G = h->multi;
+        std::vector<double> t(G->kids.size(), -1.);
+        G->run([&](int k) { t[(size_t)k] = ps_time_kernel(G->kids[(size_t)k], name, reps); return t[(size_t)k] < 0 ? (int)PS_FAILED : (int)PS_SUCCESS; });
+        double worst = -1; bool bad = false;
+        for (double v : t) { if (v < 0) bad = true; worst = std::max(worst, v); }
+        return bad ? -1 : worst;
+    }
     double ms = -1;
     guarded(h, [&] {
         Solver& S = *h->S; const std::string nm(name);
@@ -443,7 +570,7 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
             S.P.maxSolverIterations = savedMax; S.P.checkEvery = savedEvery; S.P.tolerance = savedTol;
             return 0;
         }
-        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : nm == "pass1_sweep" ? 3 : nm == "pass2_dots" ? 4 : nm == "cg_update" ? 5 : -1;
+        const int which = nm == "pass1" ? 1 : nm == "pass2" ? 2 : nm == "apply" ? 0 : nm == "pass1_sweep" ? 3 : nm == "pass2_dots" ? 4 : nm == "cg_update" ? 5 : nm == "reduced" ? 6 : -1;
         if (which < 0) throw Error("ps_time_kernel: unknown kernel name");
         // the CG kernels look at the device scalars: a fresh state that cannot converge or run out of iterations while timed (the iterates are
         // garbage -- only the memory traffic matters here)
@@ -468,6 +595,14 @@ double ps_time_kernel(ps_handle h, const char* name, int reps) {
 // (e.g. torch.cuda.Event on torch's current stream) does not see.
 double ps_timer(ps_handle h, int stop) {
     if (!h) return -1;
+    if (h->multi) {     // every rank's own stream; the slowest rank's time
+        MultiGroup* G = h->multi;
+        std::vector<double> t(G->kids.size(), -1.);
+        G->run([&](int k) { t[(size_t)k] = ps_timer(G->kids[(size_t)k], stop); return t[(size_t)k] < 0 ? (int)PS_FAILED : (int)PS_SUCCESS; });
+        double worst = -1; bool bad = false;
+        for (double v : t) { if (v < 0) bad = true; worst = std::max(worst, v); }
+        return bad ? -1 : worst;
+    }
     double ms = -1;
     guarded(h, [&] {
 #ifndef PS_EMULATE
@@ -486,6 +621,7 @@ double ps_timer(ps_handle h, int stop) {
 
 int ps_export(ps_handle h, const char* prefix, int what) {
     if (!h || !prefix) return PS_INVALID;
+    if (h->multi) { g_lastError = "ps_export: the matrices of a slab-decomposed step live on several GPUs; export from a single-GPU handle"; return PS_INVALID; }
     return guarded(h, [&] {
         Solver& S = *h->S; const std::string pre(prefix);
         bool ok = true;

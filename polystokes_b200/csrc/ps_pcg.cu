@@ -5,11 +5,10 @@
 //     y = -dt K^T Mc^-1 K x  -  J^T B^-1 J x  -  1/2 [0; mu^-1 x_tau],   K = [G D^T], J = [JG JD^T]
 // and the CG loop lib/include/pcg.h:268-340.  Here J is never stored: J = C K_red (see ps_assemble.cu), so
 //   pass 1 : w = K_ext x, one thread per face row (8-wide slot-major ELL, coalesced 8B/4B streams, x gathered
-//            through L1/L2); active rows are scaled by dt Mc^-1.  The coupled reduced rows come in chunks of <= 256 rows of
-//            one (region, face axis): a chunk does not store its products but their 10 monomial moments; the LAST chunk of
-//            a region to finish sums the moments in chunk order, t_r -> s_r = B_r^-1 t_r -> sigma_r, and writes the region's
-//            rows w_f = sigma . monomials(f) -- the whole reduced term of the operator inside the same launch
-//            (regions too large for that -- doTile off -- use the chunked kernels moments -> solve -> expand instead)
+//            through L1/L2); active rows are scaled by dt Mc^-1, coupled reduced rows keep the raw product
+//   reduced: ONE CTA per region: 10 monomial moments of its rows per face axis -> t_r -> s_r = B_r^-1 t_r -> sigma_r ->
+//            the same threads overwrite their rows with w_f = sigma . monomials(f)
+//            (regions too large for one CTA -- doTile off -- use the chunked kernels moments -> solve -> expand instead)
 //   pass 2 : y = -K_ext^T w - 1/2 mu^-1 x_tau         (one thread per DOF row, ELL widths 6/2/4), fused with
 //            the dot products p.Ap, r.Ap, Ap.Ap (warp shuffle -> CTA partial -> last CTA finishes in fixed order)
 // All CG scalars live in device memory; the host only polls a convergence flag every few iterations.
@@ -160,194 +159,40 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
     return last;
 }
 
-// sums of v[0..9] over the 32 lanes of a warp by recursive halving (12 double shuffles instead of 50): after the call lane
-// L with (L & 1) == 0 holds the total of value warp_reduce10_index(L) (or -1: padding).  Fixed association: deterministic.
-__device__ __forceinline__ double warp_reduce10(const double* v) {
-    const unsigned lane = threadIdx.x & 31u;
-    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u, b1 = lane & 2u;
-    double u[5], t[3], q[2];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) { const double send = b4 ? v[i] : v[i + 5], keep = b4 ? v[i + 5] : v[i]; u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
-    const double u5 = 0.;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { const double hi = i + 3 < 5 ? u[i + 3 < 5 ? i + 3 : 4] : u5; const double send = b3 ? u[i] : hi, keep = b3 ? hi : u[i]; t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { const double hi = i + 2 < 3 ? t[2] : 0.; const double send = b2 ? t[i] : hi, keep = b2 ? hi : t[i]; q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
-    const double send = b1 ? q[0] : q[1], keep = b1 ? q[1] : q[0];
-    double z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    z += __shfl_xor_sync(0xffffffffu, z, 1);
-    return z;
-}
-__device__ __forceinline__ int warp_reduce10_index(unsigned lane) {
-    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u, b1 = lane & 2u;
-    int k;
-    if (!b3) k = !b2 ? (b1 ? 1 : 0) : (b1 ? -1 : 2);
-    else k = !b2 ? (b1 ? 4 : 3) : -1;
-    return k < 0 ? -1 : k + (b4 ? 5 : 0);
-}
 // pass 1: one thread per face row.  Per row: 8 B of codes + 6 x 4 B columns (+ 1 B mass code) in coalesced slot-major
-// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.  Work items = 256-row blocks of the x / y / z face rows and row chunks
-// (<= 256 rows of one (region, face axis)) of the coupled reduced rows, merged by position in tile order and walked grid-stride.
-// There is NO CTA barrier in the sweep: the 8 warps of a CTA run through their items independently (the gathers need every
-// warp's loads in flight), so everything the region term needs is done at warp granularity:
-//   * a warp leaves the 10 monomial moments of its 32 rows (12 shuffles, fixed order);
-//   * the last warp of a chunk (ticket) adds the 8 warp partials in warp order, the last chunk of a region (ticket) makes
-//     that warp solve the region: moments in chunk order -> t -> s = B^-1 t -> sigma, then it raises the region's flag;
-//   * after its share of the sweep every warp expands its share of the row chunks, w_f = sigma[axis] . monomials(f),
-//     waiting on the region's flag -- which by then is almost always up: regions complete in sweep order.
-// The waiting is deadlock free: the sweep never waits, and all CTAs of the persistent grid are resident.
+// streams, <= 8 gathers of x (L1 / L2), 8 B of w out.  No barrier, no atomics: the 8 warps of a CTA walk their rows independently,
+// two rows in flight per thread -- the sweep is bound by the two dependent round trips of a row (columns, then gathers), so
+// anything that stalls a warp between rows (tickets, fences; an acquire also invalidates the L1 the gathers live in) costs more
+// than it saves: the fused region term measured 2 - 4x slower than sweep + region kernel (profiles/r02_probe_s3_256_v1..v4.log).
 // (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
-constexpr int P1_MAX_CHUNKS = 32;      // chunks of one region the fused solve can sum (Solver::constructMatrixBlocks keeps larger regions on the chunked kernels)
-__device__ __forceinline__ double pass1_row(const OpArgs& A, int64_t r, const double* __restrict__ x, double sc) {
-    const uint64_t word = __ldcs(A.kcode + r);
-    int32_t c[6];
-#pragma unroll
-    for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
-    const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
-    const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
-    const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
-    double xv[8];
-#pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
-    double s = 0.;
-#pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
-    return s;
-}
-// ticket with release / acquire semantics in ONE instruction.  (__threadfence() is fence.sc.gpu: sequentially consistent fences are
-// ordered globally, and one per warp and item -- 10^5 per launch -- serialises the whole kernel: 2 ns each, profiles/r02_probe_s3_256_v3.log)
-__device__ __forceinline__ unsigned atom_inc_acq_rel(unsigned* p, unsigned wrap) {
-    unsigned old;
-    asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(wrap) : "memory");
-    return old;
-}
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-// The solve of one region by ONE warp (the warp whose chunk completed the region); buf = 64 doubles of warp-private shared memory.
-__device__ __forceinline__ void region_solve_warp(const OpArgs& A, const RegionOp& R, int region, double* buf) {
-    const int lane = threadIdx.x & 31;
-    const int chS = __ldg(R.rowChunkStart + region), nch = __ldg(R.rowChunkStart + region + 1) - chS;
-    // chunks of a region are ordered by face axis: contiguous chunk ranges per axis from one ballot each
-    const int myAxis = lane < nch ? __ldg(A.rowChunk + 4 * (chS + lane) + 3) : -1;
-    const unsigned m0 = __ballot_sync(0xffffffffu, myAxis == 0), m1 = __ballot_sync(0xffffffffu, myAxis == 1), m2 = __ballot_sync(0xffffffffu, myAxis == 2);
-    double Mv = 0.;
-    if (lane < 30) {
-        const int axis = lane / 10, k = lane % 10;
-        const unsigned mk = axis == 0 ? m0 : axis == 1 ? m1 : m2;
-        const int first = mk ? __ffs(mk) - 1 : 0, cnt = __popc(mk);
-        const double* P0 = R.partial + (size_t)(chS + first) * 10 + k;
-#pragma unroll 4
-        for (int c = 0; c < cnt; ++c) Mv += __ldcg(P0 + (size_t)c * 10);
-        buf[lane] = Mv;
-    }
-    __syncwarp();
-    if (lane == 0) moments_to_t(buf, buf + 32);
-    __syncwarp();
-    if (lane < RDOF) { double v = R.tScale * buf[32 + lane]; if (R.extra) v += R.extraScale * R.extra[(size_t)region * RDOF + lane]; buf[32 + lane] = v; }
-    __syncwarp();
-    double si = 0.;
-    if (lane < RDOF) {      // row `lane` of B^-1, a few independent loads at a time (this path runs once per region and launch)
-        const double* B = R.Binv + (size_t)region * RDOF * RDOF + lane * RDOF;
-#pragma unroll 1
-        for (int j0 = 0; j0 < RDOF; j0 += 13) {
-            double bj[13];
-#pragma unroll
-            for (int j = 0; j < 13; ++j) bj[j] = __ldg(B + j0 + j);
-#pragma unroll
-            for (int j = 0; j < 13; ++j) si += bj[j] * buf[32 + j0 + j];
-        }
-    }
-    __syncwarp();
-    if (lane < RDOF) buf[lane] = si;
-    __syncwarp();
-    if (lane == 0) s_to_sigma(buf, buf + 32);
-    __syncwarp();
-    if (lane < 30) __stcg(R.sigma + (size_t)region * 30 + lane, buf[32 + lane]);
-    __syncwarp();
-    if (lane == 0) st_release_u32(R.solved + region, R.seq);      // releases sigma (ordered before it by __syncwarp)
-}
-// flags: bit 1 = walk the schedule backwards (A/B knob, Solver::solve)
-template <int UNROLL>
-__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const __grid_constant__ RegionOp R, const double* __restrict__ x, double* __restrict__ w,
-                                                              double activeScale, const PcgScalars* S, int flags) {
-    pdl_sync();
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S, int reverse) {    pdl_sync();
+
     __shared__ double lut[65];
-    __shared__ double wbuf[HOT_THREADS / 32][64];
     if (S && S->done) return;
-    const bool reverse = flags & 2;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
     __syncthreads();
     const double sc = A.valScale;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // ---- the sweep: owned rows in the merged block order of the four ranges (SchedRanges, ps_solver.hpp)
-#pragma unroll UNROLL
+    // owned rows in the merged block order of the four ranges (SchedRanges, ps_solver.hpp)
+#pragma unroll 2
     for (int g = blockIdx.x; g < A.nSched1; g += gridDim.x) {
         const int32_t e = __ldg(A.sched1 + (reverse ? A.nSched1 - 1 - g : g));
         const int k = (int)((uint32_t)e >> 28);
-        if (k < 3) {
-            const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
-            if (r < A.s1.hi[k]) w[r] = activeScale * lut[__ldcs(A.kmc + r)] * pass1_row(A, r, x, sc);
-            continue;
-        }
-        const int ch = (int)A.s1.lo[3] + (int)(e & 0x0fffffff);
-        const int begin = __ldg(A.rowChunk + 4 * ch + 1), end = __ldg(A.rowChunk + 4 * ch + 2);
-        if (R.mode == 0) {      // raw products (K_red x)_f; chunks may be longer than the CTA here (giant regions)
-            for (int row = begin + (int)threadIdx.x; row < end; row += HOT_THREADS) w[A.nActiveVs + row] = pass1_row(A, A.nActiveVs + row, x, sc);
-            continue;
-        }
-        // fused region term; a chunk holds at most one row per thread
-        const int region = __ldg(A.rowChunk + 4 * ch);
-        const int row = begin + (int)threadIdx.x;
-        const double gk = row < end ? pass1_row(A, A.nActiveVs + row, x, sc) : 0.;
-        const double cm[3] = {__ldg(R.com + 3 * region), __ldg(R.com + 3 * region + 1), __ldg(R.com + 3 * region + 2)};
-        double acc[10];
-        row_monomials(R.dx, row < end ? __ldcs(R.rowXYZ + row) : 0u, cm, acc);
+        const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
+        if (r >= A.s1.hi[k]) continue;
+        const uint64_t word = __ldcs(A.kcode + r);
+        int32_t c[6];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) acc[q] *= gk;
-        const double tot = warp_reduce10(acc);
-        const int ki = warp_reduce10_index((unsigned)lane);
-        if (!(lane & 1) && ki >= 0) __stcg(R.wpartial + ((size_t)ch * 8 + wid) * 10 + ki, tot);
-        __syncwarp();
-        unsigned last = 0;
-        if (lane == 0) last = atom_inc_acq_rel(R.chunkTicket + ch, 7u) == 7u;      // releases the warp's partials (ordered before it by __syncwarp), acquires the others'
-
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (!last) continue;
-        // last warp of the chunk: the 8 warp partials in warp order
-        if (lane < 10) {
-            double s2 = 0.;
+        for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
+        const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
+        const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
+        const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
+        double xv[8];
 #pragma unroll
-            for (int wI = 0; wI < 8; ++wI) s2 += __ldcg(R.wpartial + ((size_t)ch * 8 + wI) * 10 + lane);
-            __stcg(R.partial + (size_t)ch * 10 + lane, s2);
-        }
-        __syncwarp();
-        unsigned lastR = 0;
-        if (lane == 0) {
-            const unsigned nch = (unsigned)(__ldg(R.rowChunkStart + region + 1) - __ldg(R.rowChunkStart + region));
-            lastR = atom_inc_acq_rel(R.regionTicket + region, nch - 1) == nch - 1;
-        }
-        lastR = __shfl_sync(0xffffffffu, lastR, 0);
-        if (lastR) region_solve_warp(A, R, region, wbuf[wid]);
-    }
-    if (R.mode == 0) return;
-    // ---- expand: w_f = outScale * sigma[axis] . monomials(f) on this CTA's share of the row chunks
-    const int chLo = (int)A.s1.lo[3], chHi = (int)A.s1.hi[3];
-#pragma unroll 1
-    for (int ch = chLo + (int)blockIdx.x; ch < chHi; ch += (int)gridDim.x) {
-        const int region = __ldg(A.rowChunk + 4 * ch), begin = __ldg(A.rowChunk + 4 * ch + 1), end = __ldg(A.rowChunk + 4 * ch + 2), axis = __ldg(A.rowChunk + 4 * ch + 3);
-        const int row = begin + (int)threadIdx.x;
-        if (begin + wid * 32 >= end) continue;          // this warp has no rows in the chunk
-        const uint32_t xyz = row < end ? __ldcs(R.rowXYZ + row) : 0u;
-        const double cm[3] = {__ldg(R.com + 3 * region), __ldg(R.com + 3 * region + 1), __ldg(R.com + 3 * region + 2)};
-        if (lane == 0) { while ((int)(ld_acquire_u32(R.solved + region) - R.seq) < 0) __nanosleep(40); }
-        __syncwarp();
-        double m[10];
-        row_monomials(R.dx, xyz, cm, m);
-        const double* sg = R.sigma + (size_t)region * 30 + axis * 10;
-        double v = 0.;
+        for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
+        double s = 0.;
 #pragma unroll
-        for (int q = 0; q < 10; ++q) v += __ldcg(sg + q) * m[q];
-        if (row < end) w[A.nActiveVs + row] = R.outScale * v;
+        for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
+        w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
     }
 }
 // last CTA of a producer: v0..v2 are valid in thread 0; every rank's block receives this rank's partial sums
@@ -473,6 +318,30 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, do
 #pragma unroll 4
         for (int64_t l = tid; l < total; l += stride) {
             const int64_t i = own.at(total - 1 - l);
+            const double pi = p[i];
+            const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
+            const double pn = ri + beta * pi;
+            x[i] = xi; r[i] = ri; p[i] = pn;
+            rr += ri * ri; xp += xi * pn; pp += pn * pn;
+        }
+    } else if (!converged && own.n == 1 && !(own.lo[0] & 1)) {
+        // one owned range (a single GPU): two consecutive elements per thread and step as 16-byte accesses -- half the memory
+        // instructions of the scalar walk below
+        const int64_t base = own.lo[0], total = own.total(), pairs = total >> 1;
+#pragma unroll 2
+        for (int64_t q = tid; q < pairs; q += stride) {
+            const int64_t i = base + 2 * q;
+            const double2 pv = *reinterpret_cast<const double2*>(p + i), xv = *reinterpret_cast<const double2*>(x + i);
+            const double2 rv = *reinterpret_cast<const double2*>(r + i), av = __ldcs(reinterpret_cast<const double2*>(Ap + i));
+            double2 xo, ro, po;
+            xo.x = xv.x + alpha * pv.x; ro.x = rv.x - alpha * av.x; po.x = ro.x + beta * pv.x;
+            xo.y = xv.y + alpha * pv.y; ro.y = rv.y - alpha * av.y; po.y = ro.y + beta * pv.y;
+            *reinterpret_cast<double2*>(x + i) = xo; *reinterpret_cast<double2*>(r + i) = ro; *reinterpret_cast<double2*>(p + i) = po;
+            rr += ro.x * ro.x; xp += xo.x * po.x; pp += po.x * po.x;
+            rr += ro.y * ro.y; xp += xo.y * po.y; pp += po.y * po.y;
+        }
+        if ((total & 1) && tid == 0) {
+            const int64_t i = base + total - 1;
             const double pi = p[i];
             const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
             const double pn = ri + beta * pi;
@@ -640,11 +509,9 @@ static inline int hot_blocks(K kernel, int64_t n) {
     return (int)b;
 }
 
-void k_pass1(cudaStream_t st, const OpArgs& A, const RegionOp& R, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse) {
+void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse) {
     if (A.nSched1 <= 0) return;
-    static const int unroll = getenv("PS_PASS1_UNROLL") ? atoi(getenv("PS_PASS1_UNROLL")) : 2;      // A/B knob
-    if (unroll >= 2) launch_chain(pass1_kernel<2>, hot_blocks(pass1_kernel<2>, (int64_t)A.nSched1 * HOT_THREADS), HOT_THREADS, st, A, R, x, w, activeScale, S, reverse ? 2 : 0);
-    else launch_chain(pass1_kernel<1>, hot_blocks(pass1_kernel<1>, (int64_t)A.nSched1 * HOT_THREADS), HOT_THREADS, st, A, R, x, w, activeScale, S, reverse ? 2 : 0);
+    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, (int64_t)A.nSched1 * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, reverse ? 1 : 0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -712,41 +579,9 @@ void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double*
     PS_CUDA(cudaGetLastError());
 }
 #else  // ---- serial twins ----
-void k_pass1(cudaStream_t, const OpArgs& A, const RegionOp& R, const double* x, double* w, double activeScale, const PcgScalars* S, bool) {
+void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool) {
     if (S && S->done) return;
-    for (int k = 0; k < 3; ++k)
-        for (int64_t r = A.s1.lo[k]; r < A.s1.hi[k]; ++r) w[r] = activeScale * A.mcInvLut[A.kmc[r]] * k_row(A, r, x);
-    // row chunks of the coupled reduced rows of the owned regions
-    const int chLo = (int)A.s1.lo[3], chHi = (int)A.s1.hi[3];
-    for (int ch = chLo; ch < chHi; ++ch) {
-        const int region = A.rowChunk[4 * ch], begin = A.rowChunk[4 * ch + 1], end = A.rowChunk[4 * ch + 2];
-        double acc[10] = {0};
-        for (int row = begin; row < end; ++row) {
-            const double gk = k_row(A, A.nActiveVs + row, x);
-            if (R.mode == 0) { w[A.nActiveVs + row] = gk; continue; }
-            double m[10]; row_monomials(R.dx, R.rowXYZ[row], R.com + 3 * region, m);
-            for (int q = 0; q < 10; ++q) acc[q] += m[q] * gk;
-        }
-        if (R.mode != 0) for (int q = 0; q < 10; ++q) R.partial[(size_t)ch * 10 + q] = acc[q];
-    }
-    if (R.mode == 0 || chHi <= chLo) return;
-    for (int region = A.rowChunk[4 * chLo]; region <= A.rowChunk[4 * (chHi - 1)]; ++region) {
-        double M[30] = {0}, t[RDOF], sv[RDOF], sg[30];
-        for (int ch = R.rowChunkStart[region]; ch < R.rowChunkStart[region + 1]; ++ch)
-            for (int q = 0; q < 10; ++q) M[A.rowChunk[4 * ch + 3] * 10 + q] += R.partial[(size_t)ch * 10 + q];
-        moments_to_t(M, t);
-        for (int n = 0; n < RDOF; ++n) t[n] = R.tScale * t[n] + (R.extra ? R.extraScale * R.extra[(size_t)region * RDOF + n] : 0.);
-        for (int i = 0; i < RDOF; ++i) { double s2 = 0.; for (int j = 0; j < RDOF; ++j) s2 += R.Binv[(size_t)region * RDOF * RDOF + i * RDOF + j] * t[j]; sv[i] = s2; }
-        s_to_sigma(sv, sg);
-        if (R.sigma) for (int q = 0; q < 30; ++q) R.sigma[(size_t)region * 30 + q] = sg[q];
-        for (int row = R.rowStart[region]; row < R.rowStart[region + 1]; ++row) {
-            const uint32_t xyz = R.rowXYZ[row];
-            double m[10]; row_monomials(R.dx, xyz, R.com + 3 * region, m);
-            double v = 0.;
-            for (int q = 0; q < 10; ++q) v += sg[10 * (int)(xyz >> 30) + q] * m[q];
-            w[A.nActiveVs + row] = R.outScale * v;
-        }
-    }
+    for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInvLut[A.kmc[r]] * s : s; }
 }
 void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode, const double* r2, bool) {
     if (S && S->done) return;
@@ -1034,6 +869,131 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, 
         wRows[row] = scale * v;
     }
 }
+// The whole reduced term of one apply for tiled regions, ONE CTA per region: w_f <- scale * c_f . B_r^-1 (sum_f c_f w_f).
+// Three groups of REG_GROUP threads take the region's x / y / z rows (rowAxisStart), so every load of the region is in flight
+// at once; the 3 x 10 moments are reduced in a fixed order (warp shuffles, then the group's warps in order), B^-1 (staged in
+// shared memory while the rows stream in) is applied by 26 threads, and the same threads that read a row overwrite it with the
+// expanded value.  No inter-CTA hand-off: this replaces moments + last-chunk solve + expand (3 dependent stages, 2 launches)
+// by one launch whose critical path is one row round trip + one 26x26 product.  Regions too large for one CTA (doTile off)
+// keep the chunked kernels above.
+// GROUP threads per axis, ROWS rows per thread kept in registers between the two phases (0: re-read rowXYZ through L1/L2)
+template <int GROUP, int ROWS, int MINB>
+__global__ void __launch_bounds__(3 * GROUP, MINB) reduced_region_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ rowAxisStart, const double* __restrict__ com,
+                                                                       const double* __restrict__ Binv, double* __restrict__ wRows, double scale, const PcgScalars* S, int region0) {
+    constexpr int NW = GROUP / 32, KEEP = ROWS > 0 ? ROWS : 1;
+    __shared__ double Bs[RDOF * RDOF];
+    __shared__ double red[3][NW][10];
+    __shared__ double M[30], t[RDOF], sv[RDOF], sg[30];
+    const int r = region0 + blockIdx.x;
+    // B^-1, the row table and the centres of mass are setup data: they may be fetched before the previous kernel has finished
+    for (int i = threadIdx.x; i < RDOF * RDOF; i += 3 * GROUP) Bs[i] = __ldg(Binv + (size_t)r * RDOF * RDOF + i);
+    const int axis = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+    const int begin = __ldg(rowAxisStart + 3 * r + axis), end = __ldg(rowAxisStart + 3 * r + axis + 1);
+    const double cm[3] = {__ldg(com + 3 * r), __ldg(com + 3 * r + 1), __ldg(com + 3 * r + 2)};
+    pdl_sync();
+    if (S && S->done) return;
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.;
+    uint32_t xyz[KEEP];
+    if (ROWS > 0) {
+        double gk[KEEP];
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int row = begin + lane + i * GROUP;
+            xyz[i] = row < end ? __ldcs(rowXYZ + row) : 0u;
+            gk[i] = row < end ? __ldcs(wRows + row) : 0.;
+        }
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            double m[10];
+            row_monomials(dx, xyz[i], cm, m);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc[k] += m[k] * gk[i];
+        }
+    }
+#pragma unroll 4
+    for (int row = begin + lane + ROWS * GROUP; row < end; row += GROUP) {
+        double m[10];
+        row_monomials(dx, __ldg(rowXYZ + row), cm, m);
+        const double g1 = __ldcs(wRows + row);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] += m[k] * g1;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        const double v = warp_sum(acc[k]);
+        if ((lane & 31) == 0) red[axis][lane >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 30) {
+        const int a = threadIdx.x / 10, k = threadIdx.x % 10;
+        double s = 0.;
+#pragma unroll
+        for (int wI = 0; wI < NW; ++wI) s += red[a][wI][k];
+        M[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) moments_to_t(M, t);
+    __syncthreads();
+    if (threadIdx.x < RDOF) {
+        const double* B = Bs + threadIdx.x * RDOF;
+        double s = 0.;
+#pragma unroll
+        for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
+        sv[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_to_sigma(sv, sg);
+    __syncthreads();
+    double sgl[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sgl[k] = sg[axis * 10 + k];
+    if (ROWS > 0) {
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int row = begin + lane + i * GROUP;
+            if (row < end) {
+                double m[10];
+                row_monomials(dx, xyz[i], cm, m);
+                double v = 0.;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
+                wRows[row] = scale * v;
+            }
+        }
+    }
+#pragma unroll 4
+    for (int row = begin + lane + ROWS * GROUP; row < end; row += GROUP) {
+        double m[10];
+        row_monomials(dx, __ldg(rowXYZ + row), cm, m);
+        double v = 0.;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
+        wRows[row] = scale * v;
+    }
+}
+template <int GROUP, int ROWS, int MINB>
+static void launch_region(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    launch_chain(reduced_region_kernel<GROUP, ROWS, MINB>, (unsigned)(RG.regHi - RG.regLo), 3 * GROUP, st, g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, wRows, scale, S, RG.regLo);
+}
+// w_f <- scale * c_f . B^-1 J w on the coupled reduced rows (the reduced term of one operator apply)
+void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
+    if (RG.regHi <= RG.regLo) return;
+    if (RG.maxRegionRows > fuseLimit) { reduced_moments(st, g, RG, wRows, S, true); reduced_expand(st, g, RG, wRows, scale, S); return; }
+    // A/B knob.  Default: 64 lanes per axis, 6 CTAs per SM for many regions (throughput); few regions per GPU (slab decomposition) are
+    // latency bound -- 128 lanes per axis with the rows kept in registers put every load of a region in flight at once
+    static const int forced = getenv("PS_REGION_VARIANT") ? atoi(getenv("PS_REGION_VARIANT")) : -1;
+    const int variant = forced >= 0 ? forced : (RG.regHi - RG.regLo <= 900 ? 1 : 0);
+    if (variant == 1) launch_region<128, 8, 2>(st, g, RG, wRows, scale, S);
+    else if (variant == 2) launch_region<64, 8, 4>(st, g, RG, wRows, scale, S);
+    else if (variant == 3) launch_region<32, 0, 10>(st, g, RG, wRows, scale, S);
+    else if (variant == 4) launch_region<128, 0, 3>(st, g, RG, wRows, scale, S);
+    else launch_region<64, 0, 6>(st, g, RG, wRows, scale, S);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
 void reduced_moments(cudaStream_t st, const Geom& g, const RegionData& RG, const double* wRows, const PcgScalars* S, bool solve) {
     if (RG.rowChunkHi <= RG.rowChunkLo) return;
     launch_chain(reduced_moments_kernel, (unsigned)(RG.rowChunkHi - RG.rowChunkLo), MOM_THREADS, st, g.dx, RG.rowXYZ.p, RG.rowChunk.p, RG.rowChunkStart.p, RG.com.p, wRows, RG.partial.p, RG.Binv.p, RG.sigma.p,
@@ -1083,6 +1043,9 @@ void reduced_finish(cudaStream_t, const Geom&, const RegionData& RG, const doubl
         s_to_sigma(sv, sg);
         for (int k = 0; k < 30; ++k) RG.sigma.p[(size_t)r * 30 + k] = sg[k];
     }
+}
+void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
+    reduced_moments(st, g, RG, wRows, S, true); reduced_expand(st, g, RG, wRows, scale, S);
 }
 void reduced_expand(cudaStream_t, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
     if (S && S->done) return;

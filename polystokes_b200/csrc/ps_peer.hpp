@@ -43,6 +43,7 @@ struct PeerLink {
     bool needResync = false;                      // a wait timed out / a solve was cancelled: flags and sequence numbers are re-agreed at the next setup
     int rank = 0, nranks = 1;
     void* block[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // block[rank] = mine, others IPC-mapped
+    bool sameProcess[PEER_MAX_RANKS] = {false, false, false, false, false, false, false, false};          // peers of this process: plain peer access to their pointer
     size_t cap = 0;                               // doubles per halo receive buffer
     unsigned long long seqHalo[2] = {0, 0}, seqRed[PEER_SLOTS] = {0, 0};
     PeerSync* sync(int r) const { return (PeerSync*)block[r]; }

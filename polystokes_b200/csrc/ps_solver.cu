@@ -4,6 +4,7 @@
 #include <climits>
 #include <chrono>
 #include <memory>
+#include <unistd.h>
 
 namespace ps {
 
@@ -115,7 +116,7 @@ void Solver::closePeer() {
     if (st) cudaStreamSynchronize(st);
     for (int r = 0; r < PEER_MAX_RANKS; ++r) {
         if (!peer.block[r]) continue;
-        if (r == peer.rank) cudaFree(peer.block[r]); else cudaIpcCloseMemHandle(peer.block[r]);
+        if (r == peer.rank) cudaFree(peer.block[r]); else if (!peer.sameProcess[r]) cudaIpcCloseMemHandle(peer.block[r]);
         peer.block[r] = nullptr;
     }
 #endif
@@ -136,24 +137,36 @@ void Solver::setupPeer() {
     double okLocal = 1.;
     void* mine = nullptr;
     if (cudaMalloc(&mine, peer.bytes()) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; mine = nullptr; }
-    cudaIpcMemHandle_t hMine; memset(&hMine, 0, sizeof hMine);
+    // what every rank publishes: an IPC handle for ranks in other processes, the raw pointer + device for ranks of THIS process
+    // (ps_create_multi: one host thread per GPU; cudaIpcOpenMemHandle refuses handles of the calling process)
+    struct Card { cudaIpcMemHandle_t ipc; unsigned long long pid, ptr; int dev, pad; };
+    Card card; memset(&card, 0, sizeof card);
+    card.pid = (unsigned long long)getpid(); card.ptr = (unsigned long long)(uintptr_t)mine; card.dev = P.device;
     if (mine) {
         PS_CUDA(cudaMemsetAsync(mine, 0, peer.bytes(), st));
-        if (cudaIpcGetMemHandle(&hMine, mine) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; }
+        if (cudaIpcGetMemHandle(&card.ipc, mine) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; }
     }
     DBuf<uint8_t> dSend, dAll;
     DBuf<double> dOk;
-    dSend.alloc(sizeof hMine); dAll.alloc(sizeof hMine * (size_t)part.nranks); dOk.alloc(1);
-    copy_h2d(dSend.p, &hMine, sizeof hMine, st);
-    comm->allgather(dSend.p, dAll.p, sizeof hMine, st);
-    std::vector<uint8_t> all = dAll.to_host(st, sizeof hMine * (size_t)part.nranks);
+    dSend.alloc(sizeof card); dAll.alloc(sizeof card * (size_t)part.nranks); dOk.alloc(1);
+    copy_h2d(dSend.p, &card, sizeof card, st);
+    comm->allgather(dSend.p, dAll.p, sizeof card, st);
+    std::vector<uint8_t> all = dAll.to_host(st, sizeof card * (size_t)part.nranks);
     peer.block[part.rank] = mine;
     if (okLocal > 0.) {
         for (int r = 0; r < part.nranks && okLocal > 0.; ++r) {
             if (r == part.rank) continue;
-            cudaIpcMemHandle_t h; memcpy(&h, all.data() + sizeof h * (size_t)r, sizeof h);
+            Card c; memcpy(&c, all.data() + sizeof c * (size_t)r, sizeof c);
             void* ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; break; }
+            if (c.pid == card.pid) {
+                int can = 0;
+                if (c.ptr == 0 || cudaDeviceCanAccessPeer(&can, P.device, c.dev) != cudaSuccess || !can) { cudaGetLastError(); okLocal = 0.; break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(c.dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); okLocal = 0.; break; }
+                cudaGetLastError();
+                ptr = (void*)(uintptr_t)c.ptr;
+                peer.sameProcess[r] = true;
+            } else if (cudaIpcOpenMemHandle(&ptr, c.ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); okLocal = 0.; break; }
             peer.block[r] = ptr;
         }
     }
@@ -697,31 +710,19 @@ void Solver::constructMatrixBlocks() {
         RG.rowXYZ.alloc((size_t)nRows + 1);
         k_rows_finalize(st, g, nLocal, RG.rowRegion.p + rowOff, RG.rowFace.p + rowOff, rc.p, RG.rowXYZ.p + rowOff);
         std::vector<int> perRA = rc.to_host(st, (size_t)3 * R);
-        // chunk table: rows are sorted by (region, axis, voxel order); a chunk holds rows of one (region, axis).  Regions small
-        // enough for the fused epilogue of pass 1 (ps_pcg.cu) get chunks of <= 256 rows (one row per thread; the rows of a
-        // (region, axis) are split evenly, in multiples of a warp); giant regions (doTile off) keep 2048-row chunks.
-        static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
+        // chunk table: rows are sorted by (region, axis, voxel order); a chunk holds <= 2048 rows of one (region, axis)
         std::vector<int32_t> start((size_t)R + 1, 0), chunkStart((size_t)R + 1, 0), table, axisStart((size_t)3 * R + 1, 0);
         RG.maxRegionRows = 0;
         for (int r = 0; r < R; ++r) RG.maxRegionRows = std::max(RG.maxRegionRows, (int32_t)(perRA[3 * r] + perRA[3 * r + 1] + perRA[3 * r + 2]));
-        // the fused solve sums at most 32 chunks per region (P1_MAX_CHUNKS, ps_pcg.cu): 3 axes x (rows / 256 + 1) pieces
-        {
-            int maxPieces = 0;
-            for (int r = 0; r < R; ++r) { int pc = 0; for (int a = 0; a < 3; ++a) pc += (perRA[3 * r + a] + SCHED_BLOCK - 1) / SCHED_BLOCK; maxPieces = std::max(maxPieces, pc); }
-            RG.fusedRegions = RG.maxRegionRows <= fuseLimit && maxPieces <= 32;
-            // every rank must take the same path (the row numbering does not depend on it, but keep the ranks alike)
-            if (part.local) RG.fusedRegions = hostAllreduceSum(RG.fusedRegions ? 0. : 1.) < 0.5;
-        }
+        if (part.local) RG.maxRegionRows = (int32_t)std::llround(hostAllreduceSum((double)RG.maxRegionRows));      // every rank takes the same kernels (an upper bound is enough)
         int32_t pos = 0;
         for (int r = 0; r < R; ++r) {
             if (part.local && r == RG.regLo) pos = (int32_t)rowOff;      // the regions below belong to other ranks (no rows here)
             start[r] = pos; chunkStart[r] = (int32_t)(table.size() / 4);
             for (int a = 0; a < 3; ++a) {
                 axisStart[3 * r + a] = pos;
-                const int32_t cntRA = perRA[3 * r + a], e = pos + cntRA;
-                int32_t len = 2048;
-                if (RG.fusedRegions && cntRA > 0) { const int32_t pieces = (cntRA + SCHED_BLOCK - 1) / SCHED_BLOCK; len = ((cntRA + pieces - 1) / pieces + 31) / 32 * 32; }
-                for (int32_t b = pos; b < e; b += len) { table.push_back(r); table.push_back(b); table.push_back(std::min(b + len, e)); table.push_back(a); }
+                const int32_t e = pos + perRA[3 * r + a];
+                for (int32_t b = pos; b < e; b += 2048) { table.push_back(r); table.push_back(b); table.push_back(std::min(b + 2048, e)); table.push_back(a); }
                 pos = e;
             }
         }
@@ -730,9 +731,6 @@ void Solver::constructMatrixBlocks() {
         RG.rowChunkLo = chunkStart[RG.regLo]; RG.rowChunkHi = chunkStart[RG.regHi];
         RG.ownRowLo = start[RG.regLo]; RG.ownRowHi = start[RG.regHi];
         RG.regionTicket.alloc((size_t)R + 1); RG.regionTicket.zero(st, (size_t)R + 1);
-        RG.wpartial.alloc((size_t)RG.nRowChunks * 80 + 1);
-        RG.chunkTicket.alloc((size_t)RG.nRowChunks + 1); RG.chunkTicket.zero(st, (size_t)RG.nRowChunks + 1);
-        RG.solved.alloc((size_t)R + 1); RG.solved.zero(st, (size_t)R + 1); RG.solveSeq = 0;
         if (!part.local) for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
         axisStart[(size_t)3 * R] = pos;
         RG.rowAxisStart.from_host(st, axisStart.data(), axisStart.size());
@@ -763,7 +761,6 @@ void Solver::constructMatrixBlocks() {
     b.alloc(n); x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); w.alloc((size_t)C.nRowsExt + 1);
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
     dotPartial.alloc(8192);
-    sched1Ctl.alloc(2); sched1Ctl.zero(st, 2);
     computeOwnership();
     buildSchedules();
     buildHalos();
@@ -818,7 +815,7 @@ void Solver::buildSchedules() {
     const int k = part.rank;
     sr1 = SchedRanges(); sr2 = SchedRanges();
     for (int a = 0; a < 3; ++a) sr1.add(C.faceOff[a] + part.slotCut[SL_FACE + a][k], C.faceOff[a] + part.slotCut[SL_FACE + a][k + 1]);
-    sr1.addItems(RG.rowChunkLo, RG.rowChunkHi - RG.rowChunkLo);          // the coupled reduced rows of the owned regions: one item per row chunk
+    sr1.add(C.nActiveVs + part.redRowCut[k], C.nActiveVs + part.redRowCut[k + 1]);
     sr2.add(part.slotCut[SL_CENTER][k], part.slotCut[SL_CENTER][k + 1]);
     for (int e = 0; e < 3; ++e) { const int64_t off = C.stressOff[3 + e] - 3 * C.nCenter; sr2.add(off + part.slotCut[SL_EDGE + e][k], off + part.slotCut[SL_EDGE + e][k + 1]); }
     const std::vector<int32_t> a = merge_schedule(sr1), b = merge_schedule(sr2);
@@ -929,29 +926,15 @@ static OpArgs make_op(const Solver& S) {
     A.uInv = S.uInv.p; A.valScale = S.g.invDx / 64.;
     A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsE = S.ownE;
     A.s1 = S.sr1; A.s2 = S.sr2; A.sched1 = S.sched1.p; A.sched2 = S.sched2.p; A.nSched1 = S.nSched1; A.nSched2 = S.nSched2;
-    A.sched1Ctl = S.sched1Ctl.p; A.rowChunk = S.RG.rowChunk.p;
     return A;
 }
-RegionOp Solver::regionOp(int mode, const double* extra, double extraScale, double tScale, double outScale) const {
-    RegionOp R;
-    R.mode = (RG.count > 0 && RG.rowChunkHi > RG.rowChunkLo) ? mode : 0;
-    R.dx = g.dx;
-    R.rowXYZ = RG.rowXYZ.p; R.rowChunkStart = RG.rowChunkStart.p; R.rowStart = RG.rowStart.p;
-    R.com = RG.com.p; R.Binv = RG.Binv.p; R.partial = RG.partial.p; R.regionTicket = RG.regionTicket.p;
-    R.extra = extra; R.extraScale = extraScale; R.tScale = tScale; R.outScale = outScale;
-    R.sigma = RG.sigma.p;
-    R.wpartial = RG.wpartial.p; R.chunkTicket = RG.chunkTicket.p; R.solved = RG.solved.p;
-    if (R.mode == 1) R.seq = ++RG.solveSeq;
-    return R;
-}
+OpArgs Solver::make_op_args() const { return make_op(*this); }
+
 // pass 1 of an operator apply including the reduced term: w = [dt Mc^-1 K x ; c_f . B^-1 J x]
 void Solver::pass1Apply(const OpArgs& A, const double* xin, const PcgScalars* S, bool reverse) {
-    if (RG.count > 0 && RG.fusedRegions) { k_pass1(st, A, regionOp(1), xin, w.p, g.dt, S, reverse); return; }
-    k_pass1(st, A, regionOp(0), xin, w.p, g.dt, S, reverse);
-    if (RG.count > 0) { reduced_moments(st, g, RG, w.p + C.nActiveVs, S, true); reduced_expand(st, g, RG, w.p + C.nActiveVs, 1.0, S); }
+    k_pass1(st, A, xin, w.p, g.dt, S, reverse);
+    if (RG.count > 0) reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, S);          // moments -> B^-1 -> expand, one CTA per region
 }
-
-OpArgs Solver::make_op_args() const { return make_op(*this); }
 
 // assembleSystemPressureStressFactored (S_AS:432-470):
 //   b = -[G^T; D] Mc^-1 rhs_u - (1/dt) [JG^T; DJ^T] B^-1 rhs_r + [rhs_p; rhs_tau]  =  -K_ext^T w + rhs_pt
@@ -986,7 +969,8 @@ void Solver::timedOperator(int which) {
     const OpArgs A = make_op(*this);
     if (which == 0) { applyOperator(b.p, Ap.p, nullptr); return; }
     if (which == 1) pass1Apply(A, b.p, nullptr);                       // includes the reduced term (fused region epilogue)
-    else if (which == 3) k_pass1(st, A, regionOp(0), b.p, w.p, g.dt, nullptr);   // the same sweep without the reduced term (raw products on the coupled rows)
+    else if (which == 3) k_pass1(st, A, b.p, w.p, g.dt, nullptr);            // the sweep alone (raw products on the coupled reduced rows)
+    else if (which == 6 && RG.count > 0) reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, nullptr);
     else if (which == 5) k_cg_update(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, PeerCtx());   // rank-local (timing only)
     else k_pass2(st, A, w.p, b.p, Ap.p, 0.5, nullptr, dotPartial.p, PeerCtx(), scal.p, which == 4 ? 3 : 0, r.p);      // 4: with the three fused dot products of the CG loop
 }
@@ -1209,7 +1193,7 @@ int Solver::solveBiCGStab() {
 void Solver::recoverVelocityFromPressureStress() {
     const OpArgs A = make_op(*this);
     exchange(haloX, x.p, nullptr);
-    k_pass1(st, A, regionOp(0), x.p, w.p, g.dt, nullptr);            // active rows: dt Mc^-1 (G p + D^T tau); coupled reduced rows: raw (K_red x)_f
+    k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau); coupled reduced rows: raw (K_red x)_f
     RowSet act;                                                      // the owned active face rows
     for (int a = 0; a < 3; ++a) act.add(C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank], C.faceOff[a] + part.slotCut[SL_FACE + a][part.rank + 1]);
     k_recover_active(st, g, act, w.p, mcInv.p, rhsU.p, velSol.p);
@@ -1222,10 +1206,10 @@ void Solver::recoverVelocityFromPressureStress() {
 }
 
 // buildValidFaces (S_Cls:4-54) + applySolutionToVelocity (S.cpp:937-1028)
-// the voxels of a slot this rank delivers to the caller: its slab with slab-local setup (the caller's arrays are full-grid, every rank
-// fills its part), everything otherwise
+// the voxels of a slot this rank delivers to the caller: its slab (the caller's arrays are full-grid; every rank fills its part, so ranks
+// of one process can share them), everything on one GPU
 void Solver::outRange(int slot, int64_t& lo, int64_t& hi) const {
-    if (part.local) z_range(g, slot, g.zLo, g.zHi, lo, hi); else { lo = 0; hi = g.n[slot]; }
+    if (part.multi()) z_range(g, slot, g.zLo, g.zHi, lo, hi); else { lo = 0; hi = g.n[slot]; }
 }
 
 void Solver::applySolutionToVelocity(const ps_fields_out& out) {
@@ -1239,7 +1223,7 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
         int64_t oLo, oHi, kLo, kHi;
         outRange(SL_FACE + a, oLo, oHi);
         // the kernel also visits the plane above the slab: z-faces there can belong to a region of this rank (merged below)
-        if (part.local) z_range(g, SL_FACE + a, g.zLo, std::min(g.nz, g.zHi + (a == 2 ? 1 : 0)), kLo, kHi); else { kLo = 0; kHi = (int64_t)nf; }
+        if (part.multi()) z_range(g, SL_FACE + a, g.zLo, std::min(g.nz, g.zHi + (a == 2 ? 1 : 0)), kLo, kHi); else { kLo = 0; kHi = (int64_t)nf; }
         float* velDev = nullptr; float* validDev = nullptr;
         // velocity staging starts as the input velocity: invalid faces are left untouched (S.cpp:975-978)
         if (out.velocity[a] && writeVel) {

@@ -80,13 +80,9 @@ struct RegionData {
     DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
     DBuf<int32_t> rowAxisStart;  // [3R+1] first coupled reduced row of (region, face axis): the row ranges of reduced_region_kernel
     int32_t maxRegionRows = 0;   // largest number of coupled reduced rows of one region (decides fused vs chunked reduced kernels)
-    bool fusedRegions = false;   // regions small enough for the fused epilogue of pass 1 (row chunks of <= 256 rows)
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
     DBuf<unsigned int> regionTicket;   // [R] chunks of the region that have delivered their moments (self-resetting)
-    DBuf<double> wpartial;             // [nRowChunks][8][10] per-warp moments of the fused region term (ps_pcg.cu, pass 1)
-    DBuf<unsigned int> chunkTicket, solved;   // [nRowChunks] / [R], see RegionOp
-    mutable unsigned int solveSeq = 0; // launches of the fused region term so far
     int32_t ownRowLo = 0, ownRowHi = 0;   // coupled reduced rows of the owned regions
     // owned pieces of this rank (everything on one GPU): regions [regLo, regHi) and their chunk ranges
     int32_t regLo = 0, regHi = 0, cellChunkLo = 0, cellChunkHi = 0, rowChunkLo = 0, rowChunkHi = 0;
@@ -135,23 +131,6 @@ struct ExplicitA {
     DBuf<double> val;
 };
 struct OpArgs;
-// What pass 1 does with the coupled reduced rows of the owned regions.  mode 0: store the raw products (K_red x)_f in w.
-// mode 1 (regions of <= a few thousand rows, RegionData::fusedRegions): the reduced term of the operator in the same launch --
-// every row chunk leaves its 10 monomial moments, the last chunk of a region to finish sums them in chunk order,
-// s = B^-1 (tScale t + extraScale extra), sigma, and overwrites the region's rows with w_f = outScale * c_f . s.
-struct RegionOp {
-    int mode = 0;
-    double dx = 0;
-    const uint32_t* rowXYZ = nullptr; const int32_t* rowChunkStart = nullptr; const int32_t* rowStart = nullptr;
-    const double* com = nullptr; const double* Binv = nullptr; double* partial = nullptr; unsigned int* regionTicket = nullptr;
-    const double* extra = nullptr; double extraScale = 0, tScale = 1, outScale = 1;
-    double* sigma = nullptr;
-    double* wpartial = nullptr;        // [nChunks][8][10] moments of the 8 warps of a chunk
-    unsigned int* chunkTicket = nullptr;   // [nChunks] warps of the chunk that have delivered (self-resetting)
-    unsigned int* solved = nullptr;    // [R] sequence number of the last launch that solved the region
-    unsigned int seq = 0;              // this launch's sequence number
-};
-
 class Solver {
 public:
     explicit Solver(const ps_params& p);
@@ -258,8 +237,6 @@ public:
     CompactOp Op;                 // K_ext and K_ext^T
     SchedRanges sr1, sr2;         // block schedules of pass 1 / pass 2 over the owned rows (merge_schedule)
     DBuf<int32_t> sched1, sched2;
-    DBuf<unsigned int> sched1Ctl; // dynamic-schedule counters of pass 1 (OpArgs::sched1Ctl)
-    RegionOp regionOp(int mode, const double* extra = nullptr, double extraScale = 0., double tScale = 1., double outScale = 1.) const;
     int nSched1 = 0, nSched2 = 0;
     void buildSchedules();
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
@@ -329,17 +306,15 @@ void k_assemble_Kt(cudaStream_t, const Geom&, const Fields&, const Counts&, Comp
 // ps_pcg.cu
 struct OpArgs {   // everything one operator apply touches
     int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
-    SchedRanges s1, s2;           // pass 1: face rows x, y, z, row chunks of the coupled reduced rows; pass 2: cells, edges yz, xz, xy (edge numbering)
+    SchedRanges s1, s2;           // pass 1: face rows x, y, z, coupled reduced rows; pass 2: cells, edges yz, xz, xy (edge numbering)
     const int32_t* sched1; const int32_t* sched2; int nSched1, nSched2;
-    unsigned int* sched1Ctl;      // [0] next item of pass 1's dynamic schedule, [1] CTAs that have run out of items (the last one resets both)
-    const int32_t* rowChunk;      // [nChunks][4] = region, begin, end, axis of the row chunks (RegionData)
     RowSet rowsK, rowsP, rowsE;   // rows this rank computes (all rows on one GPU); the centre-stress rows follow rowsP
     const uint64_t* kcode; const int32_t* kcol; const uint8_t* kmc; const double* mcInvLut;
     const uint64_t* ccode; const int32_t* ccol; const uint32_t* ecode; const int32_t* ecol;
     const double* uInv;
     double valScale;              // invDx / 64
 };
-void k_pass1(cudaStream_t, const OpArgs&, const RegionOp&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false);
+void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false);
 // mode bit 0: dot(x, y) (p.Ap) -> red[0]; bit 1: also dot(r2, y), dot(y, y) (r.Ap, Ap.Ap) -> red[1], red[2]
 void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode,
              const double* r2 = nullptr, bool reverse = false);
@@ -347,6 +322,8 @@ void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, doub
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal, bool solve = false);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
+// the reduced term of one apply: w_f <- scale * c_f . B^-1 (sum_f c_f w_f); one fused launch for tiled regions, moments + expand otherwise
+void reduced_apply(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
 void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse = false);
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
 void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);

@@ -58,7 +58,9 @@ def _is_device(a):
 
 
 class PolyStokesSolver:
-    def __init__(self, nx, ny, nz, dx, dt, density, lib_path=None, **params):
+    def __init__(self, nx, ny, nz, dx, dt, density, lib_path=None, devices=None, **params):
+        """``devices``: a list of CUDA device ordinals -> ONE handle that slab-decomposes the step over those GPUs inside this
+        process (ps_create_multi: one host thread per GPU); the step then takes HOST arrays."""
         self.lib = _capi.load(lib_path)
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         p = dict(DEFAULTS)
@@ -78,16 +80,21 @@ class PolyStokesSolver:
         self.params = p
         self._P = P
         self.h = C.c_void_p()
-        rc = self.lib.ps_create(C.byref(P), C.byref(self.h))
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is not None:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            rc = self.lib.ps_create_multi(C.byref(P), len(self.devices), arr, C.byref(self.h))
+        else:
+            rc = self.lib.ps_create(C.byref(P), C.byref(self.h))
         if rc != PS_SUCCESS:
             raise PolyStokesError(f"ps_create failed ({rc}): {self.last_error()}")
         self.stats = None
 
     @classmethod
-    def from_scene(cls, scene, lib_path=None, **overrides):
+    def from_scene(cls, scene, lib_path=None, devices=None, **overrides):
         p = dict(scene.params)
         p.update(overrides)
-        return cls(scene.nx, scene.ny, scene.nz, scene.dx, scene.dt, scene.density, lib_path=lib_path, **p)
+        return cls(scene.nx, scene.ny, scene.nz, scene.dx, scene.dt, scene.density, lib_path=lib_path, devices=devices, **p)
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

@@ -38,6 +38,7 @@ DIST_CASES = {
     "box48_uniform": lambda: (scenes.box_scene(48, doReduced=0, tolerance=1e-6), {}),
     "blob_36x40x64_tile16": lambda: (scenes.blob_scene((36, 40, 64), seed=8, tile=16, pad=2), {}),
     "blob64_tile16": lambda: (scenes.blob_scene(64, seed=13, tile=16, pad=2), {}),
+    "s3_128": lambda: (scenes.scene_s3(128), {}),
     "blob48_tile16_pad3_layers33": lambda: (scenes.blob_scene(48, seed=5, tile=16, pad=3, liquidLayers=3, solidLayers=3), {}),
     # CG runs out of iterations -> BiCGSTAB fallback, itself stopped after 6 iterations (results kept): checks the arithmetic
     "blob48_bicgstab6": lambda: (scenes.blob_scene(48, seed=21, tile=8, pad=1, maxIterations=6, tolerance=1e-12, keepNonConvergedResults=1), {}),
@@ -282,14 +283,7 @@ def check_distributed(case, ranks):
         for r in ranks:
             lo, hi = int(r["zlo"]), int(r["zhi"])
             assert np.array_equal(own(r[f"valid{a}"], r), own(ovalid[a], r)), f"valid axis {a} rank {int(r['rank'])}"
-            if int(r["local"]):                       # slab-local: a rank delivers its slab (the last one the top plane too)
-                own(merged, r)[...] = own(r[f"vel{a}"], r)
-                continue
-            top = hi + 1 if (a == 2) else hi          # z-faces: the closure of the slab
-            merged[lo:top] = r[f"vel{a}"][lo:top]
-            if a == 2 and lo > 0:                     # the shared plane must agree with the lower rank's copy
-                below = [q for q in ranks if int(q["zhi"]) == lo][0]
-                assert np.array_equal(below["vel2"][lo], r["vel2"][lo]), f"shared z-face plane {lo} differs between ranks"
+            own(merged, r)[...] = own(r[f"vel{a}"], r)       # a rank delivers its slab (the last one the top plane too)
         scale = max(float(np.abs(ovel[a]).max()), 1e-30)
         assert float(np.abs(ovel[a] - merged).max()) <= tol * scale, f"velocity axis {a}: {float(np.abs(ovel[a] - merged).max()) / scale:.2e}"
     assert all(bool(r["repeat_ok"]) for r in ranks), "second step on the same handle differs"
