@@ -110,6 +110,39 @@ def mem_available_gb():
     return 0.0
 
 
+def _ref_verify(R, sc, res):
+    """Item by item against the committed digest of this configuration (tests/golden/fullsize_S3.json, made from the oracle): the compiled
+    reference at FULL size must give the same counts, label / index / weight fields (SHA-256), G and D^T (pattern + values), |b|, iteration count
+    (within 1 %: the setup sums are accumulated per job), valid masks and -- within 10 x tol -- the velocity sample."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_fullsize as mf
+    path = os.path.join(ROOT, "tests", "golden", "fullsize_S3.json")
+    if sc.nx != SCENE_N or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        g = json.load(f)
+    bad = [k for k in mf.COUNTS if R.count(k) != g["counts"][k]]
+    fields = mf.field_digests(R.index_field, R.weight_field)
+    bad += [k for k in fields if fields[k] != g["fields"][k]]
+    csr = mf.csr_digests(R.csr)
+    bad += [f"csr {m} {qq}" for m in csr for qq in ("shape", "nnz", "pattern", "values") if csr[m][qq] != g["csr"][m][qq]]
+    b = R.vector("b")
+    bn = float(np.sqrt(np.dot(b, b)))
+    if abs(bn - g["b_norm"]) > 1e-10 * g["b_norm"]:
+        bad.append(f"b_norm {bn} vs {g['b_norm']}")
+    if abs(res["iterations"] - g["iterations"]) > max(2, g["iterations"] // 100):
+        bad.append(f"iterations {res['iterations']} vs {g['iterations']}")
+    vel = [R.face_field(0, a) for a in range(3)]; valid = [R.face_field(1, a) for a in range(3)]
+    got = mf.velocity_sample(vel, valid)
+    worst = max(float(np.abs(np.array(g[f"vel{a}_sample"]) - np.array(got[f"vel{a}_sample"])).max()) / g[f"vel{a}_absmax"] for a in range(3))
+    if worst > 10 * sc.params["tolerance"]:
+        bad.append(f"velocity sample rel diff {worst:.2e}")
+    bad += [f"valid{a}" for a in range(3) if got[f"valid{a}"] != g[f"valid{a}"]]
+    return {"equal": not bad, "mismatches": bad, "velocity_sample_max_rel_diff": worst,
+            "checked": "14 counts, 35 field hashes, G / D^T patterns + values, |b|, iterations, valid masks, velocity sample (10 x tol)"}
+
+
 def _ref_worker(n, threads, q):
     """One COMPLETE step of the REFERENCE'S OWN solver on S3 at n^3 (child process, so its memory goes back to the OS).
 
@@ -137,6 +170,11 @@ def _ref_worker(n, threads, q):
     out = dict(n=n, seconds=t_setup + t_solve, setup_s=t_setup, solve_s=t_solve, cg_s=R.real("solveWallclockMs") * 1e-3, iterations=int(R.count("iterations")),
                nSystemSize=int(R.count("nSystemSize")), result=int(rc), jobs=int(jobs), cores=int(threads),
                maxrss_gb=resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6)
+    if os.environ.get("PS_REF_VERIFY", "1") != "0":
+        try:
+            out["digest_check"] = _ref_verify(R, sc, out)
+        except Exception as e:          # the measurement stands even if the check cannot run
+            out["digest_check"] = {"equal": None, "error": repr(e)}
     R.close()
     q.put(out)
 
@@ -326,6 +364,7 @@ def main():
                   f"peak RSS {res['maxrss_gb']:.1f} GB; measured, not scaled; {res['note']}" + ("; reused from this box's N = 1 run" if cached else ""))
         emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": 1, "warmup": 0, "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True,
               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference", "cached": cached,
+              "reference_digest_check": res.get("digest_check"),
               "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": sample},
               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return

@@ -16,6 +16,7 @@
 #ifndef POLYSTOKES_B200_H
 #define POLYSTOKES_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -105,6 +106,13 @@ typedef struct ps_solver* ps_handle;
 /* Solver constructor (S.cpp:18-155).  Returns PS_SUCCESS or PS_FAILED/PS_INVALID. */
 int ps_create(const ps_params* params, ps_handle* out);
 void ps_destroy(ps_handle h);
+/* New per-step parameters for an existing handle: everything but the grid (nx, ny, nz, dx) and the device may change -- a DOP
+ * network calls the solver with a different dt every substep (PS.C:319), which must not rebuild streams and buffers. */
+int ps_set_params(ps_handle h, const ps_params* params);
+/* Page-locked host memory (cudaMallocHost) for callers that do not link CUDA themselves: host fields staged in it cross PCIe
+ * asynchronously, under the solver's kernels.  NULL on failure. */
+void* ps_alloc_pinned(size_t bytes);
+void ps_free_pinned(void* p);
 /* One solveGasSubclass body (PS.C:344-608): weights, classify, assemble, PCG, write-back.
  * Returns the SolverResult; `out` may be NULL (no write-back), `stats` may be NULL. */
 int ps_step(ps_handle h, const ps_fields_in* in, ps_fields_out* out, ps_stats* stats);

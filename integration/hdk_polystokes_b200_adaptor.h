@@ -14,6 +14,10 @@
 struct polystokes_b200_node_state {      // lives in the node instance (one handle per node; the grid rarely changes between substeps)
     ps_handle handle = nullptr;
     ps_params params = {};
+    int numDevices = 1;                  // > 1: one ps_create_multi handle over devices 0 .. numDevices-1 (the cook thread stays single)
+    // page-locked staging of the 9 input and 6 output fields (ps_alloc_pinned), reused while the grid keeps its size
+    float* stage[15] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stageCount[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // Returns the SolverResult of the step (S.h:61-70 == PS_* of polystokes_b200.h); on PS_FAILED / PS_INVALID *error holds ps_last_error().

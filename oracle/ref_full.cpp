@@ -126,6 +126,20 @@ int reffull_solve(void* hv) {
     return H->result;
 }
 
+// exec/HDK_PolyStokes.C:508-584 with "Do Solve" off: no solve (solverResult stays INCOMPLETE, the solution vector is the zero vector of
+// assemble, S_AS:466), valid faces, and -- only with keepNonConvergedResults -- velocity recovery + write-back of that zero solution
+int reffull_skip_solve(void* hv) {
+    RefFull* H = (RefFull*)hv; Solver& S = *H->S; HDK_PolyStokes& node = H->node;
+    S.constructPreconditioner();
+    H->result = (int)Solver::SolverResult::INCOMPLETE;
+    S.buildValidFaces(H->validFaces);
+    if (node.getKeepNonConvergedResults()) {
+        if (node.getMatrixScheme() == HDK_PolyStokes_Options::MatrixScheme::PRESSURE_STRESS) S.recoverVelocityFromPressureStress();
+        for (int axis : {0, 1, 2}) S.applySolutionToVelocity(*H->velocity.getField(axis), *H->validFaces.getField(axis), axis);
+    }
+    return H->result;
+}
+
 // ---- read-out ----
 static SIM_RawIndexField* index_field(Solver& S, int kind, int slot) {
     SIM_RawIndexField* fields[3][7] = {

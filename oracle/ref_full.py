@@ -38,6 +38,7 @@ def lib():
         L.reffull_destroy.argtypes = [C.c_void_p]
         L.reffull_setup.restype = C.c_int; L.reffull_setup.argtypes = [C.c_void_p]
         L.reffull_solve.restype = C.c_int; L.reffull_solve.argtypes = [C.c_void_p]
+        L.reffull_skip_solve.restype = C.c_int; L.reffull_skip_solve.argtypes = [C.c_void_p]
         L.reffull_index_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.reffull_weight_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.reffull_face_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -82,6 +83,10 @@ class RefFull:
         """solve + valid faces + velocity recovery and write-back; returns the SolverResult."""
         return int(lib().reffull_solve(self.h))
 
+    def skip_solve(self):
+        """the node with "Do Solve" off: valid faces + (keepNonConvergedResults) write-back of the zero solution; returns INCOMPLETE (-3)."""
+        return int(lib().reffull_skip_solve(self.h))
+
     def writeback(self):
         vel = [np.empty(slot_shape(1 + a, self.nx, self.ny, self.nz), dtype=np.float32) for a in range(3)]
         valid = [np.empty(slot_shape(1 + a, self.nx, self.ny, self.nz), dtype=np.float32) for a in range(3)]
@@ -122,6 +127,12 @@ class RefFull:
             raise KeyError(name)
         out = np.empty(n, dtype=np.float64)
         lib().reffull_vector(self.h, name.encode(), out.ctypes.data)
+        return out
+
+    def face_field(self, which, axis):
+        """which 0: velocity (after solve(): the written-back field), 1: valid faces"""
+        out = np.empty(slot_shape(1 + axis, self.nx, self.ny, self.nz), dtype=np.float32)
+        lib().reffull_face_field(self.h, int(which), int(axis), out.ctypes.data)
         return out
 
     def export(self, prefix, what=7):

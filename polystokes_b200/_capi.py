@@ -56,7 +56,7 @@ class ps_stats(C.Structure):
 # every symbol include/polystokes_b200.h declares
 SYMBOLS = ["ps_create", "ps_destroy", "ps_step", "ps_setup", "ps_solve", "ps_export", "ps_last_error", "ps_get_count", "ps_get_real",
            "ps_get_index_field", "ps_get_weight_field", "ps_get_csr", "ps_get_vector", "ps_apply", "ps_time_kernel", "ps_kernel_bytes", "ps_timer",
-           "ps_comm_unique_id", "ps_comm_init", "ps_get_partition", "ps_create_multi"]
+           "ps_comm_unique_id", "ps_comm_init", "ps_get_partition", "ps_create_multi", "ps_set_params", "ps_alloc_pinned", "ps_free_pinned"]
 
 _cache = {}
 
@@ -74,6 +74,9 @@ def load(path=None):
     L.ps_create.argtypes = [C.POINTER(ps_params), C.POINTER(H)]; L.ps_create.restype = C.c_int
     L.ps_create_multi.argtypes = [C.POINTER(ps_params), C.c_int, C.POINTER(C.c_int), C.POINTER(H)]; L.ps_create_multi.restype = C.c_int
     L.ps_destroy.argtypes = [H]; L.ps_destroy.restype = None
+    L.ps_set_params.argtypes = [H, C.POINTER(ps_params)]; L.ps_set_params.restype = C.c_int
+    L.ps_alloc_pinned.argtypes = [C.c_size_t]; L.ps_alloc_pinned.restype = C.c_void_p
+    L.ps_free_pinned.argtypes = [C.c_void_p]; L.ps_free_pinned.restype = None
     L.ps_step.argtypes = [H, C.POINTER(ps_fields_in), C.POINTER(ps_fields_out), C.POINTER(ps_stats)]; L.ps_step.restype = C.c_int
     L.ps_setup.argtypes = [H, C.POINTER(ps_fields_in)]; L.ps_setup.restype = C.c_int
     L.ps_solve.argtypes = [H, C.POINTER(ps_fields_out), C.POINTER(ps_stats)]; L.ps_solve.restype = C.c_int

@@ -374,6 +374,29 @@ int ps_get_partition(ps_handle h, int32_t* rank, int32_t* zLo, int32_t* zHi, int
     return p.nranks;
 }
 
+int ps_set_params(ps_handle h, const ps_params* params) {
+    if (!h || !params) { g_lastError = "ps_set_params: null argument"; return PS_INVALID; }
+    if (h->multi) { MultiGroup* G = h->multi; return G->run([&](int k) { return ps_set_params(G->kids[(size_t)k], params); }); }
+    return guarded(h, [&] { h->S->setParams(*params); return (int)PS_SUCCESS; });
+}
+// pinned host memory for callers without CUDA headers (the node adaptor's staging arrays): copies from / to it overlap with kernels
+void* ps_alloc_pinned(size_t bytes) {
+#ifndef PS_EMULATE
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); g_lastError = "ps_alloc_pinned: cudaMallocHost failed"; return nullptr; }
+    return p;
+#else
+    return malloc(bytes ? bytes : 16);
+#endif
+}
+void ps_free_pinned(void* p) {
+#ifndef PS_EMULATE
+    if (p) cudaFreeHost(p);
+#else
+    free(p);
+#endif
+}
+
 // stats of a collective call: rank 0's, with the slowest rank's stage times and the launches of all ranks
 static void merge_stats(ps_stats* dst, const std::vector<ps_stats>& all) {
     if (!dst || all.empty()) return;

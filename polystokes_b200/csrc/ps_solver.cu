@@ -83,30 +83,47 @@ static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; 
 void Solver::initComm(Comm* c) {
     std::unique_ptr<Comm> guard(c);
     if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks) throw Error("ps_comm_init: bad rank / nranks");
+    computePartition(c->rank, c->nranks);
+    delete comm;
+    comm = guard.release();
+    haveSetup = false;
+}
+// the slab decomposition as a function of the grid and the tiling / layer parameters (ps_comm_init, ps_set_params)
+void Solver::computePartition(int rank, int nranks) {
     int unit = 16;
     if (P.doReducedRegions) {
-        if (c->nranks > 1 && (!P.doTile || P.tilePadding < 1 || P.tileSize < 1))
+        if (nranks > 1 && (!P.doTile || P.tilePadding < 1 || P.tileSize < 1))
             throw Error("ps_comm_init: reduced regions need doTile with tilePadding >= 1 on more than one GPU (untiled regions may span slabs)");
         if (P.doTile && P.tileSize >= 1) unit = 16 / gcd_i(16, P.tileSize) * P.tileSize;
     }
     const int nUnits = (g.nz + unit - 1) / unit;
-    if (c->nranks > nUnits) throw Error("ps_comm_init: more ranks than z-slabs of lcm(16, tileSize) cells");
-    part.rank = c->rank; part.nranks = c->nranks;
-    part.zCut.assign((size_t)c->nranks + 1, 0);
-    for (int k = 0; k <= c->nranks; ++k) part.zCut[k] = std::min(g.nz, (int)(((int64_t)k * nUnits + c->nranks / 2) / c->nranks) * unit);
-    part.zCut[0] = 0; part.zCut[c->nranks] = g.nz;
-    for (int k = 0; k < c->nranks; ++k) if (part.zCut[k + 1] <= part.zCut[k]) throw Error("ps_comm_init: empty z-slab");
-    g.zLo = part.zCut[c->rank]; g.zHi = part.zCut[c->rank + 1];
+    if (nranks > nUnits) throw Error("ps_comm_init: more ranks than z-slabs of lcm(16, tileSize) cells");
+    part.rank = rank; part.nranks = nranks;
+    part.zCut.assign((size_t)nranks + 1, 0);
+    for (int k = 0; k <= nranks; ++k) part.zCut[k] = std::min(g.nz, (int)(((int64_t)k * nUnits + nranks / 2) / nranks) * unit);
+    part.zCut[0] = 0; part.zCut[nranks] = g.nz;
+    for (int k = 0; k < nranks; ++k) if (part.zCut[k + 1] <= part.zCut[k]) throw Error("ps_comm_init: empty z-slab");
+    g.zLo = part.zCut[rank]; g.zHi = part.zCut[rank + 1];
     // slab-local setup where regions cannot interact across a cut (ps_part.hpp); PS_SETUP_REPLICATED=1 forces the round-1 behaviour
     const bool forceRep = getenv("PS_SETUP_REPLICATED") && atoi(getenv("PS_SETUP_REPLICATED"));
-    part.local = c->nranks > 1 && !forceRep && (!P.doReducedRegions || (P.doTile && P.tilePadding >= 2));
+    part.local = nranks > 1 && !forceRep && (!P.doReducedRegions || (P.doTile && P.tilePadding >= 2));
     part.halo = std::min(16, std::max(4, P.activeLiquidBoundaryLayerSize + P.activeSolidBoundaryLayerSize + 3));
     if (part.local && P.activeLiquidBoundaryLayerSize + P.activeSolidBoundaryLayerSize + 3 > 16) part.local = false;      // the floods reach further than one tile layer
     g.wzLo = part.local ? std::max(0, g.zLo - part.halo) : 0;
     g.wzHi = part.local ? std::min(g.nz, g.zHi + part.halo) : g.nz;
     g.slabLocal = part.local ? 1 : 0;
-    delete comm;
-    comm = guard.release();
+}
+// ps_set_params: everything but the grid and the device may change between steps (dt and density change every substep in a DOP
+// network); the buffers, streams and the communicator stay
+void Solver::setParams(const ps_params& p) {
+    if (p.nx != P.nx || p.ny != P.ny || p.nz != P.nz || p.dx != P.dx) throw Error("ps_set_params: the grid (nx, ny, nz, dx) is fixed at ps_create");
+    if (!(p.dt > 0)) throw Error("ps_set_params: invalid dt");
+    const int dev = P.device;
+    P = p; P.device = dev;
+    const Geom old = g;
+    g = make_geom(P.nx, P.ny, P.nz, P.dx, P.dt, P.constantDensity);
+    g.zLo = old.zLo; g.zHi = old.zHi; g.wzLo = old.wzLo; g.wzHi = old.wzHi; g.slabLocal = old.slabLocal;
+    if (comm) computePartition(part.rank, part.nranks);
     haveSetup = false;
 }
 

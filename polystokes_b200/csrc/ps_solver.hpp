@@ -189,6 +189,8 @@ public:
     Partition part;
     Comm* comm = nullptr;
     void initComm(Comm* c);             // takes ownership; computes the z cuts
+    void computePartition(int rank, int nranks);
+    void setParams(const ps_params& p);
     void computeOwnership();            // owned row / DOF ranges of every rank from the (replicated or all-gathered) numbering
     // slab-local setup (Partition::local)
     struct LayerField { void* base; int slot; int elem; };

@@ -25,9 +25,9 @@ class _P(C.Structure):
                 ("tileSize", C.c_int32), ("tilePadding", C.c_int32), ("solverType", C.c_int32), ("useWarmStart", C.c_int32), ("keepNonConvergedResults", C.c_int32)]
 
 
-def cook(sc, backend, steps=1):
+def cook(sc, backend, steps=1, devices=1, do_solve=1):
     L = C.CDLL(ADAPTOR)
-    L.refadp_run.restype = C.c_int
+    L.refadp_run2.restype = C.c_int
     assert L.refadp_bind(backend.encode()) == 0, f"could not bind the C ABI of {backend}"      # dlopen(RTLD_LOCAL): no symbol leaks between libraries
     p = sc.params
     P = _P(sc.nx, sc.ny, sc.nz, float(sc.dx), float(sc.dt), float(sc.density), float(p["tolerance"]), int(p["maxIterations"]), int(p["liquidLayers"]), int(p["solidLayers"]),
@@ -38,13 +38,13 @@ def cook(sc, backend, steps=1):
     vel = [np.zeros_like(v) for v in keep[3:6]]; valid = [np.zeros_like(v) for v in keep[3:6]]
     arr = lambda xs: (C.c_void_p * 3)(*[x.ctypes.data for x in xs])
     err = C.create_string_buffer(512)
-    rc = L.refadp_run(C.byref(P), C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data), C.c_void_p(keep[2].ctypes.data), arr(keep[3:6]), arr(keep[6:9]),
-                      C.c_int(steps), arr(vel), arr(valid), err, C.c_int(512))
+    rc = L.refadp_run2(C.byref(P), C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data), C.c_void_p(keep[2].ctypes.data), arr(keep[3:6]), arr(keep[6:9]),
+                       C.c_int(steps), arr(vel), arr(valid), err, C.c_int(512), C.c_int(devices), C.c_int(do_solve))
     return rc, vel, valid, err.value.decode()
 
 
-def _check(sc, backend, steps=1):
-    rc, vel, valid, err = cook(sc, backend, steps)
+def _check(sc, backend, steps=1, devices=1):
+    rc, vel, valid, err = cook(sc, backend, steps, devices)
     R = ref_full.RefFull(sc).setup()
     rr = R.solve()
     rvel, rvalid = R.writeback()
@@ -70,6 +70,30 @@ def test_adaptor_reports_nonconvergence_like_the_node(built):
     assert rc == 0 and "did not converge" in err                     # PS.C:597-600
     for a in range(3):
         assert np.array_equal(vel[a], np.asarray(sc.vel[a], dtype=np.float32)), "a non-converged step must leave the velocity untouched (PS.C:566)"
+
+
+@pytest.mark.parametrize("keep", [1, 0])
+def test_adaptor_without_do_solve_matches_the_node(built, keep):
+    """"Do Solve" off (PS.C:513, 565-605): no solve, no error message; with keepNonConvergedResults the zero solution is recovered and written
+    back (u = Mc^-1 rhs_u on active faces, the least-squares polynomial on reduced ones), without it the velocity stays as it came."""
+    sc = scenes.blob_scene(32, seed=3, keepNonConvergedResults=keep)
+    rc, vel, valid, err = cook(sc, parity.EMUL_LIB, do_solve=0)
+    R = ref_full.RefFull(sc).setup()
+    rr = R.skip_solve()
+    rvel, rvalid = R.writeback()
+    assert rc == rr == -3 and err == ""
+    for a in range(3):
+        assert np.array_equal(valid[a], rvalid[a]), f"valid field axis {a}"
+        assert float(np.abs(vel[a] - rvel[a]).max()) <= 4e-7 * max(float(np.abs(rvel[a]).max()), 1e-30), f"velocity axis {a}"
+
+
+@pytest.mark.gpu
+def test_adaptor_multi_gpu_handle(built):
+    """the node state asks for two devices: one ps_create_multi handle behind the same single cook thread"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _check(scenes.scene_s3(64), PRODUCT, steps=2, devices=2)
 
 
 @pytest.mark.gpu
