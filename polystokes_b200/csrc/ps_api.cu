@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <functional>
 #include <memory>
+#include <chrono>
 
 using namespace ps;
 
@@ -26,6 +27,8 @@ struct MultiGroup {
     struct Worker {
         std::thread th; std::mutex m; std::condition_variable cv;
         std::function<int()> task; bool has = false, quit = false, done = true; int rc = 0; std::string err;
+        std::vector<void*> graveyard;            // device buffers the rank let go of during a collective call (ps_rt.hpp, g_deferredFree)
+        const char* volatile where = "idle";     // breadcrumb of the rank thread (PS_WHERE), read by the watchdog below
     };
     std::vector<ps_solver*> kids;
     std::vector<std::unique_ptr<Worker>> workers;
@@ -34,6 +37,8 @@ struct MultiGroup {
             workers.emplace_back(new Worker);
             Worker* w = workers.back().get();
             w->th = std::thread([w] {
+                g_deferredFree = &w->graveyard;
+                g_where = &w->where;
                 for (;;) {
                     std::function<int()> job;
                     { std::unique_lock<std::mutex> lk(w->m); w->cv.wait(lk, [w] { return w->has || w->quit; }); if (w->quit) return; job = w->task; w->has = false; }
@@ -41,11 +46,18 @@ struct MultiGroup {
                     try { rc = job(); if (rc == PS_FAILED || rc == PS_INVALID) err = g_lastError; }
                     catch (const std::exception& e) { rc = PS_FAILED; err = e.what(); }
                     catch (...) { rc = PS_FAILED; err = "unknown error"; }
+                    w->where = "idle";
                     { std::lock_guard<std::mutex> lk(w->m); w->rc = rc; w->err = err; w->done = true; }
                     w->cv.notify_all();
                 }
             });
         }
+    }
+    // every rank is idle (its collective call has returned): the parked frees cannot wait on anybody any more
+    void bury() {
+#ifndef PS_EMULATE
+        for (auto& w : workers) { for (void* p : w->graveyard) cudaFree(p); w->graveyard.clear(); }
+#endif
     }
     // f(rank) on every rank's thread; returns rank 0's result, or the first failure (its message goes to the caller's ps_last_error)
     int run(const std::function<int(int)>& f) {
@@ -54,18 +66,53 @@ struct MultiGroup {
             { std::lock_guard<std::mutex> lk(w->m); w->task = [f, k] { return f((int)k); }; w->has = true; w->done = false; }
             w->cv.notify_all();
         }
+        // A rank that failed never joins the collectives its peers are waiting in: once one rank has returned with an error and
+        // another is still busy 5 s later, that rank's communicator is aborted (its kernels give up, the rank fails with a message)
+        // and its peer-memory waits run into their own time-out.  PS_MULTI_WATCHDOG_S (default 120): a collective call that long
+        // is reported once on stderr with every rank's position.
+        static const int watchdog = getenv("PS_MULTI_WATCHDOG_S") ? atoi(getenv("PS_MULTI_WATCHDOG_S")) : 120;
+        bool barked = false, aborted = false;
+        const auto t0 = std::chrono::steady_clock::now();
+        auto failedRank = [&]() -> int { for (size_t j = 0; j < workers.size(); ++j) { Worker* q = workers[j].get(); if (q->done && (q->rc == PS_FAILED || q->rc == PS_INVALID)) return (int)j; } return -1; };
+        double failSeen = -1.;
         int rc0 = PS_SUCCESS; bool failed = false;
         for (size_t k = 0; k < workers.size(); ++k) {
             Worker* w = workers[k].get();
             std::unique_lock<std::mutex> lk(w->m);
-            w->cv.wait(lk, [w] { return w->done; });
+            while (!w->done) {
+                w->cv.wait_for(lk, std::chrono::milliseconds(500), [w] { return w->done; });
+                if (w->done) break;
+                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                lk.unlock();
+                if (!aborted && failedRank() >= 0) {
+                    if (failSeen < 0.) failSeen = el;
+                    else if (el - failSeen > 5.) {
+                        aborted = true;
+                        for (size_t j = 0; j < workers.size(); ++j) if (!workers[j]->done && kids[j]->S && kids[j]->S->comm) kids[j]->S->comm->abort();
+                    }
+                }
+                if (watchdog > 0 && !barked && el > watchdog) {
+                    barked = true;
+                    fprintf(stderr, "[polystokes_b200] a collective call on the multi-GPU handle has been running for %d s:", watchdog);
+                    for (size_t j = 0; j < workers.size(); ++j) {
+                        Worker* q = workers[j].get();
+                        if (q->done) fprintf(stderr, " rank %zu done (rc %d%s%s);", j, q->rc, q->err.empty() ? "" : ": ", q->err.c_str());
+                        else fprintf(stderr, " rank %zu in %s;", j, q->where);
+                    }
+                    fprintf(stderr, "\n");
+                }
+                lk.lock();
+            }
             if (k == 0) rc0 = w->rc;
             if ((w->rc == PS_FAILED || w->rc == PS_INVALID) && !failed) { failed = true; rc0 = w->rc; g_lastError = "rank " + std::to_string(k) + ": " + w->err; }
         }
+        if (aborted) g_lastError += " (the other ranks' communicators were aborted: destroy the handle)";
+        bury();
         return rc0;
     }
     void stop() {
         for (auto& w : workers) { { std::lock_guard<std::mutex> lk(w->m); w->quit = true; } w->cv.notify_all(); if (w->th.joinable()) w->th.join(); }
+        bury();
         workers.clear();
     }
 };

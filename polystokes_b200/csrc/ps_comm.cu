@@ -4,6 +4,7 @@
 #ifndef PS_EMULATE
 #include <dlfcn.h>
 #include <nccl.h>      // types and prototypes only: every entry point is resolved with dlsym below
+#include <mutex>
 #endif
 
 namespace ps {
@@ -16,6 +17,7 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclCommAbort) CommAbort = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
@@ -37,6 +39,7 @@ NcclApi& nccl() {
     PS_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
     PS_NCCL_SYM(CommInitRank, "ncclCommInitRank");
     PS_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    PS_NCCL_SYM(CommAbort, "ncclCommAbort");
     PS_NCCL_SYM(GetErrorString, "ncclGetErrorString");
     PS_NCCL_SYM(AllReduce, "ncclAllReduce");
     PS_NCCL_SYM(AllGather, "ncclAllGather");
@@ -56,12 +59,17 @@ void nccl_check(ncclResult_t r, const char* what) {
 
 struct NcclComm : Comm {
     ncclComm_t comm = nullptr;
-    ~NcclComm() override { if (comm) nccl().CommDestroy(comm); }
+    std::mutex m; bool aborted = false;
+    ~NcclComm() override { std::lock_guard<std::mutex> lk(m); if (comm) { if (aborted) nccl().CommAbort(comm); else nccl().CommDestroy(comm); } }
+    void abort() override { std::lock_guard<std::mutex> lk(m); if (comm && !aborted) { aborted = true; nccl().CommAbort(comm); comm = nullptr; } }
+    void alive() { if (aborted || !comm) throw Error("the communicator was aborted (another rank of this handle failed)"); }
     void allreduce_sum(double* buf, int n, cudaStream_t st) override {
+        alive();
         PS_NCCL(nccl().AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, comm, st));
         PS_COUNT_LAUNCH(1);
     }
     void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) override {
+        alive();
         PS_NCCL(nccl().AllGather(send, recv, bytes, ncclChar, comm, st));
         PS_COUNT_LAUNCH(1);
     }
@@ -69,6 +77,7 @@ struct NcclComm : Comm {
         bool any = false;
         for (int i = 0; i < npeers; ++i) if (peers[i] >= 0 && (sendBytes[i] || recvBytes[i])) any = true;
         if (!any) return;
+        alive();
         PS_NCCL(nccl().GroupStart());
         for (int i = 0; i < npeers; ++i) {
             if (peers[i] < 0) continue;

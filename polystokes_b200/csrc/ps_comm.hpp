@@ -14,6 +14,9 @@ namespace ps {
 struct Comm {
     int rank = 0, nranks = 1;
     virtual ~Comm() {}
+    // may be called from ANOTHER host thread: makes the collectives in flight on this communicator give up (a rank of the same
+    // process failed and will never join them).  The communicator is unusable afterwards.
+    virtual void abort() {}
     // in-place sum of n doubles living in device memory
     virtual void allreduce_sum(double* buf, int n, cudaStream_t st) = 0;
     // every rank contributes `bytes` from send; recv receives nranks * bytes in rank order (device buffers)

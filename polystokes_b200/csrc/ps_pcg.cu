@@ -165,35 +165,37 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
 // anything that stalls a warp between rows (tickets, fences; an acquire also invalidates the L1 the gathers live in) costs more
 // than it saves: the fused region term measured 2 - 4x slower than sweep + region kernel (profiles/r02_probe_s3_256_v1..v4.log).
 // (6 resident CTAs per SM at 40 registers; forcing 7 or 8 spills and costs 18 %, profiles/r01_sweep_occupancy.log)
-__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S, int reverse) {    pdl_sync();
+// one 256-row block of the sweep: entry e of a block schedule (SchedRanges, ps_solver.hpp)
+__device__ __forceinline__ void pass1_block(const OpArgs& A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const double* lut, int32_t e) {
+    const int k = (int)((uint32_t)e >> 28);
+    const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
+    if (r >= A.s1.hi[k]) return;
+    const double sc = A.valScale;
+    const uint64_t word = __ldcs(A.kcode + r);
+    int32_t c[6];
+#pragma unroll
+    for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
+    const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
+    const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
+    const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
+    double xv[8];
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
+    double s = 0.;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
+    w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
+}
+__global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S, int reverse,
+                                                             const int32_t* __restrict__ sched, int nSched) {    pdl_sync();
 
     __shared__ double lut[65];
     if (S && S->done) return;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
     __syncthreads();
-    const double sc = A.valScale;
-    // owned rows in the merged block order of the four ranges (SchedRanges, ps_solver.hpp)
+    // owned rows in the merged block order of the ranges (SchedRanges, ps_solver.hpp)
 #pragma unroll 2
-    for (int g = blockIdx.x; g < A.nSched1; g += gridDim.x) {
-        const int32_t e = __ldg(A.sched1 + (reverse ? A.nSched1 - 1 - g : g));
-        const int k = (int)((uint32_t)e >> 28);
-        const int64_t r = A.s1.lo[k] + (int64_t)(e & 0x0fffffff) * SCHED_BLOCK + threadIdx.x;
-        if (r >= A.s1.hi[k]) continue;
-        const uint64_t word = __ldcs(A.kcode + r);
-        int32_t c[6];
-#pragma unroll
-        for (int k2 = 0; k2 < 6; ++k2) c[k2] = __ldcs(A.kcol + (int64_t)k2 * A.nRowsExt + r);
-        const int64_t cOff = A.nP + (int64_t)((uint32_t)c[0] >> 30) * A.nC;
-        const int64_t c0 = c[0] & OP_COL_MASK, c1 = c[1];
-        const int64_t col[8] = {c0, c1, cOff + c0, cOff + c1, c[2], c[3], c[4], c[5]};
-        double xv[8];
-#pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) xv[k2] = ((word >> (8 * k2)) & 0xffull) ? x[col[k2]] : 0.;
-        double s = 0.;
-#pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) s += ((double)op_code(word, k2) * sc) * xv[k2];
-        w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
-    }
+    for (int g = blockIdx.x; g < nSched; g += gridDim.x) pass1_block(A, x, w, activeScale, lut, __ldg(sched + (reverse ? nSched - 1 - g : g)));
 }
 // last CTA of a producer: v0..v2 are valid in thread 0; every rank's block receives this rank's partial sums
 __device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, double v0, double v1, double v2) {
@@ -509,9 +511,11 @@ static inline int hot_blocks(K kernel, int64_t n) {
     return (int)b;
 }
 
-void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse) {
-    if (A.nSched1 <= 0) return;
-    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, (int64_t)A.nSched1 * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, reverse ? 1 : 0);
+void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse, int part) {
+    // part 0: every owned row; 1: the coupled reduced rows only (schedule 1a); the active rows alone go with the regions (k_pass1_regions)
+    const int32_t* sched = part == 1 ? A.sched1a : A.sched1; const int n = part == 1 ? A.nSched1a : A.nSched1;
+    if (n <= 0) return;
+    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, (int64_t)n * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, reverse ? 1 : 0, sched, n);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -579,7 +583,7 @@ void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double*
     PS_CUDA(cudaGetLastError());
 }
 #else  // ---- serial twins ----
-void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool) {
+void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool, int) {
     if (S && S->done) return;
     for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInvLut[A.kmc[r]] * s : s; }
 }
@@ -972,6 +976,120 @@ __global__ void __launch_bounds__(3 * GROUP, MINB) reduced_region_kernel(double 
         for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
         wRows[row] = scale * v;
     }
+}
+// Pass 1 over the ACTIVE rows and the reduced term of the same apply in ONE launch (the coupled reduced rows were swept by the
+// launch before: schedule 1a).  The region work is a latency chain (row round trip -> 30 moments -> 26x26 product -> expand) that
+// leaves the memory system idle, the sweep is bandwidth bound: run back to back they cost 0.10 + 0.05 ms, here every CTA
+// alternates between the two -- a region, a run of row blocks, a region, ... -- and odd CTAs start with rows, so at any moment
+// about half of the resident CTAs stream rows while the others sit in a region's chain.  No hand-off between CTAs: a region is
+// still summed by one CTA in the fixed order of reduced_region_kernel<64, 0, .> (bit-identical results), the rows are untouched.
+constexpr int PR_GROUP = 64, PR_NW = PR_GROUP / 32;
+struct RegionArgs { double dx; const uint32_t* rowXYZ; const int32_t* rowAxisStart; const double* com; const double* Binv; double* wRows; double scale; int regLo, regHi; };
+__global__ void __launch_bounds__(HOT_THREADS, 5) pass1_regions_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S,
+                                                                     const int32_t* __restrict__ sched, int nSched, const __grid_constant__ RegionArgs R) {
+    __shared__ double lut[65];
+    __shared__ double Bs[RDOF * RDOF];
+    __shared__ double red[3][PR_NW][10];
+    __shared__ double M[30], t[RDOF], sv[RDOF], sg[30];
+    pdl_sync();
+    if (S && S->done) return;
+    if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
+    __syncthreads();
+    const int nReg = R.regHi - R.regLo;
+    const int myRegs = (int)blockIdx.x < nReg ? (nReg - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int myBlocks = (int)blockIdx.x < nSched ? (nSched - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    bool rowsTurn = (blockIdx.x & 1) || myRegs == 0;
+    const int nRuns = myRegs + ((blockIdx.x & 1) ? 1 : 0);
+    const int run = nRuns > 0 ? (myBlocks + nRuns - 1) / nRuns : myBlocks;
+    const int axis = threadIdx.x / PR_GROUP, lane = threadIdx.x % PR_GROUP;      // axis 3: the last 64 threads only keep the barriers
+    int kb = 0, kr = 0;
+    for (;;) {
+        const bool haveB = kb < myBlocks, haveR = kr < myRegs;
+        if (!haveB && !haveR) break;
+        if ((rowsTurn && haveB) || !haveR) {
+            const int end = min(kb + run, myBlocks);
+#pragma unroll 2
+            for (int j = kb; j < end; ++j) pass1_block(A, x, w, activeScale, lut, __ldg(sched + blockIdx.x + (int64_t)j * gridDim.x));
+            kb = end;
+        } else {
+            const int r = R.regLo + (int)blockIdx.x + kr * (int)gridDim.x;
+            ++kr;
+            for (int i = threadIdx.x; i < RDOF * RDOF; i += HOT_THREADS) Bs[i] = __ldg(R.Binv + (size_t)r * RDOF * RDOF + i);
+            int begin = 0, end = 0;
+            double cm[3] = {0., 0., 0.};
+            if (axis < 3) {
+                begin = __ldg(R.rowAxisStart + 3 * r + axis); end = __ldg(R.rowAxisStart + 3 * r + axis + 1);
+                cm[0] = __ldg(R.com + 3 * r); cm[1] = __ldg(R.com + 3 * r + 1); cm[2] = __ldg(R.com + 3 * r + 2);
+            }
+            double acc[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc[k] = 0.;
+#pragma unroll 4
+            for (int row = begin + lane; row < end; row += PR_GROUP) {
+                double m[10];
+                row_monomials(R.dx, __ldg(R.rowXYZ + row), cm, m);
+                const double g1 = __ldcs(R.wRows + row);
+#pragma unroll
+                for (int k = 0; k < 10; ++k) acc[k] += m[k] * g1;
+            }
+            if (axis < 3) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    const double v = warp_sum(acc[k]);
+                    if ((lane & 31) == 0) red[axis][lane >> 5][k] = v;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 30) {
+                const int a = threadIdx.x / 10, k = threadIdx.x % 10;
+                double s = 0.;
+#pragma unroll
+                for (int wI = 0; wI < PR_NW; ++wI) s += red[a][wI][k];
+                M[threadIdx.x] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) moments_to_t(M, t);
+            __syncthreads();
+            if (threadIdx.x < RDOF) {
+                const double* B = Bs + threadIdx.x * RDOF;
+                double s = 0.;
+#pragma unroll
+                for (int j = 0; j < RDOF; ++j) s += B[j] * t[j];
+                sv[threadIdx.x] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_to_sigma(sv, sg);
+            __syncthreads();
+            if (axis < 3) {
+                double sgl[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) sgl[k] = sg[axis * 10 + k];
+#pragma unroll 4
+                for (int row = begin + lane; row < end; row += PR_GROUP) {
+                    double m[10];
+                    row_monomials(R.dx, __ldg(R.rowXYZ + row), cm, m);
+                    double v = 0.;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) v += sgl[k] * m[k];
+                    R.wRows[row] = R.scale * v;
+                }
+            }
+            __syncthreads();      // Bs / red / sg are rewritten by the CTA's next region
+        }
+        rowsTurn = !rowsTurn;
+    }
+}
+bool k_pass1_regions(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, const Geom& g, const RegionData& RG, double scale) {
+    static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
+    static const bool on = !(getenv("PS_OVERLAP") && atoi(getenv("PS_OVERLAP")) == 0);
+    if (!on || RG.regHi <= RG.regLo || RG.maxRegionRows > fuseLimit || A.nSched1a <= 0) return false;
+    k_pass1(st, A, x, w, activeScale, S, false, 1);        // the coupled reduced rows first: the regions read them
+    const RegionArgs R = {g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, w + A.nActiveVs, scale, RG.regLo, RG.regHi};
+    const int64_t items = std::max<int64_t>((int64_t)A.nSched1b, (int64_t)(RG.regHi - RG.regLo));
+    launch_chain(pass1_regions_kernel, hot_blocks(pass1_regions_kernel, items * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, A.sched1b, A.nSched1b, R);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+    return true;
 }
 template <int GROUP, int ROWS, int MINB>
 static void launch_region(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {

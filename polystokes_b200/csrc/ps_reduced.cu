@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(GRAM_CELLS) gram_moments_kernel(Geom g, Fields
 void region_gram_partials(cudaStream_t st, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
     if (RG.cellChunkHi <= RG.cellChunkLo) return;
     const size_t smem = (size_t)STAGE_DOUBLES * GRAM_CELLS * sizeof(double);
-    static bool attr = false;
-    if (!attr) { PS_CUDA(cudaFuncSetAttribute(gram_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    // a per-DEVICE attribute: set on every call (a process-wide "done" flag left the second GPU of a multi-device handle without it)
+    PS_CUDA(cudaFuncSetAttribute(gram_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gram_moments_kernel<<<RG.cellChunkHi - RG.cellChunkLo, GRAM_CELLS, smem, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial, RG.cellChunkLo);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());

@@ -36,6 +36,13 @@ namespace ps {
 struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 extern thread_local int64_t g_launches;   // kernels launched since the step began (ps_stats::gpu_launches)
 #define PS_COUNT_LAUNCH(n) (::ps::g_launches += (n))
+// Rank threads of a ps_create_multi handle (several GPUs, ONE process): cudaFree waits for the work of every device that maps the
+// allocation (peer access is on), so a free issued while another rank's kernel spins on a flag THIS rank has yet to raise would
+// never return.  Such threads park their frees here; the caller releases them once every rank has finished the collective call.
+extern thread_local std::vector<void*>* g_deferredFree;
+// where a rank thread currently is (a string literal), for the watchdog of the multi handle
+extern thread_local const char* volatile* g_where;
+#define PS_WHERE(s) do { if (::ps::g_where) *::ps::g_where = (s); } while (0)
 
 #ifndef PS_EMULATE
 inline void check(cudaError_t e, const char* what, const char* file, int line) {
@@ -79,7 +86,7 @@ inline void ps_for_range(cudaStream_t s, int64_t lo, int64_t hi, F f) {
     PS_CUDA(cudaGetLastError());
 }
 inline void* dev_alloc_bytes(size_t bytes) { void* p = nullptr; if (bytes == 0) bytes = 16; PS_CUDA(cudaMalloc(&p, bytes)); return p; }
-inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline void dev_free(void* p) { if (!p) return; if (g_deferredFree) g_deferredFree->push_back(p); else cudaFree(p); }
 inline void dev_memset(void* p, int v, size_t bytes, cudaStream_t s) { if (bytes) PS_CUDA(cudaMemsetAsync(p, v, bytes, s)); }
 inline void copy_h2d(void* d, const void* h, size_t bytes, cudaStream_t s) { if (bytes) PS_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); }
 inline void copy_d2h(void* h, const void* d, size_t bytes, cudaStream_t s) { if (bytes) { PS_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); PS_CUDA(cudaStreamSynchronize(s)); } }

@@ -11,6 +11,8 @@ namespace ps {
 thread_local std::string g_lastError;
 thread_local int64_t g_launches = 0;
 thread_local Scratch* g_scratch = nullptr;
+thread_local std::vector<void*>* g_deferredFree = nullptr;
+thread_local const char* volatile* g_where = nullptr;
 
 // ---- small helper kernels (free functions: extended lambdas may not live in private members) ----
 static void k_flag_label(cudaStream_t st, int64_t lo, int64_t hi, const int8_t* L, int value, uint8_t* flag) {
@@ -145,6 +147,7 @@ void Solver::closePeer() {
 // access, IPC refused) switches ALL ranks back to the NCCL path -- agreed on with one all-reduce.
 void Solver::setupPeer() {
 #ifndef PS_EMULATE
+    PS_WHERE("setupPeer");
     closePeer();
     if (!comm || !part.multi() || part.nranks > PEER_MAX_RANKS) return;
     const char* env = getenv("PS_COMM");
@@ -199,6 +202,7 @@ void Solver::setupPeer() {
 // sum over the ranks of one host value (collective; a host sync -- setup / poll paths only)
 double Solver::hostAllreduceSum(double v) {
     if (!part.multi() || !comm) return v;
+    PS_WHERE("hostAllreduceSum");
     hostRed.alloc(1);
     copy_h2d(hostRed.p, &v, sizeof(double), st);
     comm->allreduce_sum(hostRed.p, 1, st);
@@ -210,6 +214,7 @@ std::vector<double> Solver::hostAllgather(const std::vector<double>& mine) {
     std::vector<double> all(n, 0.);
     std::copy(mine.begin(), mine.end(), all.begin() + k * (size_t)part.rank);
     if (!part.multi() || !comm) return all;
+    PS_WHERE("hostAllgather");
     hostRed.alloc(n);
     copy_h2d(hostRed.p, all.data(), n * sizeof(double), st);
     comm->allreduce_sum(hostRed.p, (int)n, st);
@@ -233,6 +238,7 @@ void Solver::ownTileZ(int slot, int tz[2], int extraTop) const {
 // arrays addressed by global voxel index: a z-range is one contiguous byte range, the same on both sides.
 void Solver::exchangeLayers(const std::vector<LayerField>& fields) {
     if (!part.local || !comm) return;
+    PS_WHERE("exchangeLayers");
     const int H = part.halo;
     std::vector<int> peers; std::vector<const void*> sb; std::vector<size_t> sby; std::vector<void*> rb; std::vector<size_t> rby;
     for (const LayerField& f : fields) {
@@ -257,6 +263,7 @@ static void k_merge_max_i32(cudaStream_t st, int64_t n, int32_t* dst, const int3
 // to a region of the lower one.  Both sides exchange their copy of the plane and keep the larger entry (-1 = none).
 void Solver::mergeSharedPlanes(int32_t* f) {
     if (!part.local || !comm) return;
+    PS_WHERE("mergeSharedPlanes");
     const int slot = SL_FACE + 2;
     const int64_t plane = (int64_t)g.r[slot][0] * g.r[slot][1];
     xchgTmp.alloc((size_t)plane * 2 * sizeof(int32_t));
@@ -275,6 +282,7 @@ void Solver::mergeSharedPlanes(int32_t* f) {
 void Solver::checkPeer(const char* where) {
 #ifndef PS_EMULATE
     if (!peer.on) return;
+    PS_WHERE("checkPeer (stream sync)");
     int err = 0;
     copy_d2h(&err, &scal.p->peerError, sizeof(int), st);
     if (!err) return;
@@ -325,6 +333,7 @@ Solver::~Solver() {
 }
 
 void Solver::setInputs(const ps_fields_in& in) {
+    PS_WHERE("setInputs");
     StageTimer T(st, &stageMs[PS_STAGE_UPLOAD]);
     if (!in.surface || !in.collision || !in.viscosity) throw Error("ps_step: surface / collision / viscosity field missing");
     for (int a = 0; a < 3; ++a) if (!in.velocity[a] || !in.collisionvel[a]) throw Error("ps_step: velocity / collisionvel field missing");
@@ -399,6 +408,7 @@ void Solver::waitLateInputs() {
 // `valid` depends on the face labels only (S_Cls:4-54), which are final after setup: a host caller's three valid fields
 // are produced now and cross PCIe on the output stream while the CG loop runs
 void Solver::sendValidEarly(const ps_fields_out& out) {
+    PS_WHERE("sendValidEarly");
 #ifndef PS_EMULATE
     if (out.memory == PS_MEM_DEVICE || !(out.valid[0] && out.valid[1] && out.valid[2])) return;
     float* v[3];
@@ -838,6 +848,11 @@ void Solver::buildSchedules() {
     const std::vector<int32_t> a = merge_schedule(sr1), b = merge_schedule(sr2);
     nSched1 = (int)a.size(); nSched2 = (int)b.size();
     sched1.from_host(st, a.data(), a.size()); sched2.from_host(st, b.data(), b.size());
+    // the same order split into the coupled reduced rows (range 3) and the active rows: the reduced term only needs the former
+    std::vector<int32_t> a1, b1;
+    for (int32_t e : a) (((uint32_t)e >> 28) == 3u ? a1 : b1).push_back(e);
+    nSched1a = (int)a1.size(); nSched1b = (int)b1.size();
+    sched1a.from_host(st, a1.data(), a1.size() + 0); sched1b.from_host(st, b1.data(), b1.size() + 0);
     stream_sync(st);    // the vectors die here
 }
 void Solver::computeOwnership() {
@@ -849,6 +864,7 @@ void Solver::computeOwnership() {
 // agree by construction: what I receive from h = columns of my rows that h owns; what I send to h = columns of
 // h's rows that I own.  Lists are ascending in the global index.
 void Solver::buildHalos() {
+    PS_WHERE("buildHalos");
     haloX.reset(); haloW.reset();
     if (!part.multi()) return;
     const int64_t n = C.nSystemSize, nRows = C.nRowsExt;
@@ -943,12 +959,16 @@ static OpArgs make_op(const Solver& S) {
     A.uInv = S.uInv.p; A.valScale = S.g.invDx / 64.;
     A.rowsK = S.ownK; A.rowsP = S.ownP; A.rowsE = S.ownE;
     A.s1 = S.sr1; A.s2 = S.sr2; A.sched1 = S.sched1.p; A.sched2 = S.sched2.p; A.nSched1 = S.nSched1; A.nSched2 = S.nSched2;
+    A.sched1a = S.sched1a.p; A.sched1b = S.sched1b.p; A.nSched1a = S.nSched1a; A.nSched1b = S.nSched1b;
     return A;
 }
 OpArgs Solver::make_op_args() const { return make_op(*this); }
 
 // pass 1 of an operator apply including the reduced term: w = [dt Mc^-1 K x ; c_f . B^-1 J x]
 void Solver::pass1Apply(const OpArgs& A, const double* xin, const PcgScalars* S, bool reverse) {
+#ifndef PS_EMULATE
+    if (RG.count > 0 && !reverse && k_pass1_regions(st, A, xin, w.p, g.dt, S, g, RG, 1.0)) return;      // active rows and regions in one launch
+#endif
     k_pass1(st, A, xin, w.p, g.dt, S, reverse);
     if (RG.count > 0) reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, S);          // moments -> B^-1 -> expand, one CTA per region
 }
@@ -1003,6 +1023,7 @@ bool Solver::pollCancel() {
 // solveSPDwithMatrixVectorPCG (S.cpp:734-812) -> pcg_external_matrix_A (pcg.h:268-340): identity
 // preconditioner (Preconditioner.cpp:271-274), zero start, stop test min(rr, rr/xx) < tol^2.
 int Solver::solve() {
+    PS_WHERE("solve");
     StageTimer T(st, &stageMs[PS_STAGE_SOLVE]);
     // units.h:76-94: matrixSetup 0 = PRESSURE_STRESS; solverType 0 = PCG_MATRIX_VECTOR_PRODUCTS, 1 = EIGEN
     if (P.matrixSetup != 0 || (P.solverType != 0 && P.solverType != 1)) { result = R_UNSUPPORTED_SOLVER; return result; }
@@ -1208,6 +1229,7 @@ int Solver::solveBiCGStab() {
 
 // recoverVelocityFromPressureStress (S.cpp:492-510)
 void Solver::recoverVelocityFromPressureStress() {
+    PS_WHERE("recoverVelocity");
     const OpArgs A = make_op(*this);
     exchange(haloX, x.p, nullptr);
     k_pass1(st, A, x.p, w.p, g.dt, nullptr);                         // active rows: dt Mc^-1 (G p + D^T tau); coupled reduced rows: raw (K_red x)_f
@@ -1230,6 +1252,7 @@ void Solver::outRange(int slot, int64_t& lo, int64_t& hi) const {
 }
 
 void Solver::applySolutionToVelocity(const ps_fields_out& out) {
+    PS_WHERE("applySolutionToVelocity");
     const bool dev = out.memory == PS_MEM_DEVICE;
     const bool writeVel = (result == R_SUCCESS || P.keepNonConvergedResults);
 #ifndef PS_EMULATE
@@ -1292,12 +1315,15 @@ void Solver::applySolutionToVelocity(const ps_fields_out& out) {
 }
 
 void Solver::setup() {
+    PS_WHERE("setup: peerResync");
     peerResync();
     // every rank must take part in the cancel all-reduce if any rank has a callback: agree on that once per setup
     anyCancelCb = part.multi() && comm ? hostAllreduceSum(P.cancel_cb ? 1. : 0.) > 0.5 : false;
+    PS_WHERE("setup: weights");
     buildIntegrationWeightsAlt();
     {
         StageTimer T(st, &stageMs[PS_STAGE_CLASSIFY]);
+        PS_WHERE("setup: classify");
         classifyCells();
         if (P.doReducedRegions) constructReducedRegions();
         classifyFaces();
@@ -1307,12 +1333,18 @@ void Solver::setup() {
     part.regionCut.assign((size_t)part.nranks + 1, 0);
     {
         StageTimer T(st, &stageMs[PS_STAGE_REDUCED]);
+        PS_WHERE("setup: reduced indices");
         if (P.doReducedRegions) { constructCenterReducedIndices(); constructFacesReducedIndices(); constructEdgesReducedIndices(); }
     }
+    PS_WHERE("setup: active indices");
     { StageTimer T(st, &stageMs[PS_STAGE_INDICES]); constructActiveIndices(); }
+    PS_WHERE("setup: waitLateInputs");
     waitLateInputs();
+    PS_WHERE("setup: region matrices");
     { StageTimer T(st, &stageMs[PS_STAGE_REGION_MATRICES]); if (P.doReducedRegions) computeReducedRegionMatrices(); }
+    PS_WHERE("setup: matrix blocks");
     { StageTimer T(st, &stageMs[PS_STAGE_MATRIX_BLOCKS]); constructMatrixBlocks(); }
+    PS_WHERE("setup: assemble");
     haveDiag = false; haveA = false;
     { StageTimer T(st, &stageMs[PS_STAGE_ASSEMBLE]); constructGuessVectors(); assemble(); }
     haveSetup = true;

@@ -238,8 +238,8 @@ public:
     // matrices + vectors
     CompactOp Op;                 // K_ext and K_ext^T
     SchedRanges sr1, sr2;         // block schedules of pass 1 / pass 2 over the owned rows (merge_schedule)
-    DBuf<int32_t> sched1, sched2;
-    int nSched1 = 0, nSched2 = 0;
+    DBuf<int32_t> sched1, sched2, sched1a, sched1b;
+    int nSched1 = 0, nSched2 = 0, nSched1a = 0, nSched1b = 0;
     void buildSchedules();
     DBuf<double> mcInv, mc, rhsU, oldVs, uInv, uDiag, rhsPT, b;
     DBuf<double> x, r, p, Ap, w, velSol;
@@ -310,13 +310,19 @@ struct OpArgs {   // everything one operator apply touches
     int64_t nRowsExt, nActiveVs, nP, nT, nC, nE;
     SchedRanges s1, s2;           // pass 1: face rows x, y, z, coupled reduced rows; pass 2: cells, edges yz, xz, xy (edge numbering)
     const int32_t* sched1; const int32_t* sched2; int nSched1, nSched2;
+    const int32_t* sched1a; const int32_t* sched1b; int nSched1a, nSched1b;   // pass 1 split: coupled reduced rows | active rows (same merged order)
     RowSet rowsK, rowsP, rowsE;   // rows this rank computes (all rows on one GPU); the centre-stress rows follow rowsP
     const uint64_t* kcode; const int32_t* kcol; const uint8_t* kmc; const double* mcInvLut;
     const uint64_t* ccode; const int32_t* ccol; const uint32_t* ecode; const int32_t* ecol;
     const double* uInv;
     double valScale;              // invDx / 64
 };
-void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false);
+void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false, int part = 0);
+#ifndef PS_EMULATE
+// pass 1 and the reduced term of one apply in two launches: coupled reduced rows, then active rows interleaved with the regions.
+// false: not applicable (no tiled regions of this rank / PS_OVERLAP=0) -- nothing was launched, use k_pass1 + reduced_apply
+bool k_pass1_regions(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, const Geom&, const RegionData&, double scale);
+#endif
 // mode bit 0: dot(x, y) (p.Ap) -> red[0]; bit 1: also dot(r2, y), dot(y, y) (r.Ap, Ap.Ap) -> red[1], red[2]
 void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode,
              const double* r2 = nullptr, bool reverse = false);
