@@ -200,11 +200,14 @@ def run_ref_full(n, threads=None):
 
 def choose_ref_grid(budget_s, cal):
     """Largest S3 grid whose predicted reference time fits `budget_s` and whose predicted memory fits the host.  `cal` is a measured run at a small
-    grid; setup scales with the voxel count, CG with rows x iterations (iterations ~ n on S3: 63 / 97 / 129 / 258 at 64 / 96 / 128 / 256)."""
+    grid; setup scales with the voxel count, CG with rows x iterations (iterations ~ n on S3: 63 / 97 / 129 / 258 at 64 / 96 / 128 / 256) times a
+    cache factor: the 64^3 system (0.3 M rows) iterates out of the host's caches, the larger ones from DRAM -- measured on the GPU box's 16-core host
+    (profiles/r02_bench_ref_n1_v8.json): 120 ns per row and iteration at 96^3, 190 ns at 256^3, i.e. ~2 x the calibration's rate."""
     avail = mem_available_gb()
     for n in (256, 192, 128, 96):
         f3 = (n / cal["n"]) ** 3
-        pred_s = (cal["seconds"] - cal["cg_s"]) * f3 + cal["cg_s"] * f3 * (n / cal["n"])
+        dram = 2.0 if n >= 160 else 1.5 if n >= 96 else 1.0
+        pred_s = (cal["seconds"] - cal["cg_s"]) * f3 + cal["cg_s"] * f3 * (n / cal["n"]) * dram
         pred_gb = cal["maxrss_gb"] * f3 * 1.15
         if pred_s <= budget_s and pred_gb <= 0.7 * avail:
             return n, pred_s, pred_gb
@@ -322,7 +325,7 @@ def main():
         if rank != 0:
             return
         cores = host_cores()
-        budget = float(os.environ.get("PS_REF_BUDGET_S", "1300"))
+        budget = float(os.environ.get("PS_REF_BUDGET_S", "1500"))
         res = None
         cached = False
         if a.gpus > 1 and os.path.exists(REF_CACHE):

@@ -89,6 +89,9 @@ PS_D double sum_partials(const double* p, int n) { double s = 0.; for (int i = 0
 PS_D double cg_rre2(double rr, double xx) { double rre = rr; if (rr / xx < rre) rre = rr / xx; return rre; }
 PS_D double cg_next_xx(double xx, double alpha, double xp, double pp) { return xx + (2. * alpha) * xp + (alpha * alpha) * pp; }
 PS_D double cg_next_rr(double rr, double alpha, double rAp, double ApAp) { return (rr - (2. * alpha) * rAp) + (alpha * alpha) * ApAp; }
+// the element updates of r and p, written once: the halo push recomputes the new p on the boundary entries and must round like the update
+PS_D double cg_r_new(double r, double alpha, double Ap) { return fma(-alpha, Ap, r); }
+PS_D double cg_p_new(double rNew, double beta, double p) { return fma(beta, p, rNew); }
 // once per iteration, after every reader of the scalars is done (last CTA of the update): pcg.h:326-336
 PS_D void cg_advance(PcgScalars* S, double rsold, double rr, double xx, double alpha, double pAp) {
     const double rre = cg_rre2(rr, xx);
@@ -187,12 +190,13 @@ __device__ __forceinline__ void pass1_block(const OpArgs& A, const double* __res
     w[r] = r < A.nActiveVs ? activeScale * lut[__ldcs(A.kmc + r)] * s : s;     // coupled reduced rows keep the raw (K_red x)_f
 }
 __global__ void __launch_bounds__(HOT_THREADS, 6) pass1_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ x, double* __restrict__ w, double activeScale, const PcgScalars* S, int reverse,
-                                                             const int32_t* __restrict__ sched, int nSched) {    pdl_sync();
+                                                             const int32_t* __restrict__ sched, int nSched, const __grid_constant__ VecLink V) {    pdl_sync();
 
     __shared__ double lut[65];
     if (S && S->done) return;
     if (threadIdx.x < 65) lut[threadIdx.x] = A.mcInvLut[threadIdx.x];
     __syncthreads();
+    if (!vec_wait(V)) { if (threadIdx.x == 0) const_cast<PcgScalars*>(S)->peerError = 1; return; }      // the neighbours' entries of x (direct halo stores)
     // owned rows in the merged block order of the ranges (SchedRanges, ps_solver.hpp)
 #pragma unroll 2
     for (int g = blockIdx.x; g < nSched; g += gridDim.x) pass1_block(A, x, w, activeScale, lut, __ldg(sched + (reverse ? nSched - 1 - g : g)));
@@ -212,9 +216,11 @@ __device__ __forceinline__ void publish_partials(const PeerCtx& P, int slot, dou
 template <int OCC>
 __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_constant__ OpArgs A, const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
                                                               double muScale, const double* __restrict__ add, double* dotPartial, PcgScalars* S, int mode, const __grid_constant__ PeerCtx P,
-                                                              const double* __restrict__ r2, int reverse) {    pdl_sync();
+                                                              const double* __restrict__ r2, int reverse, const __grid_constant__ VecLink V) {    pdl_sync();
 
     if (S && S->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) vec_raise(V);                     // this rank's rows of w are in the neighbours' vectors (the push launch before this one)
+    if (!vec_wait(V)) { if (threadIdx.x == 0) S->peerError = 1; return; }      // the neighbours' rows of w (direct halo stores)
     const bool dot = mode & 1, dot3 = mode & 2;
     const double sc = A.valScale;
     const int64_t nC = A.nC, nP = A.nP, oE = A.nP + 3 * A.nC;
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(HOT_THREADS, OCC) pass2_kernel(const __grid_co
 // x += alpha p always (pcg.h:314 runs before the stop test); r and p are only advanced if the stop test did not fire.
 // The last CTA then advances the CG state (every CTA has read the scalars by then).
 __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, const double* __restrict__ Ap,
-                                                               double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P, int reverse) {    pdl_sync();
+                                                               double* dotPartial, PcgScalars* S, const __grid_constant__ PeerCtx P, int reverse, const __grid_constant__ VecLink V) {    pdl_sync();
 
     if (S->done) return;
     double a[3] = {S->red[0], S->red[1], S->red[2]}, b[3] = {S->red[3], S->red[4], S->red[5]};
@@ -321,8 +327,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, do
         for (int64_t l = tid; l < total; l += stride) {
             const int64_t i = own.at(total - 1 - l);
             const double pi = p[i];
-            const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
-            const double pn = ri + beta * pi;
+            const double xi = x[i] + alpha * pi, ri = cg_r_new(r[i], alpha, Ap[i]);
+            const double pn = cg_p_new(ri, beta, pi);
             x[i] = xi; r[i] = ri; p[i] = pn;
             rr += ri * ri; xp += xi * pn; pp += pn * pn;
         }
@@ -336,8 +342,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, do
             const double2 pv = *reinterpret_cast<const double2*>(p + i), xv = *reinterpret_cast<const double2*>(x + i);
             const double2 rv = *reinterpret_cast<const double2*>(r + i), av = __ldcs(reinterpret_cast<const double2*>(Ap + i));
             double2 xo, ro, po;
-            xo.x = xv.x + alpha * pv.x; ro.x = rv.x - alpha * av.x; po.x = ro.x + beta * pv.x;
-            xo.y = xv.y + alpha * pv.y; ro.y = rv.y - alpha * av.y; po.y = ro.y + beta * pv.y;
+            xo.x = xv.x + alpha * pv.x; ro.x = cg_r_new(rv.x, alpha, av.x); po.x = cg_p_new(ro.x, beta, pv.x);
+            xo.y = xv.y + alpha * pv.y; ro.y = cg_r_new(rv.y, alpha, av.y); po.y = cg_p_new(ro.y, beta, pv.y);
             *reinterpret_cast<double2*>(x + i) = xo; *reinterpret_cast<double2*>(r + i) = ro; *reinterpret_cast<double2*>(p + i) = po;
             rr += ro.x * ro.x; xp += xo.x * po.x; pp += po.x * po.x;
             rr += ro.y * ro.y; xp += xo.y * po.y; pp += po.y * po.y;
@@ -345,8 +351,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, do
         if ((total & 1) && tid == 0) {
             const int64_t i = base + total - 1;
             const double pi = p[i];
-            const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
-            const double pn = ri + beta * pi;
+            const double xi = x[i] + alpha * pi, ri = cg_r_new(r[i], alpha, Ap[i]);
+            const double pn = cg_p_new(ri, beta, pi);
             x[i] = xi; r[i] = ri; p[i] = pn;
             rr += ri * ri; xp += xi * pn; pp += pn * pn;
         }
@@ -355,8 +361,8 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, do
         for (RangeWalk<7> it(own, tid); it.valid(own); it.step(own, stride)) {
             const int64_t i = it.j;
             const double pi = p[i];
-            const double xi = x[i] + alpha * pi, ri = r[i] - alpha * Ap[i];
-            const double pn = ri + beta * pi;
+            const double xi = x[i] + alpha * pi, ri = cg_r_new(r[i], alpha, Ap[i]);
+            const double pn = cg_p_new(ri, beta, pi);
             x[i] = xi; r[i] = ri; p[i] = pn;
             rr += ri * ri; xp += xi * pn; pp += pn * pn;
         }
@@ -367,6 +373,7 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_update_kernel(RangeSet own, do
     const double brr = block_sum(rr), bxp = block_sum(xp), bpp = block_sum(pp);
     if (threadIdx.x == 0) { dotPartial[blockIdx.x] = brr; dotPartial[gridDim.x + blockIdx.x] = bxp; dotPartial[2 * gridDim.x + blockIdx.x] = bpp; }
     if (last_block(&S->ticket[3])) {
+        if (!converged && threadIdx.x == 0) vec_raise(V);      // the boundary entries of the new p reached the neighbours with the push launch before this one
         const double trr = block_sum_partials(dotPartial, gridDim.x), txp = block_sum_partials(dotPartial + gridDim.x, gridDim.x), tpp = block_sum_partials(dotPartial + 2 * gridDim.x, gridDim.x);
         if (threadIdx.x == 0) { cg_advance(S, rsold, rrNew, xxNew, alpha, a[0]); S->red[3] = trr; S->red[4] = txp; S->red[5] = tpp; }
         if (P.nranks > 1) publish_partials(P, 1, trr, txp, tpp);
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(HOT_THREADS) cg_init_kernel(RangeSet own, cons
             S->rsold = 0.; S->pAp = 0.; S->alpha = 0.; S->beta = 0.; S->rsnew = 0.; S->xmag = 0.; S->rre = 0.;
             S->red[0] = 0.; S->red[1] = 0.; S->red[2] = 0.; S->red[3] = rs; S->red[4] = 0.; S->red[5] = rs; S->red[6] = rs; S->xx = 0.;      // r = p = b: r.r = p.p = b.b; x = 0: x.p = 0
             S->iter = 0; S->done = 0; S->maxIter = maxIter; S->tol2 = tol * tol;
-            S->ticket[0] = 0; S->ticket[3] = 0;      // nothing else is in flight: heal tickets after an aborted solve
+            S->ticket[0] = 0; S->ticket[3] = 0; S->ticket[4] = 0; S->ticket[5] = 0;      // nothing else is in flight: heal tickets after an aborted solve
         }
         if (P.nranks > 1) publish_partials(P, 1, rs, 0., rs);
     }
@@ -426,6 +433,44 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int64_t n0, int64_t n1, 
             if (flag0) peer_st_flag(flag0, seq);
             if (flag1) peer_st_flag(flag1, seq);
         }
+    }
+}
+// The same push with the entries stored at their FINAL place: the neighbours map this rank's vector arena (PeerLink::vecBase), entry j
+// of my vector goes to entry j of theirs (vectors are global-length everywhere).  Nothing is unpacked on the other side: the kernel
+// that consumes the vector there waits for the flag at its head (VecLink).  This launch never waits, so it cannot stall behind a
+// slower neighbour; its tail (two system fences + the flag's NVLink trip) hides under the consumer's launch.
+__global__ void __launch_bounds__(256) halo_push_direct_kernel(int64_t n0, int64_t n1, const int32_t* __restrict__ idx, const double* __restrict__ v,
+                                                              double* __restrict__ dst0, double* __restrict__ dst1, const PcgScalars* S) {    pdl_sync();
+
+    if (S && S->done) return;
+    const int64_t n = n0 + n1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t j = idx[i];
+        const double val = v[j];
+        if (i < n0) dst0[j] = val; else dst1[j] = val;
+    }
+}
+// The push of the NEW p, launched before the x/r/p update: p_new = (r - alpha Ap) + beta p on the boundary entries, from the old
+// vectors and the same scalars the update is about to form (same reductions, same expressions -- bit-identical values).
+__global__ void __launch_bounds__(256) halo_push_p_kernel(int64_t n0, int64_t n1, const int32_t* __restrict__ idx, const double* __restrict__ r, const double* __restrict__ p,
+                                                         const double* __restrict__ Ap, double* __restrict__ dst0, double* __restrict__ dst1, PcgScalars* S, const __grid_constant__ PeerCtx P) {
+    pdl_sync();
+    if (S->done) return;
+    double a[3] = {S->red[0], S->red[1], S->red[2]}, b[3] = {S->red[3], S->red[4], S->red[5]};
+    if (P.nranks > 1) {
+        if (!peer_reduce_wait(P, 0, P.seqIn, a, 3)) { if (threadIdx.x == 0) S->peerError = 1; return; }
+        if (!peer_reduce_wait(P, 1, P.seqIn2, b, 3)) { if (threadIdx.x == 0) S->peerError = 1; return; }
+    }
+    const double rsold = b[0], alpha = rsold / a[0];
+    const double rrNew = cg_next_rr(rsold, alpha, a[1], a[2]);
+    const double xxNew = cg_next_xx(S->xx, alpha, b[1], b[2]);
+    if (cg_rre2(rrNew, xxNew) < S->tol2) return;          // the update will stop here: nobody reads another p
+    const double beta = rrNew / rsold;
+    const int64_t n = n0 + n1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t j = idx[i];
+        const double val = cg_p_new(cg_r_new(r[j], alpha, Ap[j]), beta, p[j]);
+        if (i < n0) dst0[j] = val; else dst1[j] = val;
     }
 }
 // receiver side: wait for the neighbours' flags, then scatter the received entries into the global-length vector
@@ -511,29 +556,29 @@ static inline int hot_blocks(K kernel, int64_t n) {
     return (int)b;
 }
 
-void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse, int part) {
+void k_pass1(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool reverse, int part, const VecLink& V) {
     // part 0: every owned row; 1: the coupled reduced rows only (schedule 1a); the active rows alone go with the regions (k_pass1_regions)
     const int32_t* sched = part == 1 ? A.sched1a : A.sched1; const int n = part == 1 ? A.nSched1a : A.nSched1;
-    if (n <= 0) return;
-    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, (int64_t)n * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, reverse ? 1 : 0, sched, n);
+    if (n <= 0 && !V.waitSeq) return;
+    launch_chain(pass1_kernel, hot_blocks(pass1_kernel, (int64_t)std::max(n, 1) * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, reverse ? 1 : 0, sched, n, V);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode, const double* r2, bool reverse) {
+void k_pass2(cudaStream_t st, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode, const double* r2, bool reverse, const VecLink& V) {
     // resident CTAs per SM the kernel is compiled for.  Measured on S3 256^3 (profiles/r01_sweep_occupancy.log): 4 -> 0.148 ms, 5 -> 0.137 ms,
     // 6 -> 0.132 ms, 7 / 8 spill and fall back to 0.137 ms
     static const int occ = getenv("PS_PASS2_OCC") ? atoi(getenv("PS_PASS2_OCC")) : 6;
     const int64_t rows = A.rowsP.total() + A.rowsE.total();
     if (rows <= 0 && !(mode & 1)) return;
     const int rev = reverse ? 1 : 0;
-    if (occ >= 6) launch_chain(pass2_kernel<6>, hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev);
-    else if (occ == 5) launch_chain(pass2_kernel<5>, hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev);
-    else launch_chain(pass2_kernel<4>, hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev);
+    if (occ >= 6) launch_chain(pass2_kernel<6>, hot_blocks(pass2_kernel<6>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev, V);
+    else if (occ == 5) launch_chain(pass2_kernel<5>, hot_blocks(pass2_kernel<5>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev, V);
+    else launch_chain(pass2_kernel<4>, hot_blocks(pass2_kernel<4>, rows), HOT_THREADS, st, A, w, x, y, muScale, add, dotPartial, scal, mode, P, r2, rev, V);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
-void k_cg_update(cudaStream_t st, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse) {
-    launch_chain(cg_update_kernel, hot_blocks(cg_update_kernel, own.total()), HOT_THREADS, st, own, x, r, p, Ap, dotPartial, scal, P, reverse ? 1 : 0);
+void k_cg_update(cudaStream_t st, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse, const VecLink& V) {
+    launch_chain(cg_update_kernel, hot_blocks(cg_update_kernel, own.total()), HOT_THREADS, st, own, x, r, p, Ap, dotPartial, scal, P, reverse ? 1 : 0, V);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -560,6 +605,20 @@ void k_halo_push_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* id
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
+void k_halo_push_direct(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, const PcgScalars* S) {
+    const int64_t n = n0 + n1;
+    if (n <= 0) return;
+    launch_chain(halo_push_direct_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, n0, n1, idx, v, dst0, dst1, S);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
+void k_halo_push_p(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* r, const double* p, const double* Ap, double* dst0, double* dst1, PcgScalars* S, const PeerCtx& P) {
+    const int64_t n = n0 + n1;
+    if (n <= 0) return;
+    launch_chain(halo_push_p_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, n0, n1, idx, r, p, Ap, dst0, dst1, S, P);
+    PS_COUNT_LAUNCH(1);
+    PS_CUDA(cudaGetLastError());
+}
 void k_halo_exchange_peer(cudaStream_t st, int64_t ns0, int64_t ns1, const int32_t* sendIdx, double* dst0, double* dst1, unsigned long long* dflag0, unsigned long long* dflag1,
                           int64_t nr0, int64_t nr1, const int32_t* recvIdx, const double* src0, const double* src1, const unsigned long long* sflag0, const unsigned long long* sflag1,
                           unsigned long long seq, double* v, PcgScalars* S, bool respectDone, unsigned int* ticket) {
@@ -583,11 +642,11 @@ void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double*
     PS_CUDA(cudaGetLastError());
 }
 #else  // ---- serial twins ----
-void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool, int) {
+void k_pass1(cudaStream_t, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, bool, int, const VecLink&) {
     if (S && S->done) return;
     for (int64_t l = 0; l < A.rowsK.total(); ++l) { const int64_t r = A.rowsK.at(l); const double s = k_row(A, r, x); w[r] = r < A.nActiveVs ? activeScale * A.mcInvLut[A.kmc[r]] * s : s; }
 }
-void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode, const double* r2, bool) {
+void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, double* y, double muScale, const double* add, double*, const PeerCtx&, PcgScalars* S, int mode, const double* r2, bool, const VecLink&) {
     if (S && S->done) return;
     double acc = 0., accR = 0., accY = 0.;
     auto finish = [&](int64_t j, double ktw) {
@@ -608,7 +667,7 @@ void k_pass2(cudaStream_t, const OpArgs& A, const double* w, const double* x, do
     for (int64_t l = 0; l < A.rowsE.total(); ++l) { const int64_t e = A.rowsE.at(l); finish(A.nP + 3 * A.nC + e, kt_edge_row(A, e, w)); }
     if (mode & 1) { S->red[0] = acc; S->red[1] = accR; S->red[2] = accY; }
 }
-void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double*, PcgScalars* S, const PeerCtx&, bool) {
+void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double*, PcgScalars* S, const PeerCtx&, bool, const VecLink&) {
     if (S->done) return;
     const double rsold = S->red[3], alpha = rsold / S->red[0];
     const double rrNew = cg_next_rr(rsold, alpha, S->red[1], S->red[2]);
@@ -619,7 +678,7 @@ void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double
     for (int64_t l = 0; l < own.total(); ++l) {
         const int64_t i = own.at(l);
         x[i] += alpha * p[i];
-        if (!converged) { r[i] -= alpha * Ap[i]; p[i] = r[i] + beta * p[i]; rr += r[i] * r[i]; xp += x[i] * p[i]; pp += p[i] * p[i]; }
+        if (!converged) { r[i] = cg_r_new(r[i], alpha, Ap[i]); p[i] = cg_p_new(r[i], beta, p[i]); rr += r[i] * r[i]; xp += x[i] * p[i]; pp += p[i] * p[i]; }
     }
     cg_advance(S, rsold, rrNew, xxNew, alpha, S->red[0]);
     S->red[3] = rr; S->red[4] = xp; S->red[5] = pp;
@@ -977,6 +1036,7 @@ __global__ void __launch_bounds__(3 * GROUP, MINB) reduced_region_kernel(double 
         wRows[row] = scale * v;
     }
 }
+// (A/B variant, off by default -- see pass1_regions_applicable.)
 // Pass 1 over the ACTIVE rows and the reduced term of the same apply in ONE launch (the coupled reduced rows were swept by the
 // launch before: schedule 1a).  The region work is a latency chain (row round trip -> 30 moments -> 26x26 product -> expand) that
 // leaves the memory system idle, the sweep is bandwidth bound: run back to back they cost 0.10 + 0.05 ms, here every CTA
@@ -1079,11 +1139,17 @@ __global__ void __launch_bounds__(HOT_THREADS, 5) pass1_regions_kernel(const __g
         rowsTurn = !rowsTurn;
     }
 }
-bool k_pass1_regions(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, const Geom& g, const RegionData& RG, double scale) {
+bool pass1_regions_applicable(const OpArgs& A, const RegionData& RG) {
     static const int fuseLimit = getenv("PS_REGION_FUSE_MAX") ? atoi(getenv("PS_REGION_FUSE_MAX")) : 16384;
-    static const bool on = !(getenv("PS_OVERLAP") && atoi(getenv("PS_OVERLAP")) == 0);
-    if (!on || RG.regHi <= RG.regLo || RG.maxRegionRows > fuseLimit || A.nSched1a <= 0) return false;
-    k_pass1(st, A, x, w, activeScale, S, false, 1);        // the coupled reduced rows first: the regions read them
+    // measured on S3 256^3 (profiles/r02_probe_s3_256_v8*.log): 0.181 ms against 0.141 ms for sweep + region kernel on one GPU -- a CTA
+    // sitting in a region's chain keeps 8 warps from streaming rows, and only ~half of the CTAs are in a chain at any time (5 rounds of
+    // regions instead of 2 waves).  Off by default; PS_OVERLAP=1 for A/B runs.
+    static const bool on = getenv("PS_OVERLAP") && atoi(getenv("PS_OVERLAP")) != 0;
+    return on && RG.regHi > RG.regLo && RG.maxRegionRows <= fuseLimit && A.nSched1a > 0;
+}
+bool k_pass1_regions(cudaStream_t st, const OpArgs& A, const double* x, double* w, double activeScale, const PcgScalars* S, const Geom& g, const RegionData& RG, double scale, const VecLink& V) {
+    if (!pass1_regions_applicable(A, RG)) return false;
+    k_pass1(st, A, x, w, activeScale, S, false, 1, V);        // the coupled reduced rows first: the regions read them (this launch waits for the neighbours' x)
     const RegionArgs R = {g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, w + A.nActiveVs, scale, RG.regLo, RG.regHi};
     const int64_t items = std::max<int64_t>((int64_t)A.nSched1b, (int64_t)(RG.regHi - RG.regLo));
     launch_chain(pass1_regions_kernel, hot_blocks(pass1_regions_kernel, items * HOT_THREADS), HOT_THREADS, st, A, x, w, activeScale, S, A.sched1b, A.nSched1b, R);

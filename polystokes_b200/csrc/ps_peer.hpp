@@ -27,7 +27,26 @@ struct PeerSync {                  // head of every rank's symmetric block
     unsigned long long haloFlag[2][2][2];                      // [kind x|w][parity][side: from below | from above]
     unsigned long long redFlag[2][PEER_SLOTS][PEER_MAX_RANKS]; // [parity][slot][source rank]
     double redVal[2][PEER_SLOTS][PEER_VALS][PEER_MAX_RANKS];   // [parity][slot][value][source rank]
-    unsigned long long pad[16];
+    unsigned long long vecFlag[2][2];                          // [kind p|w][side: from below | from above] direct halo stores (VecLink)
+    unsigned long long pad[12];
+};
+
+// Halo exchange without unpacking: p and w are global-length on every rank and live in one arena per rank that the z-neighbours map
+// (PeerLink::vecBase).  A small push launch stores the entries a neighbour reads at their FINAL place in the neighbour's copy -- and
+// does nothing else: no fence, no ticket, no flag, so it ends as soon as the stores are issued.  The flags are raised by ONE thread of
+// the launch that FOLLOWS on this rank, after a system fence (the launch boundary orders the stores before that thread, the fence is
+// cumulative): for p the push runs BEFORE the x/r/p update -- it recomputes p_new = (r - alpha Ap) + beta p on the boundary entries
+// from the old vectors -- so the NVLink trip of the data hides under the update, whose last CTA raises the flags; for w the push
+// follows the reduced term and the head of pass 2 raises the flags before it waits for its own.  The consuming kernel (pass 1 for
+// p, pass 2 for w) waits for its two flags at its head (VecLink) -- no receive buffer, no scatter, no launch that sits waiting.
+// Reuse is safe without a second buffer: a neighbour pushes p after its x/r/p update, which consumed the reductions of this rank's
+// pass 2, i.e. every read of the old values (pass 1) is over; it pushes w after its pass 1, which waited for this rank's p push,
+// issued after this rank's update -- behind the last reader of the old w (pass 2).
+struct VecLink {
+    const unsigned long long* wait[2] = {nullptr, nullptr}; // this rank's flags for what comes from below / above
+    unsigned long long waitSeq = 0;                         // 0: nothing to wait for
+    unsigned long long* raise[2] = {nullptr, nullptr};      // the neighbours' flags for what the PREVIOUS launch of this rank stored into their vectors
+    unsigned long long raiseSeq = 0;                        // 0: nothing to announce
 };
 
 struct PeerCtx {                   // passed by value to the CG kernels; nranks <= 1 means "no peers"
@@ -45,7 +64,13 @@ struct PeerLink {
     void* block[PEER_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // block[rank] = mine, others IPC-mapped
     bool sameProcess[PEER_MAX_RANKS] = {false, false, false, false, false, false, false, false};          // peers of this process: plain peer access to their pointer
     size_t cap = 0;                               // doubles per halo receive buffer
-    unsigned long long seqHalo[2] = {0, 0}, seqRed[PEER_SLOTS] = {0, 0};
+    unsigned long long seqHalo[2] = {0, 0}, seqRed[PEER_SLOTS] = {0, 0}, seqVec[2] = {0, 0};
+    // direct halo stores: the neighbours' vector arena ([below, above]; p at offset 0, w at vecOffW doubles), this rank's published arena
+    void* vecBase[2] = {nullptr, nullptr};
+    bool vecIpc[2] = {false, false};
+    void* vecPublished = nullptr;
+    size_t vecOffW = 0, vecOffWPeer[2] = {0, 0};
+    bool vecReady = false;
     PeerSync* sync(int r) const { return (PeerSync*)block[r]; }
     double* recv(int r, int kind, int par, int side) const { return (double*)((char*)block[r] + sizeof(PeerSync)) + ((size_t)((kind * 2 + par) * 2 + side)) * cap; }
     size_t bytes() const { return sizeof(PeerSync) + 8 * cap * sizeof(double); }
@@ -79,6 +104,30 @@ __device__ __forceinline__ bool peer_wait_flag(const unsigned long long* flag, u
         __nanosleep(20);
     }
     return true;
+}
+// ---- VecLink ----
+// head of a consuming kernel, every thread of the CTA: false on time-out.  The acquire also drops this SM's L1 copies of the
+// entries the neighbours have rewritten since the last sweep.
+__device__ __forceinline__ bool vec_wait(const VecLink& V) {
+    if (!V.waitSeq) return true;
+    __shared__ int okv;
+    if (threadIdx.x == 0) {
+        bool good = true;
+        if (V.wait[0]) good = peer_wait_flag(V.wait[0], V.waitSeq) && good;
+        if (V.wait[1]) good = peer_wait_flag(V.wait[1], V.waitSeq) && good;
+        okv = good ? 1 : 0;
+    }
+    __syncthreads();
+    const bool good = okv != 0;
+    __syncthreads();
+    return good;
+}
+// one thread, after the launch that stored into the neighbours' vectors has completed: make those stores visible system-wide, then announce
+__device__ __forceinline__ void vec_raise(const VecLink& V) {
+    if (!V.raiseSeq) return;
+    __threadfence_system();
+    if (V.raise[0]) peer_st_flag(V.raise[0], V.raiseSeq);
+    if (V.raise[1]) peer_st_flag(V.raise[1], V.raiseSeq);
 }
 // called by every thread of ONE CTA (the last CTA of the producer): thread r stores this rank's partials into rank r's block
 __device__ __forceinline__ void peer_reduce_push(const PeerCtx& P, int slot, const double* vals, int nvals) {

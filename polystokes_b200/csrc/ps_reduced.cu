@@ -272,9 +272,145 @@ __global__ void __launch_bounds__(GRAM_CELLS) gram_moments_kernel(Geom g, Fields
     __syncthreads();
     if (threadIdx.x < MOM_ITEMS) accumulate_item(g, stage, nCells, threadIdx.x, partial + (size_t)ch * MOM_COUNT);
 }
+// ---- the same moments on the FP64 tensor cores (DMMA.8x8x4) ------------------------------------------------------------------
+// Per face axis a the moments are one dense contraction over the 2 x 256 face samples of the chunk,
+//     Phi_a^T [ W_M Phi_a | W_N Phi_a | W_N u ]        Phi_a : 512 x 10 (monomials of the face offsets),   10 x 21 outputs,
+// i.e. Q^M_a, Q^N_a (both triangles) and the least-squares right-hand side in one product: 2 x 3 tiles of mma.m8n8k4.f64, 128
+// k-steps, split over the 8 warps of the CTA (64 samples each), 6 independent accumulators per warp.  The stress moments are
+// Gram products of (1, x, y, z) at the cell centres (T^c) and at the four owned edges around a cell (T^e): two sample positions
+// share one 8 x 8 tile (rows / columns 0-3 and 4-7; the off-diagonal blocks are not read).  Partial tiles are summed over the
+// warps in warp order, so the result is reproducible run to run; against the serial sum it differs by the association order only.
+constexpr int PHI_DOUBLES = 2 * GRAM_CELLS * 10;                 // Phi_a, reused for the cross-warp sums (8 warps x 12 x 32)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(GRAM_CELLS, 2) gram_moments_dmma_kernel(Geom g, Fields F, const double* __restrict__ com, const int32_t* __restrict__ cellList,
+                                                                        const int32_t* __restrict__ chunk, double* __restrict__ partial, int chunk0) {
+    extern __shared__ double stage[];              // [STAGE_DOUBLES][GRAM_CELLS] | Phi / warp partials [PHI_DOUBLES]
+    double* phi = stage + STAGE_DOUBLES * GRAM_CELLS;
+    const int ch = chunk0 + blockIdx.x;
+    const int region = chunk[3 * ch + 0], begin = chunk[3 * ch + 1], end = chunk[3 * ch + 2];
+    const int nCells = end - begin;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
+    if (tid < nCells) stage_cell(g, F, com + 3 * region, cellList[begin + tid], tid, stage);
+    else for (int f = 0; f < STAGE_DOUBLES; ++f) stage[f * GRAM_CELLS + tid] = 0.;          // empty slots: zero weights, zero offsets
+    double* out = partial + (size_t)ch * MOM_COUNT;
+    const double h = 0.5 * g.dx;
+    __syncthreads();
+    // ---- faces ----
+    for (int a = 0; a < 3; ++a) {
+        {   // Phi_a: sample s = dir * 256 + cell
+            double o[3] = {stage[tid], stage[GRAM_CELLS + tid], stage[2 * GRAM_CELLS + tid]};
+            const double ca = o[a];
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir) {
+                o[a] = dir ? ca + h : ca - h;
+                double* m = phi + (size_t)(dir * GRAM_CELLS + tid) * 10;
+                m[0] = 1.; m[1] = o[0]; m[2] = o[1]; m[3] = o[2]; m[4] = o[0] * o[0]; m[5] = o[0] * o[1]; m[6] = o[0] * o[2]; m[7] = o[1] * o[1]; m[8] = o[1] * o[2]; m[9] = o[2] * o[2];
+            }
+        }
+        __syncthreads();
+        double acc[2][3][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { acc[i][t][0] = 0.; acc[i][t][1] = 0.; }
+        // column r of the three B tiles: [wM m_r] [wM m_8, wM m_9, wN m_0 .. wN m_5] [wN m_6 .. wN m_9, wN u, 0, 0, 0]
+        const int k1 = r < 2 ? r + 8 : r - 2, k2 = r < 4 ? r + 6 : 0;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+            const int sIdx = wid * 64 + ks * 4 + q;
+            const int dir = sIdx >> 8, cell = sIdx & (GRAM_CELLS - 1);
+            const double* m = phi + (size_t)sIdx * 10;
+            const double mr = m[r], m1 = m[k1], m2 = m[k2];
+            const double wM = stage[(3 + 2 * a + dir) * GRAM_CELLS + cell], wN = stage[(9 + 2 * a + dir) * GRAM_CELLS + cell], wU = stage[(15 + 2 * a + dir) * GRAM_CELLS + cell];
+            const double a0 = mr, a1 = r < 2 ? m1 : 0.;
+            const double b0 = wM * mr, b1 = (r < 2 ? wM : wN) * m1, b2 = r < 4 ? wN * m2 : (r == 4 ? wU : 0.);
+            dmma884(acc[0][0][0], acc[0][0][1], a0, b0); dmma884(acc[0][1][0], acc[0][1][1], a0, b1); dmma884(acc[0][2][0], acc[0][2][1], a0, b2);
+            dmma884(acc[1][0][0], acc[1][0][1], a1, b0); dmma884(acc[1][1][0], acc[1][1][1], a1, b1); dmma884(acc[1][2][0], acc[1][2][1], a1, b2);
+        }
+        __syncthreads();                 // every warp is done reading Phi_a: it becomes the table of warp partials [wid][row 16][col 24]
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) phi[(size_t)wid * 384 + (r + 8 * i) * 24 + 8 * t + 2 * q + e] = acc[i][t][e];
+        __syncthreads();
+        if (tid < 120) {                 // 55 + 55 + 10 outputs of this axis, summed over the warps in warp order
+            int row, col;
+            if (tid < 110) { int k, l; sym_pair(10, tid % 55, k, l); row = k; col = l + (tid < 55 ? 0 : 10); }
+            else { row = tid - 110; col = 20; }
+            double sum = 0.;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) sum += phi[(size_t)w8 * 384 + row * 24 + col];
+            if (tid < 55) out[MOM_QM + a * 55 + tid] = sum;
+            else if (tid < 110) out[MOM_QN + a * 55 + (tid - 55)] = sum;
+            else out[MOM_RHS + a * 10 + (tid - 110)] = sum;
+        }
+        __syncthreads();
+    }
+    // ---- stresses: T^c (cell centres) and T^e (edge axis e, four owned edges around the cell) ----
+    {
+        double tc[2] = {0., 0.}, te[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
+        const int comp = r & 3, hiHalf = r >> 2;          // rows / columns 0-3: first sample position, 4-7: second
+#pragma unroll 2
+        for (int ks = 0; ks < 8; ++ks) {
+            const int cell = wid * 32 + ks * 4 + q;
+            const double x = stage[cell], y = stage[GRAM_CELLS + cell], z = stage[2 * GRAM_CELLS + cell];
+            {
+                const double v = comp == 0 ? 1. : (comp == 1 ? x : (comp == 2 ? y : z));
+                const double av = hiHalf ? 0. : v;
+                dmma884(tc[0], tc[1], av, stage[21 * GRAM_CELLS + cell] * av);
+            }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int ea = e == 0 ? 1 : 0, eb = e == 2 ? 1 : 2;
+#pragma unroll
+                for (int db = 0; db < 2; ++db) {
+                    // first position (da = 0) in rows 0-3, second (da = 1) in rows 4-7
+                    double o[3] = {x, y, z};
+                    o[ea] = hiHalf ? o[ea] + h : o[ea] - h;
+                    o[eb] = db ? o[eb] + h : o[eb] - h;
+                    const double v = comp == 0 ? 1. : (comp == 1 ? o[0] : (comp == 2 ? o[1] : o[2]));
+                    const double mu = stage[(22 + e * 4 + db * 2 + hiHalf) * GRAM_CELLS + cell];
+                    dmma884(te[e][0], te[e][1], v, mu * v);
+                }
+            }
+        }
+        // warp partials: [wid][4 tiles][row 8][col 8]
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            phi[(size_t)wid * 256 + 0 * 64 + r * 8 + 2 * q + e2] = tc[e2];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) phi[(size_t)wid * 256 + (1 + e) * 64 + r * 8 + 2 * q + e2] = te[e][e2];
+        }
+        __syncthreads();
+        if (tid < 40) {
+            const int tile = tid / 10; int k, l; sym_pair(4, tid % 10, k, l);
+            double sum = 0.;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) {
+                const double* t8 = phi + (size_t)w8 * 256 + tile * 64;
+                sum += tile == 0 ? t8[k * 8 + l] : t8[k * 8 + l] + t8[(k + 4) * 8 + l + 4];
+            }
+            if (tile == 0) out[MOM_TC + tid] = sum; else out[MOM_TE + (tile - 1) * 10 + tid % 10] = sum;
+        }
+    }
+}
 void region_gram_partials(cudaStream_t st, const Geom& g, const Fields& F, const RegionData& RG, double* partial) {
     if (RG.cellChunkHi <= RG.cellChunkLo) return;
     const size_t smem = (size_t)STAGE_DOUBLES * GRAM_CELLS * sizeof(double);
+    // PS_GRAM_DMMA=0: the scalar kernel (one work item per moment), kept for A/B timing and as the summation-order reference
+    static const bool dmma = !(getenv("PS_GRAM_DMMA") && atoi(getenv("PS_GRAM_DMMA")) == 0);
+    if (dmma) {
+        const size_t smem2 = smem + (size_t)PHI_DOUBLES * sizeof(double);
+        PS_CUDA(cudaFuncSetAttribute(gram_moments_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));      // a per-DEVICE attribute: set on every call
+        gram_moments_dmma_kernel<<<RG.cellChunkHi - RG.cellChunkLo, GRAM_CELLS, smem2, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial, RG.cellChunkLo);
+        PS_COUNT_LAUNCH(1);
+        PS_CUDA(cudaGetLastError());
+        return;
+    }
     // a per-DEVICE attribute: set on every call (a process-wide "done" flag left the second GPU of a multi-device handle without it)
     PS_CUDA(cudaFuncSetAttribute(gram_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gram_moments_kernel<<<RG.cellChunkHi - RG.cellChunkLo, GRAM_CELLS, smem, st>>>(g, F, RG.com.p, RG.cellList.p, RG.cellChunk.p, partial, RG.cellChunkLo);

@@ -141,15 +141,21 @@ template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool view = false;                   // p points into somebody else's allocation (adopt)
     DBuf() = default;
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
-    ~DBuf() { dev_free(p); }
+    ~DBuf() { if (!view) dev_free(p); }
     void alloc(size_t count) {
         if (count <= n && p) return;     // grow-only: buffers persist across steps (no per-step cudaMalloc)
-        dev_free(p); p = nullptr; n = 0;
+        if (!view) dev_free(p);
+        p = nullptr; n = 0; view = false;
         p = (T*)dev_alloc_bytes(count * sizeof(T)); n = count;
     }
+    // non-owning window of `count` elements at q
+    void adopt(T* q, size_t count) { if (!view) dev_free(p); p = q; n = count; view = true; }
+    // hands the allocation over (the caller frees it with dev_free)
+    T* release() { T* q = view ? nullptr : p; p = nullptr; n = 0; view = false; return q; }
     void zero(cudaStream_t s, size_t count) { dev_memset(p, 0, count * sizeof(T), s); }
     void fill_byte(cudaStream_t s, int v, size_t count) { dev_memset(p, v, count * sizeof(T), s); }
     std::vector<T> to_host(cudaStream_t s, size_t count) const { std::vector<T> h(count); copy_d2h(h.data(), p, count * sizeof(T), s); return h; }

@@ -133,6 +133,7 @@ void Solver::setParams(const ps_params& p) {
 void Solver::closePeer() {
 #ifndef PS_EMULATE
     if (st) cudaStreamSynchronize(st);
+    closeVectorMaps();
     for (int r = 0; r < PEER_MAX_RANKS; ++r) {
         if (!peer.block[r]) continue;
         if (r == peer.rank) cudaFree(peer.block[r]); else if (!peer.sameProcess[r]) cudaIpcCloseMemHandle(peer.block[r]);
@@ -307,6 +308,7 @@ void Solver::peerResync() {
     dev_memset(&scal.p->peerError, 0, sizeof(int), st);
     for (auto& q : peer.seqHalo) q = 0;
     for (auto& q : peer.seqRed) q = 0;
+    for (auto& q : peer.seqVec) q = 0;
     stream_sync(st);
     hostAllreduceSum(0.);          // barrier: every block is clean before anybody stores into it again
 #endif
@@ -324,6 +326,7 @@ PeerCtx Solver::reduceCtx(int slotIn, int slotOut, int slotIn2) {
 
 Solver::~Solver() {
     closePeer();
+    if (arenaGraveyard) { dev_free(arenaGraveyard); arenaGraveyard = nullptr; }
     delete comm;
 #ifndef PS_EMULATE
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -785,12 +788,85 @@ void Solver::constructMatrixBlocks() {
     uInv.alloc((size_t)C.nStresses); uDiag.alloc((size_t)C.nStresses); rhsPT.alloc((size_t)C.nSystemSize);
     k_assemble_Kt(st, g, F, C, Op, uInv.p, uDiag.p, rhsPT.p, part.local);
     const size_t n = (size_t)C.nSystemSize;
-    b.alloc(n); x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); w.alloc((size_t)C.nRowsExt + 1);
+    b.alloc(n); x.alloc(n); r.alloc(n); Ap.alloc(n); allocVectors(n, (size_t)C.nRowsExt + 1);
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
     dotPartial.alloc(8192);
     computeOwnership();
     buildSchedules();
     buildHalos();
+    exchangeVectorPointers();
+}
+
+// p and w: with the peer transport both live in ONE arena of their own (an IPC handle covers exactly that allocation), which the
+// z-neighbours map so that the kernels can store halo entries straight into their copies (VecLink, ps_peer.hpp)
+void Solver::allocVectors(size_t n, size_t nRows) {
+#ifndef PS_EMULATE
+    if (peer.on) {
+        const size_t offW = (n + 31) & ~(size_t)31;
+        const size_t need = offW + nRows;
+        if (!vecArena.p || vecArena.n < need) {
+            if (arenaGraveyard) { dev_free(arenaGraveyard); arenaGraveyard = nullptr; }
+            arenaGraveyard = vecArena.release();          // the neighbours still map it: freed after they have let go (exchangeVectorPointers)
+            vecArena.alloc(std::max(need + need / 8, (size_t)1 << 19));
+        }
+        p.adopt(vecArena.p, n); w.adopt(vecArena.p + offW, nRows);
+        peer.vecOffW = offW;
+        return;
+    }
+#endif
+    p.alloc(n); w.alloc(nRows);
+}
+void Solver::closeVectorMaps() {
+#ifndef PS_EMULATE
+    for (int i = 0; i < 2; ++i) {
+        if (peer.vecBase[i] && peer.vecIpc[i]) cudaIpcCloseMemHandle(peer.vecBase[i]);
+        peer.vecBase[i] = nullptr; peer.vecIpc[i] = false;
+    }
+    peer.vecReady = false;
+#endif
+}
+// Collective (every setup with the peer transport on): one host all-reduce tells whether any rank's arena moved (first step, or a
+// larger system) and whether every rank can run the fused form; only then the arenas are published and mapped again.
+void Solver::exchangeVectorPointers() {
+    fusedHalo = false;
+#ifndef PS_EMULATE
+    if (!peer.on || !comm || !part.multi()) return;
+    PS_WHERE("exchangeVectorPointers");
+    static const bool env = !(getenv("PS_HALO_FUSED") && atoi(getenv("PS_HALO_FUSED")) == 0);
+    const bool okHere = env;
+    const bool moved = (void*)vecArena.p != peer.vecPublished;
+    const double code = hostAllreduceSum((moved ? 1. : 0.) + (okHere ? 0. : 1024.));
+    const bool anyMoved = std::fmod(code, 1024.) > 0.5, allOk = code < 1023.5;
+    if (anyMoved) {
+        stream_sync(st);
+        closeVectorMaps();
+        struct Card { cudaIpcMemHandle_t ipc; unsigned long long pid, ptr, offW; int dev, ok; };
+        Card card; memset(&card, 0, sizeof card);
+        card.pid = (unsigned long long)getpid(); card.ptr = (unsigned long long)(uintptr_t)vecArena.p; card.offW = peer.vecOffW; card.dev = P.device; card.ok = 1;
+        if (cudaIpcGetMemHandle(&card.ipc, vecArena.p) != cudaSuccess) { cudaGetLastError(); card.ok = 0; }
+        DBuf<uint8_t> dSend, dAll;
+        dSend.alloc(sizeof card); dAll.alloc(sizeof card * (size_t)part.nranks);
+        copy_h2d(dSend.p, &card, sizeof card, st);
+        comm->allgather(dSend.p, dAll.p, sizeof card, st);
+        const std::vector<uint8_t> all = dAll.to_host(st, sizeof card * (size_t)part.nranks);
+        bool ok = card.ok != 0;
+        for (int i = 0; i < 2; ++i) {
+            const int pr = i == 0 ? part.rank - 1 : part.rank + 1;
+            if (pr < 0 || pr >= part.nranks) continue;
+            Card c; memcpy(&c, all.data() + sizeof c * (size_t)pr, sizeof c);
+            if (!c.ok || !c.ptr) { ok = false; continue; }
+            void* ptr = nullptr;
+            if (c.pid == card.pid) { ptr = (void*)(uintptr_t)c.ptr; peer.vecIpc[i] = false; }              // peer access was enabled in setupPeer
+            else if (cudaIpcOpenMemHandle(&ptr, c.ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; continue; }
+            else peer.vecIpc[i] = true;
+            peer.vecBase[i] = ptr; peer.vecOffWPeer[i] = (size_t)c.offW;
+        }
+        peer.vecPublished = vecArena.p;
+        peer.vecReady = hostAllreduceSum(ok ? 0. : 1.) < 0.5;        // also the barrier: every neighbour has closed its mapping of the previous arena
+        if (arenaGraveyard) { dev_free(arenaGraveyard); arenaGraveyard = nullptr; }
+    }
+    fusedHalo = peer.vecReady && allOk;
+#endif
 }
 
 // ---- ownership (ps_part.hpp): row / DOF ranges of rank k in the global numbering ----
@@ -948,6 +1024,26 @@ void Solver::exchange(Halo& H, double* v, const PcgScalars* S) {
     comm->sendrecv(2, H.peers, sb, sbytes, rb, rbytes, st);
     k_halo_unpack(st, H.recvTotal(), H.recvIdx.p, H.recvBuf.p, v, S);
 }
+// My boundary entries of w (kind 1), or of the p the coming update will produce (kind 0, `updateCtx` = the update's reduction context),
+// straight into the neighbours' vectors.  The launch only stores; the returned link tells the NEXT launch which flags to raise.
+VecLink Solver::pushDirect(Halo& H, int kind, const PeerCtx* updateCtx) {
+    VecLink L;
+#ifndef PS_EMULATE
+    L.raiseSeq = ++peer.seqVec[kind];
+    double* dst[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        const int pr = H.peers[i];
+        if (pr < 0) continue;
+        dst[i] = (double*)peer.vecBase[i] + (kind == 0 ? 0 : peer.vecOffWPeer[i]);
+        L.raise[i] = &peer.sync(pr)->vecFlag[kind][1 - i];       // the lower neighbour sees this rank as its "above" side
+    }
+    if (kind == 0) k_halo_push_p(st, H.nSend[0], H.nSend[1], H.sendIdx.p, r.p, p.p, Ap.p, dst[0], dst[1], scal.p, *updateCtx);
+    else k_halo_push_direct(st, H.nSend[0], H.nSend[1], H.sendIdx.p, w.p, dst[0], dst[1], scal.p);
+#else
+    (void)H; (void)kind; (void)updateCtx;
+#endif
+    return L;
+}
 void Solver::allreduce(double* devBuf, int n) { if (part.multi() && comm && !peer.on) comm->allreduce_sum(devBuf, n, st); }
 
 static OpArgs make_op(const Solver& S) {
@@ -965,11 +1061,11 @@ static OpArgs make_op(const Solver& S) {
 OpArgs Solver::make_op_args() const { return make_op(*this); }
 
 // pass 1 of an operator apply including the reduced term: w = [dt Mc^-1 K x ; c_f . B^-1 J x]
-void Solver::pass1Apply(const OpArgs& A, const double* xin, const PcgScalars* S, bool reverse) {
+void Solver::pass1Apply(const OpArgs& A, const double* xin, const PcgScalars* S, bool reverse, const VecLink& V) {
 #ifndef PS_EMULATE
-    if (RG.count > 0 && !reverse && k_pass1_regions(st, A, xin, w.p, g.dt, S, g, RG, 1.0)) return;      // active rows and regions in one launch
+    if (RG.count > 0 && !reverse && k_pass1_regions(st, A, xin, w.p, g.dt, S, g, RG, 1.0, V)) return;      // active rows and regions in one launch
 #endif
-    k_pass1(st, A, xin, w.p, g.dt, S, reverse);
+    k_pass1(st, A, xin, w.p, g.dt, S, reverse, 0, V);       // V: wait for the neighbours' entries of x at the head (direct halo stores)
     if (RG.count > 0) reduced_apply(st, g, RG, w.p + C.nActiveVs, 1.0, S);          // moments -> B^-1 -> expand, one CTA per region
 }
 
@@ -1046,6 +1142,15 @@ int Solver::solve() {
     auto rctx = [&](int slotIn, int slotOut, int slotIn2 = -1) { return (dbgSkip & 2) ? PeerCtx() : reduceCtx(slotIn, slotOut, slotIn2); };
     auto xchg = [&](Halo& H, double* v) { if (!(dbgSkip & 1)) exchange(H, v, scal.p); };
     auto ared = [&](double* buf, int cnt) { if (!(dbgSkip & 2)) allreduce(buf, cnt); };
+    const bool fused = fusedHalo && peer.on && !dbgSkip && !zigzag;
+#ifndef PS_EMULATE
+    auto myFlag = [&](int kind, int side) -> const unsigned long long* {
+        const int pr = side == 0 ? part.rank - 1 : part.rank + 1;
+        return (pr < 0 || pr >= part.nranks) ? nullptr : &peer.sync(part.rank)->vecFlag[kind][side];
+    };
+#else
+    auto myFlag = [&](int, int) -> const unsigned long long* { return nullptr; };
+#endif
     // PS_TRACE=<iteration>: CUDA-event timeline of that CG iteration on stderr (diagnostic; events cost a few us each)
     static const int traceIter = getenv("PS_TRACE") ? atoi(getenv("PS_TRACE")) : -1;
     std::vector<std::pair<const char*, double>> trace;
@@ -1065,12 +1170,24 @@ int Solver::solve() {
             // has been evicted.  Results do not depend on the direction (every row is computed the same way; the dot products are
             // summed per CTA, then over the CTAs in index order).
             const bool rev = zigzag && ((it + k) & 1);
-            xchg(haloX, p.p);                                   mark(tr, "halo p");
-            pass1Apply(A, p.p, scal.p, rev);                    mark(tr, "pass1 + regions");          // w = [dt Mc^-1 K p ; c_f . B^-1 J p]
-            xchg(haloW, w.p);                                   mark(tr, "halo w");
-            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, rctx(-1, 0), scal.p, 3, r.p, zigzag && !rev);   // + this rank's p.Ap, r.Ap, Ap.Ap to every rank
+            // halos: with the peer transport the boundary entries are stored straight into the neighbours' vectors by a short push launch
+            // and the consuming kernel waits at its head (VecLink); only the very first p of a solve goes by the exchange kernel
+            VecLink l1, l2;
+            if (fused) {
+                if (it + k > 0) { l1.wait[0] = myFlag(0, 0); l1.wait[1] = myFlag(0, 1); l1.waitSeq = peer.seqVec[0]; }
+                else xchg(haloX, p.p);
+            } else xchg(haloX, p.p);
+            mark(tr, "halo p");
+            pass1Apply(A, p.p, scal.p, rev, l1);                mark(tr, "pass1 + regions");          // w = [dt Mc^-1 K p ; c_f . B^-1 J p]
+            if (fused) { l2 = pushDirect(haloW, 1, nullptr); l2.wait[0] = myFlag(1, 0); l2.wait[1] = myFlag(1, 1); l2.waitSeq = peer.seqVec[1]; }
+            else xchg(haloW, w.p);
+            mark(tr, "halo w");
+            k_pass2(st, A, w.p, p.p, Ap.p, 0.5, nullptr, dotPartial.p, rctx(-1, 0), scal.p, 3, r.p, zigzag && !rev, l2);   // + this rank's p.Ap, r.Ap, Ap.Ap to every rank
             ared(scal.p->red, 3);                               mark(tr, "pass2 (+allreduce)");
-            k_cg_update(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, rctx(0, 1, 1), rev);    // global p.Ap.. and the previous r.r, x.p, p.p in; new r.r, x.p, p.p out
+            const PeerCtx uc = rctx(0, 1, 1);                   // global p.Ap.. and the previous r.r, x.p, p.p in; new r.r, x.p, p.p out
+            VecLink l3;
+            if (fused) l3 = pushDirect(haloX, 0, &uc);          // the boundary entries of the p this update is about to form, on their way while it runs
+            k_cg_update(st, ownSys, x.p, r.p, p.p, Ap.p, dotPartial.p, scal.p, uc, rev, l3);
             ared(scal.p->red + 3, 3);                           mark(tr, "update x,r,p (+allreduce)");
         }
         it += batch;

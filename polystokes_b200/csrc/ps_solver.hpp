@@ -201,6 +201,14 @@ public:
     std::vector<int64_t> cutsFromCounts(const std::vector<double>& all, int stride, int item) const;
     DBuf<uint8_t> xchgTmp;
     void buildHalos();                  // send / receive index lists of p (system vector) and w (K_ext rows)
+    // direct halo stores (VecLink, ps_peer.hpp): p and w live in one arena that the z-neighbours map; masks of the entries they read
+    DBuf<double> vecArena;
+    VecLink pushDirect(Halo& H, int kind, const PeerCtx* updateCtx);   // my boundary entries of w (kind 1) / of the NEW p (kind 0) -> the neighbours' vectors; returns what the next launch must announce
+    void allocVectors(size_t n, size_t nRows);      // p and w (in the arena when the peer transport is on)
+    void exchangeVectorPointers();                  // collective: publish / map the arenas when any rank's moved
+    void closeVectorMaps();
+    bool fusedHalo = false;                         // agreed by all ranks in exchangeVectorPointers
+    void* arenaGraveyard = nullptr;                 // the previous arena, alive until the neighbours have let go of it
     void exchange(Halo& H, double* v, const PcgScalars* S);
     void allreduce(double* devBuf, int n);   // host-enqueued NCCL all-reduce; a no-op when the peer transport fuses it into the kernels
     PeerLink peer;                      // NVLink peer-memory transport (ps_peer.hpp); off => NCCL for everything
@@ -221,7 +229,7 @@ public:
 
     // operator y = A x on device vectors (Apply.h:102-179)
     void applyOperator(const double* x, double* y, double* pApPartial);
-    void pass1Apply(const OpArgs& A, const double* x, const PcgScalars* S, bool reverse = false);   // pass 1 + the reduced term
+    void pass1Apply(const OpArgs& A, const double* x, const PcgScalars* S, bool reverse = false, const VecLink& V = VecLink());   // pass 1 + the reduced term
     void timedOperator(int which);     // 0 = whole apply, 1 = pass 1 only, 2 = pass 2 only (on b -> Ap)
 
     // ---- device state ----
@@ -317,22 +325,22 @@ struct OpArgs {   // everything one operator apply touches
     const double* uInv;
     double valScale;              // invDx / 64
 };
-void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false, int part = 0);
+void k_pass1(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, bool reverse = false, int part = 0, const VecLink& V = VecLink());
 #ifndef PS_EMULATE
 // pass 1 and the reduced term of one apply in two launches: coupled reduced rows, then active rows interleaved with the regions.
 // false: not applicable (no tiled regions of this rank / PS_OVERLAP=0) -- nothing was launched, use k_pass1 + reduced_apply
-bool k_pass1_regions(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, const Geom&, const RegionData&, double scale);
+bool k_pass1_regions(cudaStream_t, const OpArgs&, const double* x, double* w, double activeScale, const PcgScalars* scal, const Geom&, const RegionData&, double scale, const VecLink& V = VecLink());
 #endif
 // mode bit 0: dot(x, y) (p.Ap) -> red[0]; bit 1: also dot(r2, y), dot(y, y) (r.Ap, Ap.Ap) -> red[1], red[2]
 void k_pass2(cudaStream_t, const OpArgs&, const double* w, const double* x, double* y, double muScale, const double* add, double* dotPartial, const PeerCtx& P, PcgScalars* scal, int mode,
-             const double* r2 = nullptr, bool reverse = false);
+             const double* r2 = nullptr, bool reverse = false, const VecLink& V = VecLink());
 // moments of w_f per chunk; with `solve` the last chunk of every region also runs reduced_finish(nullptr, 0, 1) for it (one launch less)
 void reduced_moments(cudaStream_t, const Geom&, const RegionData&, const double* wRows, const PcgScalars* scal, bool solve = false);
 void reduced_finish(cudaStream_t, const Geom&, const RegionData&, const double* extraRhs, double extraScale, double tScale, const PcgScalars* scal);
 void reduced_expand(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
 // the reduced term of one apply: w_f <- scale * c_f . B^-1 (sum_f c_f w_f); one fused launch for tiled regions, moments + expand otherwise
 void reduced_apply(cudaStream_t, const Geom&, const RegionData&, double* wRows, double scale, const PcgScalars* scal);
-void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse = false);
+void k_cg_update(cudaStream_t, const RangeSet& own, double* x, double* r, double* p, const double* Ap, double* dotPartial, PcgScalars* scal, const PeerCtx& P, bool reverse = false, const VecLink& V = VecLink());
 void k_cg_init(cudaStream_t, const RangeSet& own, const double* b, double* x, double* r, double* p, double* dotPartial, PcgScalars* scal, double tol, int maxIter, const PeerCtx& P);
 void k_cg_begin(cudaStream_t, PcgScalars* scal, const PeerCtx& P);
 // BiCGSTAB fallback (pcg.h:134-200).  Dot products land rank-local in scal->bred[], the host enqueues the all-reduce
@@ -357,6 +365,8 @@ void k_eig_update_p(cudaStream_t, const RangeSet& own, const double* diag, doubl
 #ifndef PS_EMULATE
 void k_halo_push_peer(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
                       unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket);
+void k_halo_push_direct(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, const PcgScalars* S);
+void k_halo_push_p(cudaStream_t, int64_t n0, int64_t n1, const int32_t* idx, const double* r, const double* p, const double* Ap, double* dst0, double* dst1, PcgScalars* S, const PeerCtx& P);
 void k_halo_exchange_peer(cudaStream_t, int64_t ns0, int64_t ns1, const int32_t* sendIdx, double* dst0, double* dst1, unsigned long long* dflag0, unsigned long long* dflag1,
                           int64_t nr0, int64_t nr1, const int32_t* recvIdx, const double* src0, const double* src1, const unsigned long long* sflag0, const unsigned long long* sflag1,
                           unsigned long long seq, double* v, PcgScalars* S, bool respectDone, unsigned int* ticket);

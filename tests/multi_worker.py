@@ -50,10 +50,14 @@ def main(case, ndev):
     half = PolyStokesSolver(sc.nx, sc.ny, sc.nz, sc.dx, float(sc.dt) * 0.5, sc.density, **sc.params)
     rc4, vel4, valid4 = half.step_scene(sc)
     assert rc3 == rc4 == 1
+    its3, its4 = many.count("iterations"), half.count("iterations")
+    worst = 0.0
     for a in range(3):
         assert np.array_equal(valid3[a], valid4[a])
         scale = max(float(np.abs(vel4[a]).max()), 1e-30)
-        assert float(np.abs(vel3[a] - vel4[a]).max()) <= tol * scale, f"dt/2: velocity axis {a}"
+        worst = max(worst, float(np.abs(vel3[a] - vel4[a]).max()) / scale)
+    print(f"dt/2 on the same handle: iterations {its3} (multi) vs {its4} (fresh single-GPU handle), velocity max rel diff {worst:.3e} (gate {tol:.1e})")
+    assert abs(its3 - its4) <= max(2, its4 // 100) and worst <= tol, "dt/2 step differs from a fresh handle's"
     its = many.count("iterations")
     one.close(); many.close(); half.close()
     print(f"multi ok: {case} on {ndev} GPUs, {its} iterations")
