@@ -518,7 +518,7 @@ def main():
         by = solver.kernel_bytes(k) / world          # per-GPU share of the algorithmic bytes (rows are split ~evenly over the slabs)
         kern[k] = {"ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
     # the dominant kernel = the longest of the three kernels of a CG iteration, as timed above
-    names = {"pass1": "pass1_kernel (w = K_ext p with dt Mc^-1, fused region term: moments -> B^-1 -> expand)",
+    names = {"pass1": "pass1_kernel + reduced_region_kernel (w = K_ext p with dt Mc^-1, then the region term: moments -> B^-1 -> expand, one CTA per region)",
              "pass2_dots": "pass2_kernel (Ap = -K_ext^T w - 1/2 mu^-1 p, fused p.Ap, r.Ap, Ap.Ap)",
              "cg_update": "cg_update_kernel (x += a p, r -= a Ap, p = r + b p, fused r.r, x.p, p.p)"}
     dom = max(names, key=lambda k: kern[k]["ms"])
@@ -593,8 +593,10 @@ def main():
                "ms_per_step": elapsed / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": dict(config, parallelism="single GPU" if world == 1 else
                                                    f"z-slab decomposition over {world} GPUs, cuts {part[4]} (one process per GPU; per CG iteration: halo exchange of p and w + "
-                                                   "2 scalar all-reduces, " + ("fused into the kernels over NVLink peer memory" if solver.count("peerTransport") else "NCCL") +
-                                                   "; classification replicated)",
+                                                   "2 scalar all-reduces, " + ("over NVLink peer memory: boundary entries stored straight into the neighbours' vectors, reductions fused into the kernels"
+                                                                             if solver.count("peerTransport") else "NCCL") +
+                                                   ("; slab-local setup and I/O: every rank classifies / assembles / uploads its slab + halo layers" if solver.count("slabLocal")
+                                                    else "; classification replicated") + ")",
                                                    counts=counts, timing="CUDA events on the solver's stream around the K timed steps (max over ranks), bracketed by "
                                                    "barrier + synchronize; wall_ms_per_step = host clock over the same region; "
                                                    "device_ms_per_step = sum of per-stage CUDA-event times"),

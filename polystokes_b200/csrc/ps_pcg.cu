@@ -105,7 +105,7 @@ PS_D void cg_advance(PcgScalars* S, double rsold, double rr, double xx, double a
 
 #ifndef PS_EMULATE
 constexpr int HOT_THREADS = 256;
-constexpr int HOT_MAX_BLOCKS = 148 * 8;
+constexpr int HOT_MAX_BLOCKS = 1 << 14;      // bound of the partial-sum tables; the grids themselves are SM count x resident CTAs (hot_blocks)
 static_assert(HOT_THREADS == SCHED_BLOCK, "one schedule block per CTA iteration");
 
 // Programmatic dependent launch (PDL): the kernels of the CG loop form one dependency chain on one stream, ~10 launches
@@ -544,8 +544,8 @@ static inline int hot_blocks(K kernel, int64_t n) {
     int resident = 0;
     for (auto& e : cache) if (e.first == (const void*)kernel) resident = e.second;
     if (!resident) {
-        int dev = 0, sms = 148, per = 1;
-        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int per = 1;
+        const int sms = sm_count();
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, HOT_THREADS, 0);
         resident = std::min(sms * std::max(per, 1), HOT_MAX_BLOCKS);
         cache.push_back({(const void*)kernel, resident});
@@ -594,28 +594,28 @@ void k_cg_begin(cudaStream_t st, PcgScalars* scal, const PeerCtx& P) {
 }
 void k_halo_pack(cudaStream_t st, int64_t n, const int32_t* idx, const double* v, double* buf, const PcgScalars* S) {
     if (n <= 0) return;
-    launch_chain(halo_pack_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, st, n, idx, v, buf, S);
+    launch_chain(halo_pack_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 4), 256, st, n, idx, v, buf, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_push_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, unsigned long long* flag0, unsigned long long* flag1,
                       unsigned long long seq, PcgScalars* S, bool respectDone, unsigned int* ticket) {
     const int64_t n = n0 + n1;
-    launch_chain(halo_push_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, n0, n1, idx, v, dst0, dst1, flag0, flag1, seq, S, respectDone ? 1 : 0, ticket);
+    launch_chain(halo_push_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count())), 256, st, n0, n1, idx, v, dst0, dst1, flag0, flag1, seq, S, respectDone ? 1 : 0, ticket);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_push_direct(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* v, double* dst0, double* dst1, const PcgScalars* S) {
     const int64_t n = n0 + n1;
     if (n <= 0) return;
-    launch_chain(halo_push_direct_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, n0, n1, idx, v, dst0, dst1, S);
+    launch_chain(halo_push_direct_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count())), 256, st, n0, n1, idx, v, dst0, dst1, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_push_p(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* r, const double* p, const double* Ap, double* dst0, double* dst1, PcgScalars* S, const PeerCtx& P) {
     const int64_t n = n0 + n1;
     if (n <= 0) return;
-    launch_chain(halo_push_p_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, n0, n1, idx, r, p, Ap, dst0, dst1, S, P);
+    launch_chain(halo_push_p_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count())), 256, st, n0, n1, idx, r, p, Ap, dst0, dst1, S, P);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -623,7 +623,7 @@ void k_halo_exchange_peer(cudaStream_t st, int64_t ns0, int64_t ns1, const int32
                           int64_t nr0, int64_t nr1, const int32_t* recvIdx, const double* src0, const double* src1, const unsigned long long* sflag0, const unsigned long long* sflag1,
                           unsigned long long seq, double* v, PcgScalars* S, bool respectDone, unsigned int* ticket) {
     const int64_t n = std::max(ns0 + ns1, nr0 + nr1);
-    launch_chain(halo_exchange_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148)), 256, st, ns0, ns1, sendIdx, dst0, dst1, dflag0, dflag1,
+    launch_chain(halo_exchange_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count())), 256, st, ns0, ns1, sendIdx, dst0, dst1, dflag0, dflag1,
                  nr0, nr1, recvIdx, src0, src1, sflag0, sflag1, seq, v, S, respectDone ? 1 : 0, ticket);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
@@ -631,13 +631,13 @@ void k_halo_exchange_peer(cudaStream_t st, int64_t ns0, int64_t ns1, const int32
 void k_halo_unpack_peer(cudaStream_t st, int64_t n0, int64_t n1, const int32_t* idx, const double* src0, const double* src1, const unsigned long long* flag0, const unsigned long long* flag1,
                         unsigned long long seq, double* v, PcgScalars* S, bool respectDone) {
     const int64_t n = n0 + n1;
-    launch_chain(halo_wait_unpack_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 2)), 256, st, n0, n1, idx, src0, src1, flag0, flag1, seq, v, S, respectDone ? 1 : 0);
+    launch_chain(halo_wait_unpack_kernel, (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 2)), 256, st, n0, n1, idx, src0, src1, flag0, flag1, seq, v, S, respectDone ? 1 : 0);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
 void k_halo_unpack(cudaStream_t st, int64_t n, const int32_t* idx, const double* buf, double* v, const PcgScalars* S) {
     if (n <= 0) return;
-    launch_chain(halo_unpack_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 4), 256, st, n, idx, buf, v, S);
+    launch_chain(halo_unpack_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 4), 256, st, n, idx, buf, v, S);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }
@@ -1194,7 +1194,7 @@ void reduced_finish(cudaStream_t st, const Geom&, const RegionData& RG, const do
 void reduced_expand(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
     if (RG.ownRowHi <= RG.ownRowLo) return;
     const int n = RG.ownRowHi - RG.ownRowLo;
-    launch_chain(reduced_expand_kernel, (unsigned)std::min((n + RED_THREADS - 1) / RED_THREADS, 148 * 8), RED_THREADS, st, g.dx, RG.rowXYZ.p, RG.rowRegion.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.ownRowLo, RG.ownRowHi);
+    launch_chain(reduced_expand_kernel, (unsigned)std::min((n + RED_THREADS - 1) / RED_THREADS, sm_count() * 8), RED_THREADS, st, g.dx, RG.rowXYZ.p, RG.rowRegion.p, RG.com.p, RG.sigma.p, wRows, scale, S, RG.ownRowLo, RG.ownRowHi);
     PS_COUNT_LAUNCH(1);
     PS_CUDA(cudaGetLastError());
 }

@@ -54,16 +54,24 @@ inline void check(cudaError_t e, const char* what, const char* file, int line) {
 }
 #define PS_CUDA(x) ::ps::check((x), #x, __FILE__, __LINE__)
 
+// SM count of the CURRENT device (grids are sized in multiples of it); cached per host thread and device
+inline int sm_count() {
+    static thread_local int cachedDev = -1, cachedSms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cachedSms;
+    if (dev != cachedDev) { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) { cachedSms = sms; cachedDev = dev; } }
+    return cachedSms;
+}
 template <class F>
 __global__ void __launch_bounds__(256) ps_for_kernel(int64_t n, F f) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
 }
-// one thread per item, grid capped at a multiple of the SM count (148 SMs x 16 resident CTAs of 256)
+// one thread per item, grid capped at a multiple of the SM count (16 CTAs of 256 threads per SM)
 template <class F>
 inline void ps_for(cudaStream_t s, int64_t n, F f) {
     if (n <= 0) return;
     int64_t blocks = (n + 255) / 256;
-    const int64_t cap = 148 * 16;
+    const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     ps_for_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, f);
     PS_COUNT_LAUNCH(1);
@@ -79,7 +87,7 @@ inline void ps_for_range(cudaStream_t s, int64_t lo, int64_t hi, F f) {
     const int64_t n = hi - lo;
     if (n <= 0) return;
     int64_t blocks = (n + 255) / 256;
-    const int64_t cap = 148 * 16;
+    const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     ps_for_range_kernel<<<(unsigned)blocks, 256, 0, s>>>(lo, n, f);
     PS_COUNT_LAUNCH(1);

@@ -68,6 +68,7 @@ Solver::Solver(const ps_params& p) : P(p) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error("ps_create: no CUDA device (this library has no CPU path)");
     PS_CUDA(cudaSetDevice(p.device));
+    smCount = sm_count();
     PS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     PS_CUDA(cudaStreamCreateWithFlags(&stIn, cudaStreamNonBlocking));
     PS_CUDA(cudaStreamCreateWithFlags(&stOut, cudaStreamNonBlocking));
@@ -790,7 +791,7 @@ void Solver::constructMatrixBlocks() {
     const size_t n = (size_t)C.nSystemSize;
     b.alloc(n); x.alloc(n); r.alloc(n); Ap.alloc(n); allocVectors(n, (size_t)C.nRowsExt + 1);
     velSol.alloc((size_t)(C.nActiveVs + C.nReducedVs) + 1);
-    dotPartial.alloc(8192);
+    dotPartial.alloc(3 * 16384);      // three partial sums per CTA of a hot sweep (grids: SM count x resident CTAs, at most 2^14: ps_pcg.cu)
     computeOwnership();
     buildSchedules();
     buildHalos();
@@ -1506,7 +1507,7 @@ void Solver::fillStats(ps_stats* s) const {
                           (double)C.nFace[0], (double)C.nFace[1], (double)C.nFace[2], (double)C.nReducedVs,
                           (double)C.nPressures, (double)C.nStresses, (double)C.nCenter, (double)C.nCenter, (double)C.nCenter,
                           (double)C.nEdge[0], (double)C.nEdge[1], (double)C.nEdge[2], (double)C.nTotalDOFs, (double)C.nSystemSize,
-                          148.0 /* "thread count": SMs */, 0.0, (double)RG.count, g.dx, g.dt};
+                          (double)smCount /* "thread count": SMs */, 0.0, (double)RG.count, g.dx, g.dt};
     for (int i = 0; i < 27; ++i) s->dimData[i] = d[i];
     double setupMs = 0;
     for (int i = PS_STAGE_WEIGHTS; i <= PS_STAGE_ASSEMBLE; ++i) setupMs += stageMs[i];

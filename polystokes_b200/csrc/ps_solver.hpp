@@ -155,6 +155,7 @@ public:
     int usedBiCGStab = 0;
     bool cgOnly = false;                // ps_time_kernel("cg_iteration"): run exactly maxSolverIterations CG iterations, no fallback
     int fixLoops = 0;
+    int smCount = 148;                  // SMs of the handle's device (the "thread count" of the exported statistics)
     double stageMs[PS_NUM_STAGES] = {0};
 
     // ---- the reference's per-step sequence (exec/HDK_PolyStokes.C:344-584) ----
