@@ -40,9 +40,17 @@ DIST_CASES = {
     "blob64_tile16": lambda: (scenes.blob_scene(64, seed=13, tile=16, pad=2), {}),
     "s3_128": lambda: (scenes.scene_s3(128), {}),
     "blob48_tile16_pad3_layers33": lambda: (scenes.blob_scene(48, seed=5, tile=16, pad=3, liquidLayers=3, solidLayers=3), {}),
+    # tile 32: cuts at multiples of lcm(16, 32) = 32 -- 3 units over 2 ranks give slabs of 64 / 32 layers (the unequal case of S4 384^3 on 8 GPUs)
+    "blob_40x36x96_tile32_pad3": lambda: (scenes.blob_scene((40, 36, 96), seed=11, tile=32, pad=3, liquidLayers=3, solidLayers=3, tolerance=1e-6), {}),
     # CG runs out of iterations -> BiCGSTAB fallback, itself stopped after 6 iterations (results kept): checks the arithmetic
     "blob48_bicgstab6": lambda: (scenes.blob_scene(48, seed=21, tile=8, pad=1, maxIterations=6, tolerance=1e-12, keepNonConvergedResults=1), {}),
 }
+
+
+# Velocity gate of the distributed comparison where 10 x tol is not meaningful: a long, thin domain is ill conditioned (650 iterations), two
+# correct CG runs that sum their dot products in different orders stop at iterates whose recovered velocities differ by ~200 x tol.  The stop
+# rule itself is re-verified from scratch on the merged solution for every case (check_distributed).
+DIST_VEL_GATE = {"blob_40x36x96_tile32_pad3": 1e-3}
 
 
 def empty_scene():
@@ -277,7 +285,15 @@ def check_distributed(case, ranks):
     assert all(int(r["rc"]) == ro for r in ranks) and len(set(its)) == 1, f"results {[int(r['rc']) for r in ranks]} iterations {its} (oracle {ro})"
     io = o.count("iterations")
     assert abs(io - its[0]) <= max(2, int(0.01 * io)), f"iterations oracle {io} vs {its[0]}"
-    tol = max(10 * dict(sc.params, **ov)["tolerance"], 4e-7)      # the velocity fields are fp32
+    # the reference's stop rule min(rr, rr / xx) < tol^2 (pcg.h:316-325), recomputed from scratch on the merged solution with the ORACLE's operator
+    if n and ro == 1:
+        x, b = tot("solution"), o.vector("b")
+        e = b - o.apply(x)
+        rr, xx = float(e @ e), float(x @ x)
+        t2 = dict(sc.params, **ov)["tolerance"] ** 2
+        got = min(rr, rr / max(xx, 1e-300))      # slack 1.5: the solver tests its recursively updated residual, this is the true one
+        assert got < 1.5 * t2, f"merged solution does not satisfy the stop rule: {got:.3e} >= {t2:.1e}"
+    tol = DIST_VEL_GATE.get(case, max(10 * dict(sc.params, **ov)["tolerance"], 4e-7))      # the velocity fields are fp32
     for a in range(3):
         merged = np.empty_like(ovel[a])
         for r in ranks:
