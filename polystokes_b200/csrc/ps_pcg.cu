@@ -942,12 +942,13 @@ __global__ void __launch_bounds__(RED_THREADS) reduced_expand_kernel(double dx, 
 // GROUP threads per axis, ROWS rows per thread kept in registers between the two phases (0: re-read rowXYZ through L1/L2)
 template <int GROUP, int ROWS, int MINB>
 __global__ void __launch_bounds__(3 * GROUP, MINB) reduced_region_kernel(double dx, const uint32_t* __restrict__ rowXYZ, const int32_t* __restrict__ rowAxisStart, const double* __restrict__ com,
-                                                                       const double* __restrict__ Binv, double* __restrict__ wRows, double scale, const PcgScalars* S, int region0) {
+                                                                       const double* __restrict__ Binv, double* __restrict__ wRows, double scale, const PcgScalars* S, int region0,
+                                                                       const int32_t* __restrict__ order) {
     constexpr int NW = GROUP / 32, KEEP = ROWS > 0 ? ROWS : 1;
     __shared__ double Bs[RDOF * RDOF];
     __shared__ double red[3][NW][10];
     __shared__ double M[30], t[RDOF], sv[RDOF], sg[30];
-    const int r = region0 + blockIdx.x;
+    const int r = order ? __ldg(order + region0 + blockIdx.x) : region0 + blockIdx.x;      // order: longest region first (setup data)
     // B^-1, the row table and the centres of mass are setup data: they may be fetched before the previous kernel has finished
     for (int i = threadIdx.x; i < RDOF * RDOF; i += 3 * GROUP) Bs[i] = __ldg(Binv + (size_t)r * RDOF * RDOF + i);
     const int axis = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
@@ -1159,7 +1160,10 @@ bool k_pass1_regions(cudaStream_t st, const OpArgs& A, const double* x, double* 
 }
 template <int GROUP, int ROWS, int MINB>
 static void launch_region(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {
-    launch_chain(reduced_region_kernel<GROUP, ROWS, MINB>, (unsigned)(RG.regHi - RG.regLo), 3 * GROUP, st, g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, wRows, scale, S, RG.regLo);
+    // PS_REGION_LPT=1: regions in the order of decreasing row count (A/B knob)
+    static const bool lpt = getenv("PS_REGION_LPT") && atoi(getenv("PS_REGION_LPT")) != 0;
+    const int32_t* order = lpt && RG.regionOrder.n >= (size_t)RG.regHi ? RG.regionOrder.p : nullptr;
+    launch_chain(reduced_region_kernel<GROUP, ROWS, MINB>, (unsigned)(RG.regHi - RG.regLo), 3 * GROUP, st, g.dx, RG.rowXYZ.p, RG.rowAxisStart.p, RG.com.p, RG.Binv.p, wRows, scale, S, RG.regLo, order);
 }
 // w_f <- scale * c_f . B^-1 J w on the coupled reduced rows (the reduced term of one operator apply)
 void reduced_apply(cudaStream_t st, const Geom& g, const RegionData& RG, double* wRows, double scale, const PcgScalars* S) {

@@ -765,6 +765,13 @@ void Solver::constructMatrixBlocks() {
         if (!part.local) for (int k = 0; k <= part.nranks; ++k) part.redRowCut[k] = start[part.regionCut[k]];
         axisStart[(size_t)3 * R] = pos;
         RG.rowAxisStart.from_host(st, axisStart.data(), axisStart.size());
+        {   // one CTA per region: start the long ones first, so that the last wave is made of short CTAs
+            std::vector<int32_t> order((size_t)R);
+            for (int r = 0; r < R; ++r) order[r] = r;
+            auto rowsOf = [&](int32_t r) { return perRA[3 * r] + perRA[3 * r + 1] + perRA[3 * r + 2]; };
+            std::stable_sort(order.begin() + RG.regLo, order.begin() + RG.regHi, [&](int32_t a, int32_t b) { return rowsOf(a) > rowsOf(b); });
+            RG.regionOrder.from_host(st, order.data(), order.size());
+        }
         RG.rowStart.from_host(st, start.data(), start.size());
         RG.rowChunk.from_host(st, table.data(), table.size());
         RG.rowChunkStart.from_host(st, chunkStart.data(), chunkStart.size());

@@ -80,6 +80,7 @@ struct RegionData {
     DBuf<int32_t> cellChunkStart, rowChunkStart;  // [R+1] first chunk of each region
     DBuf<int32_t> rowAxisStart;  // [3R+1] first coupled reduced row of (region, face axis): the row ranges of reduced_region_kernel
     int32_t maxRegionRows = 0;   // largest number of coupled reduced rows of one region (decides fused vs chunked reduced kernels)
+    DBuf<int32_t> regionOrder;   // [R] launch order of reduced_region_kernel: the owned regions by decreasing row count (longest CTA first)
     DBuf<double> partial;    // per-chunk partial sums
     DBuf<double> t, s;       // [R][26] per-apply moment / B^-1 t
     DBuf<unsigned int> regionTicket;   // [R] chunks of the region that have delivered their moments (self-resetting)
