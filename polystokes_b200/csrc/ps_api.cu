@@ -473,7 +473,7 @@ int ps_setup(ps_handle h, const ps_fields_in* in) {
     if (!h || !in) { g_lastError = "ps_setup: null argument"; return PS_INVALID; }
     if (h->multi) { MultiGroup* G = h->multi; return G->run([&](int k) { return ps_setup(G->kids[(size_t)k], in); }); }
     return guarded(h, [&] { Solver& S = *h->S; for (double& m : S.stageMs) m = 0; g_launches = 0; 
-        try { S.setInputs(*in); S.setup(); }
+        try { S.setInputsAndSetup(*in); }
         catch (...) { stream_sync(S.stIn); S.lateInputsPending = false; throw; }   // no copy may outlive the error return
         return (int)PS_SUCCESS; });
 }

@@ -69,7 +69,7 @@ struct PeerLink {
     void* vecBase[2] = {nullptr, nullptr};
     bool vecIpc[2] = {false, false};
     void* vecPublished = nullptr;
-    size_t vecOffW = 0, vecOffWPeer[2] = {0, 0};
+    size_t vecOffW = 0;                          // offset of w in EVERY rank's arena this step (doubles; from the global system size)
     bool vecReady = false;
     PeerSync* sync(int r) const { return (PeerSync*)block[r]; }
     double* recv(int r, int kind, int par, int side) const { return (double*)((char*)block[r] + sizeof(PeerSync)) + ((size_t)((kind * 2 + par) * 2 + side)) * cap; }

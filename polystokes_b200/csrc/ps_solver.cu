@@ -109,7 +109,7 @@ void Solver::computePartition(int rank, int nranks) {
     g.zLo = part.zCut[rank]; g.zHi = part.zCut[rank + 1];
     // slab-local setup where regions cannot interact across a cut (ps_part.hpp); PS_SETUP_REPLICATED=1 forces the round-1 behaviour
     const bool forceRep = getenv("PS_SETUP_REPLICATED") && atoi(getenv("PS_SETUP_REPLICATED"));
-    part.local = nranks > 1 && !forceRep && (!P.doReducedRegions || (P.doTile && P.tilePadding >= 2));
+    part.local = nranks > 1 && !forceRep && !replicatedSetup && (!P.doReducedRegions || (P.doTile && P.tilePadding >= 2));
     part.halo = std::min(16, std::max(4, P.activeLiquidBoundaryLayerSize + P.activeSolidBoundaryLayerSize + 3));
     if (part.local && P.activeLiquidBoundaryLayerSize + P.activeSolidBoundaryLayerSize + 3 > 16) part.local = false;      // the floods reach further than one tile layer
     g.wzLo = part.local ? std::max(0, g.zLo - part.halo) : 0;
@@ -121,6 +121,9 @@ void Solver::computePartition(int rank, int nranks) {
 void Solver::setParams(const ps_params& p) {
     if (p.nx != P.nx || p.ny != P.ny || p.nz != P.nz || p.dx != P.dx) throw Error("ps_set_params: the grid (nx, ny, nz, dx) is fixed at ps_create");
     if (!(p.dt > 0)) throw Error("ps_set_params: invalid dt");
+    if (p.doReducedRegions != P.doReducedRegions || p.doTile != P.doTile || p.tileSize != P.tileSize || p.tilePadding != P.tilePadding ||
+        p.activeLiquidBoundaryLayerSize != P.activeLiquidBoundaryLayerSize || p.activeSolidBoundaryLayerSize != P.activeSolidBoundaryLayerSize)
+        replicatedSetup = false;        // other regions: slab-local setup gets another chance
     const int dev = P.device;
     P = p; P.device = dev;
     const Geom old = g;
@@ -502,7 +505,7 @@ void Solver::constructCenterReducedIndices() {
             if (part.local) {
                 // padding >= 2 keeps two regions at least two cells apart: the sweep has nothing to do; anything else would need the
                 // serial order across the cuts
-                if (hostAllreduceSum(any ? 1. : 0.) > 0.5) throw Error("slab-local setup met a cell between two reduced regions (boundary fix-up across slabs): set PS_SETUP_REPLICATED=1");
+                if (hostAllreduceSum(any ? 1. : 0.) > 0.5) throw NeedReplicatedSetup();      // every rank leaves here together (setInputsAndSetup)
                 break;
             }
             if (!any) break;            // sweep finds nothing to fix -> done
@@ -848,9 +851,9 @@ void Solver::exchangeVectorPointers() {
     if (anyMoved) {
         stream_sync(st);
         closeVectorMaps();
-        struct Card { cudaIpcMemHandle_t ipc; unsigned long long pid, ptr, offW; int dev, ok; };
+        struct Card { cudaIpcMemHandle_t ipc; unsigned long long pid, ptr; int dev, ok; };
         Card card; memset(&card, 0, sizeof card);
-        card.pid = (unsigned long long)getpid(); card.ptr = (unsigned long long)(uintptr_t)vecArena.p; card.offW = peer.vecOffW; card.dev = P.device; card.ok = 1;
+        card.pid = (unsigned long long)getpid(); card.ptr = (unsigned long long)(uintptr_t)vecArena.p; card.dev = P.device; card.ok = 1;
         if (cudaIpcGetMemHandle(&card.ipc, vecArena.p) != cudaSuccess) { cudaGetLastError(); card.ok = 0; }
         DBuf<uint8_t> dSend, dAll;
         dSend.alloc(sizeof card); dAll.alloc(sizeof card * (size_t)part.nranks);
@@ -867,7 +870,7 @@ void Solver::exchangeVectorPointers() {
             if (c.pid == card.pid) { ptr = (void*)(uintptr_t)c.ptr; peer.vecIpc[i] = false; }              // peer access was enabled in setupPeer
             else if (cudaIpcOpenMemHandle(&ptr, c.ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; continue; }
             else peer.vecIpc[i] = true;
-            peer.vecBase[i] = ptr; peer.vecOffWPeer[i] = (size_t)c.offW;
+            peer.vecBase[i] = ptr;
         }
         peer.vecPublished = vecArena.p;
         peer.vecReady = hostAllreduceSum(ok ? 0. : 1.) < 0.5;        // also the barrier: every neighbour has closed its mapping of the previous arena
@@ -1042,7 +1045,9 @@ VecLink Solver::pushDirect(Halo& H, int kind, const PeerCtx* updateCtx) {
     for (int i = 0; i < 2; ++i) {
         const int pr = H.peers[i];
         if (pr < 0) continue;
-        dst[i] = (double*)peer.vecBase[i] + (kind == 0 ? 0 : peer.vecOffWPeer[i]);
+        // w starts at the same offset in every rank's arena: it follows from the GLOBAL system size of THIS step (allocVectors), which
+        // changes from step to step while the arenas stay where they are -- so it is recomputed, never remembered from the last exchange
+        dst[i] = (double*)peer.vecBase[i] + (kind == 0 ? 0 : peer.vecOffW);
         L.raise[i] = &peer.sync(pr)->vecFlag[kind][1 - i];       // the lower neighbour sees this rank as its "above" side
     }
     if (kind == 0) k_halo_push_p(st, H.nSend[0], H.nSend[1], H.sendIdx.p, r.p, p.p, Ap.p, dst[0], dst[1], scal.p, *updateCtx);
@@ -1476,13 +1481,26 @@ void Solver::setup() {
     result = R_INCOMPLETE;
 }
 
+// inputs + setup; a slab-local attempt that meets work for the boundary fix-up is repeated with the setup replicated (collective: the
+// decision comes from an all-reduce, every rank throws and restarts at the same point)
+void Solver::setInputsAndSetup(const ps_fields_in& in) {
+    try { setInputs(in); setup(); }
+    catch (const NeedReplicatedSetup&) {
+        stream_sync(stIn); stream_sync(st);
+        lateInputsPending = false;
+        replicatedSetup = true;
+        computePartition(part.rank, part.nranks);
+        setInputs(in);
+        setup();
+    }
+}
+
 int Solver::step(const ps_fields_in& in, const ps_fields_out* out, ps_stats* stats) {
     for (double& m : stageMs) m = 0;
     g_launches = 0;
     int res = R_INCOMPLETE;
     try {
-        setInputs(in);
-        setup();
+        setInputsAndSetup(in);
         if (out) sendValidEarly(*out);
         if (P.doSolve) res = solve();
         else { x.alloc((size_t)std::max<int64_t>(C.nSystemSize, 1)); x.zero(st, (size_t)C.nSystemSize); result = R_INCOMPLETE; }     // solutionVector = 0 (S_AS:466), PS.C:513

@@ -192,6 +192,12 @@ public:
     Comm* comm = nullptr;
     void initComm(Comm* c);             // takes ownership; computes the z cuts
     void computePartition(int rank, int nranks);
+    // Slab-local setup assumes that the boundary fix-up (S_Cls:1073-1172, a serial sweep) has nothing to do.  A step that finds a
+    // candidate cell -- all ranks learn it from one all-reduce -- is restarted with the setup replicated (the round-1 form); the
+    // handle stays there until the tiling / layer parameters change.
+    struct NeedReplicatedSetup {};
+    bool replicatedSetup = false;
+    void setInputsAndSetup(const ps_fields_in& in);
     void setParams(const ps_params& p);
     void computeOwnership();            // owned row / DOF ranges of every rank from the (replicated or all-gathered) numbering
     // slab-local setup (Partition::local)

@@ -99,6 +99,16 @@ def main():
     # a second step on the same handle must reproduce the first bit for bit
     rc2, vel2, _ = s.step_scene(sc)
     out["repeat_ok"] = bool(rc2 == rc and all(np.array_equal(vel[a], vel2[a]) for a in range(3)))
+    if case in parity.DIST_NEXT:        # a different scene on the same handle
+        sc2 = parity.DIST_NEXT[case]()
+        rc3, vel3, valid3 = s.step_scene(sc2)
+        out["next_rc"] = rc3
+        out["next_iterations"] = s.count("iterations")
+        out["next_nSystemSize"] = s.count("nSystemSize")
+        out["next_regionCount"] = s.count("regionCount")
+        for a in range(3):
+            out[f"next_vel{a}"] = vel3[a]
+            out[f"next_valid{a}"] = valid3[a]
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), **out)
     dist.barrier()
     dist.destroy_process_group()

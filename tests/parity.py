@@ -38,6 +38,7 @@ DIST_CASES = {
     "box48_uniform": lambda: (scenes.box_scene(48, doReduced=0, tolerance=1e-6), {}),
     "blob_36x40x64_tile16": lambda: (scenes.blob_scene((36, 40, 64), seed=8, tile=16, pad=2), {}),
     "blob64_tile16": lambda: (scenes.blob_scene(64, seed=13, tile=16, pad=2), {}),
+    "blob64_tile16_then_shrunk": lambda: (scenes.blob_scene(64, seed=13, tile=16, pad=2, tolerance=1e-7), {}),
     "s3_128": lambda: (scenes.scene_s3(128), {}),
     "blob48_tile16_pad3_layers33": lambda: (scenes.blob_scene(48, seed=5, tile=16, pad=3, liquidLayers=3, solidLayers=3), {}),
     # tile 32: cuts at multiples of lcm(16, 32) = 32 -- 3 units over 2 ranks give slabs of 64 / 32 layers (the unequal case of S4 384^3 on 8 GPUs)
@@ -47,10 +48,22 @@ DIST_CASES = {
 }
 
 
+def _shrunk(sc, cells):
+    sc.surface = sc.surface + cells * sc.dx
+    return sc
+
+
+# a second, DIFFERENT scene stepped on the same distributed handle (other system size, same grid): every per-step table and the
+# layout of the shared vector arena must follow (tests/dist_worker.py steps it after the case's own scene)
+DIST_NEXT = {"blob64_tile16_then_shrunk": lambda: _shrunk(scenes.blob_scene(64, seed=13, tile=16, pad=2, tolerance=1e-7), 3.0)}
+
 # Velocity gate of the distributed comparison where 10 x tol is not meaningful: a long, thin domain is ill conditioned (650 iterations), two
 # correct CG runs that sum their dot products in different orders stop at iterates whose recovered velocities differ by ~200 x tol.  The stop
 # rule itself is re-verified from scratch on the merged solution for every case (check_distributed).
-DIST_VEL_GATE = {"blob_40x36x96_tile32_pad3": 1e-3}
+# The shrunk scene has a sliver face whose mass weight sits at the 0.01 clamp (S_CMB: M_c^-1 up to 100 / rho): the recovered velocity
+# there amplifies the CG stopping difference a hundredfold, so that case solves to 1e-7 and is compared at 1e-3 (measured 1.4e-4; a wrong
+# halo or a stale table shows up as O(1)).
+DIST_VEL_GATE = {"blob_40x36x96_tile32_pad3": 1e-3, "blob64_tile16_then_shrunk": 1e-3}
 
 
 def empty_scene():
@@ -303,4 +316,20 @@ def check_distributed(case, ranks):
         scale = max(float(np.abs(ovel[a]).max()), 1e-30)
         assert float(np.abs(ovel[a] - merged).max()) <= tol * scale, f"velocity axis {a}: {float(np.abs(ovel[a] - merged).max()) / scale:.2e}"
     assert all(bool(r["repeat_ok"]) for r in ranks), "second step on the same handle differs"
+    if case in DIST_NEXT:
+        sc2 = DIST_NEXT[case]()
+        o2 = Oracle(sc2, **ov).setup()
+        ro2 = o2.solve()
+        ovel2, ovalid2 = o2.writeback()
+        assert o2.count("nSystemSize") != o.count("nSystemSize"), "the second scene must change the system size"
+        for r in ranks:
+            assert int(r["next_rc"]) == ro2 and int(r["next_nSystemSize"]) == o2.count("nSystemSize") and int(r["next_regionCount"]) == o2.count("regionCount")
+            assert abs(int(r["next_iterations"]) - o2.count("iterations")) <= max(2, o2.count("iterations") // 100)
+        for a in range(3):
+            merged = np.empty_like(ovel2[a])
+            for r in ranks:
+                assert np.array_equal(own(r[f"next_valid{a}"], r), own(ovalid2[a], r)), f"second scene: valid axis {a} rank {int(r['rank'])}"
+                own(merged, r)[...] = own(r[f"next_vel{a}"], r)
+            scale = max(float(np.abs(ovel2[a]).max()), 1e-30)
+            assert float(np.abs(ovel2[a] - merged).max()) <= tol * scale, f"second scene: velocity axis {a}: {float(np.abs(ovel2[a] - merged).max()) / scale:.2e}"
     return io, its[0]

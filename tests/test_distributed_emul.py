@@ -37,7 +37,7 @@ def launch(case, world, outdir, port, gpu=False, extra_env=None):
 
 
 @pytest.mark.parametrize("case,world", [("blob48_tile8", 2), ("box48_uniform", 2), ("blob_36x40x64_tile16", 3), ("blob48_bicgstab6", 2), ("blob48_tile16_pad3_layers33", 3),
-                                        ("blob64_tile16", 4), ("blob_40x36x96_tile32_pad3", 2)])
+                                        ("blob64_tile16", 4), ("blob_40x36x96_tile32_pad3", 2), ("blob64_tile16_then_shrunk", 2)])
 def test_slab_decomposed_step_matches_oracle(built, tmp_path, case, world):
     port = 29600 + (os.getpid() + hash(case)) % 300
     ranks = launch(case, world, tmp_path, port)

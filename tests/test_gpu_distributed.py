@@ -17,7 +17,7 @@ def _ngpu():
 
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("case,world", [("blob48_tile8", 2), ("box48_uniform", 2), ("blob64_tile16", 2), ("blob64_tile16", 4), ("blob48_bicgstab6", 2),
-                                        ("blob48_tile16_pad3_layers33", 3), ("s3_128", 4), ("s3_128", 8)])
+                                        ("blob48_tile16_pad3_layers33", 3), ("s3_128", 4), ("s3_128", 8), ("blob64_tile16_then_shrunk", 2)])
 def test_gpu_slab_decomposed_step_matches_oracle(built, tmp_path, case, world, transport):
     """transport "peer": halo stores + fused all-reduce over NVLink peer memory (ps_peer.hpp); "nccl": the fallback."""
     if _ngpu() < world:

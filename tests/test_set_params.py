@@ -50,3 +50,33 @@ def test_multi_device_handle_needs_cuda(built):
     with pytest.raises(Exception) as e:
         PolyStokesSolver.from_scene(sc, lib_path=parity.EMUL_LIB, devices=[0, 1])
     assert "ps_create_multi" in str(e.value)
+
+
+def _reuse_for_another_scene(lib_path):
+    """a handle that has stepped one scene is handed a different one (other liquid shape, other system size, other region count): every grow-only
+    buffer and every cached table must be rebuilt -- the result equals a fresh handle's bit for bit, in both directions (larger -> smaller too)"""
+    big = scenes.blob_scene(40, seed=13, tile=8, pad=1)
+    small = scenes.blob_scene(40, seed=4, tile=8, pad=1)
+    small.surface = small.surface + 2.5 * small.dx          # shrink the blob: fewer unknowns, fewer regions than `big`
+    kw = dict(lib_path=lib_path) if lib_path else {}
+    for first, second in ((big, small), (small, big)):
+        a = PolyStokesSolver.from_scene(first, **kw)
+        assert a.step_scene(first)[0] == 1
+        n1 = a.count("nSystemSize")
+        rc, v, val = a.step_scene(second)
+        b = PolyStokesSolver.from_scene(second, **kw)
+        rcb, vb, valb = b.step_scene(second)
+        assert rc == rcb == 1 and a.count("nSystemSize") == b.count("nSystemSize") != n1
+        assert a.count("iterations") == b.count("iterations") and a.count("regionCount") == b.count("regionCount")
+        for ax in range(3):
+            assert np.array_equal(val[ax], valb[ax]) and np.array_equal(v[ax], vb[ax]), f"axis {ax} differs from a fresh handle"
+        a.close(); b.close()
+
+
+def test_handle_reused_for_another_scene_equals_a_fresh_handle(built):
+    _reuse_for_another_scene(parity.EMUL_LIB)
+
+
+@pytest.mark.gpu
+def test_gpu_handle_reused_for_another_scene_equals_a_fresh_handle(built):
+    _reuse_for_another_scene(None)
