@@ -73,7 +73,11 @@ struct MultiGroup {
         static const int watchdog = getenv("PS_MULTI_WATCHDOG_S") ? atoi(getenv("PS_MULTI_WATCHDOG_S")) : 120;
         bool barked = false, aborted = false;
         const auto t0 = std::chrono::steady_clock::now();
-        auto failedRank = [&]() -> int { for (size_t j = 0; j < workers.size(); ++j) { Worker* q = workers[j].get(); if (q->done && (q->rc == PS_FAILED || q->rc == PS_INVALID)) return (int)j; } return -1; };
+        // (called with no worker mutex held: every look at another worker's state takes that worker's mutex)
+        auto failedRank = [&]() -> int {
+            for (size_t j = 0; j < workers.size(); ++j) { Worker* q = workers[j].get(); std::lock_guard<std::mutex> g2(q->m); if (q->done && (q->rc == PS_FAILED || q->rc == PS_INVALID)) return (int)j; }
+            return -1;
+        };
         double failSeen = -1.;
         int rc0 = PS_SUCCESS; bool failed = false;
         for (size_t k = 0; k < workers.size(); ++k) {
@@ -88,7 +92,10 @@ struct MultiGroup {
                     if (failSeen < 0.) failSeen = el;
                     else if (el - failSeen > 5.) {
                         aborted = true;
-                        for (size_t j = 0; j < workers.size(); ++j) if (!workers[j]->done && kids[j]->S && kids[j]->S->comm) kids[j]->S->comm->abort();
+                        for (size_t j = 0; j < workers.size(); ++j) {
+                            bool busy; { std::lock_guard<std::mutex> g2(workers[j]->m); busy = !workers[j]->done; }
+                            if (busy && kids[j]->S && kids[j]->S->comm) kids[j]->S->comm->abort();
+                        }
                     }
                 }
                 if (watchdog > 0 && !barked && el > watchdog) {
@@ -96,6 +103,7 @@ struct MultiGroup {
                     fprintf(stderr, "[polystokes_b200] a collective call on the multi-GPU handle has been running for %d s:", watchdog);
                     for (size_t j = 0; j < workers.size(); ++j) {
                         Worker* q = workers[j].get();
+                        std::lock_guard<std::mutex> g2(q->m);
                         if (q->done) fprintf(stderr, " rank %zu done (rc %d%s%s);", j, q->rc, q->err.empty() ? "" : ": ", q->err.c_str());
                         else fprintf(stderr, " rank %zu in %s;", j, q->where);
                     }
