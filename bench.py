@@ -82,7 +82,41 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-REF_CACHE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "polystokes_b200_reference_run.json")
+# The reference arm's measured run is remembered on THIS machine (same boot, at most 12 h old) so that the N > 1 lines of a scaling run reuse
+# the N = 1 measurement instead of spending another quarter of an hour of host time each: the CPU path does not depend on N.
+REF_CACHES = [os.path.join(os.environ.get("TMPDIR", "/tmp"), "polystokes_b200_reference_run.json"),
+              os.path.join(ROOT, "gpurun_out", ".polystokes_b200_reference_run.json")]
+
+
+def _boot_id():
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            return f.read().strip()
+    except Exception:
+        return "unknown"
+
+
+def ref_cache_load():
+    for path in REF_CACHES:
+        try:
+            with open(path) as f:
+                res = json.load(f)
+            if res.get("scene") == "S3" and res.get("kind") is not None and res.get("boot_id") == _boot_id() and time.time() - float(res.get("time", 0)) < 12 * 3600:
+                return res
+        except Exception:
+            continue
+    return None
+
+
+def ref_cache_store(res):
+    res = dict(res, boot_id=_boot_id(), time=time.time())
+    for path in REF_CACHES:
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "w") as f:
+                json.dump(res, f)
+        except Exception:
+            pass
 
 
 def reference_available():
@@ -328,15 +362,9 @@ def main():
         budget = float(os.environ.get("PS_REF_BUDGET_S", "1500"))
         res = None
         cached = False
-        if a.gpus > 1 and os.path.exists(REF_CACHE):
-            try:
-                with open(REF_CACHE) as f:
-                    res = json.load(f)
-                cached = res.get("scene") == "S3" and res.get("kind") is not None
-                if not cached:
-                    res = None
-            except Exception:
-                res = None
+        if a.gpus > 1:
+            res = ref_cache_load()
+            cached = res is not None
         if res is None:
             if reference_available():
                 if a.n != SCENE_N:
@@ -352,11 +380,7 @@ def main():
                 n = a.n if a.n != SCENE_N else 128
                 res = run_cpu_sample(n)
                 res.update(kind="port", scene="S3", note="oracle/_ref absent: the oracle (CPU restatement, OpenMP, all cores) ran instead", cg_s=res["solve_s"], maxrss_gb=0.0, jobs=res["cores"])
-            try:
-                with open(REF_CACHE, "w") as f:
-                    json.dump(res, f)
-            except Exception:
-                pass
+            ref_cache_store(res)
         n = res["n"]
         value = 1.0 / res["seconds"]
         config = dict(config, grid=[n] * 3, workload=config["workload"].replace(f"{a.n}^3", f"{n}^3"),
@@ -579,8 +603,9 @@ def main():
                    "sample": f"oracle (OpenMP restatement, all host cores) ran ONE full step of S3 at {ncal}^3 (bounded sample, not scaled): {q['seconds']:.2f} s ({q['iterations']} CG its)"}
         # the full-size run of the reference arm on this box, if it ran before us (bench.py --impl reference writes it)
         try:
-            with open(REF_CACHE) as f:
-                full = json.load(f)
+            full = ref_cache_load()
+            if full is None:
+                raise KeyError("no reference run on this machine")
             gfull = {"grid": a.n, "e2e_steps_per_s": e2e["value"], "e2e_ms_per_step": e2e["ms_per_step"]} if full["n"] == a.n else gpu_step_rates(full["n"])
             same_grid = {"grid": [full["n"]] * 3, "reference_seconds_per_step": full["seconds"], "reference_cores": full["cores"], "reference_kind": full["kind"],
                          "ours_e2e_steps_per_s": gfull["e2e_steps_per_s"], "same_config_ratio": gfull["e2e_steps_per_s"] * full["seconds"],
