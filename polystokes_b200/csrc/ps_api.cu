@@ -535,6 +535,7 @@ double ps_get_real(ps_handle h, const char* name) {
 
 int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out) {
     if (!h || slot < 0 || slot >= N_SLOTS || kind < 0 || kind > 2) return -1;
+    if (h->multi) { g_lastError = "ps_get_index_field: per-voxel views of a ps_create_multi handle live on several GPUs; use a single-GPU handle"; return -1; }
     Solver& S = *h->S;
     const size_t n = (size_t)S.g.n[slot];
     if (!out) return (int64_t)n;
@@ -547,6 +548,7 @@ int64_t ps_get_index_field(ps_handle h, int kind, int slot, int32_t* out) {
 }
 int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out) {
     if (!h || slot < 0 || slot >= N_SLOTS) return -1;
+    if (h->multi) { g_lastError = "ps_get_weight_field: per-voxel views of a ps_create_multi handle live on several GPUs; use a single-GPU handle"; return -1; }
     Solver& S = *h->S;
     const size_t n = (size_t)S.g.n[slot];
     if (!out) return (int64_t)n;
@@ -556,6 +558,7 @@ int64_t ps_get_weight_field(ps_handle h, int liquid, int slot, float* out) {
 
 int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int64_t* nnz, int64_t* rowptr, int32_t* colidx, double* vals) {
     if (!h || !name) return PS_INVALID;
+    if (h->multi) { g_lastError = "ps_get_csr: the matrices of a ps_create_multi handle live on several GPUs; use a single-GPU handle"; return PS_INVALID; }
     return guarded(h, [&] {
         HostCsr m;
         if (!get_matrix(*h->S, name, m)) { g_lastError = std::string("ps_get_csr: unknown matrix ") + name; return (int)PS_INVALID; }
@@ -569,6 +572,7 @@ int ps_get_csr(ps_handle h, const char* name, int64_t* rows, int64_t* cols, int6
 }
 int64_t ps_get_vector(ps_handle h, const char* name, double* out) {
     if (!h || !name) return -1;
+    if (h->multi) { g_lastError = "ps_get_vector: the vectors of a ps_create_multi handle live on several GPUs; use a single-GPU handle"; return -1; }
     int64_t n = -1;
     guarded(h, [&] { std::vector<double> v; if (get_vector(*h->S, name, v)) { n = (int64_t)v.size(); if (out) std::copy(v.begin(), v.end(), out); } return 0; });
     return n;
